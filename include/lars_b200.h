@@ -1,0 +1,166 @@
+/* lars_b200 -- C ABI of the B200-native RGNir per-pixel analysis path.
+ *
+ * The reference (lars-uav/lars-image-processing) has no FFI: its boundary for this path is
+ * a set of module-level Python helpers over NumPy.  Each entry
+ * point below names the reference interface whose arithmetic it replaces (file:line
+ * relative to the reference repository); lars_image_processing_b200/*.py re-exposes them
+ * under the reference's own function names, and INTEGRATION.md shows the ctypes stub a
+ * maintainer would add.
+ *
+ * Conventions
+ *  - Every data pointer is a DEVICE pointer (sm_100a, B200).  The library never allocates,
+ *    never copies host<->device on the data path and never synchronises the stream; the
+ *    caller (PyTorch host code: tensor.data_ptr(), torch.cuda.current_stream()) owns memory
+ *    and ordering.  `stream` is a cudaStream_t passed as void*.
+ *  - Return value: 0 (LARS_OK) or a negative LARS_ERR_* code; lars_last_error() returns a
+ *    thread-local description.  The library never calls abort()/exit().
+ *  - Thread safety: all entry points are re-entrant; lars_init() is idempotent and
+ *    internally locked.  There is no CPU fallback: without a B200 every compute entry
+ *    point fails with LARS_ERR_CUDA / LARS_ERR_UNSUPPORTED.
+ *  - Frames are interleaved HWC, treated as flat arrays of n_pixels pixels.  Frame f of a
+ *    batch starts at base + f * frame_stride; every frame start must be 16-byte aligned
+ *    and each frame slot must be padded to a whole number of 16-pixel groups (the kernels
+ *    move 16-byte vectors and TMA bulk copies; bytes past n_pixels in a slot are scratch).
+ */
+#ifndef LARS_B200_H_
+#define LARS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LARS_OK 0
+#define LARS_ERR_INVALID (-1)     /* bad argument (NULL, misaligned, out of range) */
+#define LARS_ERR_CUDA (-2)        /* CUDA runtime / launch failure */
+#define LARS_ERR_UNSUPPORTED (-3) /* not an sm_100 device, or an unsupported variant */
+#define LARS_ERR_NOT_INIT (-4)    /* lars_init() has not succeeded for the current device */
+
+#define LARS_NDVI 0  /* (NIR - R) / (NIR + R + eps)   process-images.py:466-470 */
+#define LARS_GNDVI 1 /* (NIR - G) / (NIR + G + eps)   process-images.py:472-476 */
+#define LARS_NDWI 2  /* (G - NIR) / (G + NIR + eps)   process-images.py:478-482 */
+#define LARS_NUM_INDICES 3
+
+#define LARS_MAX_BINS 64      /* histogram bins supported by the fused pass (reference: 50) */
+#define LARS_PIXEL_GROUP 16   /* frame slots are padded to this many pixels */
+
+#define LARS_CMAP_RDYLGN 0 /* process-images.py:692 */
+#define LARS_CMAP_RDYLBU 1 /* process-images.py:690 */
+#define LARS_CMAP_BWR 2    /* process-images.py:956 */
+
+#define LARS_DTYPE_U8 0
+#define LARS_DTYPE_U16 1
+
+/* Statistics of one index map of one frame (replaces analyze_index, process-images.py:492-513,
+ * the inline statistics at :647-658 / :830-832, analyze_ndvi_statistics, process-ndvi.py:50-73,
+ * and the 50-bin histogram at process-ndvi.py:97). 576 bytes, all fields naturally aligned. */
+typedef struct lars_index_stats {
+  uint64_t count;       /* pixels                                                        */
+  uint64_t count_above; /* pixels with x > threshold, compared in float32 (0.2f / 0.0f)   */
+  double sum;           /* sum of x      (float64 accumulation of the float32 values)     */
+  double sumsq;         /* sum of x * x                                                    */
+  double mean;          /* sum / count                                                     */
+  double std;           /* population standard deviation, sqrt(sumsq/count - mean^2)       */
+  float min;
+  float max;
+  float threshold;
+  uint32_t bins;
+  uint64_t hist[LARS_MAX_BINS]; /* np.histogram(x, bins, range=(-1, 1)); entries >= bins are 0 */
+} lars_index_stats;
+
+/* Arguments of the fused Pass 2 (one struct so the ABI can grow without breaking callers). */
+typedef struct lars_fused_args {
+  uint32_t struct_bytes;      /* = sizeof(lars_fused_args), checked                         */
+  int32_t n_frames;
+  int32_t channels;           /* 3 (RGN) or 4 (RGNA; alpha is ignored and written as 0)     */
+  int32_t bins;               /* 1..LARS_MAX_BINS                                            */
+  int64_t n_pixels;           /* pixels per frame                                            */
+  const uint8_t* src;         /* raw frames                                                  */
+  int64_t src_frame_stride;   /* bytes                                                       */
+  const uint8_t* wb_lut;      /* [frame][3][256] stretch LUTs, NULL = identity (no WB)       */
+  int64_t lut_frame_stride;   /* bytes between frames' LUTs; 0 = one LUT set for all frames  */
+  uint8_t* wb_out;            /* white-balanced frames, same channel count as src, or NULL   */
+  int64_t wb_frame_stride;    /* bytes                                                       */
+  float* maps[LARS_NUM_INDICES];   /* float32 index maps (NDVI, GNDVI, NDWI), each or all NULL */
+  int64_t map_frame_stride;   /* elements                                                    */
+  uint8_t* rgb[LARS_NUM_INDICES];  /* colormapped HWC RGB images, each or all NULL            */
+  int64_t rgb_frame_stride;   /* bytes                                                       */
+  int32_t cmap[LARS_NUM_INDICES];  /* LARS_CMAP_* per index (reference: RdYlGn, RdYlGn, RdYlBu) */
+  float thresholds[LARS_NUM_INDICES]; /* coverage thresholds (reference: 0.2, 0.2, 0.0)      */
+  lars_index_stats* stats;    /* [frame][3] or NULL                                          */
+  void* workspace;            /* lars_fused_workspace_bytes(n_frames) bytes, 16-byte aligned */
+  size_t workspace_bytes;
+} lars_fused_args;
+
+/* ---- lifecycle ---------------------------------------------------------------------- */
+int lars_init(int device_ordinal); /* checks sm_100, sets kernel attributes, uploads colormaps */
+int lars_shutdown(void);
+const char* lars_last_error(void);
+int lars_abi_version(void);
+int lars_sm_count(void);
+
+/* ---- host-only helpers (no GPU needed) ----------------------------------------------- */
+/* matplotlib 'RdYlGn' / 'RdYlBu' / 'bwr' as 256 RGB byte triplets
+ * (process-images.py:689-695, :956; backend-process.py:42; process-ndvi.py:38). */
+int lars_colormap_table(int cmap_id, uint8_t* rgb_out /* [256][3] host */);
+/* np.linspace(-1, 1, bins + 1) rounded to float32 (numpy/lib/_histograms_impl.py:440-447). */
+int lars_histogram_edges_f32(int bins, float* edges_out /* [bins + 1] host */);
+
+/* ---- Pass 1: white-balance statistics -------------------------------------------------
+ * Replaces the three np.percentile(channel, (2, 98)) calls of fix_white_balance
+ * (process-images.py:435-437; backend-process.py:21-23; process-rgn.py:28).
+ * hist is [n_frames][3][256] uint64 and is ZEROED by the call, then filled. */
+int lars_wb_hist_u8(const uint8_t* src, int32_t n_frames, int64_t n_pixels, int32_t channels,
+                    int64_t src_frame_stride, uint64_t* hist, void* stream);
+
+/* Percentiles (NumPy "linear" method, float64) and the stretch
+ * clip((v - p_lo) / (p_hi - p_lo) * 255, 0, 255) -> float32 -> uint8 for every v in 0..255
+ * (process-images.py:437-441).  n_sets histogram sets in, n_sets LUT sets out:
+ * lut [n_sets][3][256] uint8, pct [n_sets][3][2] float64 (may be NULL).
+ * q_lo / q_hi are fractions (reference: 0.02, 0.98). */
+int lars_wb_lut_build_u8(const uint64_t* hist, int32_t n_sets, double q_lo, double q_hi,
+                         uint8_t* lut, double* pct, void* stream);
+
+/* ---- Pass 2: fused WB + NDVI/GNDVI/NDWI + statistics + histogram + colormap -----------
+ * Replaces, in one read of the raw frame: the stretch application (process-images.py:438-441),
+ * calculate_index x3 (:449-490), analyze_index x3 (:492-513) minus the median, np.std
+ * (process-ndvi.py:65), the 50-bin histogram (process-ndvi.py:97) and the colormap lookup
+ * of create_index_visualization (:689-695). */
+size_t lars_fused_workspace_bytes(int32_t n_frames);
+int lars_fused_index_u8(const lars_fused_args* args, void* stream);
+
+/* ---- float-map operations next to the fused pass ---------------------------------------- */
+/* Statistics + np.histogram(x, bins, range=(-1, 1)) of arbitrary float32 maps: replaces
+ * analyze_index on a caller-supplied array (process-images.py:492-513), the inline statistics
+ * at :647-658 / :830-832, analyze_ndvi_statistics (process-ndvi.py:50-73) and plt.hist (:97).
+ * data is [n_maps][stride] float32 (16-byte aligned rows), stats is [n_maps]. */
+size_t lars_map_stats_workspace_bytes(int32_t n_maps);
+int lars_map_stats_f32(const float* data, int32_t n_maps, int64_t n, int64_t stride, int32_t bins,
+                       float threshold, lars_index_stats* stats, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* Exact order statistics of a float32 map (np.median, process-images.py:508, :654;
+ * process-ndvi.py:62): out3 (device) = { x[rank_lo], x[rank_hi], float32 mean of the two }
+ * of the sorted data.  4-pass radix select, no sort, no host round trip. */
+size_t lars_select_workspace_bytes(void);
+int lars_select_f32(const float* data, int64_t n, uint64_t rank_lo, uint64_t rank_hi, float* out3,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Normalize(vmin, vmax) + colormap lookup of a float32 map -> [n][3] uint8 (the per-pixel part of
+ * create_index_visualization, process-images.py:689-695; 'bwr' +-0.5 for change detection, :956). */
+int lars_colormap_f32(const float* data, int64_t n, int32_t cmap_id, float vmin, float vmax,
+                      uint8_t* rgb, void* stream);
+
+/* float64 NDVI of a raw uint8 frame, no white balance (calculate_ndvi, process-ndvi.py:18-31). */
+int lars_ndvi_f64_u8(const uint8_t* src, int64_t n_pixels, int32_t channels, double* out, void* stream);
+
+/* clip((hi - lo) / (hi + lo + 1e-10), -1, 1) on separate float32 planes
+ * (calculate_index(red, green, nir, index_type), backend-process.py:28-38). */
+int lars_index_planes_f32(const float* hi, const float* lo, int64_t n, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LARS_B200_H_ */

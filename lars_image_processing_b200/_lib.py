@@ -1,0 +1,156 @@
+"""ctypes binding of liblars_b200.so (the C ABI in include/lars_b200.h).
+
+There is no fallback: if the CUDA library cannot be loaded the package raises.
+ctypes releases the GIL for the duration of every call, so Streamlit's per-session threads
+("Threading") can enter the library concurrently.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+from . import build as _build
+
+LARS_OK = 0
+NUM_INDICES = 3
+MAX_BINS = 64
+PIXEL_GROUP = 16
+CMAP_IDS = {"RdYlGn": 0, "RdYlBu": 1, "bwr": 2}
+
+EXPORTED_SYMBOLS = (
+    "lars_init", "lars_shutdown", "lars_last_error", "lars_abi_version", "lars_sm_count",
+    "lars_colormap_table", "lars_histogram_edges_f32",
+    "lars_wb_hist_u8", "lars_wb_lut_build_u8",
+    "lars_fused_workspace_bytes", "lars_fused_index_u8",
+    "lars_map_stats_workspace_bytes", "lars_map_stats_f32", "lars_select_workspace_bytes",
+    "lars_select_f32", "lars_colormap_f32", "lars_ndvi_f64_u8", "lars_index_planes_f32",
+)
+
+
+class LarsError(RuntimeError):
+    """A C-ABI call returned a negative status."""
+
+
+class FusedArgs(C.Structure):
+    """Mirror of ``lars_fused_args`` (include/lars_b200.h)."""
+    _fields_ = [
+        ("struct_bytes", C.c_uint32),
+        ("n_frames", C.c_int32),
+        ("channels", C.c_int32),
+        ("bins", C.c_int32),
+        ("n_pixels", C.c_int64),
+        ("src", C.c_void_p),
+        ("src_frame_stride", C.c_int64),
+        ("wb_lut", C.c_void_p),
+        ("lut_frame_stride", C.c_int64),
+        ("wb_out", C.c_void_p),
+        ("wb_frame_stride", C.c_int64),
+        ("maps", C.c_void_p * NUM_INDICES),
+        ("map_frame_stride", C.c_int64),
+        ("rgb", C.c_void_p * NUM_INDICES),
+        ("rgb_frame_stride", C.c_int64),
+        ("cmap", C.c_int32 * NUM_INDICES),
+        ("thresholds", C.c_float * NUM_INDICES),
+        ("stats", C.c_void_p),
+        ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_size_t),
+    ]
+
+
+# numpy view of ``lars_index_stats`` (576 bytes)
+INDEX_STATS_DTYPE = np.dtype([
+    ("count", "<u8"), ("count_above", "<u8"),
+    ("sum", "<f8"), ("sumsq", "<f8"), ("mean", "<f8"), ("std", "<f8"),
+    ("min", "<f4"), ("max", "<f4"), ("threshold", "<f4"), ("bins", "<u4"),
+    ("hist", "<u8", (MAX_BINS,)),
+])
+assert INDEX_STATS_DTYPE.itemsize == 576
+
+_lock = threading.Lock()
+_lib = None
+
+
+def _declare(lib):
+    vp, i32, i64, f64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_float
+    lib.lars_init.argtypes = [C.c_int]
+    lib.lars_init.restype = C.c_int
+    lib.lars_shutdown.argtypes = []
+    lib.lars_shutdown.restype = C.c_int
+    lib.lars_last_error.argtypes = []
+    lib.lars_last_error.restype = C.c_char_p
+    lib.lars_abi_version.argtypes = []
+    lib.lars_abi_version.restype = C.c_int
+    lib.lars_sm_count.argtypes = []
+    lib.lars_sm_count.restype = C.c_int
+    lib.lars_colormap_table.argtypes = [C.c_int, vp]
+    lib.lars_colormap_table.restype = C.c_int
+    lib.lars_histogram_edges_f32.argtypes = [C.c_int, vp]
+    lib.lars_histogram_edges_f32.restype = C.c_int
+    lib.lars_wb_hist_u8.argtypes = [vp, i32, i64, i32, i64, vp, vp]
+    lib.lars_wb_hist_u8.restype = C.c_int
+    lib.lars_wb_lut_build_u8.argtypes = [vp, i32, f64, f64, vp, vp, vp]
+    lib.lars_wb_lut_build_u8.restype = C.c_int
+    lib.lars_fused_workspace_bytes.argtypes = [i32]
+    lib.lars_fused_workspace_bytes.restype = C.c_size_t
+    lib.lars_fused_index_u8.argtypes = [C.POINTER(FusedArgs), vp]
+    lib.lars_fused_index_u8.restype = C.c_int
+    lib.lars_map_stats_workspace_bytes.argtypes = [i32]
+    lib.lars_map_stats_workspace_bytes.restype = C.c_size_t
+    lib.lars_map_stats_f32.argtypes = [vp, i32, i64, i64, i32, f32, vp, vp, C.c_size_t, vp]
+    lib.lars_map_stats_f32.restype = C.c_int
+    lib.lars_select_workspace_bytes.argtypes = []
+    lib.lars_select_workspace_bytes.restype = C.c_size_t
+    lib.lars_select_f32.argtypes = [vp, i64, C.c_uint64, C.c_uint64, vp, vp, C.c_size_t, vp]
+    lib.lars_select_f32.restype = C.c_int
+    lib.lars_colormap_f32.argtypes = [vp, i64, i32, f32, f32, vp, vp]
+    lib.lars_colormap_f32.restype = C.c_int
+    lib.lars_ndvi_f64_u8.argtypes = [vp, i64, i32, vp, vp]
+    lib.lars_ndvi_f64_u8.restype = C.c_int
+    lib.lars_index_planes_f32.argtypes = [vp, vp, i64, vp, vp]
+    lib.lars_index_planes_f32.restype = C.c_int
+
+
+def load():
+    """Load (building first if the .so is absent and nvcc is available) and return the CDLL."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB_PATH
+        if not os.path.isfile(path):
+            try:
+                _build.build()
+            except Exception as exc:  # no CPU fallback -- fail loudly
+                raise ImportError(
+                    f"liblars_b200.so is missing at {path} and could not be built ({exc}); "
+                    "run `python -c 'import __graft_entry__ as g; g.build()'`") from exc
+        lib = C.CDLL(path)
+        missing = [s for s in EXPORTED_SYMBOLS if not hasattr(lib, s)]
+        if missing:
+            raise ImportError(f"{path} does not export {missing}; rebuild it")
+        _declare(lib)
+        _lib = lib
+        return lib
+
+
+def check(status: int, what: str = "") -> int:
+    if status < 0:
+        msg = load().lars_last_error().decode("utf-8", "replace")
+        raise LarsError(f"{what or 'lars call'} failed ({status}): {msg}")
+    return status
+
+
+def colormap_table(name: str) -> np.ndarray:
+    """(256, 3) uint8 table of a built-in colormap (host-only, no GPU needed)."""
+    out = np.empty((256, 3), np.uint8)
+    check(load().lars_colormap_table(CMAP_IDS[name], out.ctypes.data), "lars_colormap_table")
+    return out
+
+
+def histogram_edges(bins: int) -> np.ndarray:
+    out = np.empty(bins + 1, np.float32)
+    check(load().lars_histogram_edges_f32(bins, out.ctypes.data), "lars_histogram_edges_f32")
+    return out

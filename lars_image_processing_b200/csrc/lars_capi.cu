@@ -1,0 +1,426 @@
+// C ABI of liblars_b200.so (declared in include/lars_b200.h).  Host-side validation and
+// launches only: no allocation, no host<->device copies of image data, no stream syncs.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "../../include/lars_b200.h"
+#include "host_tables.h"
+#include "lars_kernels.cuh"
+#include "lars_map_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define LARS_CUDA(call)                                                                   \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(LARS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                    \
+  } while (0)
+
+constexpr int kMaxDevices = 64;
+struct DeviceState {
+  bool ready = false;
+  int sm_count = 0;
+  uint32_t* cmaps = nullptr;  // [3][256] packed RGB, device
+};
+DeviceState g_dev[kMaxDevices];
+std::mutex g_mu;
+
+int current_state(DeviceState** out) {
+  int dev = -1;
+  LARS_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) return fail(LARS_ERR_INVALID, "device ordinal %d out of range", dev);
+  if (!g_dev[dev].ready)
+    return fail(LARS_ERR_NOT_INIT, "lars_init(%d) has not been called for the current device", dev);
+  *out = &g_dev[dev];
+  return LARS_OK;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+const char* lars_last_error(void) { return g_err; }
+int lars_abi_version(void) { return 1; }
+
+int lars_init(int device) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  if (device < 0 || device >= kMaxDevices) return fail(LARS_ERR_INVALID, "bad device ordinal %d", device);
+  int count = 0;
+  LARS_CUDA(cudaGetDeviceCount(&count));
+  if (device >= count) return fail(LARS_ERR_INVALID, "device %d not present (%d visible)", device, count);
+  if (g_dev[device].ready) return LARS_OK;
+  int prev = -1;
+  LARS_CUDA(cudaGetDevice(&prev));
+  LARS_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  LARS_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    cudaSetDevice(prev);
+    return fail(LARS_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library only contains sm_100a code (B200)",
+                device, prop.major, prop.minor);
+  }
+  DeviceState& st = g_dev[device];
+  st.sm_count = prop.multiProcessorCount;
+
+  LARS_CUDA(cudaFuncSetAttribute(lars::wb_hist_u8_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 lars::K1_SMEM_BYTES));
+  LARS_CUDA(cudaFuncSetAttribute(lars::wb_hist_u8_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 lars::K1_SMEM_BYTES));
+  LARS_CUDA(cudaFuncSetAttribute(lars::fused_index_u8_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 lars::K2Smem<3>::TOTAL));
+  LARS_CUDA(cudaFuncSetAttribute(lars::fused_index_u8_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 lars::K2Smem<4>::TOTAL));
+  LARS_CUDA(cudaFuncSetAttribute(lars::select_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 lars::SEL_SMEM_BYTES));
+
+  // colormap tables: 3 x 256 packed R | G << 8 | B << 16
+  static uint32_t packed[3 * 256];
+  for (int c = 0; c < 3; ++c) {
+    uint8_t t[256][3];
+    lars_host::build_colormap(c, t);
+    for (int i = 0; i < 256; ++i)
+      packed[c * 256 + i] = (uint32_t)t[i][0] | ((uint32_t)t[i][1] << 8) | ((uint32_t)t[i][2] << 16);
+  }
+  LARS_CUDA(cudaMalloc(&st.cmaps, sizeof(packed)));  // 3 KB of constants, lives until lars_shutdown
+  LARS_CUDA(cudaMemcpy(st.cmaps, packed, sizeof(packed), cudaMemcpyHostToDevice));
+  st.ready = true;
+  if (prev >= 0 && prev != device) LARS_CUDA(cudaSetDevice(prev));
+  return LARS_OK;
+}
+
+int lars_shutdown(void) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  for (int d = 0; d < kMaxDevices; ++d) {
+    if (g_dev[d].ready) {
+      int prev = -1;
+      cudaGetDevice(&prev);
+      cudaSetDevice(d);
+      cudaFree(g_dev[d].cmaps);
+      if (prev >= 0) cudaSetDevice(prev);
+      g_dev[d] = DeviceState();
+    }
+  }
+  return LARS_OK;
+}
+
+int lars_sm_count(void) {
+  DeviceState* st = nullptr;
+  int rc = current_state(&st);
+  if (rc != LARS_OK) return rc;
+  return st->sm_count;
+}
+
+int lars_colormap_table(int cmap_id, uint8_t* rgb_out) {
+  if (!rgb_out) return fail(LARS_ERR_INVALID, "rgb_out is NULL");
+  uint8_t t[256][3];
+  if (!lars_host::build_colormap(cmap_id, t)) return fail(LARS_ERR_INVALID, "unknown colormap id %d", cmap_id);
+  memcpy(rgb_out, t, sizeof(t));
+  return LARS_OK;
+}
+
+int lars_histogram_edges_f32(int bins, float* edges_out) {
+  if (!edges_out || bins < 1) return fail(LARS_ERR_INVALID, "bad histogram edge request (bins=%d)", bins);
+  lars_host::histogram_edges_f32(bins, edges_out);
+  return LARS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Pass 1
+// ------------------------------------------------------------------------------------------
+int lars_wb_hist_u8(const uint8_t* src, int32_t n_frames, int64_t n_pixels, int32_t channels,
+                    int64_t src_frame_stride, uint64_t* hist, void* stream) {
+  DeviceState* st = nullptr;
+  int rc = current_state(&st);
+  if (rc != LARS_OK) return rc;
+  if (!src || !hist) return fail(LARS_ERR_INVALID, "lars_wb_hist_u8: NULL pointer");
+  if (n_frames < 1 || n_pixels < 1) return fail(LARS_ERR_INVALID, "lars_wb_hist_u8: empty input (frames=%d, pixels=%lld)", n_frames, (long long)n_pixels);
+  if (channels != 3 && channels != 4) return fail(LARS_ERR_UNSUPPORTED, "lars_wb_hist_u8: channels must be 3 or 4, got %d", channels);
+  if (!aligned16(src) || (src_frame_stride & 15) || src_frame_stride < n_pixels * channels)
+    return fail(LARS_ERR_INVALID, "lars_wb_hist_u8: src / frame stride must be 16-byte aligned and cover a frame");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  LARS_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint64_t) * 768 * (size_t)n_frames, s));
+
+  const long long frame_bytes = (long long)n_pixels * channels;
+  const long long unit = (channels == 3) ? lars::K1Unit<3>::BYTES : lars::K1Unit<4>::BYTES;
+  lars::K1Params p;
+  p.src = src;
+  p.hist = reinterpret_cast<unsigned long long*>(hist);
+  p.n_pixels = n_pixels;
+  p.frame_stride = src_frame_stride;
+  p.units_per_frame = (frame_bytes + unit - 1) / unit;
+  p.total_units = p.units_per_frame * n_frames;
+  p.n_frames = n_frames;
+  const long long target_ctas = 2ll * st->sm_count;  // 2 resident CTAs per SM (96 KB smem each)
+  const int grid = (int)(p.total_units < target_ctas ? p.total_units : target_ctas);
+  if (channels == 3)
+    lars::wb_hist_u8_kernel<3><<<grid, lars::K1_THREADS, lars::K1_SMEM_BYTES, s>>>(p);
+  else
+    lars::wb_hist_u8_kernel<4><<<grid, lars::K1_THREADS, lars::K1_SMEM_BYTES, s>>>(p);
+  LARS_CUDA(cudaGetLastError());
+  return LARS_OK;
+}
+
+int lars_wb_lut_build_u8(const uint64_t* hist, int32_t n_sets, double q_lo, double q_hi, uint8_t* lut,
+                         double* pct, void* stream) {
+  DeviceState* st = nullptr;
+  int rc = current_state(&st);
+  if (rc != LARS_OK) return rc;
+  if (!hist || !lut) return fail(LARS_ERR_INVALID, "lars_wb_lut_build_u8: NULL pointer");
+  if (n_sets < 1) return fail(LARS_ERR_INVALID, "lars_wb_lut_build_u8: n_sets=%d", n_sets);
+  if (!(q_lo >= 0.0 && q_lo <= 1.0 && q_hi >= 0.0 && q_hi <= 1.0))
+    return fail(LARS_ERR_INVALID, "lars_wb_lut_build_u8: quantiles must be fractions in [0,1]");
+  lars::K1bParams p;
+  p.hist = reinterpret_cast<const unsigned long long*>(hist);
+  p.lut = lut;
+  p.pct = pct;
+  p.q_lo = q_lo;
+  p.q_hi = q_hi;
+  lars::wb_lut_build_u8_kernel<<<n_sets * 3, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  LARS_CUDA(cudaGetLastError());
+  return LARS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Pass 2
+// ------------------------------------------------------------------------------------------
+static int fused_grid(int sm_count) {
+  int g = sm_count * 2;
+  return g > lars::K2_MAX_GRID ? lars::K2_MAX_GRID : g;
+}
+
+size_t lars_fused_workspace_bytes(int32_t n_frames) {
+  if (n_frames < 1) return 0;
+  const size_t slots = (size_t)lars::K2_MAX_GRID / (size_t)n_frames + 2;
+  return slots * (size_t)n_frames * sizeof(lars::K2Partial);
+}
+
+int lars_fused_index_u8(const lars_fused_args* a, void* stream) {
+  DeviceState* st = nullptr;
+  int rc = current_state(&st);
+  if (rc != LARS_OK) return rc;
+  if (!a) return fail(LARS_ERR_INVALID, "lars_fused_index_u8: args is NULL");
+  if (a->struct_bytes != sizeof(lars_fused_args))
+    return fail(LARS_ERR_INVALID, "lars_fused_index_u8: struct_bytes=%u, library expects %zu", a->struct_bytes,
+                sizeof(lars_fused_args));
+  if (!a->src) return fail(LARS_ERR_INVALID, "lars_fused_index_u8: src is NULL");
+  if (a->n_frames < 1 || a->n_pixels < 1)
+    return fail(LARS_ERR_INVALID, "lars_fused_index_u8: empty input (frames=%d, pixels=%lld)", a->n_frames, (long long)a->n_pixels);
+  if (a->channels != 3 && a->channels != 4)
+    return fail(LARS_ERR_UNSUPPORTED, "lars_fused_index_u8: channels must be 3 or 4, got %d", a->channels);
+  if (a->bins < 1 || a->bins > LARS_MAX_BINS)
+    return fail(LARS_ERR_INVALID, "lars_fused_index_u8: bins must be in 1..%d, got %d", LARS_MAX_BINS, a->bins);
+  const int C = a->channels;
+  const int64_t padded_px = (a->n_pixels + LARS_PIXEL_GROUP - 1) / LARS_PIXEL_GROUP * LARS_PIXEL_GROUP;
+  if (!aligned16(a->src) || (a->src_frame_stride & 15) || a->src_frame_stride < padded_px * C)
+    return fail(LARS_ERR_INVALID, "lars_fused_index_u8: src must be 16-byte aligned with a 16-pixel padded frame stride");
+  if (a->wb_out && (!aligned16(a->wb_out) || (a->wb_frame_stride & 15) || a->wb_frame_stride < padded_px * C))
+    return fail(LARS_ERR_INVALID, "lars_fused_index_u8: wb_out alignment / stride");
+  for (int i = 0; i < 3; ++i) {
+    if (a->maps[i] && (!aligned16(a->maps[i]) || (a->map_frame_stride & 3) || a->map_frame_stride < padded_px))
+      return fail(LARS_ERR_INVALID, "lars_fused_index_u8: maps[%d] alignment / stride", i);
+    if (a->rgb[i] && (!aligned16(a->rgb[i]) || (a->rgb_frame_stride & 15) || a->rgb_frame_stride < padded_px * 3))
+      return fail(LARS_ERR_INVALID, "lars_fused_index_u8: rgb[%d] alignment / stride", i);
+    if (a->cmap[i] < 0 || a->cmap[i] > 2) return fail(LARS_ERR_INVALID, "lars_fused_index_u8: cmap[%d]=%d", i, a->cmap[i]);
+  }
+  if (a->wb_lut && a->lut_frame_stride != 0 && a->lut_frame_stride < 768)
+    return fail(LARS_ERR_INVALID, "lars_fused_index_u8: lut_frame_stride must be 0 or >= 768");
+  if (a->stats) {
+    if (!a->workspace || !aligned16(a->workspace) || a->workspace_bytes < lars_fused_workspace_bytes(a->n_frames))
+      return fail(LARS_ERR_INVALID, "lars_fused_index_u8: workspace too small (%zu < %zu) or misaligned",
+                  a->workspace_bytes, lars_fused_workspace_bytes(a->n_frames));
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+
+  lars::K2Params p;
+  memset(&p, 0, sizeof(p));
+  p.src = a->src;
+  p.wb_lut = a->wb_lut;
+  p.wb_out = a->wb_out;
+  for (int i = 0; i < 3; ++i) {
+    p.maps[i] = a->maps[i];
+    p.rgb[i] = a->rgb[i];
+    p.cmap_id[i] = a->cmap[i];
+    p.thresholds[i] = a->thresholds[i];
+  }
+  p.cmaps = st->cmaps;
+  p.n_pixels = a->n_pixels;
+  p.src_frame_stride = a->src_frame_stride;
+  p.lut_frame_stride = a->lut_frame_stride;
+  p.wb_frame_stride = a->wb_frame_stride;
+  p.map_frame_stride = a->map_frame_stride;
+  p.rgb_frame_stride = a->rgb_frame_stride;
+  p.tiles_per_frame = (a->n_pixels + lars::K2_TILE_PX - 1) / lars::K2_TILE_PX;
+  p.total_tiles = p.tiles_per_frame * a->n_frames;
+  p.n_frames = a->n_frames;
+  p.bins = a->bins;
+  long long grid = fused_grid(st->sm_count);
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  p.slots_per_frame = (int)(grid / a->n_frames + 2);
+  p.partials = nullptr;
+  if (a->stats) {
+    p.partials = static_cast<lars::K2Partial*>(a->workspace);
+    LARS_CUDA(cudaMemsetAsync(a->workspace, 0,
+                              (size_t)p.slots_per_frame * a->n_frames * sizeof(lars::K2Partial), s));
+  }
+  if (C == 3)
+    lars::fused_index_u8_kernel<3><<<(int)grid, lars::K2_THREADS, lars::K2Smem<3>::TOTAL, s>>>(p);
+  else
+    lars::fused_index_u8_kernel<4><<<(int)grid, lars::K2_THREADS, lars::K2Smem<4>::TOTAL, s>>>(p);
+  LARS_CUDA(cudaGetLastError());
+  if (a->stats) {
+    lars::K2fParams f;
+    f.partials = p.partials;
+    f.stats = a->stats;
+    f.slots_per_frame = p.slots_per_frame;
+    f.bins = a->bins;
+    for (int i = 0; i < 3; ++i) f.thresholds[i] = a->thresholds[i];
+    lars::fused_finalize_kernel<<<a->n_frames, 3 * lars::K2_BINS_PAD, 0, s>>>(f);
+    LARS_CUDA(cudaGetLastError());
+  }
+  return LARS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// float-map operations
+// ------------------------------------------------------------------------------------------
+static int map_parts(int sm_count) { return sm_count * 4; }
+
+size_t lars_map_stats_workspace_bytes(int32_t n_maps) {
+  if (n_maps < 1) return 0;
+  return (size_t)n_maps * (size_t)(148 * 4) * sizeof(lars::MapPartial);
+}
+
+int lars_map_stats_f32(const float* data, int32_t n_maps, int64_t n, int64_t stride, int32_t bins,
+                       float threshold, lars_index_stats* stats, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  DeviceState* st = nullptr;
+  int rc = current_state(&st);
+  if (rc != LARS_OK) return rc;
+  if (!data || !stats || !workspace) return fail(LARS_ERR_INVALID, "lars_map_stats_f32: NULL pointer");
+  if (n_maps < 1 || n < 1) return fail(LARS_ERR_INVALID, "lars_map_stats_f32: empty input");
+  if (bins < 1 || bins > LARS_MAX_BINS) return fail(LARS_ERR_INVALID, "lars_map_stats_f32: bins must be in 1..%d", LARS_MAX_BINS);
+  if (!aligned16(data) || (n_maps > 1 && (stride & 3))) return fail(LARS_ERR_INVALID, "lars_map_stats_f32: rows must be 16-byte aligned");
+  int parts = map_parts(st->sm_count);
+  if (parts > 148 * 4) parts = 148 * 4;
+  const long long nvec = n / 4;
+  if (parts > nvec) parts = (int)(nvec > 0 ? nvec : 1);
+  if (workspace_bytes < (size_t)n_maps * parts * sizeof(lars::MapPartial) || !aligned16(workspace))
+    return fail(LARS_ERR_INVALID, "lars_map_stats_f32: workspace too small or misaligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  lars::MapStatsParams p;
+  p.data = data; p.n = n; p.stride = stride;
+  p.partials = static_cast<lars::MapPartial*>(workspace);
+  p.threshold = threshold; p.bins = bins;
+  const size_t smem = (size_t)bins * 128 + (size_t)((bins + 1 + 3) / 4) * 16 + 8 * 8 * 8;
+  lars::map_stats_f32_kernel<<<dim3(parts, n_maps), lars::MAP_THREADS, smem, s>>>(p);
+  LARS_CUDA(cudaGetLastError());
+  lars::MapFinalizeParams f;
+  f.partials = p.partials; f.data = data; f.stride = stride; f.stats = stats;
+  f.n_parts = parts; f.bins = bins; f.threshold = threshold;
+  lars::map_stats_finalize_kernel<<<n_maps, lars::MAP_HIST_ROWS, 0, s>>>(f);
+  LARS_CUDA(cudaGetLastError());
+  return LARS_OK;
+}
+
+size_t lars_select_workspace_bytes(void) { return sizeof(lars::SelectState); }
+
+int lars_select_f32(const float* data, int64_t n, uint64_t rank_lo, uint64_t rank_hi, float* out3,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  DeviceState* st = nullptr;
+  int rc = current_state(&st);
+  if (rc != LARS_OK) return rc;
+  if (!data || !out3 || !workspace) return fail(LARS_ERR_INVALID, "lars_select_f32: NULL pointer");
+  if (n < 1 || rank_lo >= (uint64_t)n || rank_hi >= (uint64_t)n || rank_lo > rank_hi)
+    return fail(LARS_ERR_INVALID, "lars_select_f32: ranks out of range");
+  if (!aligned16(data)) return fail(LARS_ERR_INVALID, "lars_select_f32: data must be 16-byte aligned");
+  if (workspace_bytes < sizeof(lars::SelectState) || !aligned16(workspace))
+    return fail(LARS_ERR_INVALID, "lars_select_f32: workspace too small or misaligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  lars::SelectState* state = static_cast<lars::SelectState*>(workspace);
+  lars::select_init_kernel<<<1, 256, 0, s>>>(state, rank_lo, rank_hi);
+  long long want = (n / 4 + lars::SEL_THREADS - 1) / lars::SEL_THREADS;
+  int grid = st->sm_count * 2;
+  if (want < grid) grid = (int)(want > 0 ? want : 1);
+  for (int pass = 0; pass < 4; ++pass) {
+    lars::select_pass_kernel<<<grid, lars::SEL_THREADS, lars::SEL_SMEM_BYTES, s>>>(data, n, state, pass);
+    lars::select_scan_kernel<<<1, 256, 0, s>>>(state, pass);
+  }
+  LARS_CUDA(cudaGetLastError());
+  LARS_CUDA(cudaMemcpyAsync(out3, reinterpret_cast<const char*>(state) + offsetof(lars::SelectState, value),
+                            3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return LARS_OK;
+}
+
+int lars_colormap_f32(const float* data, int64_t n, int32_t cmap_id, float vmin, float vmax, uint8_t* rgb,
+                      void* stream) {
+  DeviceState* st = nullptr;
+  int rc = current_state(&st);
+  if (rc != LARS_OK) return rc;
+  if (!data || !rgb) return fail(LARS_ERR_INVALID, "lars_colormap_f32: NULL pointer");
+  if (n < 1) return fail(LARS_ERR_INVALID, "lars_colormap_f32: empty input");
+  if (cmap_id < 0 || cmap_id > 2) return fail(LARS_ERR_INVALID, "lars_colormap_f32: unknown colormap %d", cmap_id);
+  if (!(vmax > vmin)) return fail(LARS_ERR_INVALID, "lars_colormap_f32: vmax must exceed vmin");
+  if (!aligned16(data) || (reinterpret_cast<uintptr_t>(rgb) & 3))
+    return fail(LARS_ERR_INVALID, "lars_colormap_f32: data must be 16-byte and rgb 4-byte aligned");
+  lars::ColormapParams p;
+  p.data = data; p.rgb = rgb; p.cmap = st->cmaps + cmap_id * 256; p.n = n;
+  p.vmin = vmin; p.vmax = vmax; p.unit_range = (vmin == -1.0f && vmax == 1.0f) ? 1 : 0;
+  long long groups = (n + 127) / 128;
+  long long want = (groups + 7) / 8;
+  int grid = st->sm_count * 8;
+  if (want < grid) grid = (int)want;
+  lars::colormap_f32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  LARS_CUDA(cudaGetLastError());
+  return LARS_OK;
+}
+
+int lars_ndvi_f64_u8(const uint8_t* src, int64_t n_pixels, int32_t channels, double* out, void* stream) {
+  DeviceState* st = nullptr;
+  int rc = current_state(&st);
+  if (rc != LARS_OK) return rc;
+  if (!src || !out) return fail(LARS_ERR_INVALID, "lars_ndvi_f64_u8: NULL pointer");
+  if (n_pixels < 1 || channels < 3) return fail(LARS_ERR_INVALID, "lars_ndvi_f64_u8: need >= 1 pixel and >= 3 channels");
+  long long want = (n_pixels + 255) / 256;
+  int grid = st->sm_count * 8;
+  if (want < grid) grid = (int)want;
+  lars::ndvi_f64_u8_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, out, n_pixels, channels);
+  LARS_CUDA(cudaGetLastError());
+  return LARS_OK;
+}
+
+int lars_index_planes_f32(const float* hi, const float* lo, int64_t n, float* out, void* stream) {
+  DeviceState* st = nullptr;
+  int rc = current_state(&st);
+  if (rc != LARS_OK) return rc;
+  if (!hi || !lo || !out) return fail(LARS_ERR_INVALID, "lars_index_planes_f32: NULL pointer");
+  if (n < 1) return fail(LARS_ERR_INVALID, "lars_index_planes_f32: empty input");
+  if (!aligned16(hi) || !aligned16(lo) || !aligned16(out))
+    return fail(LARS_ERR_INVALID, "lars_index_planes_f32: planes must be 16-byte aligned");
+  long long want = (n / 4 + 255) / 256;
+  int grid = st->sm_count * 8;
+  if (want < grid) grid = (int)(want > 0 ? want : 1);
+  lars::index_planes_f32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(hi, lo, out, n);
+  LARS_CUDA(cudaGetLastError());
+  return LARS_OK;
+}
+
+}  // extern "C"

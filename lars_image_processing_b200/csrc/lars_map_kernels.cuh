@@ -1,0 +1,401 @@
+// Kernels over float maps / raw frames that sit next to the fused pass:
+//
+//   K3  select_*            exact order statistics (median) of a float32 map: 4-pass 8-bit
+//                           radix select on order-preserving keys (np.median,
+//                           process-images.py:508, :654; process-ndvi.py:62)
+//   K4  map_stats_f32       statistics + np.histogram of an arbitrary float32 map
+//                           (analyze_index process-images.py:492-513 called on a host array;
+//                           analyze_ndvi_statistics process-ndvi.py:50-73; plt.hist :97)
+//   K5  colormap_f32        Normalize(vmin, vmax) + colormap LUT of a float32 map
+//                           (process-images.py:689-695, :949-956)
+//   K6  ndvi_f64_u8         float64 NDVI of a raw uint8 frame (calculate_ndvi, process-ndvi.py:18-31)
+//   K7  index_planes_f32    (hi - lo) / (hi + lo + eps) clipped, separate float32 planes
+//                           (backend-process.py:28-38)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/lars_b200.h"
+#include "pixel_math.h"
+#include "ptx_sm100.cuh"
+
+namespace lars {
+
+constexpr int MAP_THREADS = 256;
+constexpr int MAP_HIST_ROWS = LARS_MAX_BINS;  // bins supported by the generic map kernels
+
+// ------------------------------------------------------------------------------------------
+// K4: statistics of a float32 map
+// ------------------------------------------------------------------------------------------
+struct __align__(16) MapPartial {
+  double sx, sd, sdd;
+  float mn, mx;
+  uint32_t above;
+  uint32_t has_nan;
+  unsigned long long count;
+  uint32_t hist[MAP_HIST_ROWS];
+};
+
+struct MapStatsParams {
+  const float* data;       // [n_maps][stride]
+  long long n;             // elements per map
+  long long stride;        // elements
+  MapPartial* partials;    // [n_maps][gridDim.x]
+  float threshold;
+  int bins;
+};
+
+__device__ __forceinline__ void map_stats_accum(float x, float k, float thr, const float* edges_s, int bins,
+                                                uint32_t* hist_lane, float& mn, float& mx, float& gx,
+                                                float& gd, float& gdd, uint32_t& above, uint32_t& nan) {
+  mn = fminf(mn, x);
+  mx = fmaxf(mx, x);
+  above += (x > thr) ? 1u : 0u;
+  nan |= (x != x) ? 1u : 0u;
+  const float d = LARS_FSUB(x, k);
+  gx += x;
+  gd += d;
+  gdd = fmaf(d, d, gdd);
+  if (x >= -1.0f && x <= 1.0f) {  // np.histogram drops out-of-range values (and NaN)
+    const int b = lars_hist_bin_edges(x, edges_s, bins);
+    atomicAdd(hist_lane + b * 32, 1u);
+  }
+}
+
+__global__ void __launch_bounds__(MAP_THREADS) map_stats_f32_kernel(const MapStatsParams p) {
+  extern __shared__ __align__(16) uint8_t ms_smem[];
+  uint32_t* hist = reinterpret_cast<uint32_t*>(ms_smem);                       // [bins][32]
+  float* edges_s = reinterpret_cast<float*>(ms_smem + (size_t)p.bins * 32 * 4);  // [bins + 1]
+  double* red = reinterpret_cast<double*>(ms_smem + (size_t)p.bins * 32 * 4 + ((p.bins + 1 + 3) / 4) * 16);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int map = blockIdx.y;
+  const float* x = p.data + (long long)map * p.stride;
+  for (int i = tid; i < p.bins * 32; i += MAP_THREADS) hist[i] = 0u;
+  {  // np.linspace(-1, 1, bins + 1) in float64, rounded to float32, last edge exact
+    const double step = LARS_DDIV(2.0, (double)p.bins);
+    for (int i = tid; i <= p.bins; i += MAP_THREADS)
+      edges_s[i] = (i == p.bins) ? 1.0f : (float)LARS_DADD(LARS_DMUL((double)i, step), -1.0);
+  }
+  __syncthreads();
+
+  const float k = x[0];
+  const float thr = p.threshold;
+  float mn = INFINITY, mx = -INFINITY;
+  double sx = 0.0, sd = 0.0, sdd = 0.0;
+  uint32_t above = 0, nan = 0;
+  unsigned long long count = 0;
+  uint32_t* hist_lane = hist + lane;
+
+  // contiguous chunk per CTA, 16-byte vectors inside (map bases are 16-byte aligned)
+  const long long nvec = p.n / 4;
+  const long long per = (nvec + gridDim.x - 1) / gridDim.x;
+  const long long v0 = (long long)blockIdx.x * per;
+  const long long v1 = (v0 + per < nvec) ? v0 + per : nvec;
+  const float4* xv = reinterpret_cast<const float4*>(x);
+  for (long long v = v0 + tid; v < v1; v += MAP_THREADS) {
+    const float4 q = __ldg(xv + v);
+    float gx = 0.f, gd = 0.f, gdd = 0.f;
+    map_stats_accum(q.x, k, thr, edges_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
+    map_stats_accum(q.y, k, thr, edges_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
+    map_stats_accum(q.z, k, thr, edges_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
+    map_stats_accum(q.w, k, thr, edges_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
+    sx += (double)gx; sd += (double)gd; sdd += (double)gdd;
+    count += 4;
+  }
+  if (blockIdx.x == gridDim.x - 1) {  // scalar tail (n % 4 elements)
+    for (long long i = nvec * 4 + tid; i < p.n; i += MAP_THREADS) {
+      float gx = 0.f, gd = 0.f, gdd = 0.f;
+      map_stats_accum(x[i], k, thr, edges_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
+      sx += (double)gx; sd += (double)gd; sdd += (double)gdd;
+      count += 1;
+    }
+  }
+  // block reduction
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    sx += __shfl_xor_sync(0xffffffffu, sx, d);
+    sd += __shfl_xor_sync(0xffffffffu, sd, d);
+    sdd += __shfl_xor_sync(0xffffffffu, sdd, d);
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    above += __shfl_xor_sync(0xffffffffu, above, d);
+    nan |= __shfl_xor_sync(0xffffffffu, nan, d);
+    count += __shfl_xor_sync(0xffffffffu, count, d);
+  }
+  if (lane == 0) {
+    double* r = red + warp * 8;
+    r[0] = sx; r[1] = sd; r[2] = sdd; r[3] = (double)mn; r[4] = (double)mx;
+    r[5] = (double)above; r[6] = (double)nan; r[7] = (double)count;
+  }
+  __syncthreads();
+  MapPartial* rec = p.partials + (long long)map * gridDim.x + blockIdx.x;
+  for (int b = tid; b < p.bins; b += MAP_THREADS) {
+    uint32_t s = 0;
+    for (int l = 0; l < 32; ++l) s += hist[b * 32 + ((l + tid) & 31)];
+    rec->hist[b] = s;
+  }
+  if (tid == 0) {
+    double a[8];
+    for (int q = 0; q < 8; ++q) a[q] = red[q];
+    for (int w = 1; w < MAP_THREADS / 32; ++w) {
+      const double* r = red + w * 8;
+      a[0] += r[0]; a[1] += r[1]; a[2] += r[2];
+      a[3] = fmin(a[3], r[3]); a[4] = fmax(a[4], r[4]);
+      a[5] += r[5]; a[6] += r[6]; a[7] += r[7];
+    }
+    rec->sx = a[0]; rec->sd = a[1]; rec->sdd = a[2];
+    rec->mn = (float)a[3]; rec->mx = (float)a[4];
+    rec->above = (uint32_t)a[5]; rec->has_nan = a[6] != 0.0 ? 1u : 0u;
+    rec->count = (unsigned long long)a[7];
+  }
+}
+
+struct MapFinalizeParams {
+  const MapPartial* partials;  // [n_maps][n_parts]
+  const float* data;
+  long long stride;
+  lars_index_stats* stats;     // [n_maps]
+  int n_parts, bins;
+  float threshold;
+};
+
+__global__ void __launch_bounds__(MAP_HIST_ROWS) map_stats_finalize_kernel(const MapFinalizeParams p) {
+  const int map = blockIdx.x, tid = threadIdx.x;
+  const MapPartial* recs = p.partials + (long long)map * p.n_parts;
+  lars_index_stats& o = p.stats[map];
+  if (tid < LARS_MAX_BINS) {
+    unsigned long long h = 0;
+    if (tid < p.bins)
+      for (int s = 0; s < p.n_parts; ++s) h += recs[s].hist[tid];
+    o.hist[tid] = h;
+  }
+  if (tid == 0) {
+    double sx = 0.0, sd = 0.0, sdd = 0.0;
+    float mn = INFINITY, mx = -INFINITY;
+    unsigned long long cnt = 0, above = 0;
+    uint32_t nan = 0;
+    for (int s = 0; s < p.n_parts; ++s) {
+      const MapPartial& r = recs[s];
+      if (!r.count) continue;
+      sx += r.sx; sd += r.sd; sdd += r.sdd;
+      mn = fminf(mn, r.mn); mx = fmaxf(mx, r.mx);
+      cnt += r.count; above += r.above; nan |= r.has_nan;
+    }
+    const double n = (double)cnt;
+    const double mean = cnt ? sx / n : 0.0;
+    const double md = cnt ? sd / n : 0.0;
+    double var = cnt ? sdd / n - md * md : 0.0;
+    var = var > 0.0 ? var : 0.0;
+    o.count = cnt; o.count_above = above;
+    o.sum = sx; o.sumsq = cnt ? (var + mean * mean) * n : 0.0;
+    o.mean = nan ? NAN : mean; o.std = nan ? NAN : sqrt(var);
+    o.min = nan ? NAN : mn; o.max = nan ? NAN : mx;
+    o.threshold = p.threshold; o.bins = (uint32_t)p.bins;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: exact order statistics by radix select
+// ------------------------------------------------------------------------------------------
+struct SelectState {
+  unsigned long long rank[2];   // remaining rank inside the current prefix bucket
+  uint32_t prefix[2];           // selected high digits so far
+  float value[2];               // the two order statistics (written after the last pass)
+  float median;                 // float32 mean of the two (np.median for even n)
+  uint32_t pad_;
+  unsigned long long hist[2][256];
+};
+
+__device__ __forceinline__ uint32_t float_order_key(float x) {
+  const uint32_t b = __float_as_uint(x);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float float_from_order_key(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+__global__ void select_init_kernel(SelectState* st, unsigned long long r0, unsigned long long r1) {
+  const int t = threadIdx.x;
+  if (t == 0) {
+    st->rank[0] = r0; st->rank[1] = r1;
+    st->prefix[0] = st->prefix[1] = 0u;
+    st->value[0] = st->value[1] = st->median = 0.f;
+  }
+  st->hist[0][t] = 0ull;
+  st->hist[1][t] = 0ull;
+}
+
+constexpr int SEL_THREADS = 512;
+constexpr int SEL_SMEM_BYTES = 2 * 256 * 32 * 4;
+
+__global__ void __launch_bounds__(SEL_THREADS) select_pass_kernel(const float* __restrict__ data, long long n,
+                                                                   SelectState* st, int pass) {
+  extern __shared__ __align__(16) uint32_t sel_hist[];  // [2][256][32] lane-private
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < 2 * 256 * 32; i += SEL_THREADS) sel_hist[i] = 0u;
+  __syncthreads();
+  const uint32_t p0 = st->prefix[0], p1 = st->prefix[1];
+  const bool same = (pass == 0) || (p0 == p1);
+  const int hi_shift = 32 - 8 * pass;     // bits above the current digit
+  const int dg_shift = 24 - 8 * pass;
+  uint32_t* h0 = sel_hist + lane;
+  uint32_t* h1 = sel_hist + 256 * 32 + lane;
+
+  auto visit = [&](float x) {
+    const uint32_t key = float_order_key(x);
+    const uint32_t hi = (pass == 0) ? 0u : (key >> hi_shift);
+    const uint32_t dg = (key >> dg_shift) & 0xFFu;
+    if (hi == p0) atomicAdd(h0 + dg * 32, 1u);
+    if (!same && hi == p1) atomicAdd(h1 + dg * 32, 1u);
+  };
+  const long long nvec = n / 4;
+  const float4* xv = reinterpret_cast<const float4*>(data);
+  for (long long v = (long long)blockIdx.x * SEL_THREADS + tid; v < nvec; v += (long long)gridDim.x * SEL_THREADS) {
+    const float4 q = __ldg(xv + v);
+    visit(q.x); visit(q.y); visit(q.z); visit(q.w);
+  }
+  if (blockIdx.x == 0)
+    for (long long i = nvec * 4 + tid; i < n; i += SEL_THREADS) visit(data[i]);
+  __syncthreads();
+  for (int b = tid; b < 2 * 256; b += SEL_THREADS) {
+    if (same && b >= 256) break;
+    uint32_t s = 0;
+    for (int l = 0; l < 32; ++l) s += sel_hist[b * 32 + ((l + tid) & 31)];
+    if (s) atomicAdd(&st->hist[b >> 8][b & 255], (unsigned long long)s);
+  }
+}
+
+__global__ void __launch_bounds__(256) select_scan_kernel(SelectState* st, int pass) {
+  __shared__ unsigned long long cum[256];
+  __shared__ unsigned long long wtot[8];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const bool same = (pass == 0) || (st->prefix[0] == st->prefix[1]);
+  __syncthreads();
+  for (int r = 0; r < 2; ++r) {
+    const int src = same ? 0 : r;
+    unsigned long long x = st->hist[src][t];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) wtot[warp] = x;
+    __syncthreads();
+    unsigned long long add = 0;
+    for (int w = 0; w < warp; ++w) add += wtot[w];
+    x += add;
+    cum[t] = x;
+    __syncthreads();
+    const unsigned long long below = t ? cum[t - 1] : 0ull;
+    const unsigned long long rk = st->rank[r];
+    __syncthreads();
+    if (below <= rk && rk < x) {
+      st->prefix[r] = (st->prefix[r] << 8) | (uint32_t)t;
+      st->rank[r] = rk - below;
+    }
+    __syncthreads();
+  }
+  st->hist[0][t] = 0ull;
+  st->hist[1][t] = 0ull;
+  if (pass == 3 && t == 0) {
+    const float a = float_from_order_key(st->prefix[0]);
+    const float b = float_from_order_key(st->prefix[1]);
+    st->value[0] = a;
+    st->value[1] = b;
+    st->median = LARS_FMUL(LARS_FADD(a, b), 0.5f);  // np.mean of the two middle float32 values
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: colormap a float32 map
+// ------------------------------------------------------------------------------------------
+struct ColormapParams {
+  const float* data;
+  uint8_t* rgb;            // [n][3]
+  const uint32_t* cmap;    // [256] packed R | G<<8 | B<<16
+  long long n;
+  float vmin, vmax;
+  int unit_range;          // vmin == -1 && vmax == 1 -> single-FMA slot formula
+};
+
+__global__ void __launch_bounds__(256) colormap_f32_kernel(const ColormapParams p) {
+  __shared__ uint32_t cm[256];
+  __shared__ uint32_t stage[8][96];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  cm[tid] = p.cmap[tid];
+  __syncthreads();
+  // each warp iteration: 128 pixels in (32 x float4), 384 bytes out (3 x 32 words)
+  const long long ngroups = (p.n + 127) / 128;
+  uint32_t* out32 = reinterpret_cast<uint32_t*>(p.rgb);
+  for (long long g = (long long)blockIdx.x * 8 + warp; g < ngroups; g += (long long)gridDim.x * 8) {
+    const long long px = g * 128 + 4 * lane;
+    float v[4];
+    if (px + 4 <= p.n) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(p.data + px));
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = (px + j < p.n) ? p.data[px + j] : 0.f;
+    }
+    uint32_t c[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float x = v[j];
+      if (x != x) { c[j] = 0u; continue; }  // matplotlib "bad" colour: transparent black
+      // out-of-range values saturate to the first / last slot (matplotlib under / over colours)
+      const int k = p.unit_range ? lars_cmap_index(x) : lars_cmap_index_range(x, p.vmin, p.vmax);
+      c[j] = cm[k];
+    }
+    stage[warp][3 * lane + 0] = prmt(c[0], c[1], 0x4210);
+    stage[warp][3 * lane + 1] = prmt(c[1], c[2], 0x5421);
+    stage[warp][3 * lane + 2] = prmt(c[2], c[3], 0x6542);
+    __syncwarp();
+    const long long wbase = g * 96;                 // output word index of this group
+    const long long total_bytes = p.n * 3;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const long long w = wbase + r * 32 + lane;
+      const uint32_t val = stage[warp][r * 32 + lane];
+      if (w * 4 + 4 <= total_bytes) {
+        out32[w] = val;
+      } else {
+        for (int b = 0; b < 4; ++b)
+          if (w * 4 + b < total_bytes) p.rgb[w * 4 + b] = (uint8_t)(val >> (8 * b));
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K6: float64 NDVI of a raw uint8 frame (process-ndvi.py:18-31)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ndvi_f64_u8_kernel(const uint8_t* __restrict__ src, double* __restrict__ out,
+                                                          long long n, int channels) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint8_t* px = src + i * channels;
+    out[i] = lars_ratio_clip_f64((double)px[2], (double)px[0]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K7: normalized difference of two float32 planes (backend-process.py:28-38)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) index_planes_f32_kernel(const float* __restrict__ hi, const float* __restrict__ lo,
+                                                               float* __restrict__ out, long long n) {
+  const long long nvec = n / 4;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
+       v += (long long)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(hi) + v);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(lo) + v);
+    float4 r;
+    r.x = lars_ratio_clip_f32(a.x, b.x); r.y = lars_ratio_clip_f32(a.y, b.y);
+    r.z = lars_ratio_clip_f32(a.z, b.z); r.w = lars_ratio_clip_f32(a.w, b.w);
+    reinterpret_cast<float4*>(out)[v] = r;
+  }
+  if (blockIdx.x == 0)
+    for (long long i = nvec * 4 + threadIdx.x; i < n; i += blockDim.x) out[i] = lars_ratio_clip_f32(hi[i], lo[i]);
+}
+
+}  // namespace lars

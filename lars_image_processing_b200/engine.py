@@ -1,0 +1,343 @@
+"""Host side of the B200 RGNir analysis path.
+
+PyTorch is used for plumbing only -- device / pinned memory, streams, ``torch.distributed``;
+every byte of arithmetic happens in the hand-written sm_100a kernels behind the C ABI
+(``include/lars_b200.h``).  There is no CPU fallback: without the CUDA library and a B200
+the constructor raises.
+
+Two levels:
+  * device-resident: :class:`DeviceFrames` in, :class:`DeviceOutputs` out, nothing leaves HBM
+    (what ``bench.py`` times as ``value``);
+  * host arrays: :meth:`Engine.analyze_frame` / :meth:`Engine.analyze_batch` take NumPy
+    frames and return NumPy results, with the H2D / D2H copies inside (what the reference's
+    helper signatures need, and what ``bench.py`` times as ``e2e``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import FusedArgs, INDEX_STATS_DTYPE, LarsError, PIXEL_GROUP, check
+
+INDEX_TYPES = ("NDVI", "GNDVI", "NDWI")                 # process-images.py:466,472,478
+DEFAULT_THRESHOLDS = (0.2, 0.2, 0.0)                    # process-images.py:498-504
+DEFAULT_CMAPS = ("RdYlGn", "RdYlGn", "RdYlBu")          # process-images.py:689-692
+DEFAULT_BINS = 50                                       # process-ndvi.py:97
+DEFAULT_QUANTILES = (0.02, 0.98)                        # process-images.py:437
+ALL_OUTPUTS = ("wb", "maps", "rgb", "stats")
+
+
+def _pad_px(n_pixels: int) -> int:
+    return (n_pixels + PIXEL_GROUP - 1) // PIXEL_GROUP * PIXEL_GROUP
+
+
+@dataclass
+class DeviceFrames:
+    """A batch of equally-sized interleaved uint8 frames resident in HBM.
+
+    ``data`` is ``[n_frames, padded_pixels * channels]`` uint8: every frame slot starts
+    16-byte aligned and is padded to a whole number of 16-pixel groups.
+    """
+    data: torch.Tensor
+    n_pixels: int
+    channels: int
+    shape: tuple  # (H, W)
+
+    @property
+    def n_frames(self) -> int:
+        return self.data.shape[0]
+
+    @property
+    def stride_bytes(self) -> int:
+        return self.data.stride(0)
+
+
+@dataclass
+class DeviceOutputs:
+    """Device-resident results of one pass over a :class:`DeviceFrames` batch."""
+    frames: DeviceFrames
+    wb_hist: Optional[torch.Tensor] = None      # [F, 3, 256] int64 (bit pattern of uint64)
+    wb_lut: Optional[torch.Tensor] = None       # [F, 3, 256] uint8
+    wb_pct: Optional[torch.Tensor] = None       # [F, 3, 2] float64 (p2, p98)
+    wb: Optional[torch.Tensor] = None           # [F, padded_px * C] uint8
+    maps: Optional[torch.Tensor] = None         # [3, F, padded_px] float32
+    rgb: Optional[torch.Tensor] = None          # [3, F, padded_px * 3] uint8
+    stats: Optional[torch.Tensor] = None        # [F, 3, 576] uint8 (lars_index_stats records)
+    bins: int = DEFAULT_BINS
+    map_mask: tuple = (True, True, True)
+    rgb_mask: tuple = (True, True, True)
+    _keep: list = field(default_factory=list)   # workspace kept alive until the stream is done
+
+
+def stats_records_to_dicts(records: np.ndarray, bins: int) -> List[Dict[str, dict]]:
+    """[F, 3] structured ``lars_index_stats`` -> per-frame {index: {...}} dictionaries."""
+    out = []
+    for f in range(records.shape[0]):
+        per = {}
+        for i, name in enumerate(INDEX_TYPES):
+            r = records[f, i]
+            n = int(r["count"])
+            per[name] = {
+                "count": n,
+                "count_above": int(r["count_above"]),
+                "sum": float(r["sum"]),
+                "sumsq": float(r["sumsq"]),
+                "mean": float(r["mean"]),
+                "std": float(r["std"]),
+                "min": float(r["min"]),
+                "max": float(r["max"]),
+                "threshold": float(r["threshold"]),
+                "coverage_pct": (float(r["count_above"]) / n * 100.0) if n else 0.0,
+                "hist": np.array(r["hist"][:bins], dtype=np.int64),
+            }
+        out.append(per)
+    return out
+
+
+class Engine:
+    """One engine per process and GPU.  Thread-safe: each calling thread gets its own stream."""
+
+    def __init__(self, device: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError(
+                "lars_image_processing_b200 needs an NVIDIA B200 (sm_100a): torch.cuda is not "
+                "available and there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        with torch.cuda.device(self.device):
+            check(self.lib.lars_init(self.device_index), "lars_init")
+            self.sm_count = check(self.lib.lars_sm_count(), "lars_sm_count")
+        self._tls = threading.local()
+
+    # ------------------------------------------------------------------ plumbing
+    def stream(self) -> torch.cuda.Stream:
+        s = getattr(self._tls, "stream", None)
+        if s is None:
+            s = torch.cuda.Stream(device=self.device)
+            self._tls.stream = s
+        return s
+
+    def _alloc(self, shape, dtype, stream=None):
+        # allocate under the stream that will use the block so the caching allocator's
+        # reuse-after-free ordering is tied to that stream
+        with torch.cuda.stream(stream or self.stream()):
+            return torch.empty(shape, dtype=dtype, device=self.device)
+
+    # ------------------------------------------------------------------ device-resident API
+    def alloc_frames(self, n_frames: int, height: int, width: int, channels: int = 3,
+                     stream=None) -> DeviceFrames:
+        n_px = height * width
+        data = self._alloc((n_frames, _pad_px(n_px) * channels), torch.uint8, stream)
+        return DeviceFrames(data, n_px, channels, (height, width))
+
+    def upload(self, frames: Sequence[np.ndarray], stream: Optional[torch.cuda.Stream] = None) -> DeviceFrames:
+        """Copy equally-shaped HWC uint8 host frames into a padded device batch."""
+        first = np.asarray(frames[0])
+        h, w, c = first.shape
+        s = stream or self.stream()
+        dev = self.alloc_frames(len(frames), h, w, c, s)
+        nbytes = h * w * c
+        with torch.cuda.stream(s):
+            for i, fr in enumerate(frames):
+                fr = np.ascontiguousarray(fr)
+                if fr.shape != first.shape or fr.dtype != np.uint8:
+                    raise ValueError("all frames of a batch must share shape and be uint8")
+                src = torch.from_numpy(fr.reshape(-1))
+                dev.data[i, :nbytes].copy_(src, non_blocking=True)
+        return dev
+
+    def wb_histogram(self, frames: DeviceFrames, stream=None) -> torch.Tensor:
+        """Pass 1 (K1): [F, 3, 256] per-channel value counts (int64 view of uint64)."""
+        s = stream or self.stream()
+        hist = self._alloc((frames.n_frames, 3, 256), torch.int64, s)
+        with torch.cuda.device(self.device):
+            check(self.lib.lars_wb_hist_u8(frames.data.data_ptr(), frames.n_frames, frames.n_pixels,
+                                           frames.channels, frames.stride_bytes, hist.data_ptr(),
+                                           s.cuda_stream), "lars_wb_hist_u8")
+        return hist
+
+    def wb_lut(self, hist: torch.Tensor, quantiles=DEFAULT_QUANTILES, stream=None):
+        """K1b: histograms -> (uint8 LUTs [S,3,256], float64 percentiles [S,3,2])."""
+        s = stream or self.stream()
+        n_sets = hist.shape[0]
+        lut = self._alloc((n_sets, 3, 256), torch.uint8, s)
+        pct = self._alloc((n_sets, 3, 2), torch.float64, s)
+        with torch.cuda.device(self.device):
+            check(self.lib.lars_wb_lut_build_u8(hist.data_ptr(), n_sets, float(quantiles[0]),
+                                                float(quantiles[1]), lut.data_ptr(), pct.data_ptr(),
+                                                s.cuda_stream), "lars_wb_lut_build_u8")
+        return lut, pct
+
+    def fused(self, frames: DeviceFrames, lut: Optional[torch.Tensor], outputs=ALL_OUTPUTS,
+              indices=INDEX_TYPES, bins: int = DEFAULT_BINS, thresholds=DEFAULT_THRESHOLDS,
+              cmaps=DEFAULT_CMAPS, rgb_indices=None, out: Optional[DeviceOutputs] = None,
+              stream=None) -> DeviceOutputs:
+        """Pass 2 (K2): one read of the raw frames -> every requested product.
+
+        ``lut`` None means identity (``calculate_index`` on an already white-balanced frame).
+        ``indices`` selects which fp32 maps are written; ``rgb_indices`` (default: same)
+        which colormapped images.  Statistics are always produced for all three indices
+        when "stats" is requested (they share the arithmetic).
+        """
+        s = stream or self.stream()
+        F, npx, ch = frames.n_frames, frames.n_pixels, frames.channels
+        ppx = _pad_px(npx)
+        res = out or DeviceOutputs(frames=frames)
+        res.frames = frames
+        res.bins = bins
+        rgb_indices = indices if rgb_indices is None else rgb_indices
+        res.map_mask = tuple(n in indices for n in INDEX_TYPES)
+        res.rgb_mask = tuple(n in rgb_indices for n in INDEX_TYPES)
+        a = FusedArgs()
+        a.struct_bytes = C.sizeof(FusedArgs)
+        a.n_frames, a.channels, a.bins, a.n_pixels = F, ch, bins, npx
+        a.src, a.src_frame_stride = frames.data.data_ptr(), frames.stride_bytes
+        if lut is not None:
+            if lut.shape[0] not in (1, F):
+                raise ValueError("lut must hold one set per frame or a single shared set")
+            a.wb_lut = lut.data_ptr()
+            a.lut_frame_stride = 768 if lut.shape[0] == F else 0
+        if "wb" in outputs:
+            if res.wb is None:
+                res.wb = self._alloc((F, ppx * ch), torch.uint8, s)
+            a.wb_out, a.wb_frame_stride = res.wb.data_ptr(), res.wb.stride(0)
+        if "maps" in outputs:
+            if res.maps is None:
+                res.maps = self._alloc((3, F, ppx), torch.float32, s)
+            for i in range(3):
+                a.maps[i] = res.maps[i].data_ptr() if res.map_mask[i] else None
+            a.map_frame_stride = res.maps.stride(1)
+        if "rgb" in outputs:
+            if res.rgb is None:
+                res.rgb = self._alloc((3, F, ppx * 3), torch.uint8, s)
+            for i in range(3):
+                a.rgb[i] = res.rgb[i].data_ptr() if res.rgb_mask[i] else None
+            a.rgb_frame_stride = res.rgb.stride(1)
+        for i in range(3):
+            a.cmap[i] = _lib.CMAP_IDS[cmaps[i]]
+            a.thresholds[i] = float(thresholds[i])
+        if "stats" in outputs:
+            if res.stats is None:
+                res.stats = self._alloc((F, 3, INDEX_STATS_DTYPE.itemsize), torch.uint8, s)
+            ws_bytes = int(self.lib.lars_fused_workspace_bytes(F))
+            ws = self._alloc((ws_bytes,), torch.uint8, s)
+            res._keep = [ws]
+            a.stats, a.workspace, a.workspace_bytes = res.stats.data_ptr(), ws.data_ptr(), ws_bytes
+        with torch.cuda.device(self.device):
+            check(self.lib.lars_fused_index_u8(C.byref(a), s.cuda_stream), "lars_fused_index_u8")
+        return res
+
+    def process_device(self, frames: DeviceFrames, outputs=ALL_OUTPUTS, white_balance: bool = True,
+                       quantiles=DEFAULT_QUANTILES, out: Optional[DeviceOutputs] = None,
+                       stream=None, **kw) -> DeviceOutputs:
+        """Pass 1 + LUT + Pass 2 on a device-resident batch; nothing is synchronised."""
+        s = stream or self.stream()
+        res = out or DeviceOutputs(frames=frames)
+        lut = None
+        if white_balance:
+            res.wb_hist = self.wb_histogram(frames, stream=s)
+            res.wb_lut, res.wb_pct = self.wb_lut(res.wb_hist, quantiles, stream=s)
+            lut = res.wb_lut
+        return self.fused(frames, lut, outputs=outputs, out=res, stream=s, **kw)
+
+    # ------------------------------------------------------------------ host-array API
+    def download(self, res: DeviceOutputs, stream=None, pinned: bool = True) -> List[dict]:
+        """Copy the requested products of every frame back to host memory -> list of dicts."""
+        s = stream or self.stream()
+        fr = res.frames
+        F, npx, ch = fr.n_frames, fr.n_pixels, fr.channels
+        h, w = fr.shape
+
+        def host(shape, dtype):
+            return torch.empty(shape, dtype=dtype, pin_memory=pinned)
+
+        with torch.cuda.stream(s):
+            h_wb = h_maps = h_rgb = h_stats = h_pct = None
+            if res.wb is not None:
+                h_wb = host((F, npx * ch), torch.uint8)
+                h_wb.copy_(res.wb[:, :npx * ch], non_blocking=True)
+            if res.maps is not None:
+                sel = [i for i in range(3) if res.map_mask[i]]
+                h_maps = host((len(sel), F, npx), torch.float32)
+                for k, i in enumerate(sel):
+                    h_maps[k].copy_(res.maps[i, :, :npx], non_blocking=True)
+            if res.rgb is not None:
+                selr = [i for i in range(3) if res.rgb_mask[i]]
+                h_rgb = host((len(selr), F, npx * 3), torch.uint8)
+                for k, i in enumerate(selr):
+                    h_rgb[k].copy_(res.rgb[i, :, :npx * 3], non_blocking=True)
+            if res.stats is not None:
+                h_stats = host(tuple(res.stats.shape), torch.uint8)
+                h_stats.copy_(res.stats, non_blocking=True)
+            if res.wb_pct is not None:
+                h_pct = host(tuple(res.wb_pct.shape), torch.float64)
+                h_pct.copy_(res.wb_pct, non_blocking=True)
+        s.synchronize()
+
+        stats = None
+        if h_stats is not None:
+            rec = h_stats.numpy().view(INDEX_STATS_DTYPE).reshape(F, 3)
+            stats = stats_records_to_dicts(rec, res.bins)
+        results = []
+        for f in range(F):
+            d: dict = {}
+            if h_wb is not None:
+                d["wb"] = h_wb[f].numpy().reshape(h, w, ch)
+            if h_maps is not None:
+                d["maps"] = {INDEX_TYPES[i]: h_maps[k, f].numpy().reshape(h, w) for k, i in enumerate(sel)}
+            if h_rgb is not None:
+                d["rgb"] = {INDEX_TYPES[i]: h_rgb[k, f].numpy().reshape(h, w, 3) for k, i in enumerate(selr)}
+            if stats is not None:
+                d["stats"] = stats[f]
+            if h_pct is not None:
+                d["percentiles"] = h_pct[f].numpy().copy()
+            results.append(d)
+        return results
+
+    @staticmethod
+    def _check_frame(img: np.ndarray) -> np.ndarray:
+        img = np.asarray(img)
+        if img.ndim != 3:
+            # the reference indexes img[:, :, i] and raises IndexError on 2-D input
+            raise IndexError("too many indices for array: expected an HxWxC frame, "
+                             f"got {img.ndim}-dimensional input")
+        if img.shape[2] < 3:
+            raise IndexError(f"index 2 is out of bounds for axis 2 with size {img.shape[2]}")
+        if img.shape[2] > 4:
+            raise LarsError(f"frames with {img.shape[2]} channels are not supported (3 or 4)")
+        if img.dtype != np.uint8:
+            raise LarsError(f"dtype {img.dtype} is not supported by the uint8 path")
+        return img
+
+    def analyze_batch(self, frames: Sequence[np.ndarray], outputs=ALL_OUTPUTS, white_balance=True,
+                      **kw) -> List[dict]:
+        """Host frames in, host results out (H2D, Pass 1, LUT, Pass 2, D2H, one sync)."""
+        frames = [self._check_frame(f) for f in frames]
+        s = self.stream()
+        dev = self.upload(frames, stream=s)
+        res = self.process_device(dev, outputs=outputs, white_balance=white_balance, stream=s, **kw)
+        return self.download(res, stream=s)
+
+    def analyze_frame(self, img: np.ndarray, outputs=ALL_OUTPUTS, white_balance=True, **kw) -> dict:
+        """The fused entry point for one frame: {wb, maps, rgb, stats, percentiles}."""
+        return self.analyze_batch([img], outputs=outputs, white_balance=white_balance, **kw)[0]
+
+
+_default_engine: Optional[Engine] = None
+_default_lock = threading.Lock()
+
+
+def get_engine() -> Engine:
+    """Process-wide engine on the current CUDA device (created on first use)."""
+    global _default_engine
+    with _default_lock:
+        if _default_engine is None:
+            _default_engine = Engine()
+        return _default_engine

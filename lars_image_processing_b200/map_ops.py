@@ -1,0 +1,185 @@
+"""GPU operations on caller-supplied index maps / raw frames next to the fused pass.
+
+These back the reference helpers whose input is *not* a raw uint8 frame: ``analyze_index`` and
+``analyze_ndvi_statistics`` receive a float map, ``create_index_visualization`` colours one,
+``calculate_ndvi`` (process-ndvi.py) wants a float64 NDVI of the raw pixels and
+``backend-process.py``'s ``calculate_index`` takes separate float32 planes.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import INDEX_STATS_DTYPE, LarsError, check
+from .engine import DEFAULT_BINS, INDEX_TYPES, Engine, get_engine, stats_records_to_dicts
+
+
+def _to_device_f32(eng: Engine, arr: np.ndarray, s) -> torch.Tensor:
+    flat = np.ascontiguousarray(arr, dtype=np.float32).reshape(-1)
+    with torch.cuda.stream(s):
+        dev = torch.empty(flat.size, dtype=torch.float32, device=eng.device)
+        dev.copy_(torch.from_numpy(flat), non_blocking=True)
+    return dev
+
+
+def device_map_statistics(eng: Engine, dev_map: torch.Tensor, n: int, threshold: float,
+                          bins: int = DEFAULT_BINS, median: bool = False, stream=None):
+    """Statistics (and optionally the exact median) of one device-resident float32 map.
+    Returns (stats tensor [576] uint8, median tensor [3] float32 or None); nothing is synced."""
+    lib = eng.lib
+    s = stream or eng.stream()
+    with torch.cuda.stream(s):
+        stats = torch.empty(INDEX_STATS_DTYPE.itemsize, dtype=torch.uint8, device=eng.device)
+        ws_bytes = int(lib.lars_map_stats_workspace_bytes(1))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=eng.device)
+        med = None
+        with torch.cuda.device(eng.device):
+            check(lib.lars_map_stats_f32(dev_map.data_ptr(), 1, n, n, bins, float(threshold),
+                                         stats.data_ptr(), ws.data_ptr(), ws_bytes, s.cuda_stream),
+                  "lars_map_stats_f32")
+            if median:
+                med = torch.empty(3, dtype=torch.float32, device=eng.device)
+                sel_bytes = int(lib.lars_select_workspace_bytes())
+                sel_ws = torch.empty(sel_bytes, dtype=torch.uint8, device=eng.device)
+                check(lib.lars_select_f32(dev_map.data_ptr(), n, (n - 1) // 2, n // 2, med.data_ptr(),
+                                          sel_ws.data_ptr(), sel_bytes, s.cuda_stream), "lars_select_f32")
+    return stats, med
+
+
+def map_statistics(index_array, threshold: float = 0.2, bins: int = DEFAULT_BINS, median: bool = True) -> dict:
+    """mean / std / min / max / coverage / histogram (/ exact median) of a host float map."""
+    arr = np.asarray(index_array)
+    if arr.size == 0:
+        return {}
+    eng = get_engine()
+    s = eng.stream()
+    dev = _to_device_f32(eng, arr, s)
+    stats, med = device_map_statistics(eng, dev, arr.size, threshold, bins, median, s)
+    with torch.cuda.stream(s):
+        h_stats = stats.cpu()
+        h_med = med.cpu() if med is not None else None
+    s.synchronize()
+    rec = h_stats.numpy().view(INDEX_STATS_DTYPE)[0]
+    n = int(rec["count"])
+    out = {
+        "count": n, "mean": float(rec["mean"]), "std": float(rec["std"]),
+        "min": float(rec["min"]), "max": float(rec["max"]),
+        "count_above": int(rec["count_above"]),
+        "coverage_pct": float(rec["count_above"]) / n * 100.0,
+        "sum": float(rec["sum"]), "sumsq": float(rec["sumsq"]),
+        "hist": np.array(rec["hist"][:bins], dtype=np.int64),
+    }
+    if h_med is not None:
+        out["median"] = float(h_med[2])
+        out["middle_values"] = (float(h_med[0]), float(h_med[1]))
+    return out
+
+
+def colormap_map(index_array, cmap: str = "RdYlGn", vmin: float = -1.0, vmax: float = 1.0) -> np.ndarray:
+    """HxW float map -> HxWx3 uint8 through the colormap LUT (Normalize(vmin, vmax))."""
+    arr = np.asarray(index_array)
+    eng = get_engine()
+    lib = eng.lib
+    s = eng.stream()
+    dev = _to_device_f32(eng, arr, s)
+    with torch.cuda.stream(s):
+        rgb = torch.empty(arr.size * 3, dtype=torch.uint8, device=eng.device)
+        with torch.cuda.device(eng.device):
+            check(lib.lars_colormap_f32(dev.data_ptr(), arr.size, _lib.CMAP_IDS[cmap], float(vmin), float(vmax),
+                                        rgb.data_ptr(), s.cuda_stream), "lars_colormap_f32")
+        host = rgb.cpu()
+    s.synchronize()
+    return host.numpy().reshape(arr.shape + (3,))
+
+
+def ndvi_float64(img_array) -> np.ndarray:
+    """float64 NDVI of the raw pixels (process-ndvi.py:18-31), no white balance."""
+    img = np.ascontiguousarray(img_array)
+    if img.ndim != 3 or img.shape[2] < 3:
+        raise IndexError("expected an HxWxC frame with at least 3 channels")
+    if img.dtype != np.uint8:
+        raise LarsError(f"dtype {img.dtype} is not supported by the uint8 NDVI path")
+    eng = get_engine()
+    lib = eng.lib
+    s = eng.stream()
+    n = img.shape[0] * img.shape[1]
+    with torch.cuda.stream(s):
+        dev = torch.empty(img.size, dtype=torch.uint8, device=eng.device)
+        dev.copy_(torch.from_numpy(img.reshape(-1)), non_blocking=True)
+        out = torch.empty(n, dtype=torch.float64, device=eng.device)
+        with torch.cuda.device(eng.device):
+            check(lib.lars_ndvi_f64_u8(dev.data_ptr(), n, img.shape[2], out.data_ptr(), s.cuda_stream),
+                  "lars_ndvi_f64_u8")
+        host = out.cpu()
+    s.synchronize()
+    return host.numpy().reshape(img.shape[:2])
+
+
+def index_from_planes(hi_plane, lo_plane) -> np.ndarray:
+    """clip((hi - lo) / (hi + lo + 1e-10), -1, 1) on float32 planes (backend-process.py:28-38)."""
+    hi = np.asarray(hi_plane)
+    lo = np.asarray(lo_plane)
+    if hi.shape != lo.shape:
+        raise ValueError("planes must have the same shape")
+    eng = get_engine()
+    lib = eng.lib
+    s = eng.stream()
+    dh, dl = _to_device_f32(eng, hi, s), _to_device_f32(eng, lo, s)
+    with torch.cuda.stream(s):
+        out = torch.empty(hi.size, dtype=torch.float32, device=eng.device)
+        with torch.cuda.device(eng.device):
+            check(lib.lars_index_planes_f32(dh.data_ptr(), dl.data_ptr(), hi.size, out.data_ptr(), s.cuda_stream),
+                  "lars_index_planes_f32")
+        host = out.cpu()
+    s.synchronize()
+    return host.numpy().reshape(hi.shape)
+
+
+def frame_statistics_rows(image_data_list, index_type: str) -> List[dict]:
+    """Rows of calculate_index_statistics_by_timeframe (process-images.py:633-663).
+
+    Frames are grouped by (shape, needs-white-balance) and each group goes through the fused
+    pass as one batch with statistics only; the exact median comes from the radix select on
+    the index map of each frame.
+    """
+    eng = get_engine()
+    i_idx = INDEX_TYPES.index(index_type)
+    feature = "Water" if index_type == "NDWI" else "Vegetation"
+    thr = 0.0 if index_type == "NDWI" else 0.2
+    rows: List[Optional[dict]] = [None] * len(image_data_list)
+    groups: Dict[tuple, list] = {}
+    for pos, img_data in enumerate(image_data_list):
+        cached = img_data.get("corrected_array") if isinstance(img_data, dict) else None
+        arr = cached if cached is not None else img_data["array"]
+        arr = eng._check_frame(arr)
+        groups.setdefault((arr.shape, cached is None), []).append((pos, arr))
+    s = eng.stream()
+    for (shape, needs_wb), members in groups.items():
+        dev = eng.upload([a for _, a in members], stream=s)
+        res = eng.process_device(dev, outputs=("maps", "stats"), white_balance=needs_wb,
+                                 indices=(index_type,), stream=s)
+        n = dev.n_pixels
+        meds = []
+        for k in range(len(members)):
+            _, med = device_map_statistics(eng, res.maps[i_idx, k], n, thr, median=True, stream=s)
+            meds.append(med)
+        with torch.cuda.stream(s):
+            h_stats = res.stats.cpu()
+            h_meds = torch.stack(meds).cpu()
+        s.synchronize()
+        rec = h_stats.numpy().view(INDEX_STATS_DTYPE).reshape(len(members), 3)
+        per = stats_records_to_dicts(rec, res.bins)
+        for k, (pos, _) in enumerate(members):
+            st = per[k][index_type]
+            rows[pos] = {
+                "Date": image_data_list[pos]["metadata"]["upload_date"],
+                "Mean": st["mean"],
+                "Median": float(h_meds[k, 2]),
+                "Min": st["min"],
+                "Max": st["max"],
+                f"{feature} Coverage (%)": st["coverage_pct"],
+            }
+    return [r for r in rows if r is not None]

@@ -1,0 +1,106 @@
+"""Drop-in GPU replacements for the per-pixel helpers of the reference's ``process-images.py``.
+
+Same names, argument meaning, return types and error behaviour as the reference functions
+(``/root/reference/process-images.py``): ``None``/empty in -> ``None`` out (or ``{}``), unknown
+index -> ``ValueError("Unknown index type: ...")``, 2-D input -> ``IndexError``.  Arrays go
+in and come out as host NumPy arrays exactly as the Streamlit front end expects
+(SURVEY.md section 8(b)); every operation in between runs in the sm_100a kernels.  Importing this
+module does not need a GPU; calling a helper without one raises (no CPU fallback).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+
+from .engine import (DEFAULT_BINS, INDEX_TYPES, get_engine)
+
+__all__ = ["fix_white_balance", "calculate_index", "analyze_index", "analyze_frame",
+           "calculate_index_statistics_by_timeframe", "create_index_visualization"]
+
+
+def _feature_name(index_type: str) -> str:
+    return "Water" if index_type == "NDWI" else "Vegetation"        # process-images.py:500-504
+
+
+def _check_index_type(index_type: str) -> None:
+    if index_type not in INDEX_TYPES:
+        raise ValueError(f"Unknown index type: {index_type}")       # process-images.py:485
+
+
+def fix_white_balance(img_array):
+    """process-images.py:424-447 -- per-channel 2nd/98th percentile stretch, uint8 out.
+
+    GPU path: K1 histogram -> K1b percentiles + LUT -> K2 (white-balance output only).
+    """
+    if img_array is None or img_array.size == 0:                     # :427-428
+        return None
+    return get_engine().analyze_frame(img_array, outputs=("wb",))["wb"]
+
+
+def calculate_index(img_array, index_type):
+    """process-images.py:449-490 -- float32 NDVI / GNDVI / NDWI map of an HxWx3 frame."""
+    if img_array is None or img_array.size == 0:                     # :452-453
+        return None
+    _check_index_type(index_type)
+    res = get_engine().analyze_frame(img_array, outputs=("maps",), white_balance=False,
+                                     indices=(index_type,))
+    return res["maps"][index_type]
+
+
+def analyze_frame(img_array, indices=INDEX_TYPES, bins: int = DEFAULT_BINS, white_balance: bool = True,
+                  outputs=("wb", "maps", "rgb", "stats")) -> Optional[dict]:
+    """Fused entry point (SURVEY.md section 8(b) "Ownership"): one trip to the GPU returns the
+    white-balanced frame, the requested index maps, their colormapped RGB images and all
+    statistics, instead of three separate helper calls."""
+    if img_array is None or img_array.size == 0:
+        return None
+    for name in indices:
+        _check_index_type(name)
+    return get_engine().analyze_frame(img_array, outputs=outputs, white_balance=white_balance,
+                                      indices=tuple(indices), bins=bins)
+
+
+def analyze_index(index_array, index_type):
+    """process-images.py:492-513 -- mean / median / min / max / coverage of an index map."""
+    if index_array is None or index_array.size == 0:                 # :495-496
+        return {}
+    from .map_ops import map_statistics                               # GPU statistics of a float map
+    thr = 0.0 if index_type == "NDWI" else 0.2                        # :498-504
+    st = map_statistics(index_array, threshold=thr, median=True)
+    return {
+        f"Mean {index_type}": st["mean"],
+        f"Median {index_type}": st["median"],
+        f"Min {index_type}": st["min"],
+        f"Max {index_type}": st["max"],
+        f"{_feature_name(index_type)} Coverage (%)": st["coverage_pct"],
+    }
+
+
+def calculate_index_statistics_by_timeframe(image_data_list, index_type):
+    """process-images.py:619-667 -- per-frame statistics of a time series -> DataFrame.
+
+    All frames that still need white balance and share a shape go through the GPU as one
+    batch (Pass 1 + LUT + Pass 2 with statistics only); frames with a cached
+    ``'corrected_array'`` skip Pass 1 (identity LUT), as in the reference (:638-641).
+    """
+    import pandas as pd
+    from .map_ops import frame_statistics_rows
+    _check_index_type(index_type) if image_data_list else None
+    rows = frame_statistics_rows(image_data_list, index_type)
+    return pd.DataFrame(rows)
+
+
+def create_index_visualization(index_array, index_type):
+    """process-images.py:669-716 -- colour visualisation of an index map as a PIL image.
+
+    The reference renders a decorated matplotlib figure; the per-pixel product north_star
+    asks for is the colormap lookup itself ('RdYlBu' for NDWI else 'RdYlGn', vmin=-1,
+    vmax=1, :689-695), returned here at full resolution as an RGB ``PIL.Image``.
+    """
+    if index_array is None or index_array.size == 0:                 # :672-673
+        return None
+    from PIL import Image
+    from .map_ops import colormap_map
+    cmap = "RdYlBu" if index_type == "NDWI" else "RdYlGn"
+    return Image.fromarray(colormap_map(index_array, cmap, -1.0, 1.0))
