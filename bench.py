@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Benchmark of the RGNir per-pixel analysis path (BASELINE.json metric: RGNir Mpix/s for
+WB + NDVI/GNDVI/NDWI + stats [+ colormap], % of HBM peak).
+
+    python bench.py --gpus N --steps K --warmup W          # our CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's NumPy path on host cores
+
+A "step" is one pass of the hot path (Pass 1 histogram -> LUT -> fused Pass 2 -> statistics
+finalize [-> dataset-statistics exchange when N > 1]) over one batch of synthetic frames of the
+workload configuration (BASELINE config 2: 4000x3000 uint8 RGNir frames).  Each rank holds its
+own batch (weak scaling: frames are independent units).
+
+One JSON line on stdout (rank 0).  `value` is device-resident throughput (inputs in HBM when
+the timed region starts, CUDA events, max over ranks); `e2e` goes through the host-array API
+with pinned host buffers and H2D / D2H inside the timed region; `roofline` is the fused Pass-2
+kernel against the measured HBM copy bandwidth; `cpu_baseline` is the NumPy oracle port timed
+on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "RGNir Mpix/s (WB+NDVI/GNDVI/NDWI+stats+colormap)"
+UNIT = "Mpix/s"
+U8_PASS1_BYTES_PER_PX = 3            # K1 reads the raw frame once
+U8_PASS2_BYTES_PER_PX = 3 + 3 + 12 + 9   # K2: read raw, write WB u8 + 3 fp32 maps + 3 RGB images
+FALLBACK_HBM_GBS = 6650.0            # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=16, help="frames per rank per step")
+    ap.add_argument("--height", type=int, default=3000)
+    ap.add_argument("--width", type=int, default=4000)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps (capped at 5)")
+    ap.add_argument("--cpu-frames", type=int, default=3, help="frames of the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--chunk", type=int, default=2, help="frames per pipeline chunk in the e2e path")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"C2: {a.width}x{a.height} uint8 RGNir frames, white balance + NDVI/GNDVI/NDWI fp32 maps + "
+            f"statistics/histograms + colormap RGB; {a.frames} distinct frames per GPU per step")
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------
+# clocks: sampled DURING the timed region through NVML
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU side: the oracle port of the reference's NumPy path
+# ------------------------------------------------------------------------------------------
+def _cpu_one_frame(args):
+    seed, h, w = args
+    import warnings
+    import numpy as np  # noqa: F401
+    from oracle import oracle_np as o
+    from oracle import synth
+    img = synth.vegetation_frame(seed, h, w)
+    t0 = time.perf_counter()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        o.reference_cpu_path(img)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline_single(frames_host):
+    """Sequential, one core: the NumPy calls of the path are single-threaded."""
+    import warnings
+    from oracle import oracle_np as o
+    t0 = time.perf_counter()
+    for img in frames_host:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            o.reference_cpu_path(img)
+    dt = time.perf_counter() - t0
+    npx = sum(f.shape[0] * f.shape[1] for f in frames_host)
+    return npx / dt / 1e6, dt
+
+
+def run_reference(a):
+    """--impl reference: the reference's CPU implementation (NumPy oracle port; the reference is
+    Python and cannot travel to this box) on all host cores: one independent frame per worker
+    process per step, like the reference's own per-file loop (backend-process.py:92-97)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 64))
+    ctx = mp.get_context("spawn")
+    npx = a.height * a.width
+    with ctx.Pool(workers) as pool:
+        for w in range(max(1, min(a.warmup, 1))):
+            pool.map(_cpu_one_frame, [(9000 + i, a.height // 4, a.width // 4) for i in range(workers)])
+        t0 = time.perf_counter()
+        for k in range(a.steps):
+            pool.map(_cpu_one_frame, [(2 + k * workers + i, a.height, a.width) for i in range(workers)])
+        dt = time.perf_counter() - t0
+    value = workers * a.steps * npx / dt / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sample": f"{workers} frames per step, one per worker process"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
+                         "sample": f"{workers * a.steps} frames of {a.width}x{a.height} over {workers} processes "
+                                   "(NumPy oracle port of process-images.py:424-513 + std + hist(50) + colormap)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------
+def synth_frames_device(eng, n_frames, h, w, seed):
+    """Vegetation-like frames generated on the device: R~N(90,35) G~N(110,35) NIR~N(150,45)."""
+    import torch
+    frames = eng.alloc_frames(n_frames, h, w, 3)
+    npx = h * w
+    g = torch.Generator(device=eng.device)
+    g.manual_seed(seed)
+    mean = torch.tensor([90.0, 110.0, 150.0], device=eng.device)
+    std = torch.tensor([35.0, 35.0, 45.0], device=eng.device)
+    for f in range(n_frames):
+        x = torch.randn((npx, 3), generator=g, device=eng.device) * std + mean
+        frames.data[f, :npx * 3] = x.round_().clamp_(0, 255).to(torch.uint8).reshape(-1)
+        del x
+    torch.cuda.synchronize(eng.device)
+    return frames
+
+
+def run_ours(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from lars_image_processing_b200 import distributed as ld
+    from lars_image_processing_b200.engine import ALL_OUTPUTS, Engine
+
+    rank, world, local_rank = ld.init_from_env()
+    if world != a.gpus and rank == 0:
+        print(f"[bench] note: --gpus {a.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+    torch.cuda.set_device(local_rank)
+    eng = Engine(local_rank)
+    s = eng.stream()
+    F, h, w = a.frames, a.height, a.width
+    npx = h * w
+    frames = synth_frames_device(eng, F, h, w, seed=2 + rank)
+    res = eng.alloc_outputs(frames, ALL_OUTPUTS, s)
+
+    fused_ms = []
+
+    def step(timed):
+        hist = eng.wb_histogram(frames, stream=s)
+        lut, _pct = eng.wb_lut(hist, stream=s)
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s)
+        eng.fused(frames, lut, outputs=ALL_OUTPUTS, out=res, stream=s)
+        if timed:
+            e1.record(s)
+            fused_ms.append((e0, e1))
+        ld.dataset_statistics(eng, res.stats, stream=s)     # local merge (+ one NCCL all-gather when N > 1)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step(False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record(s)
+    for _ in range(a.steps):
+        step(True)
+    t_end.record(s)
+    barrier()
+    clocks = sampler.stop()
+    ms = t_start.elapsed_time(t_end)
+    k2_ms = sum(e0.elapsed_time(e1) for e0, e1 in fused_ms) / len(fused_ms)
+    t = torch.tensor([ms, k2_ms], device=eng.device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, k2_ms = float(t[0]), float(t[1])
+    value = world * F * npx * a.steps / (ms * 1e-3) / 1e6
+
+    # sanity: the timed work really happened (histogram totals == pixels)
+    rec = ld.records_to_numpy(res.stats)
+    assert int(rec["hist"][0, 0].sum()) == npx and int(rec["count"][-1, 2]) == npx
+
+    # ---- end to end through the host-array API (pinned buffers, H2D + D2H in the timed region)
+    e2e = None
+    if not a.no_e2e:
+        host_in = torch.empty((F, npx * 3), dtype=torch.uint8, pin_memory=True)
+        host_in.copy_(frames.data[:, :npx * 3])
+        torch.cuda.synchronize()
+        host_out = eng.alloc_host_outputs(F, h, w, 3, ALL_OUTPUTS)
+        k_e2e = a.e2e_steps or min(a.steps, 5)
+        eng.run_host_batch(host_in, (h, w, 3), host_out, chunk=a.chunk)      # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            eng.run_host_batch(host_in, (h, w, 3), host_out, chunk=a.chunk)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device=eng.device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt[0])
+        h2d = F * npx * 3
+        d2h = F * (npx * 3 + 3 * npx * 4 + 3 * npx * 3 + 3 * 576)
+        e2e = {"value": world * F * npx * k_e2e / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": k_e2e, "api": "Engine.run_host_batch (pinned, pipelined)"}
+        # the host results are the real thing
+        rec_h = host_out["stats"].numpy().view(rec.dtype).reshape(F, 3)
+        assert np.array_equal(rec_h["hist"], rec["hist"])
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_hbm_peak()
+    launch_bytes = U8_PASS2_BYTES_PER_PX * F * npx
+    achieved = launch_bytes / (k2_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload_name(a), "frames_per_gpu": F, "height": h, "width": w,
+                   "l2": f"inputs larger than L2 ({F * npx * 3 / 1e6:.0f} MB raw per GPU per step)",
+                   "parallelism": f"frames sharded over {world} GPU(s), one dataset-statistics all-gather per step"
+                   if world > 1 else "single GPU"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "fused_index_u8_kernel<3> (+ its statistics finalize)",
+                     "algorithmic_bytes_per_px": U8_PASS2_BYTES_PER_PX, "ms_per_launch": k2_ms,
+                     "peak_source": peak_src,
+                     "whole_step_GBps": (U8_PASS1_BYTES_PER_PX + U8_PASS2_BYTES_PER_PX) * F * npx * a.steps
+                     / (ms * 1e-3) / 1e9},
+        "clocks": clocks,
+        "gpu_launches": 5 * a.steps,   # wb_hist, wb_lut_build, fused_index, fused_finalize, stats_merge
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if world == 1 and not a.no_cpu_baseline:
+        sample = [frames.data[i, :npx * 3].cpu().numpy().reshape(h, w, 3) for i in range(min(a.cpu_frames, F))]
+        v, dt = cpu_baseline_single(sample)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"{len(sample)} of the step's {w}x{h} frames, sequential NumPy oracle port "
+                                          f"(WB + 3 indices + analyze_index + std + hist(50) + colormap), {dt:.1f} s; "
+                                          f"host has {os.cpu_count()} cores, the reference path is single-threaded"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

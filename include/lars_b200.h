@@ -160,6 +160,10 @@ int lars_ndvi_f64_u8(const uint8_t* src, int64_t n_pixels, int32_t channels, dou
  * (calculate_index(red, green, nir, index_type), backend-process.py:28-38). */
 int lars_index_planes_f32(const float* hi, const float* lo, int64_t n, float* out, void* stream);
 
+/* Merge n_sets x 3 statistics records (per frame, or per rank after the NCCL all-gather) into
+ * 3 dataset-wide records, in index order of the input -- the exchange step of SURVEY.md 8(e). */
+int lars_stats_merge(const lars_index_stats* in, int32_t n_sets, lars_index_stats* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

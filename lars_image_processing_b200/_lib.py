@@ -27,6 +27,7 @@ EXPORTED_SYMBOLS = (
     "lars_fused_workspace_bytes", "lars_fused_index_u8",
     "lars_map_stats_workspace_bytes", "lars_map_stats_f32", "lars_select_workspace_bytes",
     "lars_select_f32", "lars_colormap_f32", "lars_ndvi_f64_u8", "lars_index_planes_f32",
+    "lars_stats_merge",
 )
 
 
@@ -111,6 +112,8 @@ def _declare(lib):
     lib.lars_ndvi_f64_u8.restype = C.c_int
     lib.lars_index_planes_f32.argtypes = [vp, vp, i64, vp, vp]
     lib.lars_index_planes_f32.restype = C.c_int
+    lib.lars_stats_merge.argtypes = [vp, i32, vp, vp]
+    lib.lars_stats_merge.restype = C.c_int
 
 
 def load():

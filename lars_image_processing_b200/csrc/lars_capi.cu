@@ -423,4 +423,15 @@ int lars_index_planes_f32(const float* hi, const float* lo, int64_t n, float* ou
   return LARS_OK;
 }
 
+int lars_stats_merge(const lars_index_stats* in, int32_t n_sets, lars_index_stats* out, void* stream) {
+  DeviceState* st = nullptr;
+  int rc = current_state(&st);
+  if (rc != LARS_OK) return rc;
+  if (!in || !out) return fail(LARS_ERR_INVALID, "lars_stats_merge: NULL pointer");
+  if (n_sets < 1) return fail(LARS_ERR_INVALID, "lars_stats_merge: n_sets=%d", n_sets);
+  lars::stats_merge_kernel<<<3, LARS_MAX_BINS, 0, static_cast<cudaStream_t>(stream)>>>(in, n_sets, out);
+  LARS_CUDA(cudaGetLastError());
+  return LARS_OK;
+}
+
 }  // extern "C"

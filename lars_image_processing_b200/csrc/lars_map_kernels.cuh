@@ -398,4 +398,42 @@ __global__ void __launch_bounds__(256) index_planes_f32_kernel(const float* __re
     for (long long i = nvec * 4 + threadIdx.x; i < n; i += blockDim.x) out[i] = lars_ratio_clip_f32(hi[i], lo[i]);
 }
 
+// ------------------------------------------------------------------------------------------
+// Dataset-wide statistics: merge n_sets x 3 per-frame (or per-rank) records into 3, in order.
+// This is the local half of the multi-GPU exchange: every rank merges its
+// own frames, the packed records are all-gathered over NCCL, and the same kernel merges the
+// per-rank records in rank order -- deterministic, no floating-point atomics.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LARS_MAX_BINS) stats_merge_kernel(const lars_index_stats* __restrict__ in,
+                                                                    int n_sets, lars_index_stats* __restrict__ out) {
+  const int idx = blockIdx.x;   // index 0..2
+  const int tid = threadIdx.x;  // histogram bin
+  unsigned long long h = 0;
+  for (int s = 0; s < n_sets; ++s) h += in[(long long)s * 3 + idx].hist[tid];
+  out[idx].hist[tid] = h;
+  if (tid == 0) {
+    unsigned long long cnt = 0, above = 0;
+    double sum = 0.0, sumsq = 0.0;
+    float mn = INFINITY, mx = -INFINITY, thr = 0.f;
+    uint32_t bins = 0;
+    for (int s = 0; s < n_sets; ++s) {
+      const lars_index_stats& r = in[(long long)s * 3 + idx];
+      if (!r.count) continue;
+      cnt += r.count; above += r.count_above;
+      sum += r.sum; sumsq += r.sumsq;
+      mn = fminf(mn, r.min); mx = fmaxf(mx, r.max);
+      thr = r.threshold; bins = r.bins;
+    }
+    const double n = (double)cnt;
+    const double mean = cnt ? sum / n : 0.0;
+    double var = cnt ? sumsq / n - mean * mean : 0.0;
+    var = var > 0.0 ? var : 0.0;
+    lars_index_stats& o = out[idx];
+    o.count = cnt; o.count_above = above; o.sum = sum; o.sumsq = sumsq;
+    o.mean = mean; o.std = sqrt(var);
+    o.min = cnt ? mn : 0.f; o.max = cnt ? mx : 0.f;
+    o.threshold = thr; o.bins = bins;
+  }
+}
+
 }  // namespace lars

@@ -1,0 +1,97 @@
+"""Multi-GPU plumbing: one process per GPU, ``torch.distributed`` (NCCL over NVLink / NVSwitch).
+
+The path shards by independent frames: white-balance percentiles are per
+frame, so no data crosses GPUs inside a frame.  The only exchange is the dataset-wide
+statistics merge at the end: every rank folds its own per-frame records into 3 records
+(``lars_stats_merge``), ONE all-gather moves the packed 3 x 576-byte records, and the same
+kernel merges them in rank order -- deterministic, SUM and MIN/MAX in a single collective.
+
+For one huge image sharded by tiles (config 4) the white-balance histogram is global to the
+image: ``allreduce_wb_histogram`` SUM-reduces the 3 x 256 counters between Pass 1 and the
+LUT build so that every rank derives the identical LUT.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ._lib import INDEX_STATS_DTYPE, check
+
+RECORD_BYTES = INDEX_STATS_DTYPE.itemsize
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block [begin, end) of ``n_items`` owned by ``rank`` (sizes differ by <= 1)."""
+    base, extra = divmod(n_items, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def shard_round_robin(n_items: int, rank: int, world: int) -> List[int]:
+    """Round-robin assignment (frame i -> GPU i % world), the layout of BASELINE config 3."""
+    return list(range(rank, n_items, world))
+
+
+def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """Initialise the default process group from torchrun's environment -> (rank, world, local_rank)."""
+    import os
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend)
+    return rank, world, local_rank
+
+
+def merge_records_device(engine, records: torch.Tensor, stream=None) -> torch.Tensor:
+    """[S, 3, 576] uint8 device records -> [3, 576] merged (GPU kernel, fixed order)."""
+    s = stream or engine.stream()
+    n_sets = records.shape[0]
+    with torch.cuda.stream(s):
+        out = torch.empty((3, RECORD_BYTES), dtype=torch.uint8, device=engine.device)
+        with torch.cuda.device(engine.device):
+            check(engine.lib.lars_stats_merge(records.data_ptr(), n_sets, out.data_ptr(), s.cuda_stream),
+                  "lars_stats_merge")
+    return out
+
+
+def gather_records(local: torch.Tensor, group=None) -> torch.Tensor:
+    """All-gather the packed per-rank records -> [world, 3, 576] on every rank (one collective)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return local.unsqueeze(0)
+    out = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    return out
+
+
+def dataset_statistics(engine, per_frame_records: torch.Tensor, group=None, stream=None) -> torch.Tensor:
+    """Per-frame records of this rank -> dataset-wide records over all ranks ([3, 576] uint8)."""
+    s = stream or engine.stream()
+    local = merge_records_device(engine, per_frame_records, s)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return local
+    with torch.cuda.stream(s):
+        gathered = gather_records(local, group)       # NCCL runs on the current (= engine) stream
+    return merge_records_device(engine, gathered, s)
+
+
+def allreduce_wb_histogram(hist: torch.Tensor, group=None) -> torch.Tensor:
+    """SUM-allreduce of the [*, 3, 256] int64 white-balance histogram (tile-sharded image)."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    return hist
+
+
+def records_to_numpy(records: torch.Tensor) -> np.ndarray:
+    return records.cpu().numpy().view(INDEX_STATS_DTYPE).reshape(records.shape[:-1])

@@ -175,6 +175,21 @@ class Engine:
                                                 s.cuda_stream), "lars_wb_lut_build_u8")
         return lut, pct
 
+    def alloc_outputs(self, frames: DeviceFrames, outputs=ALL_OUTPUTS, stream=None) -> DeviceOutputs:
+        """Pre-allocate the device buffers of a batch (reused across steps via ``out=``)."""
+        s = stream or self.stream()
+        F, ch, ppx = frames.n_frames, frames.channels, _pad_px(frames.n_pixels)
+        res = DeviceOutputs(frames=frames)
+        if "wb" in outputs:
+            res.wb = self._alloc((F, ppx * ch), torch.uint8, s)
+        if "maps" in outputs:
+            res.maps = self._alloc((3, F, ppx), torch.float32, s)
+        if "rgb" in outputs:
+            res.rgb = self._alloc((3, F, ppx * 3), torch.uint8, s)
+        if "stats" in outputs:
+            res.stats = self._alloc((F, 3, INDEX_STATS_DTYPE.itemsize), torch.uint8, s)
+        return res
+
     def fused(self, frames: DeviceFrames, lut: Optional[torch.Tensor], outputs=ALL_OUTPUTS,
               indices=INDEX_TYPES, bins: int = DEFAULT_BINS, thresholds=DEFAULT_THRESHOLDS,
               cmaps=DEFAULT_CMAPS, rgb_indices=None, out: Optional[DeviceOutputs] = None,
@@ -300,6 +315,94 @@ class Engine:
                 d["percentiles"] = h_pct[f].numpy().copy()
             results.append(d)
         return results
+
+    # ------------------------------------------------------------------ pinned, pipelined host API
+    def alloc_host_outputs(self, n_frames: int, height: int, width: int, channels: int = 3,
+                           outputs=ALL_OUTPUTS) -> Dict[str, torch.Tensor]:
+        """Pinned host buffers for :meth:`run_host_batch` (allocate once, reuse every step)."""
+        npx = height * width
+        out: Dict[str, torch.Tensor] = {}
+        if "wb" in outputs:
+            out["wb"] = torch.empty((n_frames, npx * channels), dtype=torch.uint8, pin_memory=True)
+        if "maps" in outputs:
+            out["maps"] = torch.empty((3, n_frames, npx), dtype=torch.float32, pin_memory=True)
+        if "rgb" in outputs:
+            out["rgb"] = torch.empty((3, n_frames, npx * 3), dtype=torch.uint8, pin_memory=True)
+        if "stats" in outputs:
+            out["stats"] = torch.empty((n_frames, 3, INDEX_STATS_DTYPE.itemsize), dtype=torch.uint8,
+                                       pin_memory=True)
+        return out
+
+    def run_host_batch(self, host_frames: torch.Tensor, shape, host_out: Dict[str, torch.Tensor],
+                       chunk: int = 4, white_balance: bool = True, **kw) -> None:
+        """Host frames in (pinned ``[F, H*W*C]`` uint8), host results out, software-pipelined.
+
+        The batch is cut into chunks of ``chunk`` frames; H2D of chunk c+1, the kernels of chunk
+        c and D2H of chunk c-1 run concurrently on three streams over double-buffered device
+        slots, so the PCIe copy engines stay busy in both directions while the SMs work.
+        Returns after everything has landed in ``host_out``.
+        """
+        h, w, ch = shape
+        F = host_frames.shape[0]
+        npx = h * w
+        nbytes = npx * ch
+        outputs = tuple(k for k in ALL_OUTPUTS if k in host_out)
+        st = getattr(self._tls, "pipe", None)
+        key = (chunk, h, w, ch, outputs)
+        if st is None or st["key"] != key:
+            s_in, s_cmp, s_out = (torch.cuda.Stream(device=self.device) for _ in range(3))
+            slots = []
+            for _ in range(2):
+                frames = self.alloc_frames(chunk, h, w, ch, s_cmp)
+                slots.append({"frames": frames, "res": self.alloc_outputs(frames, outputs, s_cmp)})
+            st = {"key": key, "streams": (s_in, s_cmp, s_out), "slots": slots}
+            self._tls.pipe = st
+        s_in, s_cmp, s_out = st["streams"]
+        slots = st["slots"]
+        n_chunks = (F + chunk - 1) // chunk
+        ev_in = [torch.cuda.Event() for _ in range(n_chunks)]
+        ev_cmp = [torch.cuda.Event() for _ in range(n_chunks)]
+        ev_out = [torch.cuda.Event() for _ in range(n_chunks)]
+        for c in range(n_chunks):
+            a, b = c * chunk, min(F, (c + 1) * chunk)
+            k = b - a
+            slot = slots[c & 1]
+            fr: DeviceFrames = slot["frames"]
+            view = DeviceFrames(fr.data[:k], fr.n_pixels, fr.channels, fr.shape)
+            with torch.cuda.stream(s_in):
+                if c >= 2:
+                    s_in.wait_event(ev_cmp[c - 2])          # slot's input consumed
+                view.data[:, :nbytes].copy_(host_frames[a:b], non_blocking=True)
+                ev_in[c].record(s_in)
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(ev_in[c])
+                if c >= 2:
+                    s_cmp.wait_event(ev_out[c - 2])         # slot's outputs drained
+                res = slot["res"]
+                sub = DeviceOutputs(frames=view,
+                                    wb=None if res.wb is None else res.wb[:k],
+                                    maps=None if res.maps is None else res.maps[:, :k],
+                                    rgb=None if res.rgb is None else res.rgb[:, :k],
+                                    stats=None if res.stats is None else res.stats[:k])
+                self.process_device(view, outputs=outputs, white_balance=white_balance, out=sub,
+                                    stream=s_cmp, **kw)
+                ev_cmp[c].record(s_cmp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_cmp[c])
+                if "wb" in host_out:
+                    host_out["wb"][a:b].copy_(sub.wb[:k, :nbytes], non_blocking=True)
+                if "maps" in host_out:
+                    for i in range(3):
+                        if sub.map_mask[i]:
+                            host_out["maps"][i, a:b].copy_(sub.maps[i, :k, :npx], non_blocking=True)
+                if "rgb" in host_out:
+                    for i in range(3):
+                        if sub.rgb_mask[i]:
+                            host_out["rgb"][i, a:b].copy_(sub.rgb[i, :k, :npx * 3], non_blocking=True)
+                if "stats" in host_out:
+                    host_out["stats"][a:b].copy_(sub.stats[:k], non_blocking=True)
+                ev_out[c].record(s_out)
+        s_out.synchronize()
 
     @staticmethod
     def _check_frame(img: np.ndarray) -> np.ndarray:

@@ -1,0 +1,52 @@
+// TEST INFRASTRUCTURE ONLY.  Compiles the device arithmetic header (pixel_math.h) for the
+// host with -ffp-contract=off so that the -m "not gpu" tests can check, exhaustively and
+// bit for bit, the exact formulas the kernels evaluate against the NumPy oracle.  The product
+// never loads this library.
+#include <stdint.h>
+#include <string.h>
+
+#include "../../lars_image_processing_b200/csrc/pixel_math.h"
+
+extern "C" {
+
+// All 65,536 (hi, lo) uint8 pairs: value bits, pair-domain bin, literal-edge bin, cmap slot,
+// coverage flag, and the NDWI value derived by negation.
+void hc_pair_tables(int bins, const float* edges, float threshold, float* value, int32_t* bin_pair,
+                    int32_t* bin_edges, int32_t* cmap, uint8_t* above, float* negated) {
+  const float half = 0.5f * (float)bins;
+  const float bias = half + LARS_HIST_BIAS;
+  for (int hi = 0; hi < 256; ++hi)
+    for (int lo = 0; lo < 256; ++lo) {
+      const int k = hi * 256 + lo;
+      const float x = lars_ratio_f32((float)hi, (float)lo);
+      value[k] = x;
+      bin_pair[k] = lars_hist_bin_pair(x, half, bias, bins - 1);
+      bin_edges[k] = lars_hist_bin_edges(x, edges, bins);
+      cmap[k] = lars_cmap_index(x);
+      above[k] = x > threshold ? 1 : 0;
+      negated[k] = lars_negate_index(x);
+    }
+}
+
+void hc_hist_bin_edges(const float* x, int64_t n, int bins, const float* edges, int32_t* out) {
+  for (int64_t i = 0; i < n; ++i) out[i] = lars_hist_bin_edges(x[i], edges, bins);
+}
+
+void hc_cmap_index_range(const float* x, int64_t n, float vmin, float vmax, int32_t* out) {
+  for (int64_t i = 0; i < n; ++i) out[i] = lars_cmap_index_range(x[i], vmin, vmax);
+}
+
+void hc_wb_lut(double lo, double hi, int domain, uint8_t* out) {
+  for (int v = 0; v < domain; ++v) out[v] = lars_wb_lut_entry((double)v, lo, hi);
+}
+
+double hc_percentile_lerp(double a, double b, double gamma) { return lars_percentile_lerp(a, b, gamma); }
+
+void hc_ratio_clip_f64(const double* hi, const double* lo, int64_t n, double* out) {
+  for (int64_t i = 0; i < n; ++i) out[i] = lars_ratio_clip_f64(hi[i], lo[i]);
+}
+
+void hc_ratio_clip_f32(const float* hi, const float* lo, int64_t n, float* out) {
+  for (int64_t i = 0; i < n; ++i) out[i] = lars_ratio_clip_f32(hi[i], lo[i]);
+}
+}

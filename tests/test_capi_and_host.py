@@ -1,0 +1,114 @@
+"""C-ABI library loads, exports every symbol include/lars_b200.h declares, struct layouts match
+the ctypes mirrors, host-only helpers agree with the oracle, and the drop-in helpers keep the
+reference's error conventions -- all without a GPU (no compute calls)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "lars_b200.h")
+
+
+def _declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lars_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from lars_image_processing_b200 import _lib
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 18
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in include/lars_b200.h but not exported"
+    assert set(_lib.EXPORTED_SYMBOLS) == set(declared)
+    assert lib.lars_abi_version() == 1
+
+
+def test_struct_layouts_match_header(tmp_path):
+    from lars_image_processing_b200 import _lib
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "lars_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu\\n", sizeof(lars_fused_args), sizeof(lars_index_stats),'
+                   'offsetof(lars_fused_args, maps), offsetof(lars_fused_args, stats), offsetof(lars_index_stats, hist));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    a, b, c, d, e = map(int, subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split())
+    assert a == C.sizeof(_lib.FusedArgs)
+    assert b == _lib.INDEX_STATS_DTYPE.itemsize == 576
+    assert c == _lib.FusedArgs.maps.offset and d == _lib.FusedArgs.stats.offset
+    assert e == _lib.INDEX_STATS_DTYPE.fields["hist"][1]
+
+
+def test_host_tables_match_oracle():
+    from lars_image_processing_b200 import _lib
+    from oracle import oracle_np as o
+    for name in ("RdYlGn", "RdYlBu", "bwr"):
+        assert np.array_equal(_lib.colormap_table(name), o.colormap_lut(name)), name
+    for bins in list(range(1, 65)):
+        assert np.array_equal(_lib.histogram_edges(bins), o.histogram_edges(bins)), bins
+
+
+def test_compute_entry_points_fail_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from lars_image_processing_b200 import _lib
+    from lars_image_processing_b200.engine import Engine
+    lib = _lib.load()
+    assert lib.lars_init(0) < 0 and b"failed" in lib.lars_last_error()
+    hist = np.zeros(768, np.uint64)
+    assert lib.lars_wb_hist_u8(1, 1, 16, 3, 48, hist.ctypes.data, None) < 0
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Engine()
+
+
+def test_dropin_error_conventions_need_no_gpu():
+    from lars_image_processing_b200 import process_images as pi
+    empty = np.zeros((0, 0, 3), np.uint8)
+    assert pi.fix_white_balance(None) is None and pi.fix_white_balance(empty) is None
+    assert pi.calculate_index(None, "NDVI") is None and pi.calculate_index(empty, "NDVI") is None
+    assert pi.analyze_index(None, "NDVI") == {} and pi.analyze_index(np.zeros((0,)), "NDVI") == {}
+    assert pi.create_index_visualization(None, "NDVI") is None
+    assert pi.analyze_frame(None) is None
+    with pytest.raises(ValueError, match="Unknown index type: EVI"):
+        pi.calculate_index(np.zeros((4, 4, 3), np.uint8), "EVI")
+
+
+def test_frame_validation_mirrors_reference_exceptions():
+    from lars_image_processing_b200.engine import Engine
+    from lars_image_processing_b200._lib import LarsError
+    with pytest.raises(IndexError):
+        Engine._check_frame(np.zeros((4, 4), np.uint8))           # reference: img[:, :, i] on 2-D
+    with pytest.raises(IndexError):
+        Engine._check_frame(np.zeros((4, 4, 2), np.uint8))
+    with pytest.raises(LarsError):
+        Engine._check_frame(np.zeros((4, 4, 3), np.float64))
+    assert Engine._check_frame(np.zeros((4, 4, 4), np.uint8)).shape == (4, 4, 4)
+
+
+def test_stats_record_decoding():
+    from lars_image_processing_b200._lib import INDEX_STATS_DTYPE
+    from lars_image_processing_b200.engine import stats_records_to_dicts
+    rec = np.zeros((1, 3), INDEX_STATS_DTYPE)
+    rec[0, 0]["count"], rec[0, 0]["count_above"], rec[0, 0]["mean"] = 200, 50, 0.25
+    rec[0, 0]["hist"][:50] = np.arange(50)
+    d = stats_records_to_dicts(rec, 50)[0]["NDVI"]
+    assert d["coverage_pct"] == 25.0 and d["mean"] == 0.25 and d["hist"].sum() == np.arange(50).sum()
+    assert stats_records_to_dicts(rec, 50)[0]["NDWI"]["coverage_pct"] == 0.0
+
+
+def test_oracle_is_not_imported_by_the_product():
+    pkg = os.path.join(ROOT, "lars_image_processing_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "/root/reference" not in text.replace("``/root/reference/process-images.py``", ""), f

@@ -1,0 +1,350 @@
+"""Parity of the CUDA path (through the C ABI) against the NumPy oracle and the golden vectors
+produced by the reference's own functions.  Bit-exact for histograms, uint8 white-balanced
+output, fp32 index maps (IEEE division), colormap indices / RGB bytes and counts; moments
+(mean / std) within 1e-6 * max(|value|, std, 1e-3) as stated in BASELINE.md section 5."""
+import threading
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import oracle_np as o
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+INDEX_TYPES = o.INDEX_TYPES
+MOMENT_RTOL = 1e-6
+
+
+def moment_close(got, want, std):
+    return abs(got - want) <= MOMENT_RTOL * max(abs(want), abs(std), 1e-3)
+
+
+def oracle_frame(img, bins=50):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return o.analyze_frame(img, bins=bins)
+
+
+def check_frame_result(res, img, bins=50, label=""):
+    want = oracle_frame(img, bins)
+    assert np.array_equal(res["wb"], want["wb"]), f"{label}: white-balanced frame differs"
+    for t in INDEX_TYPES:
+        g, w = res["maps"][t], want["maps"][t]
+        assert g.dtype == np.float32 and g.shape == w.shape
+        assert np.array_equal(g.view(np.uint32), w.view(np.uint32)), f"{label}: {t} map not bit-exact"
+        assert np.array_equal(res["rgb"][t], want["rgb"][t]), f"{label}: {t} colormap bytes differ"
+        gs, ws = res["stats"][t], want["stats"][t]
+        assert gs["count"] == ws["count"]
+        assert np.array_equal(gs["hist"], ws["hist"]), f"{label}: {t} histogram differs"
+        assert gs["count_above"] == ws["count_above"], f"{label}: {t} coverage count differs"
+        assert gs["min"] == ws["min"] and gs["max"] == ws["max"], f"{label}: {t} min/max differ"
+        ref_mean = float(np.mean(w))            # the reference's float32 pairwise mean
+        ref_std = float(np.std(w))
+        exact_mean = ws["sum"] / ws["count"]
+        assert moment_close(gs["mean"], ref_mean, ref_std), f"{label}: {t} mean {gs['mean']} vs {ref_mean}"
+        assert moment_close(gs["mean"], exact_mean, ref_std), f"{label}: {t} mean vs float64 sum"
+        assert moment_close(gs["std"], ref_std, ref_std), f"{label}: {t} std {gs['std']} vs {ref_std}"
+        assert gs["coverage_pct"] == float(np.mean(w > np.float32(o.coverage_threshold(t))) * 100)
+
+
+# ------------------------------------------------------------------------------------- Pass 1
+def _all_small_frames():
+    frames = dict(synth.adversarial_frames())
+    frames["veg_240x320"] = synth.vegetation_frame(21, 240, 320)
+    frames["smooth_200x300"] = synth.smooth_frame(22, 200, 300)
+    frames["veg_513x1025"] = synth.vegetation_frame(23, 513, 1025)
+    return frames
+
+
+def test_wb_histogram_matches_bincount(engine):
+    for name, img in _all_small_frames().items():
+        dev = engine.upload([img])
+        hist = engine.wb_histogram(dev)
+        engine.stream().synchronize()
+        assert np.array_equal(hist.cpu().numpy()[0], o.channel_histograms(img)), name
+
+
+def test_wb_percentiles_and_lut_match_oracle(engine):
+    for name, img in _all_small_frames().items():
+        dev = engine.upload([img])
+        lut, pct = engine.wb_lut(engine.wb_histogram(dev))
+        engine.stream().synchronize()
+        want_pct, want_lut = o.wb_luts_from_hist(o.channel_histograms(img))
+        assert np.array_equal(pct.cpu().numpy()[0], want_pct), name
+        assert np.array_equal(lut.cpu().numpy()[0], want_lut), name
+        assert np.array_equal(want_pct, np.array([np.percentile(img[:, :, c].astype(np.float32), (2, 98))
+                                                  for c in range(3)])), name
+
+
+# ------------------------------------------------------------------------------------- Pass 2
+@pytest.mark.parametrize("bins", [50, 64, 7, 1])
+def test_exhaustive_pair_domain_through_the_fused_kernel(engine, bins):
+    """Every value a white-balanced uint8 frame can produce: 65,536 (a, b) pairs, identity LUT."""
+    img = o.pair_image()
+    res = engine.analyze_frame(img, white_balance=False, bins=bins)
+    assert np.array_equal(res["wb"], img)
+    for t in INDEX_TYPES:
+        want = o.calculate_index(img, t)
+        assert np.array_equal(res["maps"][t].view(np.uint32), want.view(np.uint32)), t
+        assert np.array_equal(res["rgb"][t], o.apply_colormap(want, t)), t
+        st = res["stats"][t]
+        assert np.array_equal(st["hist"], np.histogram(want.ravel(), bins=bins, range=(-1, 1))[0]), t
+        assert st["count_above"] == int(np.count_nonzero(want > np.float32(o.coverage_threshold(t))))
+        assert st["min"] == float(want.min()) and st["max"] == float(want.max())
+        assert moment_close(st["mean"], float(want.astype(np.float64).mean()), float(np.std(want)))
+        assert moment_close(st["std"], float(want.astype(np.float64).std()), float(np.std(want)))
+
+
+def test_whole_frames_against_oracle(engine):
+    for name, img in _all_small_frames().items():
+        if img.shape[2] == 4:
+            continue
+        check_frame_result(engine.analyze_frame(img), img, label=name)
+
+
+def test_rgba_frame_alpha_ignored_and_zeroed(engine):
+    img = synth.adversarial_frames()["rgba"]
+    res = engine.analyze_frame(img)
+    want = oracle_frame(img)
+    assert res["wb"].shape == img.shape
+    assert np.array_equal(res["wb"], want["wb"]) and not res["wb"][:, :, 3].any()
+    for t in INDEX_TYPES:
+        assert np.array_equal(res["maps"][t].view(np.uint32), want["maps"][t].view(np.uint32))
+        assert np.array_equal(res["stats"][t]["hist"], want["stats"][t]["hist"])
+    big = synth.vegetation_frame(31, 300, 421, channels=4)
+    res = engine.analyze_frame(big)
+    want = oracle_frame(big)
+    assert np.array_equal(res["wb"], want["wb"])
+    for t in INDEX_TYPES:
+        assert np.array_equal(res["maps"][t].view(np.uint32), want["maps"][t].view(np.uint32))
+        assert np.array_equal(res["rgb"][t], want["rgb"][t])
+        assert np.array_equal(res["stats"][t]["hist"], want["stats"][t]["hist"])
+
+
+def test_gpu_against_reference_golden_vectors(engine, golden):
+    g = golden["frames"]
+    names = sorted({k.split("/")[0] for k in g.files})
+    for name in names:
+        img = g[f"{name}/input"]
+        if img.dtype != np.uint8:
+            continue
+        res = engine.analyze_frame(img)
+        assert np.array_equal(res["wb"], g[f"{name}/wb"]), name
+        assert np.array_equal(res["percentiles"], g[f"{name}/percentiles"]), name
+        for t in INDEX_TYPES:
+            assert np.array_equal(res["maps"][t].view(np.uint32), g[f"{name}/map_{t}"].view(np.uint32)), (name, t)
+            assert np.array_equal(res["stats"][t]["hist"], g[f"{name}/hist_{t}"]), (name, t)
+            mean, _median, mn, mx, cov = g[f"{name}/stats_{t}"]
+            std = float(g[f"{name}/std_{t}"])
+            st = res["stats"][t]
+            assert st["min"] == mn and st["max"] == mx and st["coverage_pct"] == cov, (name, t)
+            assert moment_close(st["mean"], mean, std) and moment_close(st["std"], std, std), (name, t)
+
+
+def test_batches_cross_frame_boundaries(engine):
+    """Many small frames in one launch: CTA tile ranges span several frames (LUT reload, partial
+    flush per frame) and frames span several CTAs."""
+    for shape, count in (((37, 41), 700), ((64, 80), 33), ((300, 400), 5), ((1, 1), 9)):
+        frames = [synth.vegetation_frame(1000 + i, shape[0], shape[1]) for i in range(count)]
+        frames[1] = np.zeros_like(frames[1])
+        frames[-1][..., 1] = 200
+        res = engine.analyze_batch(frames)
+        for i in (list(range(min(count, 12))) + [count // 2, count - 1]):
+            check_frame_result(res[i], frames[i], label=f"batch{shape}x{count}[{i}]")
+
+
+def test_outputs_are_optional_and_consistent(engine):
+    img = synth.vegetation_frame(41, 123, 457)
+    full = engine.analyze_frame(img)
+    only_stats = engine.analyze_frame(img, outputs=("stats",))
+    assert set(only_stats) == {"stats", "percentiles"}
+    for t in INDEX_TYPES:
+        for k in ("count", "count_above", "min", "max", "mean", "std", "sum"):
+            assert only_stats["stats"][t][k] == full["stats"][t][k]
+        assert np.array_equal(only_stats["stats"][t]["hist"], full["stats"][t]["hist"])
+    one = engine.analyze_frame(img, outputs=("maps", "rgb"), indices=("GNDVI",))
+    assert list(one["maps"]) == ["GNDVI"] and list(one["rgb"]) == ["GNDVI"]
+    assert np.array_equal(one["maps"]["GNDVI"], full["maps"]["GNDVI"])
+    assert np.array_equal(one["rgb"]["GNDVI"], full["rgb"]["GNDVI"])
+
+
+def test_determinism_bitwise(engine):
+    img = synth.vegetation_frame(43, 700, 900)
+    a = engine.analyze_frame(img, outputs=("stats",))
+    b = engine.analyze_frame(img, outputs=("stats",))
+    for t in INDEX_TYPES:
+        for k in ("sum", "sumsq", "mean", "std"):
+            assert a["stats"][t][k] == b["stats"][t][k]
+
+
+def test_full_size_c2_frame(engine):
+    """BASELINE config 2: one 4000x3000 uint8 frame, all products, against the oracle."""
+    img = synth.vegetation_frame(2, 3000, 4000)
+    res = engine.analyze_frame(img)
+    check_frame_result(res, img, label="C2")
+    n = 3000 * 4000
+    for t in INDEX_TYPES:
+        assert int(res["stats"][t]["hist"].sum()) == n
+
+
+def test_concurrent_callers(engine):
+    imgs = [synth.vegetation_frame(50 + i, 211, 307) for i in range(6)]
+    out = [None] * len(imgs)
+
+    def work(i):
+        out[i] = engine.analyze_frame(imgs[i])
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(len(imgs))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for i, img in enumerate(imgs):
+        check_frame_result(out[i], img, label=f"thread{i}")
+
+
+def test_bad_arguments_return_errors_not_crashes(engine):
+    from lars_image_processing_b200._lib import LarsError
+    img = synth.vegetation_frame(60, 16, 16)
+    with pytest.raises(LarsError, match="bins"):
+        engine.analyze_frame(img, bins=65)
+    with pytest.raises(LarsError, match="bins"):
+        engine.analyze_frame(img, bins=0)
+    lib = engine.lib
+    hist = np.zeros(768, np.uint64)
+    assert lib.lars_wb_hist_u8(None, 1, 16, 3, 48, hist.ctypes.data, None) == -1
+    assert b"NULL" in lib.lars_last_error()
+    dev = engine.upload([img])
+    assert lib.lars_wb_hist_u8(dev.data.data_ptr() + 1, 1, 16, 3, 48, dev.data.data_ptr(), None) == -1
+    assert lib.lars_wb_hist_u8(dev.data.data_ptr(), 1, 16, 5, 80, dev.data.data_ptr(), None) == -3
+
+
+# ------------------------------------------------------------------------------------- drop-ins
+def test_dropin_process_images(engine):
+    from lars_image_processing_b200 import process_images as pi
+    img = synth.vegetation_frame(70, 199, 257)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        wb_want = o.fix_white_balance_literal(img)
+    wb = pi.fix_white_balance(img)
+    assert wb.dtype == np.uint8 and np.array_equal(wb, wb_want)
+    for t in INDEX_TYPES:
+        m = pi.calculate_index(wb, t)
+        want = o.calculate_index(wb, t)
+        assert np.array_equal(m.view(np.uint32), want.view(np.uint32))
+        got, ref = pi.analyze_index(m, t), o.analyze_index(want, t)
+        assert list(got) == list(ref)                                  # exact keys, same order
+        std = float(np.std(want))
+        assert got[f"Median {t}"] == ref[f"Median {t}"]
+        assert got[f"Min {t}"] == ref[f"Min {t}"] and got[f"Max {t}"] == ref[f"Max {t}"]
+        cov_key = [k for k in ref if "Coverage" in k][0]
+        assert got[cov_key] == ref[cov_key]
+        assert moment_close(got[f"Mean {t}"], ref[f"Mean {t}"], std)
+        vis = pi.create_index_visualization(m, t)
+        assert vis.mode == "RGB" and vis.size == (257, 199)
+        assert np.array_equal(np.array(vis), o.apply_colormap(want, t))
+    fused = pi.analyze_frame(img)
+    check_frame_result(fused, img, label="pi.analyze_frame")
+
+
+def test_dropin_time_series_dataframe(engine):
+    from lars_image_processing_b200 import process_images as pi
+    frames = [synth.vegetation_frame(80 + i, 120, 160) for i in range(4)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        cached = o.fix_white_balance_literal(frames[2])
+    series = [{"metadata": {"upload_date": f"2024-09-{10 + i}"}, "array": f} for i, f in enumerate(frames)]
+    series[2]["corrected_array"] = cached
+    for t in ("NDVI", "NDWI"):
+        df = pi.calculate_index_statistics_by_timeframe(series, t)
+        feature = "Water" if t == "NDWI" else "Vegetation"
+        assert list(df.columns) == ["Date", "Mean", "Median", "Min", "Max", f"{feature} Coverage (%)"]
+        assert len(df) == 4
+        for i, f in enumerate(frames):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                m = o.calculate_index(o.fix_white_balance_literal(f), t)
+            row = df.iloc[i]
+            assert row["Date"] == f"2024-09-{10 + i}"
+            assert row["Median"] == float(np.median(m)) and row["Min"] == float(m.min()) and row["Max"] == float(m.max())
+            assert row[f"{feature} Coverage (%)"] == float(np.mean(m > o.coverage_threshold(t)) * 100)
+            assert moment_close(row["Mean"], float(np.mean(m)), float(np.std(m)))
+
+
+def test_dropin_backend_and_file_variants(engine, tmp_path, golden):
+    from PIL import Image
+    from lars_image_processing_b200 import backend_process as bp
+    from lars_image_processing_b200 import process_ndvi as pn
+    from lars_image_processing_b200 import process_rgn as pr
+    g = golden["variants"]
+    img = g["input"]
+    wb_pil = bp.fix_white_balance(Image.fromarray(img))
+    assert np.array_equal(np.array(wb_pil), g["backend_wb"])
+    f = g["backend_wb"].astype(np.float32)
+    for t in INDEX_TYPES:
+        m = bp.calculate_index(f[:, :, 0].copy(), f[:, :, 1].copy(), f[:, :, 2].copy(), t)
+        assert np.array_equal(m.view(np.uint32), g[f"backend_{t}"].view(np.uint32))
+    with pytest.raises(UnboundLocalError):
+        bp.calculate_index(f[:, :, 0], f[:, :, 1], f[:, :, 2], "EVI")
+    path = tmp_path / "frame.png"
+    Image.fromarray(img).save(path)
+    nd = pn.calculate_ndvi(str(path), visualize=False)
+    assert nd.dtype == np.float64 and np.array_equal(nd.view(np.uint64), g["ndvi_f64"].view(np.uint64))
+    st = pn.analyze_ndvi_statistics(nd)
+    assert list(st) == ["mean_ndvi", "median_ndvi", "min_ndvi", "max_ndvi", "std_ndvi", "vegetation_coverage"]
+    ref = dict(zip(st, g["ndvi_f64_stats"]))
+    for k in st:
+        assert abs(st[k] - ref[k]) <= 2e-7 * max(abs(ref[k]), 1.0), (k, st[k], ref[k])
+    arr, rep = pn.generate_ndvi_report(str(path), str(tmp_path / "report"))
+    assert (tmp_path / "report" / "ndvi_statistics.txt").read_text().startswith("NDVI Statistics:\n")
+    assert np.array_equal(np.load(tmp_path / "report" / "ndvi_histogram.npy"),
+                          np.histogram(nd.astype(np.float32).ravel(), bins=50, range=(-1, 1))[0])
+    assert np.array_equal(pr.fix_white_balance_rgnir(str(path)), g["backend_wb"])
+    assert pr.fix_white_balance_rgnir(str(path), str(tmp_path / "wb.png")) is None
+    assert np.array_equal(np.array(Image.open(tmp_path / "wb.png")), g["backend_wb"])
+    bp.process_image(path, tmp_path / "out", process_wb=True, indices=["NDVI", "NDWI"])
+    assert np.array_equal(np.array(Image.open(tmp_path / "out" / "white_balanced" / "frame_wb.tif")), g["backend_wb"])
+    ndwi_img = np.array(Image.open(tmp_path / "out" / "NDWI" / "frame_ndwi.png"))
+    assert np.array_equal(ndwi_img, o.apply_colormap(o.calculate_index(g["backend_wb"], "NDWI"), "NDWI"))
+
+
+# ------------------------------------------------------------------------------------- map ops
+def test_exact_median_radix_select(engine):
+    from lars_image_processing_b200.map_ops import map_statistics
+    rng = np.random.default_rng(17)
+    cases = [np.array([0.25], np.float32), np.array([0.5, -0.5], np.float32), np.array([1, 2, 3], np.float32) / 4,
+             np.zeros(1000, np.float32), rng.uniform(-1, 1, 4097).astype(np.float32),
+             rng.uniform(-1, 1, 100000).astype(np.float32),
+             np.round(rng.normal(0, 0.3, 65536), 2).astype(np.float32).clip(-1, 1),
+             np.concatenate([np.full(500, -0.0, np.float32), np.full(501, 0.0, np.float32)]),
+             rng.normal(0, 1e-3, 33333).astype(np.float32)]
+    for x in cases:
+        st = map_statistics(x, threshold=0.2, median=True)
+        assert st["median"] == float(np.median(x)), x.size
+        assert st["min"] == float(x.min()) and st["max"] == float(x.max())
+
+
+@pytest.mark.parametrize("bins", [50, 7, 64])
+def test_generic_map_statistics(engine, bins):
+    from lars_image_processing_b200.map_ops import map_statistics
+    rng = np.random.default_rng(19)
+    x = rng.normal(0.1, 0.45, (301, 517)).astype(np.float32)       # some values outside [-1, 1]
+    edges = o.histogram_edges(bins)
+    x.ravel()[:edges.size] = edges
+    st = map_statistics(x, threshold=0.2, bins=bins, median=False)
+    assert np.array_equal(st["hist"], np.histogram(x.ravel(), bins=bins, range=(-1, 1))[0])
+    assert st["count_above"] == int(np.count_nonzero(x > np.float32(0.2)))
+    assert st["min"] == float(x.min()) and st["max"] == float(x.max())
+    std = float(x.astype(np.float64).std())
+    assert moment_close(st["mean"], float(x.astype(np.float64).mean()), std)
+    assert moment_close(st["std"], std, std)
+
+
+def test_colormap_kernel(engine):
+    from lars_image_processing_b200.map_ops import colormap_map
+    rng = np.random.default_rng(23)
+    x = rng.uniform(-1.2, 1.2, (97, 131)).astype(np.float32)
+    x[0, :5] = [-1.0, 1.0, 0.0, -0.0, 0.999999]
+    assert np.array_equal(colormap_map(x, "RdYlGn"), o.apply_colormap(x, name="RdYlGn"))
+    assert np.array_equal(colormap_map(x, "RdYlBu"), o.apply_colormap(x, name="RdYlBu"))
+    d = rng.uniform(-0.8, 0.8, (50, 33)).astype(np.float32)
+    assert np.array_equal(colormap_map(d, "bwr", -0.5, 0.5), o.apply_colormap(d, name="bwr", vmin=-0.5, vmax=0.5))

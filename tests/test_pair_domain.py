@@ -1,0 +1,133 @@
+"""The exact formulas the kernels evaluate (pixel_math.h compiled for the host) against the
+oracle, exhaustively over every (a, b) uint8 pair -- the whole domain of the fused pass."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import oracle_np as o
+
+
+def _pair_tables(hc, bins, thr):
+    edges = o.histogram_edges(bins)
+    n = 65536
+    value = np.empty(n, np.float32)
+    bin_pair = np.empty(n, np.int32)
+    bin_edges = np.empty(n, np.int32)
+    cmap = np.empty(n, np.int32)
+    above = np.empty(n, np.uint8)
+    neg = np.empty(n, np.float32)
+    hc.hc_pair_tables(C.c_int(bins), C.c_void_p(edges.ctypes.data), C.c_float(thr),
+                      C.c_void_p(value.ctypes.data), C.c_void_p(bin_pair.ctypes.data),
+                      C.c_void_p(bin_edges.ctypes.data), C.c_void_p(cmap.ctypes.data),
+                      C.c_void_p(above.ctypes.data), C.c_void_p(neg.ctypes.data))
+    sh = (256, 256)
+    return (value.reshape(sh), bin_pair.reshape(sh), bin_edges.reshape(sh), cmap.reshape(sh),
+            above.reshape(sh).astype(bool), neg.reshape(sh))
+
+
+def test_pair_values_bins_cmap_coverage(hostcheck):
+    tabs = o.pair_tables(50)
+    # hostcheck index [hi][lo]; oracle pair image pixel (i, j) = (R=j, G=j, N=i): NDVI = (i - j)/(i + j)
+    value, bin_pair, bin_edges, cmap, above, neg = _pair_tables(hostcheck, 50, 0.2)
+    want = tabs["NDVI"]
+    assert np.array_equal(value.view(np.uint32), want["value"].view(np.uint32))
+    assert np.array_equal(bin_pair, want["bin"])
+    assert np.array_equal(bin_edges, want["bin"])
+    assert np.array_equal(cmap, want["cmap"])
+    assert np.array_equal(above, want["above"])
+    # NDWI = 0 - GNDVI bit for bit (incl. +0 where G == N), with its own bins / cmap / coverage
+    assert np.array_equal(neg.view(np.uint32), tabs["NDWI"]["value"].view(np.uint32))
+    _, _, _, _, above0, _ = _pair_tables(hostcheck, 50, 0.0)
+    assert np.array_equal((neg > np.float32(0.0)), tabs["NDWI"]["above"])
+    assert np.array_equal(above0, tabs["GNDVI"]["value"] > np.float32(0.0))
+
+
+@pytest.mark.parametrize("bins", [1, 2, 3, 5, 10, 16, 25, 32, 49, 50, 51, 63, 64])
+def test_pair_bin_formula_every_supported_bin_count(hostcheck, bins):
+    v = o.calculate_index(o.pair_image(), "NDVI")
+    want = o.histogram_bin_by_edges(v, bins)
+    _, bin_pair, bin_edges, _, _, _ = _pair_tables(hostcheck, bins, 0.2)
+    assert np.array_equal(bin_pair, want)
+    assert np.array_equal(bin_edges, want)
+    # and for the negated map (NDWI)
+    vw = o.calculate_index(o.pair_image(), "NDWI")
+    half = np.float32(0.5 * bins)
+    bias = np.float32(half + np.float32(2.0 ** -11))
+    f = (vw.astype(np.float64) * np.float64(half) + np.float64(bias)).astype(np.float32)  # one rounding == FMA
+    got = np.minimum(f.astype(np.int64), bins - 1)
+    assert np.array_equal(got, o.histogram_bin_by_edges(vw, bins))
+
+
+def test_generic_edge_bins_on_random_floats(hostcheck):
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-1, 1, 200000).astype(np.float32)
+    for bins in (7, 50, 64):
+        edges = o.histogram_edges(bins)
+        x[:bins + 1] = edges            # exactly-on-edge values
+        x[bins + 1:2 * bins + 2] = np.nextafter(edges, np.float32(-2))
+        x[2 * bins + 2:3 * bins + 3] = np.nextafter(edges, np.float32(2))
+        xc = np.clip(x, -1, 1)
+        out = np.empty(xc.size, np.int32)
+        hostcheck.hc_hist_bin_edges(C.c_void_p(xc.ctypes.data), C.c_int64(xc.size), C.c_int(bins),
+                                    C.c_void_p(edges.ctypes.data), C.c_void_p(out.ctypes.data))
+        assert np.array_equal(np.bincount(out, minlength=bins),
+                              np.histogram(xc, bins=bins, range=(-1, 1))[0])
+
+
+def test_wb_lut_entry_chain(hostcheck):
+    rng = np.random.default_rng(11)
+    cases = [(0.0, 255.0), (10.0, 10.0), (0.0, 0.0), (255.0, 255.0), (3.5, 3.5), (12.0, 201.0),
+             (4.16, 194.56), (2.8799999999999994, 155.12)]
+    for _ in range(300):
+        lo = float(rng.integers(0, 200)) + float(rng.choice([0.0, rng.random()]))
+        hi = lo + float(rng.integers(0, 56)) + float(rng.choice([0.0, rng.random()]))
+        cases.append((lo, hi))
+    for lo, hi in cases:
+        out = np.empty(256, np.uint8)
+        hostcheck.hc_wb_lut(C.c_double(lo), C.c_double(hi), C.c_int(256), C.c_void_p(out.ctypes.data))
+        assert np.array_equal(out, o.wb_lut_from_percentiles(lo, hi, 256)), (lo, hi)
+    out = np.empty(65536, np.uint8)
+    hostcheck.hc_wb_lut(C.c_double(5140.25), C.c_double(51400.75), C.c_int(65536), C.c_void_p(out.ctypes.data))
+    assert np.array_equal(out, o.wb_lut_from_percentiles(5140.25, 51400.75, 65536))
+
+
+def test_percentile_lerp_matches_numpy(hostcheck):
+    hostcheck.hc_percentile_lerp.restype = C.c_double
+    hostcheck.hc_percentile_lerp.argtypes = [C.c_double] * 3
+    rng = np.random.default_rng(5)
+    for _ in range(2000):
+        n = int(rng.integers(2, 500))
+        x = np.sort(rng.integers(0, 256, n)).astype(np.float32)
+        for q in (0.02, 0.98):
+            vi = np.float64(n - 1) * np.float64(q)
+            lo = int(np.floor(vi))
+            a, b = float(x[lo]), float(x[min(lo + 1, n - 1)])
+            got = hostcheck.hc_percentile_lerp(a, b, float(vi - lo))
+            assert got == float(np.percentile(x, (q * 100,))[0])
+
+
+def test_float64_ndvi_and_plane_ratio(hostcheck):
+    rng = np.random.default_rng(9)
+    hi = rng.integers(0, 256, 5000).astype(np.float64)
+    lo = rng.integers(0, 256, 5000).astype(np.float64)
+    hi[:3], lo[:3] = 0, 0
+    out = np.empty(5000, np.float64)
+    hostcheck.hc_ratio_clip_f64(C.c_void_p(hi.ctypes.data), C.c_void_p(lo.ctypes.data), C.c_int64(5000),
+                                C.c_void_p(out.ctypes.data))
+    want = np.clip((hi - lo) / (hi + lo + 1e-10), -1, 1)
+    assert np.array_equal(out.view(np.uint64), want.view(np.uint64))
+    h32, l32 = hi.astype(np.float32), lo.astype(np.float32)
+    out32 = np.empty(5000, np.float32)
+    hostcheck.hc_ratio_clip_f32(C.c_void_p(h32.ctypes.data), C.c_void_p(l32.ctypes.data), C.c_int64(5000),
+                                C.c_void_p(out32.ctypes.data))
+    want32 = np.clip((h32 - l32) / (h32 + l32 + 1e-10), -1, 1)
+    assert np.array_equal(out32.view(np.uint32), want32.view(np.uint32))
+
+
+def test_bwr_colormap_range_index(hostcheck):
+    x = np.linspace(-0.8, 0.8, 4001).astype(np.float32)
+    out = np.empty(x.size, np.int32)
+    hostcheck.hc_cmap_index_range(C.c_void_p(x.ctypes.data), C.c_int64(x.size), C.c_float(-0.5), C.c_float(0.5),
+                                  C.c_void_p(out.ctypes.data))
+    assert np.array_equal(out, o.colormap_index(x, -0.5, 0.5))
