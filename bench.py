@@ -101,7 +101,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.002)
 
     def start(self):
         if self.nv is not None:
@@ -313,7 +313,8 @@ def run_ours(a):
                      "whole_step_GBps": (U8_PASS1_BYTES_PER_PX + U8_PASS2_BYTES_PER_PX) * F * npx * a.steps
                      / (ms * 1e-3) / 1e9},
         "clocks": clocks,
-        "gpu_launches": 5 * a.steps,   # wb_hist, wb_lut_build, fused_index, fused_finalize, stats_merge
+        # wb_hist, wb_lut_build, fused_index, fused_finalize, stats_merge (+1 merge after the all-gather)
+        "gpu_launches": (5 if world == 1 else 6) * a.steps,
     }
     if e2e is not None:
         line["e2e"] = e2e

@@ -69,9 +69,11 @@ def gather_records(local: torch.Tensor, group=None) -> torch.Tensor:
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return local.unsqueeze(0)
-    out = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
-    return out
+    local = local.contiguous()
+    # concatenated along dim 0 (the layout every backend accepts), viewed as [world, ...]
+    flat = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(flat, local, group=group)
+    return flat.view((world,) + tuple(local.shape))
 
 
 def dataset_statistics(engine, per_frame_records: torch.Tensor, group=None, stream=None) -> torch.Tensor:
