@@ -11,6 +11,7 @@
 #include "../../include/lars_b200.h"
 #include "host_tables.h"
 #include "lars_kernels.cuh"
+#include "lars_fused_kernel.cuh"
 #include "lars_map_kernels.cuh"
 
 namespace {

@@ -1,0 +1,558 @@
+// K2: the fused Pass 2 of the RGNir analysis path, and K2f, its fixed-order statistics merge.
+//
+// One read of the raw uint8 frame produces, per pixel: the white-balanced bytes (stretch LUT,
+// process-images.py:438-441), NDVI / GNDVI / NDWI as fp32 (process-images.py:449-490), three
+// colormapped RGB pixels (process-images.py:689-695) and the per-index statistics + histogram
+// (process-images.py:492-513, process-ndvi.py:65, :97).
+//
+// CTA = 8 consumer warps + 1 TMA-load warp + 1 TMA-store warp, persistent over a balanced
+// contiguous range of 1024-pixel tiles:
+//   load warp  : cp.async.bulk global->shared into a 4-stage ring (mbarrier full / empty)
+//   consumers  : 4 pixels per thread per tile; fp32 maps leave as coalesced 128-bit streaming
+//                stores; byte outputs (WB, 3 x RGB) are staged in a 3-stage shared ring
+//   store warp : cp.async.bulk shared->global of the staged bytes (mbarrier full / empty), so
+//                no CTA-wide barrier sits on the consumers' critical path
+// Statistics: per-thread registers, lane-private shared histograms (bank == lane, conflict
+// free), one partial record per (CTA, frame) merged in fixed order by K2f -- deterministic.
+// Per-pixel arithmetic avoids the quarter-rate XU pipe: magic-number int<->float conversions
+// and a branch-free correctly-rounded division (pixel_math.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/lars_b200.h"
+#include "pixel_math.h"
+#include "ptx_sm100.cuh"
+
+namespace lars {
+
+constexpr int K2_TILE_PX = 1024;            // pixels per pipeline tile
+constexpr int K2_CONSUMERS = 256;           // 4 pixels per consumer thread per tile
+constexpr int K2_CONSUMER_WARPS = K2_CONSUMERS / 32;
+constexpr int K2_THREADS = K2_CONSUMERS + 64;  // + TMA load warp + TMA store warp
+constexpr int K2_IN_STAGES = 4;
+constexpr int K2_OUT_STAGES = 3;
+constexpr int K2_BINS_PAD = LARS_MAX_BINS;
+constexpr int K2_HIST_ROWS = LARS_MAX_BINS + 1;  // + the row that catches x == 1.0
+constexpr int K2_CMAP_SLOTS = 257;               // + the slot that catches x == 1.0
+constexpr int K2_MAX_GRID = 148 * 4;
+
+// Per-CTA, per-frame partial record; merged in fixed order by fused_finalize_kernel.
+struct __align__(16) K2Partial {
+  double sx[2];       // sum x            (NDVI, GNDVI)
+  double sd[2];       // sum (x - K)
+  double sdd[2];      // sum (x - K)^2
+  float k[2];         // the shift K (index value of the frame's first pixel)
+  float mn[2], mx[2];
+  uint32_t above[3];  // NDVI > t0, GNDVI > t1, NDWI > t2
+  uint32_t count;
+  uint32_t hist[3][K2_BINS_PAD];
+  uint32_t pad_[2];
+};
+static_assert(sizeof(K2Partial) % 16 == 0, "partial record must stay 16-byte aligned");
+
+struct K2Params {
+  const uint8_t* src;
+  const uint8_t* wb_lut;
+  uint8_t* wb_out;
+  float* maps[3];
+  uint8_t* rgb[3];
+  K2Partial* partials;      // [frame][slots_per_frame]
+  const uint32_t* cmaps;    // [3 cmaps][256] packed R | G<<8 | B<<16 (device global)
+  long long n_pixels;
+  long long src_frame_stride, lut_frame_stride, wb_frame_stride, map_frame_stride, rgb_frame_stride;
+  long long tiles_per_frame, total_tiles;
+  int n_frames, bins, slots_per_frame;
+  int cmap_id[3];
+  float thresholds[3];
+};
+
+template <int C>
+struct K2Smem {
+  static constexpr int IN_BYTES = K2_TILE_PX * C;
+  static constexpr int WB_BYTES = K2_TILE_PX * C;
+  static constexpr int RGB_BYTES = K2_TILE_PX * 3;
+  static constexpr int OUT_BYTES = WB_BYTES + 3 * RGB_BYTES;     // one output stage
+  static constexpr int OFF_LUT = 0;                              // 3 x 256 B, each table 256-aligned
+  static constexpr int OFF_CMAP = 1024;                          // 3 x 257 words
+  static constexpr int OFF_HIST = OFF_CMAP + 3104;               // 3 x 65 rows x 32 lanes x 4 B
+  static constexpr int OFF_IN = OFF_HIST + 3 * K2_HIST_ROWS * 128;
+  static constexpr int OFF_OUT = OFF_IN + K2_IN_STAGES * IN_BYTES;
+  static constexpr int OFF_RED = OFF_OUT + K2_OUT_STAGES * OUT_BYTES;
+  static constexpr int RED_BYTES = K2_CONSUMER_WARPS * 16 * 8;
+  static constexpr int OFF_BAR = OFF_RED + RED_BYTES;
+  static constexpr int N_BARS = 2 * K2_IN_STAGES + 2 * K2_OUT_STAGES;
+  static constexpr int TOTAL = OFF_BAR + N_BARS * 8;
+  static_assert(3 * K2_CMAP_SLOTS * 4 <= 3104 && OFF_HIST % 16 == 0 && OFF_IN % 16 == 0 && OFF_OUT % 16 == 0 &&
+                    OFF_RED % 8 == 0 && OFF_BAR % 8 == 0,
+                "shared layout alignment");
+};
+
+// CTA b owns the global tile range [b * T / G, (b + 1) * T / G): balanced to +-1 tile.
+__device__ __forceinline__ long long k2_range_begin(long long b, long long total, long long grid) {
+  return (b * total) / grid;
+}
+// the CTA whose range contains global tile t
+__host__ __device__ inline long long k2_owner_of_tile(long long t, long long total, long long grid) {
+  return ((t + 1) * grid - 1) / total;
+}
+
+struct K2ThreadStats {
+  float mn[2], mx[2];
+  double sx[2], sd[2], sdd[2];
+  uint32_t above[3];
+};
+
+struct K2ThreadConst {
+  uint32_t lut_addr[3];    // shared addresses of the three 256-byte stretch tables (256-aligned)
+  uint32_t hist_cst[3];    // hist_base[i] + 4 lane - (MAGIC_U << 7)   (mod 2^32)
+  uint32_t cmap_cst[3];    // cmap_base[i]          - (MAGIC_U << 2)   (mod 2^32)
+  float half_bins, half_bins_bias_m05;
+  float kshift[2];
+};
+
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void red_shared_inc(uint32_t addr) {
+  asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+}
+// One PRMT builds the LUT address: low byte = byte `K` of the raw word, upper bytes from the
+// 256-aligned table address.
+template <int K>
+__device__ __forceinline__ uint32_t lut_gather(uint32_t raw_word, uint32_t table_addr) {
+  return lds_u8(prmt(raw_word, table_addr, 0x7650u | (uint32_t)K));
+}
+__device__ __forceinline__ uint32_t pack4(uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) {
+  return prmt(prmt(b0, b1, 0x0040), prmt(b2, b3, 0x0040), 0x5410);
+}
+
+template <int C, bool FULL>
+__device__ __forceinline__ void k2_process_tile(const K2Params& p, uint8_t* smem, uint32_t smem_base,
+                                                int in_stage, int out_stage, int tid, int lane,
+                                                long long frame, long long px0, int nvalid,
+                                                const K2ThreadConst& tc, bool stage_bytes, K2ThreadStats& st) {
+  using L = K2Smem<C>;
+
+  // ---- white balance: one byte-LUT gather per sample (process-images.py:438-441) ----
+  uint32_t wb[3][4];
+  if (C == 3) {
+    const uint32_t* in = reinterpret_cast<const uint32_t*>(smem + L::OFF_IN + in_stage * L::IN_BYTES) + 3 * tid;
+    const uint32_t w0 = in[0], w1 = in[1], w2 = in[2];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_base + L::OFF_BAR + 8u * (K2_IN_STAGES + in_stage));  // stage consumed
+    wb[0][0] = lut_gather<0>(w0, tc.lut_addr[0]); wb[1][0] = lut_gather<1>(w0, tc.lut_addr[1]);
+    wb[2][0] = lut_gather<2>(w0, tc.lut_addr[2]); wb[0][1] = lut_gather<3>(w0, tc.lut_addr[0]);
+    wb[1][1] = lut_gather<0>(w1, tc.lut_addr[1]); wb[2][1] = lut_gather<1>(w1, tc.lut_addr[2]);
+    wb[0][2] = lut_gather<2>(w1, tc.lut_addr[0]); wb[1][2] = lut_gather<3>(w1, tc.lut_addr[1]);
+    wb[2][2] = lut_gather<0>(w2, tc.lut_addr[2]); wb[0][3] = lut_gather<1>(w2, tc.lut_addr[0]);
+    wb[1][3] = lut_gather<2>(w2, tc.lut_addr[1]); wb[2][3] = lut_gather<3>(w2, tc.lut_addr[2]);
+  } else {
+    const uint4 v = *(reinterpret_cast<const uint4*>(smem + L::OFF_IN + in_stage * L::IN_BYTES) + tid);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_base + L::OFF_BAR + 8u * (K2_IN_STAGES + in_stage));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      wb[0][j] = lut_gather<0>(w[j], tc.lut_addr[0]);
+      wb[1][j] = lut_gather<1>(w[j], tc.lut_addr[1]);
+      wb[2][j] = lut_gather<2>(w[j], tc.lut_addr[2]);
+    }
+  }
+  uint8_t* out_stage_ptr = smem + L::OFF_OUT + out_stage * L::OUT_BYTES;
+  if (stage_bytes && p.wb_out) {
+    uint32_t* o = reinterpret_cast<uint32_t*>(out_stage_ptr) + C * tid;
+    if (C == 3) {
+      o[0] = pack4(wb[0][0], wb[1][0], wb[2][0], wb[0][1]);
+      o[1] = pack4(wb[1][1], wb[2][1], wb[0][2], wb[1][2]);
+      o[2] = pack4(wb[2][2], wb[0][3], wb[1][3], wb[2][3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = pack4(wb[0][j], wb[1][j], wb[2][j], 0u);  // alpha = 0
+    }
+  }
+
+  // ---- indices (process-images.py:449-490) ----
+  float ndvi[4], gndvi[4], ndwi[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    ndvi[j] = lars_ratio_pair_u8((int)wb[2][j], (int)wb[0][j]);
+    gndvi[j] = lars_ratio_pair_u8((int)wb[2][j], (int)wb[1][j]);
+    ndwi[j] = lars_negate_index(gndvi[j]);
+  }
+
+  // ---- fp32 maps: one coalesced 128-bit streaming store per index ----
+  const int first = 4 * tid;
+  const bool any_valid = FULL || first < nvalid;
+  const bool all_valid = FULL || first + 4 <= nvalid;
+  {
+    const float* vals[3] = {ndvi, gndvi, ndwi};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      float* mp = p.maps[i];
+      if (mp && any_valid) {
+        float* dst = mp + frame * p.map_frame_stride + px0 + first;
+        if (all_valid) {
+          stg_stream_v4(dst, vals[i][0], vals[i][1], vals[i][2], vals[i][3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (first + j < nvalid) dst[j] = vals[i][j];
+        }
+      }
+    }
+  }
+
+  // ---- colormap (process-images.py:689-695): slot -> packed RGB -> staged bytes ----
+  if (stage_bytes) {
+    const float* vals[3] = {ndvi, gndvi, ndwi};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (p.rgb[i]) {
+        uint32_t c[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c[j] = lds_u32(lars_cmap_slot_bits(vals[i][j]) * 4u + tc.cmap_cst[i]);
+        uint32_t* o = reinterpret_cast<uint32_t*>(out_stage_ptr + L::WB_BYTES + i * L::RGB_BYTES) + 3 * tid;
+        o[0] = prmt(c[0], c[1], 0x4210);  // R0 G0 B0 R1
+        o[1] = prmt(c[1], c[2], 0x5421);  // G1 B1 R2 G2
+        o[2] = prmt(c[2], c[3], 0x6542);  // B2 R3 G3 B3
+      }
+    }
+  }
+
+  // ---- statistics + histograms ----
+  if (p.partials) {
+    float gx[2] = {0.f, 0.f}, gd[2] = {0.f, 0.f}, gdd[2] = {0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (FULL || first + j < nvalid) {
+        const float x0 = ndvi[j], x1 = gndvi[j], x2 = ndwi[j];
+        st.mn[0] = fminf(st.mn[0], x0); st.mx[0] = fmaxf(st.mx[0], x0);
+        st.mn[1] = fminf(st.mn[1], x1); st.mx[1] = fmaxf(st.mx[1], x1);
+        st.above[0] += (x0 > p.thresholds[0]) ? 1u : 0u;   // float32 compare (0.2f)
+        st.above[1] += (x1 > p.thresholds[1]) ? 1u : 0u;
+        st.above[2] += (x2 > p.thresholds[2]) ? 1u : 0u;
+        const float d0 = LARS_FSUB(x0, tc.kshift[0]), d1 = LARS_FSUB(x1, tc.kshift[1]);
+        gx[0] += x0; gd[0] += d0; gdd[0] = fmaf(d0, d0, gdd[0]);
+        gx[1] += x1; gd[1] += d1; gdd[1] = fmaf(d1, d1, gdd[1]);
+        red_shared_inc(lars_hist_row_bits(x0, tc.half_bins, tc.half_bins_bias_m05) * 128u + tc.hist_cst[0]);
+        red_shared_inc(lars_hist_row_bits(x1, tc.half_bins, tc.half_bins_bias_m05) * 128u + tc.hist_cst[1]);
+        red_shared_inc(lars_hist_row_bits(x2, tc.half_bins, tc.half_bins_bias_m05) * 128u + tc.hist_cst[2]);
+      }
+    }
+    // float32 over 4 pixels, float64 across tiles (error analysis in DESIGN.md)
+    st.sx[0] += (double)gx[0]; st.sd[0] += (double)gd[0]; st.sdd[0] += (double)gdd[0];
+    st.sx[1] += (double)gx[1]; st.sd[1] += (double)gd[1]; st.sdd[1] += (double)gdd[1];
+  }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, d));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
+  return v;
+}
+
+// tile t of the global sequence -> frame, first pixel, valid pixels
+struct K2Tile {
+  long long frame, px0;
+  int nvalid;
+};
+__device__ __forceinline__ K2Tile k2_tile(const K2Params& p, long long t) {
+  K2Tile r;
+  r.frame = t / p.tiles_per_frame;
+  r.px0 = (t - r.frame * p.tiles_per_frame) * K2_TILE_PX;
+  const long long rem = p.n_pixels - r.px0;
+  r.nvalid = rem < K2_TILE_PX ? (int)rem : K2_TILE_PX;
+  return r;
+}
+
+template <int C>
+__global__ void __launch_bounds__(K2_THREADS, 2) fused_index_u8_kernel(const K2Params p) {
+  using L = K2Smem<C>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_base + L::OFF_BAR;
+  // barrier slots: in_full[0..4) in_empty[4..8) out_full[8..11) out_empty[11..14)
+  const uint32_t bar_out_full = bar_base + 8u * (2 * K2_IN_STAGES);
+  const uint32_t bar_out_empty = bar_out_full + 8u * K2_OUT_STAGES;
+
+  const long long grid = gridDim.x;
+  const long long t_begin = k2_range_begin(blockIdx.x, p.total_tiles, grid);
+  const long long t_end = k2_range_begin(blockIdx.x + 1, p.total_tiles, grid);
+  const bool stage_bytes = (p.wb_out != nullptr) || p.rgb[0] || p.rgb[1] || p.rgb[2];
+
+  if (tid == 0) {
+    for (int s = 0; s < K2_IN_STAGES; ++s) {
+      mbar_init(bar_base + 8u * s, 1);                                   // load warp's expect_tx arrive
+      mbar_init(bar_base + 8u * (K2_IN_STAGES + s), K2_CONSUMER_WARPS);  // one arrive per consumer warp
+    }
+    for (int s = 0; s < K2_OUT_STAGES; ++s) {
+      mbar_init(bar_out_full + 8u * s, K2_CONSUMER_WARPS);
+      mbar_init(bar_out_empty + 8u * s, 1);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (tid >= K2_CONSUMERS + 32) {
+    // ===================== TMA store warp (one elected lane) =====================
+    if (lane == 0 && stage_bytes) {
+      uint32_t it = 0;
+      for (long long t = t_begin; t < t_end; ++t, ++it) {
+        const K2Tile tl = k2_tile(p, t);
+        const int so = it % K2_OUT_STAGES;
+        mbar_wait(bar_out_full + 8u * so, (it / K2_OUT_STAGES) & 1u);
+        const uint32_t stage_addr = smem_base + L::OFF_OUT + so * L::OUT_BYTES;
+        const uint32_t wb_bytes = ((uint32_t)tl.nvalid * C + 15u) & ~15u;
+        const uint32_t rgb_bytes = ((uint32_t)tl.nvalid * 3u + 15u) & ~15u;
+        if (p.wb_out) tma_store_1d(p.wb_out + tl.frame * p.wb_frame_stride + tl.px0 * C, stage_addr, wb_bytes);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          if (p.rgb[i])
+            tma_store_1d(p.rgb[i] + tl.frame * p.rgb_frame_stride + tl.px0 * 3,
+                         stage_addr + L::WB_BYTES + i * L::RGB_BYTES, rgb_bytes);
+        tma_store_commit();
+        if (it > 0) {  // the previous tile's stores have finished reading their stage: hand it back
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          mbar_arrive(bar_out_empty + 8u * ((it - 1) % K2_OUT_STAGES));
+        }
+      }
+      tma_store_wait_all();  // global writes performed before the CTA (and its smem) goes away
+    }
+    return;
+  }
+  if (tid >= K2_CONSUMERS) {
+    // ===================== TMA load warp (one elected lane) =====================
+    if (lane == 0) {
+      const uint64_t pol = l2_policy_evict_first();  // raw bytes are dead after this pass
+      uint32_t it = 0;
+      for (long long t = t_begin; t < t_end; ++t, ++it) {
+        const K2Tile tl = k2_tile(p, t);
+        const uint32_t bytes = ((uint32_t)tl.nvalid * C + 15u) & ~15u;
+        const int s = it % K2_IN_STAGES;
+        mbar_wait(bar_base + 8u * (K2_IN_STAGES + s), ((it / K2_IN_STAGES) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(bar_base + 8u * s, bytes);
+        tma_load_1d_hint(smem_base + L::OFF_IN + s * L::IN_BYTES,
+                         p.src + tl.frame * p.src_frame_stride + tl.px0 * C, bytes, bar_base + 8u * s, pol);
+      }
+    }
+    return;
+  }
+
+  // ============================== consumer warps ==============================
+  const int warp = tid >> 5;
+  uint32_t* hist = reinterpret_cast<uint32_t*>(smem + L::OFF_HIST);
+  // the stretch tables must start on a 256-byte boundary of the shared window (lut_gather);
+  // the layout reserves 1 KB for 768 B of tables so any base alignment can be absorbed
+  const uint32_t lut_shift = (256u - ((smem_base + L::OFF_LUT) & 255u)) & 255u;
+  uint8_t* lut_s = smem + L::OFF_LUT + lut_shift;
+  uint32_t* cm_s = reinterpret_cast<uint32_t*>(smem + L::OFF_CMAP);
+  double* red = reinterpret_cast<double*>(smem + L::OFF_RED);
+
+  for (int i = tid; i < 3 * K2_CMAP_SLOTS; i += K2_CONSUMERS) {
+    const int t = i / K2_CMAP_SLOTS, k = i - t * K2_CMAP_SLOTS;
+    cm_s[i] = p.cmaps[p.cmap_id[t] * 256 + (k < 256 ? k : 255)];
+  }
+
+  K2ThreadConst tc;
+  tc.half_bins = 0.5f * (float)p.bins;
+  tc.half_bins_bias_m05 = tc.half_bins + LARS_HIST_BIAS - 0.5f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    tc.lut_addr[i] = smem_base + L::OFF_LUT + lut_shift + 256u * i;
+    tc.hist_cst[i] = smem_base + L::OFF_HIST + (uint32_t)(i * K2_HIST_ROWS * 128 + 4 * lane) - (LARS_MAGIC_U << 7);
+    tc.cmap_cst[i] = smem_base + L::OFF_CMAP + (uint32_t)(i * K2_CMAP_SLOTS * 4) - (LARS_MAGIC_U << 2);
+  }
+
+  uint32_t it = 0;
+  long long t = t_begin;
+  while (t < t_end) {
+    // ---------------- one span: the part of frame `frame` owned by this CTA ----------------
+    const long long frame = t / p.tiles_per_frame;
+    const long long frame_t0 = frame * p.tiles_per_frame;
+    const long long span_end = (frame_t0 + p.tiles_per_frame < t_end) ? frame_t0 + p.tiles_per_frame : t_end;
+
+    named_bar_sync(1, K2_CONSUMERS);  // previous span's flush has finished reading hist / red / LUT users
+    if (p.wb_lut) {
+      const uint8_t* gl = p.wb_lut + frame * p.lut_frame_stride;
+      for (int i = tid; i < 3 * 256; i += K2_CONSUMERS) lut_s[i] = gl[i];
+    } else {
+      for (int i = tid; i < 3 * 256; i += K2_CONSUMERS) lut_s[i] = (uint8_t)(i & 255);
+    }
+    for (int i = tid; i < 3 * K2_HIST_ROWS * 32; i += K2_CONSUMERS) hist[i] = 0u;
+    named_bar_sync(1, K2_CONSUMERS);
+
+    // shift K = index value of the frame's first pixel (same for every CTA of the frame)
+    {
+      const uint8_t* f0 = p.src + frame * p.src_frame_stride;
+      const int r = lut_s[f0[0]], g = lut_s[256 + f0[1]], n = lut_s[512 + f0[2]];
+      tc.kshift[0] = lars_ratio_pair_u8(n, r);
+      tc.kshift[1] = lars_ratio_pair_u8(n, g);
+    }
+    K2ThreadStats st;
+    st.mn[0] = st.mn[1] = INFINITY;
+    st.mx[0] = st.mx[1] = -INFINITY;
+    st.sx[0] = st.sx[1] = st.sd[0] = st.sd[1] = st.sdd[0] = st.sdd[1] = 0.0;
+    st.above[0] = st.above[1] = st.above[2] = 0u;
+
+    for (; t < span_end; ++t, ++it) {
+      const long long px0 = (t - frame_t0) * K2_TILE_PX;
+      const long long rem = p.n_pixels - px0;
+      const int nvalid = rem < K2_TILE_PX ? (int)rem : K2_TILE_PX;
+      const int s = it % K2_IN_STAGES;
+      const int so = it % K2_OUT_STAGES;
+      if (stage_bytes) mbar_wait(bar_out_empty + 8u * so, ((it / K2_OUT_STAGES) & 1u) ^ 1u);  // stage drained
+      mbar_wait(bar_base + 8u * s, (it / K2_IN_STAGES) & 1u);                                  // tile landed
+      if (nvalid == K2_TILE_PX)
+        k2_process_tile<C, true>(p, smem, smem_base, s, so, tid, lane, frame, px0, nvalid, tc, stage_bytes, st);
+      else
+        k2_process_tile<C, false>(p, smem, smem_base, s, so, tid, lane, frame, px0, nvalid, tc, stage_bytes, st);
+      if (stage_bytes) {
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk-copy engine
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_out_full + 8u * so);
+      }
+    }
+
+    // ---------------- flush this span into its partial record ----------------
+    if (p.partials) {
+      double v[6] = {st.sx[0], st.sx[1], st.sd[0], st.sd[1], st.sdd[0], st.sdd[1]};
+#pragma unroll
+      for (int k = 0; k < 6; ++k) v[k] = warp_sum(v[k]);
+      const float mn0 = warp_min(st.mn[0]), mn1 = warp_min(st.mn[1]);
+      const float mx0 = warp_max(st.mx[0]), mx1 = warp_max(st.mx[1]);
+      const uint32_t a0 = warp_sum(st.above[0]), a1 = warp_sum(st.above[1]), a2 = warp_sum(st.above[2]);
+      if (lane == 0) {
+        double* r = red + warp * 16;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) r[k] = v[k];
+        r[6] = (double)mn0; r[7] = (double)mn1; r[8] = (double)mx0; r[9] = (double)mx1;
+        r[10] = (double)a0; r[11] = (double)a1; r[12] = (double)a2;   // exact: < 2^32
+      }
+      named_bar_sync(1, K2_CONSUMERS);
+      const long long owner0 = k2_owner_of_tile(frame_t0, p.total_tiles, grid);
+      K2Partial* rec = p.partials + frame * p.slots_per_frame + ((long long)blockIdx.x - owner0);
+      if (tid < 3 * K2_BINS_PAD) {
+        const int idx = tid / K2_BINS_PAD, bin = tid % K2_BINS_PAD;
+        const uint32_t* row = hist + (idx * K2_HIST_ROWS + bin) * 32;
+        uint32_t sum = 0;
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) sum += row[(l + tid) & 31];
+        if (bin == p.bins - 1) {  // fold the x == 1.0 row into the last bin
+#pragma unroll 8
+          for (int l = 0; l < 32; ++l) sum += row[32 + ((l + tid) & 31)];
+        }
+        rec->hist[idx][bin] = (bin < p.bins) ? sum : 0u;
+      }
+      if (tid == 0) {
+        double acc[13];
+#pragma unroll
+        for (int k = 0; k < 13; ++k) acc[k] = red[k];
+        for (int w = 1; w < K2_CONSUMER_WARPS; ++w) {
+          const double* r = red + w * 16;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) acc[k] += r[k];
+          acc[6] = fmin(acc[6], r[6]); acc[7] = fmin(acc[7], r[7]);
+          acc[8] = fmax(acc[8], r[8]); acc[9] = fmax(acc[9], r[9]);
+          acc[10] += r[10]; acc[11] += r[11]; acc[12] += r[12];
+        }
+        rec->sx[0] = acc[0]; rec->sx[1] = acc[1];
+        rec->sd[0] = acc[2]; rec->sd[1] = acc[3];
+        rec->sdd[0] = acc[4]; rec->sdd[1] = acc[5];
+        rec->k[0] = tc.kshift[0]; rec->k[1] = tc.kshift[1];
+        rec->mn[0] = (float)acc[6]; rec->mn[1] = (float)acc[7];
+        rec->mx[0] = (float)acc[8]; rec->mx[1] = (float)acc[9];
+        rec->above[0] = (uint32_t)acc[10]; rec->above[1] = (uint32_t)acc[11]; rec->above[2] = (uint32_t)acc[12];
+        const long long first_px = (t_begin > frame_t0 ? t_begin - frame_t0 : 0) * K2_TILE_PX;
+        long long last_px = (span_end - frame_t0) * K2_TILE_PX;
+        if (last_px > p.n_pixels) last_px = p.n_pixels;
+        rec->count = (uint32_t)(last_px - first_px);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2f: merge the partial records of each frame in slot order -> lars_index_stats[frame][3]
+// ------------------------------------------------------------------------------------------
+struct K2fParams {
+  const K2Partial* partials;
+  lars_index_stats* stats;
+  int slots_per_frame, bins;
+  float thresholds[3];
+};
+
+__global__ void __launch_bounds__(3 * K2_BINS_PAD) fused_finalize_kernel(const K2fParams p) {
+  const int frame = blockIdx.x;
+  const int tid = threadIdx.x;
+  const K2Partial* recs = p.partials + (long long)frame * p.slots_per_frame;
+  lars_index_stats* out = p.stats + (long long)frame * 3;
+  {  // histograms: thread (index, bin)
+    const int idx = tid / K2_BINS_PAD, bin = tid % K2_BINS_PAD;
+    unsigned long long h = 0;
+    for (int s = 0; s < p.slots_per_frame; ++s)
+      if (recs[s].count) h += recs[s].hist[idx][bin];
+    out[idx].hist[bin] = h;
+  }
+  if (tid < 3) {
+    const int i = tid;
+    const int g = (i == 0) ? 0 : 1;  // NDWI statistics derive from GNDVI's (x -> 0 - x)
+    double sx = 0.0, sd = 0.0, sdd = 0.0;
+    float mn = INFINITY, mx = -INFINITY;
+    unsigned long long cnt = 0, above = 0;
+    for (int s = 0; s < p.slots_per_frame; ++s) {
+      const K2Partial& r = recs[s];
+      if (!r.count) continue;
+      sx += r.sx[g]; sd += r.sd[g]; sdd += r.sdd[g];
+      mn = fminf(mn, r.mn[g]); mx = fmaxf(mx, r.mx[g]);
+      cnt += r.count; above += r.above[i];
+    }
+    lars_index_stats& o = out[i];
+    if (i == 2) {
+      const float t = mn;
+      mn = 0.0f - mx; mx = 0.0f - t;
+      sx = 0.0 - sx; sd = 0.0 - sd;
+    }
+    const double n = (double)cnt;
+    const double mean = cnt ? sx / n : 0.0;
+    const double md = cnt ? sd / n : 0.0;
+    double var = cnt ? sdd / n - md * md : 0.0;
+    var = var > 0.0 ? var : 0.0;
+    o.count = cnt;
+    o.count_above = above;
+    o.sum = sx;
+    o.sumsq = cnt ? (var + mean * mean) * n : 0.0;
+    o.mean = mean;
+    o.std = sqrt(var);
+    o.min = cnt ? mn : 0.f;
+    o.max = cnt ? mx : 0.f;
+    o.threshold = p.thresholds[i];
+    o.bins = (uint32_t)p.bins;
+  }
+}
+
+}  // namespace lars

@@ -49,4 +49,20 @@ void hc_ratio_clip_f64(const double* hi, const double* lo, int64_t n, double* ou
 void hc_ratio_clip_f32(const float* hi, const float* lo, int64_t n, float* out) {
   for (int64_t i = 0; i < n; ++i) out[i] = lars_ratio_clip_f32(hi[i], lo[i]);
 }
+// The conversion-free forms the fused kernel uses, over all pairs.
+void hc_pair_tables_fast(int bins, float* value, int32_t* row, int32_t* slot) {
+  const float half = 0.5f * (float)bins;
+  const float bias = half + LARS_HIST_BIAS - 0.5f;
+  for (int hi = 0; hi < 256; ++hi)
+    for (int lo = 0; lo < 256; ++lo) {
+      const int k = hi * 256 + lo;
+      const float x = lars_ratio_pair_u8(hi, lo);
+      value[k] = x;
+      row[k] = (int32_t)(lars_hist_row_bits(x, half, bias) - LARS_MAGIC_U);
+      slot[k] = (int32_t)(lars_cmap_slot_bits(x) - LARS_MAGIC_U);
+      const float xn = lars_negate_index(x);
+      row[65536 + k] = (int32_t)(lars_hist_row_bits(xn, half, bias) - LARS_MAGIC_U);
+      slot[65536 + k] = (int32_t)(lars_cmap_slot_bits(xn) - LARS_MAGIC_U);
+    }
+}
 }

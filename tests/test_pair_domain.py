@@ -131,3 +131,24 @@ def test_bwr_colormap_range_index(hostcheck):
     hostcheck.hc_cmap_index_range(C.c_void_p(x.ctypes.data), C.c_int64(x.size), C.c_float(-0.5), C.c_float(0.5),
                                   C.c_void_p(out.ctypes.data))
     assert np.array_equal(out, o.colormap_index(x, -0.5, 0.5))
+
+
+@pytest.mark.parametrize("bins", [1, 2, 3, 5, 7, 10, 16, 25, 32, 49, 50, 51, 63, 64])
+def test_conversion_free_forms_of_the_fused_kernel(hostcheck, bins):
+    """Magic-number int->float, floor-by-rounding histogram row and colormap slot (the forms the
+    fused kernel evaluates) against the oracle over all pairs, for x and for 0 - x (NDWI)."""
+    value = np.empty(65536, np.float32)
+    row = np.empty(2 * 65536, np.int32)
+    slot = np.empty(2 * 65536, np.int32)
+    hostcheck.hc_pair_tables_fast(C.c_int(bins), C.c_void_p(value.ctypes.data), C.c_void_p(row.ctypes.data),
+                                  C.c_void_p(slot.ctypes.data))
+    v = o.calculate_index(o.pair_image(), "NDVI")
+    vw = o.calculate_index(o.pair_image(), "NDWI")
+    assert np.array_equal(value.reshape(256, 256).view(np.uint32), v.view(np.uint32))
+    fold = lambda r: np.minimum(r, bins - 1)              # the kernel folds row `bins` into the last bin
+    assert np.array_equal(fold(row[:65536].reshape(256, 256)), o.histogram_bin_by_edges(v, bins))
+    assert np.array_equal(fold(row[65536:].reshape(256, 256)), o.histogram_bin_by_edges(vw, bins))
+    assert row.min() >= 0 and row.max() <= bins
+    assert np.array_equal(np.minimum(slot[:65536], 255).reshape(256, 256), o.colormap_index(v))
+    assert np.array_equal(np.minimum(slot[65536:], 255).reshape(256, 256), o.colormap_index(vw))
+    assert slot.min() >= 0 and slot.max() <= 256
