@@ -111,9 +111,11 @@ int lars_histogram_edges_f32(int bins, float* edges_out /* [bins + 1] host */);
 /* ---- Pass 1: white-balance statistics -------------------------------------------------
  * Replaces the three np.percentile(channel, (2, 98)) calls of fix_white_balance
  * (process-images.py:435-437; backend-process.py:21-23; process-rgn.py:28).
- * hist is [n_frames][3][256] uint64 and is ZEROED by the call, then filled. */
+ * hist is [n_frames][3][256] uint64 and is ZEROED by the call, then filled.  With shared_hist != 0
+ * all frames accumulate into ONE [3][256] set: the frames are tiles of a single image whose
+ * percentiles are global (tile-sharded orthomosaic). */
 int lars_wb_hist_u8(const uint8_t* src, int32_t n_frames, int64_t n_pixels, int32_t channels,
-                    int64_t src_frame_stride, uint64_t* hist, void* stream);
+                    int64_t src_frame_stride, uint64_t* hist, int32_t shared_hist, void* stream);
 
 /* Percentiles (NumPy "linear" method, float64) and the stretch
  * clip((v - p_lo) / (p_hi - p_lo) * 255, 0, 255) -> float32 -> uint8 for every v in 0..255

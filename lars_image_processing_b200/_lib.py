@@ -90,7 +90,7 @@ def _declare(lib):
     lib.lars_colormap_table.restype = C.c_int
     lib.lars_histogram_edges_f32.argtypes = [C.c_int, vp]
     lib.lars_histogram_edges_f32.restype = C.c_int
-    lib.lars_wb_hist_u8.argtypes = [vp, i32, i64, i32, i64, vp, vp]
+    lib.lars_wb_hist_u8.argtypes = [vp, i32, i64, i32, i64, vp, i32, vp]
     lib.lars_wb_hist_u8.restype = C.c_int
     lib.lars_wb_lut_build_u8.argtypes = [vp, i32, f64, f64, vp, vp, vp]
     lib.lars_wb_lut_build_u8.restype = C.c_int

@@ -60,7 +60,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 extern "C" {
 
 const char* lars_last_error(void) { return g_err; }
-int lars_abi_version(void) { return 1; }
+int lars_abi_version(void) { return 2; }
 
 int lars_init(int device) {
   std::lock_guard<std::mutex> lock(g_mu);
@@ -148,7 +148,7 @@ int lars_histogram_edges_f32(int bins, float* edges_out) {
 // Pass 1
 // ------------------------------------------------------------------------------------------
 int lars_wb_hist_u8(const uint8_t* src, int32_t n_frames, int64_t n_pixels, int32_t channels,
-                    int64_t src_frame_stride, uint64_t* hist, void* stream) {
+                    int64_t src_frame_stride, uint64_t* hist, int32_t shared_hist, void* stream) {
   DeviceState* st = nullptr;
   int rc = current_state(&st);
   if (rc != LARS_OK) return rc;
@@ -158,7 +158,7 @@ int lars_wb_hist_u8(const uint8_t* src, int32_t n_frames, int64_t n_pixels, int3
   if (!aligned16(src) || (src_frame_stride & 15) || src_frame_stride < n_pixels * channels)
     return fail(LARS_ERR_INVALID, "lars_wb_hist_u8: src / frame stride must be 16-byte aligned and cover a frame");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  LARS_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint64_t) * 768 * (size_t)n_frames, s));
+  LARS_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint64_t) * 768 * (size_t)(shared_hist ? 1 : n_frames), s));
 
   const long long frame_bytes = (long long)n_pixels * channels;
   const long long unit = (channels == 3) ? lars::K1Unit<3>::BYTES : lars::K1Unit<4>::BYTES;
@@ -170,6 +170,7 @@ int lars_wb_hist_u8(const uint8_t* src, int32_t n_frames, int64_t n_pixels, int3
   p.units_per_frame = (frame_bytes + unit - 1) / unit;
   p.total_units = p.units_per_frame * n_frames;
   p.n_frames = n_frames;
+  p.hist_set_stride = shared_hist ? 0 : 768;
   const long long target_ctas = 2ll * st->sm_count;  // 2 resident CTAs per SM (96 KB smem each)
   const int grid = (int)(p.total_units < target_ctas ? p.total_units : target_ctas);
   if (channels == 3)

@@ -109,6 +109,7 @@ struct K2ThreadConst {
   uint32_t cmap_cst[3];    // cmap_base[i]          - (MAGIC_U << 2)   (mod 2^32)
   float half_bins, half_bins_bias_m05;
   float kshift[2];
+  bool ndwi_by_sign;       // thresholds[2] == 0: count NDWI > 0 from the sign bit of GNDVI
 };
 
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
@@ -129,6 +130,17 @@ __device__ __forceinline__ void red_shared_inc(uint32_t addr) {
 template <int K>
 __device__ __forceinline__ uint32_t lut_gather(uint32_t raw_word, uint32_t table_addr) {
   return lds_u8(prmt(raw_word, table_addr, 0x7650u | (uint32_t)K));
+}
+// three-input min / max (FMNMX3 on sm_100a)
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
 }
 __device__ __forceinline__ uint32_t pack4(uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) {
   return prmt(prmt(b0, b1, 0x0040), prmt(b2, b3, 0x0040), 0x5410);
@@ -230,15 +242,24 @@ __device__ __forceinline__ void k2_process_tile(const K2Params& p, uint8_t* smem
   // ---- statistics + histograms ----
   if (p.partials) {
     float gx[2] = {0.f, 0.f}, gd[2] = {0.f, 0.f}, gdd[2] = {0.f, 0.f};
+    if (FULL) {
+      st.mn[0] = fmin3(fmin3(st.mn[0], ndvi[0], ndvi[1]), ndvi[2], ndvi[3]);
+      st.mx[0] = fmax3(fmax3(st.mx[0], ndvi[0], ndvi[1]), ndvi[2], ndvi[3]);
+      st.mn[1] = fmin3(fmin3(st.mn[1], gndvi[0], gndvi[1]), gndvi[2], gndvi[3]);
+      st.mx[1] = fmax3(fmax3(st.mx[1], gndvi[0], gndvi[1]), gndvi[2], gndvi[3]);
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (FULL || first + j < nvalid) {
         const float x0 = ndvi[j], x1 = gndvi[j], x2 = ndwi[j];
-        st.mn[0] = fminf(st.mn[0], x0); st.mx[0] = fmaxf(st.mx[0], x0);
-        st.mn[1] = fminf(st.mn[1], x1); st.mx[1] = fmaxf(st.mx[1], x1);
+        if (!FULL) {
+          st.mn[0] = fminf(st.mn[0], x0); st.mx[0] = fmaxf(st.mx[0], x0);
+          st.mn[1] = fminf(st.mn[1], x1); st.mx[1] = fmaxf(st.mx[1], x1);
+        }
         st.above[0] += (x0 > p.thresholds[0]) ? 1u : 0u;   // float32 compare (0.2f)
         st.above[1] += (x1 > p.thresholds[1]) ? 1u : 0u;
-        st.above[2] += (x2 > p.thresholds[2]) ? 1u : 0u;
+        if (tc.ndwi_by_sign) st.above[2] += __float_as_uint(x1) >> 31;   // NDWI > 0  <=>  GNDVI < 0
+        else st.above[2] += (x2 > p.thresholds[2]) ? 1u : 0u;
         const float d0 = LARS_FSUB(x0, tc.kshift[0]), d1 = LARS_FSUB(x1, tc.kshift[1]);
         gx[0] += x0; gd[0] += d0; gdd[0] = fmaf(d0, d0, gdd[0]);
         gx[1] += x1; gd[1] += d1; gdd[1] = fmaf(d1, d1, gdd[1]);
@@ -274,20 +295,6 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// tile t of the global sequence -> frame, first pixel, valid pixels
-struct K2Tile {
-  long long frame, px0;
-  int nvalid;
-};
-__device__ __forceinline__ K2Tile k2_tile(const K2Params& p, long long t) {
-  K2Tile r;
-  r.frame = t / p.tiles_per_frame;
-  r.px0 = (t - r.frame * p.tiles_per_frame) * K2_TILE_PX;
-  const long long rem = p.n_pixels - r.px0;
-  r.nvalid = rem < K2_TILE_PX ? (int)rem : K2_TILE_PX;
-  return r;
-}
-
 template <int C>
 __global__ void __launch_bounds__(K2_THREADS, 2) fused_index_u8_kernel(const K2Params p) {
   using L = K2Smem<C>;
@@ -320,26 +327,33 @@ __global__ void __launch_bounds__(K2_THREADS, 2) fused_index_u8_kernel(const K2P
 
   if (tid >= K2_CONSUMERS + 32) {
     // ===================== TMA store warp (one elected lane) =====================
-    if (lane == 0 && stage_bytes) {
-      uint32_t it = 0;
-      for (long long t = t_begin; t < t_end; ++t, ++it) {
-        const K2Tile tl = k2_tile(p, t);
-        const int so = it % K2_OUT_STAGES;
-        mbar_wait(bar_out_full + 8u * so, (it / K2_OUT_STAGES) & 1u);
+    if (lane == 0 && stage_bytes && t_begin < t_end) {
+      long long frame = t_begin / p.tiles_per_frame;          // one division, then incremental
+      long long tile = t_begin - frame * p.tiles_per_frame;
+      uint32_t so = 0, phase = 0;
+      uint32_t prev_so = 0;
+      for (long long t = t_begin; t < t_end; ++t) {
+        const long long px0 = tile * K2_TILE_PX;
+        const long long rem = p.n_pixels - px0;
+        const uint32_t nvalid = rem < K2_TILE_PX ? (uint32_t)rem : (uint32_t)K2_TILE_PX;
+        mbar_wait(bar_out_full + 8u * so, phase);
         const uint32_t stage_addr = smem_base + L::OFF_OUT + so * L::OUT_BYTES;
-        const uint32_t wb_bytes = ((uint32_t)tl.nvalid * C + 15u) & ~15u;
-        const uint32_t rgb_bytes = ((uint32_t)tl.nvalid * 3u + 15u) & ~15u;
-        if (p.wb_out) tma_store_1d(p.wb_out + tl.frame * p.wb_frame_stride + tl.px0 * C, stage_addr, wb_bytes);
+        const uint32_t wb_bytes = (nvalid * C + 15u) & ~15u;
+        const uint32_t rgb_bytes = (nvalid * 3u + 15u) & ~15u;
+        if (p.wb_out) tma_store_1d(p.wb_out + frame * p.wb_frame_stride + px0 * C, stage_addr, wb_bytes);
 #pragma unroll
         for (int i = 0; i < 3; ++i)
           if (p.rgb[i])
-            tma_store_1d(p.rgb[i] + tl.frame * p.rgb_frame_stride + tl.px0 * 3,
+            tma_store_1d(p.rgb[i] + frame * p.rgb_frame_stride + px0 * 3,
                          stage_addr + L::WB_BYTES + i * L::RGB_BYTES, rgb_bytes);
         tma_store_commit();
-        if (it > 0) {  // the previous tile's stores have finished reading their stage: hand it back
+        if (t > t_begin) {  // the previous tile's stores have finished reading their stage: hand it back
           asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          mbar_arrive(bar_out_empty + 8u * ((it - 1) % K2_OUT_STAGES));
+          mbar_arrive(bar_out_empty + 8u * prev_so);
         }
+        prev_so = so;
+        if (++so == K2_OUT_STAGES) { so = 0; phase ^= 1u; }
+        if (++tile == p.tiles_per_frame) { tile = 0; ++frame; }
       }
       tma_store_wait_all();  // global writes performed before the CTA (and its smem) goes away
     }
@@ -347,17 +361,22 @@ __global__ void __launch_bounds__(K2_THREADS, 2) fused_index_u8_kernel(const K2P
   }
   if (tid >= K2_CONSUMERS) {
     // ===================== TMA load warp (one elected lane) =====================
-    if (lane == 0) {
+    if (lane == 0 && t_begin < t_end) {
       const uint64_t pol = l2_policy_evict_first();  // raw bytes are dead after this pass
-      uint32_t it = 0;
-      for (long long t = t_begin; t < t_end; ++t, ++it) {
-        const K2Tile tl = k2_tile(p, t);
-        const uint32_t bytes = ((uint32_t)tl.nvalid * C + 15u) & ~15u;
-        const int s = it % K2_IN_STAGES;
-        mbar_wait(bar_base + 8u * (K2_IN_STAGES + s), ((it / K2_IN_STAGES) & 1u) ^ 1u);
+      long long frame = t_begin / p.tiles_per_frame;
+      long long tile = t_begin - frame * p.tiles_per_frame;
+      uint32_t s = 0, phase = 0;
+      for (long long t = t_begin; t < t_end; ++t) {
+        const long long px0 = tile * K2_TILE_PX;
+        const long long rem = p.n_pixels - px0;
+        const uint32_t nvalid = rem < K2_TILE_PX ? (uint32_t)rem : (uint32_t)K2_TILE_PX;
+        const uint32_t bytes = (nvalid * C + 15u) & ~15u;
+        mbar_wait(bar_base + 8u * (K2_IN_STAGES + s), phase ^ 1u);
         mbar_arrive_expect_tx(bar_base + 8u * s, bytes);
         tma_load_1d_hint(smem_base + L::OFF_IN + s * L::IN_BYTES,
-                         p.src + tl.frame * p.src_frame_stride + tl.px0 * C, bytes, bar_base + 8u * s, pol);
+                         p.src + frame * p.src_frame_stride + px0 * C, bytes, bar_base + 8u * s, pol);
+        if (++s == K2_IN_STAGES) { s = 0; phase ^= 1u; }
+        if (++tile == p.tiles_per_frame) { tile = 0; ++frame; }
       }
     }
     return;
@@ -381,6 +400,7 @@ __global__ void __launch_bounds__(K2_THREADS, 2) fused_index_u8_kernel(const K2P
   K2ThreadConst tc;
   tc.half_bins = 0.5f * (float)p.bins;
   tc.half_bins_bias_m05 = tc.half_bins + LARS_HIST_BIAS - 0.5f;
+  tc.ndwi_by_sign = (p.thresholds[2] == 0.0f);
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     tc.lut_addr[i] = smem_base + L::OFF_LUT + lut_shift + 256u * i;
@@ -388,7 +408,7 @@ __global__ void __launch_bounds__(K2_THREADS, 2) fused_index_u8_kernel(const K2P
     tc.cmap_cst[i] = smem_base + L::OFF_CMAP + (uint32_t)(i * K2_CMAP_SLOTS * 4) - (LARS_MAGIC_U << 2);
   }
 
-  uint32_t it = 0;
+  uint32_t s_in = 0, ph_in = 0, s_out = 0, ph_out = 0;
   long long t = t_begin;
   while (t < t_end) {
     // ---------------- one span: the part of frame `frame` owned by this CTA ----------------
@@ -419,23 +439,23 @@ __global__ void __launch_bounds__(K2_THREADS, 2) fused_index_u8_kernel(const K2P
     st.sx[0] = st.sx[1] = st.sd[0] = st.sd[1] = st.sdd[0] = st.sdd[1] = 0.0;
     st.above[0] = st.above[1] = st.above[2] = 0u;
 
-    for (; t < span_end; ++t, ++it) {
+    for (; t < span_end; ++t) {
       const long long px0 = (t - frame_t0) * K2_TILE_PX;
       const long long rem = p.n_pixels - px0;
       const int nvalid = rem < K2_TILE_PX ? (int)rem : K2_TILE_PX;
-      const int s = it % K2_IN_STAGES;
-      const int so = it % K2_OUT_STAGES;
-      if (stage_bytes) mbar_wait(bar_out_empty + 8u * so, ((it / K2_OUT_STAGES) & 1u) ^ 1u);  // stage drained
-      mbar_wait(bar_base + 8u * s, (it / K2_IN_STAGES) & 1u);                                  // tile landed
+      if (stage_bytes) mbar_wait(bar_out_empty + 8u * s_out, ph_out ^ 1u);  // staging buffer drained
+      mbar_wait(bar_base + 8u * s_in, ph_in);                               // tile landed
       if (nvalid == K2_TILE_PX)
-        k2_process_tile<C, true>(p, smem, smem_base, s, so, tid, lane, frame, px0, nvalid, tc, stage_bytes, st);
+        k2_process_tile<C, true>(p, smem, smem_base, s_in, s_out, tid, lane, frame, px0, nvalid, tc, stage_bytes, st);
       else
-        k2_process_tile<C, false>(p, smem, smem_base, s, so, tid, lane, frame, px0, nvalid, tc, stage_bytes, st);
+        k2_process_tile<C, false>(p, smem, smem_base, s_in, s_out, tid, lane, frame, px0, nvalid, tc, stage_bytes, st);
       if (stage_bytes) {
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk-copy engine
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_out_full + 8u * so);
+        if (lane == 0) mbar_arrive(bar_out_full + 8u * s_out);
+        if (++s_out == K2_OUT_STAGES) { s_out = 0; ph_out ^= 1u; }
       }
+      if (++s_in == K2_IN_STAGES) { s_in = 0; ph_in ^= 1u; }
     }
 
     // ---------------- flush this span into its partial record ----------------

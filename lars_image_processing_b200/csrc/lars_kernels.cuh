@@ -38,6 +38,7 @@ struct K1Params {
   long long frame_stride;    // bytes
   long long units_per_frame; // work unit = K1_CTA_BYTES (C == 3) / 16 * K1_THREADS bytes (C == 4)
   long long total_units;
+  long long hist_set_stride; // elements between frames' histogram sets: 768, or 0 = one shared set
   int n_frames;
 };
 
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) wb_hist_u8_kernel(const K1Param
       uint32_t sum = 0;
 #pragma unroll 8
       for (int l = 0; l < 32; ++l) sum += k1_hist[b * 32 + ((l + tid) & 31)];
-      if (sum) atomicAdd(&p.hist[frame * 768 + b], (unsigned long long)sum);
+      if (sum) atomicAdd(&p.hist[frame * p.hist_set_stride + b], (unsigned long long)sum);
     }
     __syncthreads();
   }

@@ -95,5 +95,19 @@ def allreduce_wb_histogram(hist: torch.Tensor, group=None) -> torch.Tensor:
     return hist
 
 
+def process_mosaic_tiles(engine, tiles, outputs=("wb", "maps", "rgb", "stats"), group=None, stream=None, **kw):
+    """One huge image (orthomosaic, BASELINE config 4) held as equally-sized tiles / row bands.
+
+    Every rank passes the tiles it owns.  Pass 1 accumulates ONE histogram over the local tiles,
+    a SUM all-reduce makes it global, every rank builds the identical LUT, Pass 2 runs per tile
+    with that shared LUT, and the per-tile statistics are merged into image-wide records with
+    the usual single all-gather.  Returns (DeviceOutputs of the local tiles, [3, 576] records)."""
+    s = stream or engine.stream()
+    res = engine.process_device(tiles, outputs=outputs, tiles_of_one_image=True,
+                                hist_hook=lambda h: allreduce_wb_histogram(h, group), stream=s, **kw)
+    whole = dataset_statistics(engine, res.stats, group, s) if res.stats is not None else None
+    return res, whole
+
+
 def records_to_numpy(records: torch.Tensor) -> np.ndarray:
     return records.cpu().numpy().view(INDEX_STATS_DTYPE).reshape(records.shape[:-1])

@@ -153,14 +153,15 @@ class Engine:
                 dev.data[i, :nbytes].copy_(src, non_blocking=True)
         return dev
 
-    def wb_histogram(self, frames: DeviceFrames, stream=None) -> torch.Tensor:
-        """Pass 1 (K1): [F, 3, 256] per-channel value counts (int64 view of uint64)."""
+    def wb_histogram(self, frames: DeviceFrames, shared: bool = False, stream=None) -> torch.Tensor:
+        """Pass 1 (K1): [F, 3, 256] per-channel value counts (int64 view of uint64).
+        ``shared=True``: the frames are tiles of one image -> a single [1, 3, 256] histogram."""
         s = stream or self.stream()
-        hist = self._alloc((frames.n_frames, 3, 256), torch.int64, s)
+        hist = self._alloc((1 if shared else frames.n_frames, 3, 256), torch.int64, s)
         with torch.cuda.device(self.device):
             check(self.lib.lars_wb_hist_u8(frames.data.data_ptr(), frames.n_frames, frames.n_pixels,
                                            frames.channels, frames.stride_bytes, hist.data_ptr(),
-                                           s.cuda_stream), "lars_wb_hist_u8")
+                                           1 if shared else 0, s.cuda_stream), "lars_wb_hist_u8")
         return hist
 
     def wb_lut(self, hist: torch.Tensor, quantiles=DEFAULT_QUANTILES, stream=None):
@@ -251,13 +252,21 @@ class Engine:
 
     def process_device(self, frames: DeviceFrames, outputs=ALL_OUTPUTS, white_balance: bool = True,
                        quantiles=DEFAULT_QUANTILES, out: Optional[DeviceOutputs] = None,
-                       stream=None, **kw) -> DeviceOutputs:
-        """Pass 1 + LUT + Pass 2 on a device-resident batch; nothing is synchronised."""
+                       stream=None, tiles_of_one_image: bool = False, hist_hook=None, **kw) -> DeviceOutputs:
+        """Pass 1 + LUT + Pass 2 on a device-resident batch; nothing is synchronised.
+
+        ``tiles_of_one_image``: the frames are tiles / row bands of ONE image (orthomosaic): the
+        white-balance percentiles are global, so a single histogram is accumulated over all
+        tiles and one LUT serves every tile.  ``hist_hook(hist)`` runs between Pass 1 and the
+        LUT build (the multi-GPU path SUM-all-reduces the histogram there)."""
         s = stream or self.stream()
         res = out or DeviceOutputs(frames=frames)
         lut = None
         if white_balance:
-            res.wb_hist = self.wb_histogram(frames, stream=s)
+            res.wb_hist = self.wb_histogram(frames, shared=tiles_of_one_image, stream=s)
+            if hist_hook is not None:
+                with torch.cuda.stream(s):
+                    hist_hook(res.wb_hist)
             res.wb_lut, res.wb_pct = self.wb_lut(res.wb_hist, quantiles, stream=s)
             lut = res.wb_lut
         return self.fused(frames, lut, outputs=outputs, out=res, stream=s, **kw)

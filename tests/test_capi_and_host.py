@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in include/lars_b200.h but not exported"
     assert set(_lib.EXPORTED_SYMBOLS) == set(declared)
-    assert lib.lars_abi_version() == 1
+    assert lib.lars_abi_version() == 2
 
 
 def test_struct_layouts_match_header(tmp_path):
@@ -64,7 +64,7 @@ def test_compute_entry_points_fail_loudly_without_gpu():
     lib = _lib.load()
     assert lib.lars_init(0) < 0 and b"failed" in lib.lars_last_error()
     hist = np.zeros(768, np.uint64)
-    assert lib.lars_wb_hist_u8(1, 1, 16, 3, 48, hist.ctypes.data, None) < 0
+    assert lib.lars_wb_hist_u8(1, 1, 16, 3, 48, hist.ctypes.data, 0, None) < 0
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         Engine()
 

@@ -211,11 +211,11 @@ def test_bad_arguments_return_errors_not_crashes(engine):
         engine.analyze_frame(img, bins=0)
     lib = engine.lib
     hist = np.zeros(768, np.uint64)
-    assert lib.lars_wb_hist_u8(None, 1, 16, 3, 48, hist.ctypes.data, None) == -1
+    assert lib.lars_wb_hist_u8(None, 1, 16, 3, 48, hist.ctypes.data, 0, None) == -1
     assert b"NULL" in lib.lars_last_error()
     dev = engine.upload([img])
-    assert lib.lars_wb_hist_u8(dev.data.data_ptr() + 1, 1, 16, 3, 48, dev.data.data_ptr(), None) == -1
-    assert lib.lars_wb_hist_u8(dev.data.data_ptr(), 1, 16, 5, 80, dev.data.data_ptr(), None) == -3
+    assert lib.lars_wb_hist_u8(dev.data.data_ptr() + 1, 1, 16, 3, 48, dev.data.data_ptr(), 0, None) == -1
+    assert lib.lars_wb_hist_u8(dev.data.data_ptr(), 1, 16, 5, 80, dev.data.data_ptr(), 0, None) == -3
 
 
 # ------------------------------------------------------------------------------------- drop-ins
@@ -348,3 +348,36 @@ def test_colormap_kernel(engine):
     assert np.array_equal(colormap_map(x, "RdYlBu"), o.apply_colormap(x, name="RdYlBu"))
     d = rng.uniform(-0.8, 0.8, (50, 33)).astype(np.float32)
     assert np.array_equal(colormap_map(d, "bwr", -0.5, 0.5), o.apply_colormap(d, name="bwr", vmin=-0.5, vmax=0.5))
+
+
+# ------------------------------------------------------------------------------------- mosaic tiles
+def test_mosaic_tiles_share_global_percentiles(engine):
+    """BASELINE config 4 in miniature: one image cut into row bands processed as tiles with ONE
+    global white-balance histogram / LUT and image-wide merged statistics."""
+    from lars_image_processing_b200 import distributed as ld
+    from lars_image_processing_b200.engine import stats_records_to_dicts
+    img = synth.vegetation_frame(90, 768, 1000)
+    img[:128] //= 3                                   # bands differ, so per-band percentiles would be wrong
+    bands = [np.ascontiguousarray(b) for b in np.split(img, 6, axis=0)]
+    dev = engine.upload(bands)
+    res, whole = ld.process_mosaic_tiles(engine, dev)
+    out = engine.download(res)
+    want = oracle_frame(img)
+    got_wb = np.concatenate([o_["wb"] for o_ in out], axis=0)
+    assert np.array_equal(got_wb, want["wb"])
+    for t in INDEX_TYPES:
+        got = np.concatenate([o_["maps"][t] for o_ in out], axis=0)
+        assert np.array_equal(got.view(np.uint32), want["maps"][t].view(np.uint32))
+        assert np.array_equal(np.concatenate([o_["rgb"][t] for o_ in out], axis=0), want["rgb"][t])
+    rec = ld.records_to_numpy(whole).reshape(1, 3)
+    st = stats_records_to_dicts(rec, 50)[0]
+    for t in INDEX_TYPES:
+        ws = want["stats"][t]
+        assert st[t]["count"] == ws["count"] and st[t]["count_above"] == ws["count_above"]
+        assert np.array_equal(st[t]["hist"], ws["hist"])
+        assert st[t]["min"] == ws["min"] and st[t]["max"] == ws["max"]
+        std = float(np.std(want["maps"][t]))
+        assert moment_close(st[t]["mean"], float(np.mean(want["maps"][t])), std)
+        assert moment_close(st[t]["std"], std, std)
+    assert np.array_equal(out[0]["percentiles"], np.array([np.percentile(img[:, :, c].astype(np.float32), (2, 98))
+                                                           for c in range(3)]))
