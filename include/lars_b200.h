@@ -70,6 +70,16 @@ typedef struct lars_index_stats {
   uint64_t hist[LARS_MAX_BINS]; /* np.histogram(x, bins, range=(-1, 1)); entries >= bins are 0 */
 } lars_index_stats;
 
+/* White-balance stretch of one channel of a uint16 frame: the monotone map
+ * v -> uint8(clip((v - p_lo) / (p_hi - p_lo) * 255, 0, 255)) (process-images.py:438-441) stored as
+ * its 256 step positions, thr[k] = smallest v with LUT(v) >= k (thr[0] = 0, unreachable k and
+ * thr[256..257] = 65536), plus the float parameters of a first guess.  1040 bytes. */
+typedef struct lars_stretch_u16 {
+  float lo;          /* p_lo rounded to float32             */
+  float scale;       /* 255 / (p_hi - p_lo), 0 if degenerate */
+  uint32_t thr[258];
+} lars_stretch_u16;
+
 /* Arguments of the fused Pass 2 (one struct so the ABI can grow without breaking callers). */
 typedef struct lars_fused_args {
   uint32_t struct_bytes;      /* = sizeof(lars_fused_args), checked                         */
@@ -77,9 +87,10 @@ typedef struct lars_fused_args {
   int32_t channels;           /* 3 (RGN) or 4 (RGNA; alpha is ignored and written as 0)     */
   int32_t bins;               /* 1..LARS_MAX_BINS                                            */
   int64_t n_pixels;           /* pixels per frame                                            */
-  const uint8_t* src;         /* raw frames                                                  */
+  const uint8_t* src;         /* raw frames (uint8 samples, or little-endian uint16 for *_u16) */
   int64_t src_frame_stride;   /* bytes                                                       */
-  const uint8_t* wb_lut;      /* [frame][3][256] stretch LUTs, NULL = identity (no WB)       */
+  const uint8_t* wb_lut;      /* u8: [frame][3][256] stretch LUTs, NULL = identity (no WB);
+                                 u16: [frame][3] lars_stretch_u16 (required)                 */
   int64_t lut_frame_stride;   /* bytes between frames' LUTs; 0 = one LUT set for all frames  */
   uint8_t* wb_out;            /* white-balanced frames, same channel count as src, or NULL   */
   int64_t wb_frame_stride;    /* bytes                                                       */
@@ -132,6 +143,21 @@ int lars_wb_lut_build_u8(const uint64_t* hist, int32_t n_sets, double q_lo, doub
  * of create_index_visualization (:689-695). */
 size_t lars_fused_workspace_bytes(int32_t n_frames);
 int lars_fused_index_u8(const lars_fused_args* args, void* stream);
+
+/* ---- uint16 frames (16-bit TIFF batches, BASELINE config 3) ----------------------------------
+ * fix_white_balance accepts uint16 arrays and still returns uint8 0..255.
+ * Pass 1 = two-level radix histogram (high byte, then the low byte of the buckets that hold the
+ * four percentile ranks) -> exact NumPy percentiles -> lars_stretch_u16 per channel.  src strides
+ * are in BYTES; workspace from lars_wb_u16_workspace_bytes(n_sets), n_sets = shared_hist ? 1 :
+ * n_frames.  stretch is [n_sets][3], pct [n_sets][3][2] (may be NULL). */
+size_t lars_wb_u16_workspace_bytes(int32_t n_sets);
+int lars_wb_stretch_build_u16(const uint16_t* src, int32_t n_frames, int64_t n_pixels, int32_t channels,
+                              int64_t src_frame_stride, double q_lo, double q_hi, lars_stretch_u16* stretch,
+                              double* pct, void* workspace, size_t workspace_bytes, int32_t shared_hist,
+                              void* stream);
+/* Pass 2 on uint16 frames: same products as lars_fused_index_u8 (WB output is uint8);
+ * lut_frame_stride = 3 * sizeof(lars_stretch_u16) or 0 for one shared set. */
+int lars_fused_index_u16(const lars_fused_args* args, void* stream);
 
 /* ---- float-map operations next to the fused pass ---------------------------------------- */
 /* Statistics + np.histogram(x, bins, range=(-1, 1)) of arbitrary float32 maps: replaces

@@ -18,6 +18,7 @@ LARS_OK = 0
 NUM_INDICES = 3
 MAX_BINS = 64
 PIXEL_GROUP = 16
+STRETCH_U16_BYTES = 1040   # sizeof(lars_stretch_u16)
 CMAP_IDS = {"RdYlGn": 0, "RdYlBu": 1, "bwr": 2}
 
 EXPORTED_SYMBOLS = (
@@ -28,6 +29,7 @@ EXPORTED_SYMBOLS = (
     "lars_map_stats_workspace_bytes", "lars_map_stats_f32", "lars_select_workspace_bytes",
     "lars_select_f32", "lars_colormap_f32", "lars_ndvi_f64_u8", "lars_index_planes_f32",
     "lars_stats_merge",
+    "lars_wb_u16_workspace_bytes", "lars_wb_stretch_build_u16", "lars_fused_index_u16",
 )
 
 
@@ -114,6 +116,12 @@ def _declare(lib):
     lib.lars_index_planes_f32.restype = C.c_int
     lib.lars_stats_merge.argtypes = [vp, i32, vp, vp]
     lib.lars_stats_merge.restype = C.c_int
+    lib.lars_wb_u16_workspace_bytes.argtypes = [i32]
+    lib.lars_wb_u16_workspace_bytes.restype = C.c_size_t
+    lib.lars_wb_stretch_build_u16.argtypes = [vp, i32, i64, i32, i64, f64, f64, vp, vp, vp, C.c_size_t, i32, vp]
+    lib.lars_wb_stretch_build_u16.restype = C.c_int
+    lib.lars_fused_index_u16.argtypes = [C.POINTER(FusedArgs), vp]
+    lib.lars_fused_index_u16.restype = C.c_int
 
 
 def load():

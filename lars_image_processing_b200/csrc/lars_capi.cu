@@ -13,6 +13,7 @@
 #include "lars_kernels.cuh"
 #include "lars_fused_kernel.cuh"
 #include "lars_map_kernels.cuh"
+#include "lars_u16_kernels.cuh"
 
 namespace {
 
@@ -86,10 +87,18 @@ int lars_init(int device) {
                                  lars::K1_SMEM_BYTES));
   LARS_CUDA(cudaFuncSetAttribute(lars::wb_hist_u8_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  lars::K1_SMEM_BYTES));
-  LARS_CUDA(cudaFuncSetAttribute(lars::fused_index_u8_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 lars::K2Smem<3>::TOTAL));
-  LARS_CUDA(cudaFuncSetAttribute(lars::fused_index_u8_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 lars::K2Smem<4>::TOTAL));
+  LARS_CUDA(cudaFuncSetAttribute(lars::fused_index_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 lars::K2Smem<3, 1>::TOTAL));
+  LARS_CUDA(cudaFuncSetAttribute(lars::fused_index_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 lars::K2Smem<4, 1>::TOTAL));
+  LARS_CUDA(cudaFuncSetAttribute(lars::fused_index_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 lars::K2Smem<3, 2>::TOTAL));
+  LARS_CUDA(cudaFuncSetAttribute(lars::fused_index_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 lars::K2Smem<4, 2>::TOTAL));
+  LARS_CUDA(cudaFuncSetAttribute(lars::wb_hist_u16_hi_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lars::K1_SMEM_BYTES));
+  LARS_CUDA(cudaFuncSetAttribute(lars::wb_hist_u16_hi_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lars::K1_SMEM_BYTES));
+  LARS_CUDA(cudaFuncSetAttribute(lars::wb_hist_u16_lo_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lars::U16_LO_SMEM_BYTES));
+  LARS_CUDA(cudaFuncSetAttribute(lars::wb_hist_u16_lo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lars::U16_LO_SMEM_BYTES));
   LARS_CUDA(cudaFuncSetAttribute(lars::select_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  lars::SEL_SMEM_BYTES));
 
@@ -215,7 +224,11 @@ size_t lars_fused_workspace_bytes(int32_t n_frames) {
   return slots * (size_t)n_frames * sizeof(lars::K2Partial);
 }
 
-int lars_fused_index_u8(const lars_fused_args* a, void* stream) {
+static int fused_index_impl(const lars_fused_args* a, void* stream, int BPS);
+int lars_fused_index_u8(const lars_fused_args* a, void* stream) { return fused_index_impl(a, stream, 1); }
+int lars_fused_index_u16(const lars_fused_args* a, void* stream) { return fused_index_impl(a, stream, 2); }
+
+static int fused_index_impl(const lars_fused_args* a, void* stream, int BPS) {
   DeviceState* st = nullptr;
   int rc = current_state(&st);
   if (rc != LARS_OK) return rc;
@@ -232,8 +245,12 @@ int lars_fused_index_u8(const lars_fused_args* a, void* stream) {
     return fail(LARS_ERR_INVALID, "lars_fused_index_u8: bins must be in 1..%d, got %d", LARS_MAX_BINS, a->bins);
   const int C = a->channels;
   const int64_t padded_px = (a->n_pixels + LARS_PIXEL_GROUP - 1) / LARS_PIXEL_GROUP * LARS_PIXEL_GROUP;
-  if (!aligned16(a->src) || (a->src_frame_stride & 15) || a->src_frame_stride < padded_px * C)
+  if (!aligned16(a->src) || (a->src_frame_stride & 15) || a->src_frame_stride < padded_px * C * BPS)
     return fail(LARS_ERR_INVALID, "lars_fused_index_u8: src must be 16-byte aligned with a 16-pixel padded frame stride");
+  if (BPS == 2 && !a->wb_lut)
+    return fail(LARS_ERR_INVALID, "lars_fused_index_u16: wb_lut (lars_stretch_u16[frame][3]) is required");
+  if (BPS == 2 && (!aligned16(a->wb_lut) || (a->lut_frame_stride != 0 && a->lut_frame_stride < (int64_t)(3 * sizeof(lars_stretch_u16)))))
+    return fail(LARS_ERR_INVALID, "lars_fused_index_u16: stretch tables must be 16-byte aligned, stride 0 or >= %zu", 3 * sizeof(lars_stretch_u16));
   if (a->wb_out && (!aligned16(a->wb_out) || (a->wb_frame_stride & 15) || a->wb_frame_stride < padded_px * C))
     return fail(LARS_ERR_INVALID, "lars_fused_index_u8: wb_out alignment / stride");
   for (int i = 0; i < 3; ++i) {
@@ -283,10 +300,14 @@ int lars_fused_index_u8(const lars_fused_args* a, void* stream) {
     LARS_CUDA(cudaMemsetAsync(a->workspace, 0,
                               (size_t)p.slots_per_frame * a->n_frames * sizeof(lars::K2Partial), s));
   }
-  if (C == 3)
-    lars::fused_index_u8_kernel<3><<<(int)grid, lars::K2_THREADS, lars::K2Smem<3>::TOTAL, s>>>(p);
+  if (BPS == 1 && C == 3)
+    lars::fused_index_kernel<3, 1><<<(int)grid, lars::K2_THREADS, lars::K2Smem<3, 1>::TOTAL, s>>>(p);
+  else if (BPS == 1)
+    lars::fused_index_kernel<4, 1><<<(int)grid, lars::K2_THREADS, lars::K2Smem<4, 1>::TOTAL, s>>>(p);
+  else if (C == 3)
+    lars::fused_index_kernel<3, 2><<<(int)grid, lars::K2_THREADS, lars::K2Smem<3, 2>::TOTAL, s>>>(p);
   else
-    lars::fused_index_u8_kernel<4><<<(int)grid, lars::K2_THREADS, lars::K2Smem<4>::TOTAL, s>>>(p);
+    lars::fused_index_kernel<4, 2><<<(int)grid, lars::K2_THREADS, lars::K2Smem<4, 2>::TOTAL, s>>>(p);
   LARS_CUDA(cudaGetLastError());
   if (a->stats) {
     lars::K2fParams f;
@@ -432,6 +453,76 @@ int lars_stats_merge(const lars_index_stats* in, int32_t n_sets, lars_index_stat
   if (!in || !out) return fail(LARS_ERR_INVALID, "lars_stats_merge: NULL pointer");
   if (n_sets < 1) return fail(LARS_ERR_INVALID, "lars_stats_merge: n_sets=%d", n_sets);
   lars::stats_merge_kernel<<<3, LARS_MAX_BINS, 0, static_cast<cudaStream_t>(stream)>>>(in, n_sets, out);
+  LARS_CUDA(cudaGetLastError());
+  return LARS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// uint16 Pass 1
+// ------------------------------------------------------------------------------------------
+namespace {
+struct U16Workspace {
+  unsigned long long* hist_hi;
+  unsigned long long* hist_lo;
+  lars::U16Select* select;
+};
+constexpr size_t kU16SetBytes = 3 * 256 * 8 + 3 * lars::U16_MAX_BUCKETS * 256 * 8 + 3 * sizeof(lars::U16Select);
+}  // namespace
+
+size_t lars_wb_u16_workspace_bytes(int32_t n_sets) { return n_sets < 1 ? 0 : (size_t)n_sets * kU16SetBytes; }
+
+int lars_wb_stretch_build_u16(const uint16_t* src, int32_t n_frames, int64_t n_pixels, int32_t channels,
+                              int64_t src_frame_stride, double q_lo, double q_hi, lars_stretch_u16* stretch,
+                              double* pct, void* workspace, size_t workspace_bytes, int32_t shared_hist,
+                              void* stream) {
+  DeviceState* st = nullptr;
+  int rc = current_state(&st);
+  if (rc != LARS_OK) return rc;
+  if (!src || !stretch || !workspace) return fail(LARS_ERR_INVALID, "lars_wb_stretch_build_u16: NULL pointer");
+  if (n_frames < 1 || n_pixels < 1) return fail(LARS_ERR_INVALID, "lars_wb_stretch_build_u16: empty input");
+  if (channels != 3 && channels != 4) return fail(LARS_ERR_UNSUPPORTED, "lars_wb_stretch_build_u16: channels must be 3 or 4, got %d", channels);
+  if (!aligned16(src) || (src_frame_stride & 15) || src_frame_stride < n_pixels * channels * 2)
+    return fail(LARS_ERR_INVALID, "lars_wb_stretch_build_u16: src / frame stride must be 16-byte aligned and cover a frame");
+  if (!(q_lo >= 0.0 && q_lo <= 1.0 && q_hi >= 0.0 && q_hi <= 1.0))
+    return fail(LARS_ERR_INVALID, "lars_wb_stretch_build_u16: quantiles must be fractions in [0,1]");
+  const int n_sets = shared_hist ? 1 : n_frames;
+  if (!aligned16(workspace) || !aligned16(stretch) || workspace_bytes < lars_wb_u16_workspace_bytes(n_sets))
+    return fail(LARS_ERR_INVALID, "lars_wb_stretch_build_u16: workspace too small or misaligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  unsigned long long* hist_hi = reinterpret_cast<unsigned long long*>(ws);
+  unsigned long long* hist_lo = reinterpret_cast<unsigned long long*>(ws + (size_t)n_sets * 3 * 256 * 8);
+  lars::U16Select* select = reinterpret_cast<lars::U16Select*>(ws + (size_t)n_sets * (3 * 256 * 8 + 3 * lars::U16_MAX_BUCKETS * 256 * 8));
+  LARS_CUDA(cudaMemsetAsync(workspace, 0, (size_t)n_sets * kU16SetBytes, s));
+
+  const long long frame_bytes = (long long)n_pixels * channels * 2;
+  const long long unit = (channels == 3) ? lars::U16Unit<3>::BYTES : lars::U16Unit<4>::BYTES;
+  lars::U16HistParams p;
+  p.src = reinterpret_cast<const uint8_t*>(src);
+  p.hist_hi = hist_hi; p.hist_lo = hist_lo; p.select = select;
+  p.n_pixels = n_pixels; p.frame_stride = src_frame_stride;
+  p.units_per_frame = (frame_bytes + unit - 1) / unit;
+  p.total_units = p.units_per_frame * n_frames;
+  p.set_stride = shared_hist ? 0 : 1;
+  p.n_frames = n_frames; p.lo_pass = 0;
+  const long long target = 2ll * st->sm_count;
+  const int grid = (int)(p.total_units < target ? p.total_units : target);
+  if (channels == 3) lars::wb_hist_u16_hi_kernel<3><<<grid, lars::K1_THREADS, lars::K1_SMEM_BYTES, s>>>(p);
+  else lars::wb_hist_u16_hi_kernel<4><<<grid, lars::K1_THREADS, lars::K1_SMEM_BYTES, s>>>(p);
+  LARS_CUDA(cudaGetLastError());
+  lars::U16SelectParams sp; sp.hist_hi = hist_hi; sp.select = select; sp.q_lo = q_lo; sp.q_hi = q_hi;
+  lars::wb_u16_select_kernel<<<n_sets * 3, 256, 0, s>>>(sp);
+  LARS_CUDA(cudaGetLastError());
+  for (int pass = 0; pass < 2; ++pass) {
+    p.lo_pass = pass;
+    if (channels == 3) lars::wb_hist_u16_lo_kernel<3><<<grid, lars::K1_THREADS, lars::U16_LO_SMEM_BYTES, s>>>(p);
+    else lars::wb_hist_u16_lo_kernel<4><<<grid, lars::K1_THREADS, lars::U16_LO_SMEM_BYTES, s>>>(p);
+    LARS_CUDA(cudaGetLastError());
+  }
+  lars::U16BuildParams bp;
+  bp.hist_hi = hist_hi; bp.hist_lo = hist_lo; bp.select = select; bp.stretch = stretch; bp.pct = pct;
+  bp.q_lo = q_lo; bp.q_hi = q_hi;
+  lars::wb_stretch_build_u16_kernel<<<n_sets * 3, 256, 0, s>>>(bp);
   LARS_CUDA(cudaGetLastError());
   return LARS_OK;
 }

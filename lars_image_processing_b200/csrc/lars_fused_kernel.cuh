@@ -67,14 +67,16 @@ struct K2Params {
   float thresholds[3];
 };
 
-template <int C>
+template <int C, int BPS>
 struct K2Smem {
-  static constexpr int IN_BYTES = K2_TILE_PX * C;
+  static constexpr int IN_BYTES = K2_TILE_PX * C * BPS;
   static constexpr int WB_BYTES = K2_TILE_PX * C;
   static constexpr int RGB_BYTES = K2_TILE_PX * 3;
   static constexpr int OUT_BYTES = WB_BYTES + 3 * RGB_BYTES;     // one output stage
-  static constexpr int OFF_LUT = 0;                              // 3 x 256 B, each table 256-aligned
-  static constexpr int OFF_CMAP = 1024;                          // 3 x 257 words
+  // uint8: 3 x 256 B stretch tables, each 256-aligned (1 KB reserved to absorb any base alignment)
+  // uint16: 3 x lars_stretch_u16 (guess parameters + 258 thresholds = 1040 B each)
+  static constexpr int OFF_LUT = 0;
+  static constexpr int OFF_CMAP = (BPS == 1) ? 1024 : 3136;      // 3 x 257 words
   static constexpr int OFF_HIST = OFF_CMAP + 3104;               // 3 x 65 rows x 32 lanes x 4 B
   static constexpr int OFF_IN = OFF_HIST + 3 * K2_HIST_ROWS * 128;
   static constexpr int OFF_OUT = OFF_IN + K2_IN_STAGES * IN_BYTES;
@@ -146,16 +148,50 @@ __device__ __forceinline__ uint32_t pack4(uint32_t b0, uint32_t b1, uint32_t b2,
   return prmt(prmt(b0, b1, 0x0040), prmt(b2, b3, 0x0040), 0x5410);
 }
 
-template <int C, bool FULL>
+// uint16 sample -> white-balanced uint8: float guess of the stretch, then a +-1 correction against
+// the monotone thresholds thr[k] = smallest v with LUT(v) >= k (exact: the thresholds were derived
+// from the reference's fp64 chain on all 65,536 values).
+__device__ __forceinline__ uint32_t stretch_u16(uint32_t v, const lars_stretch_u16* st) {
+  float t = (lars_small_int_to_float((int)v) - st->lo) * st->scale;
+  t = fminf(fmaxf(t, 0.0f), 255.0f);
+  int g = (int)(lars_f2u(t + LARS_MAGIC_F) - LARS_MAGIC_U);   // round to nearest: a guess is enough
+  while (v < st->thr[g]) --g;          // thr[0] == 0 stops the descent
+  while (v >= st->thr[g + 1]) ++g;     // thr[256] == 65536 stops the ascent
+  return (uint32_t)g;
+}
+
+template <int C, int BPS, bool FULL>
 __device__ __forceinline__ void k2_process_tile(const K2Params& p, uint8_t* smem, uint32_t smem_base,
                                                 int in_stage, int out_stage, int tid, int lane,
                                                 long long frame, long long px0, int nvalid,
                                                 const K2ThreadConst& tc, bool stage_bytes, K2ThreadStats& st) {
-  using L = K2Smem<C>;
+  using L = K2Smem<C, BPS>;
 
-  // ---- white balance: one byte-LUT gather per sample (process-images.py:438-441) ----
+  // ---- white balance: one stretch lookup per sample (process-images.py:438-441) ----
   uint32_t wb[3][4];
-  if (C == 3) {
+  if (BPS == 2) {
+    const lars_stretch_u16* st16 = reinterpret_cast<const lars_stretch_u16*>(smem + L::OFF_LUT);
+    uint32_t w[2 * C];
+    if (C == 3) {
+      const uint2* in = reinterpret_cast<const uint2*>(smem + L::OFF_IN + in_stage * L::IN_BYTES) + 3 * tid;
+      const uint2 a = in[0], b = in[1], c = in[2];
+      w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y; w[4] = c.x; w[5] = c.y;
+    } else {
+      const uint4* in = reinterpret_cast<const uint4*>(smem + L::OFF_IN + in_stage * L::IN_BYTES) + 2 * tid;
+      const uint4 a = in[0], b = in[1];
+      w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_base + L::OFF_BAR + 8u * (K2_IN_STAGES + in_stage));  // stage consumed
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int sidx = j * C + c;                      // sample index within the 4-pixel group
+        const uint32_t word = w[sidx >> 1];
+        wb[c][j] = stretch_u16((sidx & 1) ? (word >> 16) : (word & 0xFFFFu), st16 + c);
+      }
+  } else if (C == 3) {
     const uint32_t* in = reinterpret_cast<const uint32_t*>(smem + L::OFF_IN + in_stage * L::IN_BYTES) + 3 * tid;
     const uint32_t w0 = in[0], w1 = in[1], w2 = in[2];
     __syncwarp();
@@ -295,9 +331,9 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-template <int C>
-__global__ void __launch_bounds__(K2_THREADS, 2) fused_index_u8_kernel(const K2Params p) {
-  using L = K2Smem<C>;
+template <int C, int BPS>
+__global__ void __launch_bounds__(K2_THREADS, 2) fused_index_kernel(const K2Params p) {
+  using L = K2Smem<C, BPS>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -370,11 +406,11 @@ __global__ void __launch_bounds__(K2_THREADS, 2) fused_index_u8_kernel(const K2P
         const long long px0 = tile * K2_TILE_PX;
         const long long rem = p.n_pixels - px0;
         const uint32_t nvalid = rem < K2_TILE_PX ? (uint32_t)rem : (uint32_t)K2_TILE_PX;
-        const uint32_t bytes = (nvalid * C + 15u) & ~15u;
+        const uint32_t bytes = (nvalid * (C * BPS) + 15u) & ~15u;
         mbar_wait(bar_base + 8u * (K2_IN_STAGES + s), phase ^ 1u);
         mbar_arrive_expect_tx(bar_base + 8u * s, bytes);
         tma_load_1d_hint(smem_base + L::OFF_IN + s * L::IN_BYTES,
-                         p.src + frame * p.src_frame_stride + px0 * C, bytes, bar_base + 8u * s, pol);
+                         p.src + frame * p.src_frame_stride + px0 * (C * BPS), bytes, bar_base + 8u * s, pol);
         if (++s == K2_IN_STAGES) { s = 0; phase ^= 1u; }
         if (++tile == p.tiles_per_frame) { tile = 0; ++frame; }
       }
@@ -417,7 +453,11 @@ __global__ void __launch_bounds__(K2_THREADS, 2) fused_index_u8_kernel(const K2P
     const long long span_end = (frame_t0 + p.tiles_per_frame < t_end) ? frame_t0 + p.tiles_per_frame : t_end;
 
     named_bar_sync(1, K2_CONSUMERS);  // previous span's flush has finished reading hist / red / LUT users
-    if (p.wb_lut) {
+    if (BPS == 2) {
+      const uint32_t* gl = reinterpret_cast<const uint32_t*>(p.wb_lut + frame * p.lut_frame_stride);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(smem + L::OFF_LUT);
+      for (int i = tid; i < 3 * (int)(sizeof(lars_stretch_u16) / 4); i += K2_CONSUMERS) dst[i] = gl[i];
+    } else if (p.wb_lut) {
       const uint8_t* gl = p.wb_lut + frame * p.lut_frame_stride;
       for (int i = tid; i < 3 * 256; i += K2_CONSUMERS) lut_s[i] = gl[i];
     } else {
@@ -428,8 +468,15 @@ __global__ void __launch_bounds__(K2_THREADS, 2) fused_index_u8_kernel(const K2P
 
     // shift K = index value of the frame's first pixel (same for every CTA of the frame)
     {
-      const uint8_t* f0 = p.src + frame * p.src_frame_stride;
-      const int r = lut_s[f0[0]], g = lut_s[256 + f0[1]], n = lut_s[512 + f0[2]];
+      int r, g, n;
+      if (BPS == 2) {
+        const uint16_t* f0 = reinterpret_cast<const uint16_t*>(p.src + frame * p.src_frame_stride);
+        const lars_stretch_u16* st16 = reinterpret_cast<const lars_stretch_u16*>(smem + L::OFF_LUT);
+        r = (int)stretch_u16(f0[0], st16); g = (int)stretch_u16(f0[1], st16 + 1); n = (int)stretch_u16(f0[2], st16 + 2);
+      } else {
+        const uint8_t* f0 = p.src + frame * p.src_frame_stride;
+        r = lut_s[f0[0]]; g = lut_s[256 + f0[1]]; n = lut_s[512 + f0[2]];
+      }
       tc.kshift[0] = lars_ratio_pair_u8(n, r);
       tc.kshift[1] = lars_ratio_pair_u8(n, g);
     }
@@ -446,9 +493,9 @@ __global__ void __launch_bounds__(K2_THREADS, 2) fused_index_u8_kernel(const K2P
       if (stage_bytes) mbar_wait(bar_out_empty + 8u * s_out, ph_out ^ 1u);  // staging buffer drained
       mbar_wait(bar_base + 8u * s_in, ph_in);                               // tile landed
       if (nvalid == K2_TILE_PX)
-        k2_process_tile<C, true>(p, smem, smem_base, s_in, s_out, tid, lane, frame, px0, nvalid, tc, stage_bytes, st);
+        k2_process_tile<C, BPS, true>(p, smem, smem_base, s_in, s_out, tid, lane, frame, px0, nvalid, tc, stage_bytes, st);
       else
-        k2_process_tile<C, false>(p, smem, smem_base, s_in, s_out, tid, lane, frame, px0, nvalid, tc, stage_bytes, st);
+        k2_process_tile<C, BPS, false>(p, smem, smem_base, s_in, s_out, tid, lane, frame, px0, nvalid, tc, stage_bytes, st);
       if (stage_bytes) {
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk-copy engine
         __syncwarp();

@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import FusedArgs, INDEX_STATS_DTYPE, LarsError, PIXEL_GROUP, check
+from ._lib import FusedArgs, INDEX_STATS_DTYPE, LarsError, PIXEL_GROUP, STRETCH_U16_BYTES, check
 
 INDEX_TYPES = ("NDVI", "GNDVI", "NDWI")                 # process-images.py:466,472,478
 DEFAULT_THRESHOLDS = (0.2, 0.2, 0.0)                    # process-images.py:498-504
@@ -48,6 +48,7 @@ class DeviceFrames:
     n_pixels: int
     channels: int
     shape: tuple  # (H, W)
+    sample_bytes: int = 1   # 1 = uint8 samples, 2 = little-endian uint16 samples
 
     @property
     def n_frames(self) -> int:
@@ -132,24 +133,25 @@ class Engine:
 
     # ------------------------------------------------------------------ device-resident API
     def alloc_frames(self, n_frames: int, height: int, width: int, channels: int = 3,
-                     stream=None) -> DeviceFrames:
+                     stream=None, sample_bytes: int = 1) -> DeviceFrames:
         n_px = height * width
-        data = self._alloc((n_frames, _pad_px(n_px) * channels), torch.uint8, stream)
-        return DeviceFrames(data, n_px, channels, (height, width))
+        data = self._alloc((n_frames, _pad_px(n_px) * channels * sample_bytes), torch.uint8, stream)
+        return DeviceFrames(data, n_px, channels, (height, width), sample_bytes)
 
     def upload(self, frames: Sequence[np.ndarray], stream: Optional[torch.cuda.Stream] = None) -> DeviceFrames:
         """Copy equally-shaped HWC uint8 host frames into a padded device batch."""
         first = np.asarray(frames[0])
         h, w, c = first.shape
         s = stream or self.stream()
-        dev = self.alloc_frames(len(frames), h, w, c, s)
-        nbytes = h * w * c
+        sb = first.dtype.itemsize
+        dev = self.alloc_frames(len(frames), h, w, c, s, sample_bytes=sb)
+        nbytes = h * w * c * sb
         with torch.cuda.stream(s):
             for i, fr in enumerate(frames):
                 fr = np.ascontiguousarray(fr)
-                if fr.shape != first.shape or fr.dtype != np.uint8:
-                    raise ValueError("all frames of a batch must share shape and be uint8")
-                src = torch.from_numpy(fr.reshape(-1))
+                if fr.shape != first.shape or fr.dtype != first.dtype:
+                    raise ValueError("all frames of a batch must share shape and dtype")
+                src = torch.from_numpy(fr.reshape(-1).view(np.uint8))
                 dev.data[i, :nbytes].copy_(src, non_blocking=True)
         return dev
 
@@ -191,6 +193,24 @@ class Engine:
             res.stats = self._alloc((F, 3, INDEX_STATS_DTYPE.itemsize), torch.uint8, s)
         return res
 
+    def wb_stretch_u16(self, frames: DeviceFrames, quantiles=DEFAULT_QUANTILES, shared: bool = False,
+                       stream=None):
+        """uint16 Pass 1: two-level radix histogram -> exact percentiles -> per-channel stretch
+        thresholds.  Returns (stretch [S, 3, 1040] uint8, percentiles [S, 3, 2] float64)."""
+        s = stream or self.stream()
+        n_sets = 1 if shared else frames.n_frames
+        stretch = self._alloc((n_sets, 3, STRETCH_U16_BYTES), torch.uint8, s)
+        pct = self._alloc((n_sets, 3, 2), torch.float64, s)
+        ws_bytes = int(self.lib.lars_wb_u16_workspace_bytes(n_sets))
+        ws = self._alloc((ws_bytes,), torch.uint8, s)
+        with torch.cuda.device(self.device):
+            check(self.lib.lars_wb_stretch_build_u16(frames.data.data_ptr(), frames.n_frames, frames.n_pixels,
+                                                     frames.channels, frames.stride_bytes, float(quantiles[0]),
+                                                     float(quantiles[1]), stretch.data_ptr(), pct.data_ptr(),
+                                                     ws.data_ptr(), ws_bytes, 1 if shared else 0, s.cuda_stream),
+                  "lars_wb_stretch_build_u16")
+        return stretch, pct
+
     def fused(self, frames: DeviceFrames, lut: Optional[torch.Tensor], outputs=ALL_OUTPUTS,
               indices=INDEX_TYPES, bins: int = DEFAULT_BINS, thresholds=DEFAULT_THRESHOLDS,
               cmaps=DEFAULT_CMAPS, rgb_indices=None, out: Optional[DeviceOutputs] = None,
@@ -219,7 +239,7 @@ class Engine:
             if lut.shape[0] not in (1, F):
                 raise ValueError("lut must hold one set per frame or a single shared set")
             a.wb_lut = lut.data_ptr()
-            a.lut_frame_stride = 768 if lut.shape[0] == F else 0
+            a.lut_frame_stride = lut.stride(0) if lut.shape[0] == F else 0
         if "wb" in outputs:
             if res.wb is None:
                 res.wb = self._alloc((F, ppx * ch), torch.uint8, s)
@@ -247,7 +267,10 @@ class Engine:
             res._keep = [ws]
             a.stats, a.workspace, a.workspace_bytes = res.stats.data_ptr(), ws.data_ptr(), ws_bytes
         with torch.cuda.device(self.device):
-            check(self.lib.lars_fused_index_u8(C.byref(a), s.cuda_stream), "lars_fused_index_u8")
+            if frames.sample_bytes == 2:
+                check(self.lib.lars_fused_index_u16(C.byref(a), s.cuda_stream), "lars_fused_index_u16")
+            else:
+                check(self.lib.lars_fused_index_u8(C.byref(a), s.cuda_stream), "lars_fused_index_u8")
         return res
 
     def process_device(self, frames: DeviceFrames, outputs=ALL_OUTPUTS, white_balance: bool = True,
@@ -262,6 +285,14 @@ class Engine:
         s = stream or self.stream()
         res = out or DeviceOutputs(frames=frames)
         lut = None
+        if frames.sample_bytes == 2:
+            if not white_balance:
+                raise LarsError("uint16 frames go through the white-balance stretch (uint8 out); "
+                                "there is no identity mode for them")
+            if hist_hook is not None:
+                raise LarsError("tile-sharded uint16 mosaics across GPUs are not supported yet")
+            res.wb_lut, res.wb_pct = self.wb_stretch_u16(frames, quantiles, tiles_of_one_image, s)
+            return self.fused(frames, res.wb_lut, outputs=outputs, out=res, stream=s, **kw)
         if white_balance:
             res.wb_hist = self.wb_histogram(frames, shared=tiles_of_one_image, stream=s)
             if hist_hook is not None:
@@ -321,7 +352,7 @@ class Engine:
             if stats is not None:
                 d["stats"] = stats[f]
             if h_pct is not None:
-                d["percentiles"] = h_pct[f].numpy().copy()
+                d["percentiles"] = h_pct[f if h_pct.shape[0] == F else 0].numpy().copy()
             results.append(d)
         return results
 
@@ -424,8 +455,8 @@ class Engine:
             raise IndexError(f"index 2 is out of bounds for axis 2 with size {img.shape[2]}")
         if img.shape[2] > 4:
             raise LarsError(f"frames with {img.shape[2]} channels are not supported (3 or 4)")
-        if img.dtype != np.uint8:
-            raise LarsError(f"dtype {img.dtype} is not supported by the uint8 path")
+        if img.dtype not in (np.uint8, np.uint16):
+            raise LarsError(f"dtype {img.dtype} is not supported (uint8 or uint16 frames)")
         return img
 
     def analyze_batch(self, frames: Sequence[np.ndarray], outputs=ALL_OUTPUTS, white_balance=True,

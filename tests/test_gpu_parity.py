@@ -126,9 +126,7 @@ def test_gpu_against_reference_golden_vectors(engine, golden):
     g = golden["frames"]
     names = sorted({k.split("/")[0] for k in g.files})
     for name in names:
-        img = g[f"{name}/input"]
-        if img.dtype != np.uint8:
-            continue
+        img = g[f"{name}/input"]          # includes one uint16 frame
         res = engine.analyze_frame(img)
         assert np.array_equal(res["wb"], g[f"{name}/wb"]), name
         assert np.array_equal(res["percentiles"], g[f"{name}/percentiles"]), name
@@ -381,3 +379,56 @@ def test_mosaic_tiles_share_global_percentiles(engine):
         assert moment_close(st[t]["std"], std, std)
     assert np.array_equal(out[0]["percentiles"], np.array([np.percentile(img[:, :, c].astype(np.float32), (2, 98))
                                                            for c in range(3)]))
+
+
+# ------------------------------------------------------------------------------------- uint16 frames
+def _u16_frames():
+    rng = np.random.default_rng(77)
+    frames = {}
+    frames["veg_u16_240x320"] = synth.vegetation_frame(201, 240, 320, np.uint16)
+    frames["veg_u16_odd_97x131"] = synth.vegetation_frame(202, 97, 131, np.uint16)
+    frames["one_pixel"] = np.array([[[300, 40000, 7]]], np.uint16)
+    dark = (synth.vegetation_frame(203, 64, 96, np.uint16) >> 8).astype(np.uint16)       # all in high byte 0
+    frames["dark_one_bucket"] = dark
+    narrow = (20000 + rng.integers(0, 40, (50, 70, 3))).astype(np.uint16)                 # steep stretch
+    frames["narrow_range"] = narrow
+    const = synth.vegetation_frame(204, 40, 60, np.uint16)
+    const[:, :, 2] = 12345                                                                # p98 == p2
+    frames["constant_channel"] = const
+    frames["all_zero"] = np.zeros((9, 11, 3), np.uint16)
+    frames["full_range"] = rng.integers(0, 65536, (120, 150, 3)).astype(np.uint16)
+    straddle = np.zeros((10, 10, 3), np.uint16)                                           # ranks straddle buckets
+    straddle[..., 0] = np.repeat(np.array([255, 256, 511, 512, 65535], np.uint16), 20).reshape(10, 10)
+    straddle[..., 1] = np.arange(100, dtype=np.uint16).reshape(10, 10) * 655
+    straddle[..., 2] = 65535 - np.arange(100, dtype=np.uint16).reshape(10, 10) * 3
+    frames["straddle_buckets"] = straddle
+    frames["rgba_u16"] = synth.vegetation_frame(205, 33, 47, np.uint16, channels=4)
+    return frames
+
+
+def test_uint16_frames_against_oracle(engine):
+    for name, img in _u16_frames().items():
+        res = engine.analyze_frame(img)
+        want = oracle_frame(img)
+        assert res["wb"].dtype == np.uint8 and np.array_equal(res["wb"], want["wb"]), name
+        want_pct = np.array([np.percentile(img[:, :, c].astype(np.float32), (2, 98)) for c in range(3)])
+        assert np.array_equal(res["percentiles"], want_pct), name
+        for t in INDEX_TYPES:
+            assert np.array_equal(res["maps"][t].view(np.uint32), want["maps"][t].view(np.uint32)), (name, t)
+            assert np.array_equal(res["rgb"][t], want["rgb"][t]), (name, t)
+            assert np.array_equal(res["stats"][t]["hist"], want["stats"][t]["hist"]), (name, t)
+            assert res["stats"][t]["count_above"] == want["stats"][t]["count_above"], (name, t)
+
+
+def test_uint16_batch_config3_shape(engine):
+    """BASELINE config 3 in miniature: a batch of 16-bit frames, all indices + histograms."""
+    frames = [synth.vegetation_frame(300 + i, 152, 228, np.uint16) for i in range(9)]
+    res = engine.analyze_batch(frames, outputs=("wb", "maps", "stats"))
+    for i in (0, 4, 8):
+        want = oracle_frame(frames[i])
+        assert np.array_equal(res[i]["wb"], want["wb"])
+        for t in INDEX_TYPES:
+            assert np.array_equal(res[i]["maps"][t].view(np.uint32), want["maps"][t].view(np.uint32))
+            assert np.array_equal(res[i]["stats"][t]["hist"], want["stats"][t]["hist"])
+            std = float(np.std(want["maps"][t]))
+            assert moment_close(res[i]["stats"][t]["mean"], float(np.mean(want["maps"][t])), std)
