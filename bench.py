@@ -50,12 +50,15 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--chunk", type=int, default=2, help="frames per pipeline chunk in the e2e path")
+    ap.add_argument("--dtype", default="u8", choices=["u8", "u16"],
+                    help="sample type of the synthetic frames (u16: 16-bit frames as in BASELINE config 3)")
     return ap.parse_args()
 
 
 def workload_name(a):
-    return (f"C2: {a.width}x{a.height} uint8 RGNir frames, white balance + NDVI/GNDVI/NDWI fp32 maps + "
-            f"statistics/histograms + colormap RGB; {a.frames} distinct frames per GPU per step")
+    tag = "C2" if (a.dtype == "u8" and a.width == 4000 and a.height == 3000) else "custom"
+    return (f"{tag}: {a.width}x{a.height} {'uint8' if a.dtype == 'u8' else 'uint16'} RGNir frames, white balance + "
+            f"NDVI/GNDVI/NDWI fp32 maps + statistics/histograms + colormap RGB; {a.frames} distinct frames per GPU per step")
 
 
 def measured_hbm_peak():
@@ -187,18 +190,24 @@ def run_reference(a):
 # ------------------------------------------------------------------------------------------
 # GPU side
 # ------------------------------------------------------------------------------------------
-def synth_frames_device(eng, n_frames, h, w, seed):
-    """Vegetation-like frames generated on the device: R~N(90,35) G~N(110,35) NIR~N(150,45)."""
+def synth_frames_device(eng, n_frames, h, w, seed, sample_bytes=1):
+    """Vegetation-like frames generated on the device: R~N(90,35) G~N(110,35) NIR~N(150,45)
+    (x257 for uint16)."""
     import torch
-    frames = eng.alloc_frames(n_frames, h, w, 3)
+    frames = eng.alloc_frames(n_frames, h, w, 3, sample_bytes=sample_bytes)
     npx = h * w
     g = torch.Generator(device=eng.device)
     g.manual_seed(seed)
-    mean = torch.tensor([90.0, 110.0, 150.0], device=eng.device)
-    std = torch.tensor([35.0, 35.0, 45.0], device=eng.device)
+    scale = 1.0 if sample_bytes == 1 else 257.0
+    top = 255 if sample_bytes == 1 else 65535
+    mean = torch.tensor([90.0, 110.0, 150.0], device=eng.device) * scale
+    std = torch.tensor([35.0, 35.0, 45.0], device=eng.device) * scale
     for f in range(n_frames):
-        x = torch.randn((npx, 3), generator=g, device=eng.device) * std + mean
-        frames.data[f, :npx * 3] = x.round_().clamp_(0, 255).to(torch.uint8).reshape(-1)
+        x = (torch.randn((npx, 3), generator=g, device=eng.device) * std + mean).round_().clamp_(0, top)
+        if sample_bytes == 1:
+            frames.data[f, :npx * 3] = x.to(torch.uint8).reshape(-1)
+        else:
+            frames.data[f, :npx * 6] = x.to(torch.int32).to(torch.int16).reshape(-1).view(torch.uint8)
         del x
     torch.cuda.synchronize(eng.device)
     return frames
@@ -219,14 +228,18 @@ def run_ours(a):
     s = eng.stream()
     F, h, w = a.frames, a.height, a.width
     npx = h * w
-    frames = synth_frames_device(eng, F, h, w, seed=2 + rank)
+    sb = 1 if a.dtype == "u8" else 2
+    frames = synth_frames_device(eng, F, h, w, seed=2 + rank, sample_bytes=sb)
     res = eng.alloc_outputs(frames, ALL_OUTPUTS, s)
 
     fused_ms = []
 
     def step(timed):
-        hist = eng.wb_histogram(frames, stream=s)
-        lut, _pct = eng.wb_lut(hist, stream=s)
+        if sb == 2:
+            lut, _pct = eng.wb_stretch_u16(frames, stream=s)
+        else:
+            hist = eng.wb_histogram(frames, stream=s)
+            lut, _pct = eng.wb_lut(hist, stream=s)
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(s)
@@ -268,7 +281,7 @@ def run_ours(a):
 
     # ---- end to end through the host-array API (pinned buffers, H2D + D2H in the timed region)
     e2e = None
-    if not a.no_e2e:
+    if not a.no_e2e and sb == 1:
         host_in = torch.empty((F, npx * 3), dtype=torch.uint8, pin_memory=True)
         host_in.copy_(frames.data[:, :npx * 3])
         torch.cuda.synchronize()
@@ -296,21 +309,23 @@ def run_ours(a):
     if rank != 0:
         return
     peak, peak_src = measured_hbm_peak()
-    launch_bytes = U8_PASS2_BYTES_PER_PX * F * npx
+    pass1_b = U8_PASS1_BYTES_PER_PX if sb == 1 else 12        # u16: two-level histogram reads the frame twice
+    pass2_b = U8_PASS2_BYTES_PER_PX if sb == 1 else 30        # u16: read 6, write 3 + 12 + 9
+    launch_bytes = pass2_b * F * npx
     achieved = launch_bytes / (k2_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8", "data": "synthetic",
+        "dtype": a.dtype, "data": "synthetic",
         "config": {"workload": workload_name(a), "frames_per_gpu": F, "height": h, "width": w,
-                   "l2": f"inputs larger than L2 ({F * npx * 3 / 1e6:.0f} MB raw per GPU per step)",
+                   "l2": f"inputs larger than L2 ({F * npx * 3 * sb / 1e6:.0f} MB raw per GPU per step)",
                    "parallelism": f"frames sharded over {world} GPU(s), one dataset-statistics all-gather per step"
                    if world > 1 else "single GPU"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "kernel": "fused_index_u8_kernel<3> (+ its statistics finalize)",
-                     "algorithmic_bytes_per_px": U8_PASS2_BYTES_PER_PX, "ms_per_launch": k2_ms,
+                     "algorithmic_bytes_per_px": pass2_b, "ms_per_launch": k2_ms,
                      "peak_source": peak_src,
-                     "whole_step_GBps": (U8_PASS1_BYTES_PER_PX + U8_PASS2_BYTES_PER_PX) * F * npx * a.steps
+                     "whole_step_GBps": (pass1_b + pass2_b) * F * npx * a.steps
                      / (ms * 1e-3) / 1e9},
         "clocks": clocks,
         # wb_hist, wb_lut_build, fused_index, fused_finalize, stats_merge (+1 merge after the all-gather)
@@ -319,7 +334,8 @@ def run_ours(a):
     if e2e is not None:
         line["e2e"] = e2e
     if world == 1 and not a.no_cpu_baseline:
-        sample = [frames.data[i, :npx * 3].cpu().numpy().reshape(h, w, 3) for i in range(min(a.cpu_frames, F))]
+        raw = [frames.data[i, :npx * 3 * sb].cpu().numpy() for i in range(min(a.cpu_frames, F))]
+        sample = [(r if sb == 1 else r.view(np.uint16)).reshape(h, w, 3) for r in raw]
         v, dt = cpu_baseline_single(sample)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": f"{len(sample)} of the step's {w}x{h} frames, sequential NumPy oracle port "

@@ -7,7 +7,7 @@ import subprocess
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "liblars_b200.so")
+LIB_PATH = os.environ.get("LARS_B200_LIB") or os.path.join(PKG_DIR, "liblars_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -38,11 +38,14 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the CUDA library if missing or older than its sources; return its path."""
-    if not force and not _stale():
-        return LIB_PATH
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH, *sources()]
+def build(force: bool = False, verbose: bool = False, defines=(), out_path: str = None) -> str:
+    """Compile the CUDA library if missing or older than its sources; return its path.
+    ``defines`` / ``out_path`` build tuning variants next to the default library."""
+    if out_path is None:
+        out_path = LIB_PATH
+        if not force and not _stale():
+            return LIB_PATH
+    cmd = [find_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", out_path, *sources()]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     proc = subprocess.run(cmd, capture_output=True, text=True)
@@ -50,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
     if verbose:
         print(proc.stderr)
-    return LIB_PATH
+    return out_path
 
 
 if __name__ == "__main__":

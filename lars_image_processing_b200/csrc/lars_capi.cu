@@ -214,7 +214,7 @@ int lars_wb_lut_build_u8(const uint64_t* hist, int32_t n_sets, double q_lo, doub
 // Pass 2
 // ------------------------------------------------------------------------------------------
 static int fused_grid(int sm_count) {
-  int g = sm_count * 2;
+  int g = sm_count * lars::K2_CTAS_PER_SM;
   return g > lars::K2_MAX_GRID ? lars::K2_MAX_GRID : g;
 }
 

@@ -30,8 +30,18 @@ constexpr int K2_TILE_PX = 1024;            // pixels per pipeline tile
 constexpr int K2_CONSUMERS = 256;           // 4 pixels per consumer thread per tile
 constexpr int K2_CONSUMER_WARPS = K2_CONSUMERS / 32;
 constexpr int K2_THREADS = K2_CONSUMERS + 64;  // + TMA load warp + TMA store warp
-constexpr int K2_IN_STAGES = 4;
-constexpr int K2_OUT_STAGES = 3;
+#ifndef LARS_K2_IN_STAGES
+#define LARS_K2_IN_STAGES 4
+#endif
+#ifndef LARS_K2_OUT_STAGES
+#define LARS_K2_OUT_STAGES 3
+#endif
+#ifndef LARS_K2_CTAS_PER_SM
+#define LARS_K2_CTAS_PER_SM 2
+#endif
+constexpr int K2_IN_STAGES = LARS_K2_IN_STAGES;
+constexpr int K2_OUT_STAGES = LARS_K2_OUT_STAGES;
+constexpr int K2_CTAS_PER_SM = LARS_K2_CTAS_PER_SM;
 constexpr int K2_BINS_PAD = LARS_MAX_BINS;
 constexpr int K2_HIST_ROWS = LARS_MAX_BINS + 1;  // + the row that catches x == 1.0
 constexpr int K2_CMAP_SLOTS = 257;               // + the slot that catches x == 1.0
@@ -332,7 +342,7 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 template <int C, int BPS>
-__global__ void __launch_bounds__(K2_THREADS, 2) fused_index_kernel(const K2Params p) {
+__global__ void __launch_bounds__(K2_THREADS, K2_CTAS_PER_SM) fused_index_kernel(const K2Params p) {
   using L = K2Smem<C, BPS>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x;
