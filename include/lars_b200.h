@@ -52,6 +52,8 @@ extern "C" {
 
 #define LARS_DTYPE_U8 0
 #define LARS_DTYPE_U16 1
+#define LARS_DTYPE_F32 2
+#define LARS_DTYPE_F64 3
 
 /* Statistics of one index map of one frame (replaces analyze_index, process-images.py:492-513,
  * the inline statistics at :647-658 / :830-832, analyze_ndvi_statistics, process-ndvi.py:50-73,
@@ -191,6 +193,19 @@ int lars_index_planes_f32(const float* hi, const float* lo, int64_t n, float* ou
 /* Merge n_sets x 3 statistics records (per frame, or per rank after the NCCL all-gather) into
  * 3 dataset-wide records, in index order of the input -- the exchange step of SURVEY.md 8(e). */
 int lars_stats_merge(const lars_index_stats* in, int32_t n_sets, lars_index_stats* out, void* stream);
+
+/* Index map of an interleaved frame whose samples are not uint8 (calculate_index applies
+ * astype(float32) to whatever it is given, process-images.py:456-490).  dtype: LARS_DTYPE_U16,
+ * LARS_DTYPE_F32 or LARS_DTYPE_F64; index: LARS_NDVI / LARS_GNDVI / LARS_NDWI. */
+int lars_index_hwc(const void* src, int32_t dtype, int64_t n_pixels, int32_t channels, int32_t index,
+                   float* out, void* stream);
+
+/* Change detection between two white-balanced uint8 frames (create_change_detection_visualization,
+ * process-images.py:908-923 and :956): per-pixel index of both, diff = late - early (float32) and
+ * the 'bwr' colormap over [vmin, vmax] (reference: -0.5, 0.5).  early_map / late_map / rgb may be NULL. */
+int lars_index_change_u8(const uint8_t* early, const uint8_t* late, int64_t n_pixels, int32_t channels,
+                         int32_t index, float vmin, float vmax, float* early_map, float* late_map,
+                         float* diff, uint8_t* rgb, void* stream);
 
 #ifdef __cplusplus
 }

@@ -20,6 +20,8 @@ MAX_BINS = 64
 PIXEL_GROUP = 16
 STRETCH_U16_BYTES = 1040   # sizeof(lars_stretch_u16)
 CMAP_IDS = {"RdYlGn": 0, "RdYlBu": 1, "bwr": 2}
+INDEX_IDS = {"NDVI": 0, "GNDVI": 1, "NDWI": 2}
+DTYPE_IDS = {"uint8": 0, "uint16": 1, "float32": 2, "float64": 3}
 
 EXPORTED_SYMBOLS = (
     "lars_init", "lars_shutdown", "lars_last_error", "lars_abi_version", "lars_sm_count",
@@ -30,6 +32,7 @@ EXPORTED_SYMBOLS = (
     "lars_select_f32", "lars_colormap_f32", "lars_ndvi_f64_u8", "lars_index_planes_f32",
     "lars_stats_merge",
     "lars_wb_u16_workspace_bytes", "lars_wb_stretch_build_u16", "lars_fused_index_u16",
+    "lars_index_hwc", "lars_index_change_u8",
 )
 
 
@@ -122,6 +125,10 @@ def _declare(lib):
     lib.lars_wb_stretch_build_u16.restype = C.c_int
     lib.lars_fused_index_u16.argtypes = [C.POINTER(FusedArgs), vp]
     lib.lars_fused_index_u16.restype = C.c_int
+    lib.lars_index_hwc.argtypes = [vp, i32, i64, i32, i32, vp, vp]
+    lib.lars_index_hwc.restype = C.c_int
+    lib.lars_index_change_u8.argtypes = [vp, vp, i64, i32, i32, f32, f32, vp, vp, vp, vp, vp]
+    lib.lars_index_change_u8.restype = C.c_int
 
 
 def load():

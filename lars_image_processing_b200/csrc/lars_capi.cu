@@ -527,4 +527,64 @@ int lars_wb_stretch_build_u16(const uint16_t* src, int32_t n_frames, int64_t n_p
   return LARS_OK;
 }
 
+static bool index_channels(int index, int* hi_c, int* lo_c) {
+  switch (index) {
+    case LARS_NDVI: *hi_c = 2; *lo_c = 0; return true;
+    case LARS_GNDVI: *hi_c = 2; *lo_c = 1; return true;
+    case LARS_NDWI: *hi_c = 1; *lo_c = 2; return true;
+    default: return false;
+  }
+}
+
+int lars_index_hwc(const void* src, int32_t dtype, int64_t n_pixels, int32_t channels, int32_t index,
+                   float* out, void* stream) {
+  DeviceState* st = nullptr;
+  int rc = current_state(&st);
+  if (rc != LARS_OK) return rc;
+  if (!src || !out) return fail(LARS_ERR_INVALID, "lars_index_hwc: NULL pointer");
+  if (n_pixels < 1 || channels < 3) return fail(LARS_ERR_INVALID, "lars_index_hwc: need >= 1 pixel and >= 3 channels");
+  int hi_c, lo_c;
+  if (!index_channels(index, &hi_c, &lo_c)) return fail(LARS_ERR_INVALID, "lars_index_hwc: unknown index %d", index);
+  long long want = (n_pixels + 255) / 256;
+  int grid = st->sm_count * 8;
+  if (want < grid) grid = (int)want;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (dtype) {
+    case LARS_DTYPE_U16:
+      lars::index_hwc_kernel<uint16_t><<<grid, 256, 0, s>>>(static_cast<const uint16_t*>(src), out, n_pixels, channels, hi_c, lo_c);
+      break;
+    case LARS_DTYPE_F32:
+      lars::index_hwc_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(src), out, n_pixels, channels, hi_c, lo_c);
+      break;
+    case LARS_DTYPE_F64:
+      lars::index_hwc_kernel<double><<<grid, 256, 0, s>>>(static_cast<const double*>(src), out, n_pixels, channels, hi_c, lo_c);
+      break;
+    default:
+      return fail(LARS_ERR_UNSUPPORTED, "lars_index_hwc: dtype %d (uint8 frames go through lars_fused_index_u8)", dtype);
+  }
+  LARS_CUDA(cudaGetLastError());
+  return LARS_OK;
+}
+
+int lars_index_change_u8(const uint8_t* early, const uint8_t* late, int64_t n_pixels, int32_t channels,
+                         int32_t index, float vmin, float vmax, float* early_map, float* late_map,
+                         float* diff, uint8_t* rgb, void* stream) {
+  DeviceState* st = nullptr;
+  int rc = current_state(&st);
+  if (rc != LARS_OK) return rc;
+  if (!early || !late || !diff) return fail(LARS_ERR_INVALID, "lars_index_change_u8: NULL pointer");
+  if (n_pixels < 1 || channels < 3) return fail(LARS_ERR_INVALID, "lars_index_change_u8: need >= 1 pixel and >= 3 channels");
+  if (!(vmax > vmin)) return fail(LARS_ERR_INVALID, "lars_index_change_u8: vmax must exceed vmin");
+  lars::ChangeParams p;
+  if (!index_channels(index, &p.hi_c, &p.lo_c)) return fail(LARS_ERR_INVALID, "lars_index_change_u8: unknown index %d", index);
+  p.early = early; p.late = late; p.early_map = early_map; p.late_map = late_map; p.diff = diff; p.rgb = rgb;
+  p.cmap = st->cmaps + LARS_CMAP_BWR * 256; p.n = n_pixels; p.channels = channels; p.vmin = vmin; p.vmax = vmax;
+  long long want = (n_pixels + 255) / 256;
+  int grid = st->sm_count * 8;
+  if (want < grid) grid = (int)want;
+  lars::index_change_u8_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  LARS_CUDA(cudaGetLastError());
+  return LARS_OK;
+}
+
 }  // extern "C"

@@ -436,4 +436,55 @@ __global__ void __launch_bounds__(LARS_MAX_BINS) stats_merge_kernel(const lars_i
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// K8: index map of an interleaved frame of any sample type (calculate_index on a frame that is
+// not uint8, process-images.py:456-490: astype(float32), ratio, clip).  hi_c / lo_c select the
+// channels: NDVI (2,0), GNDVI (2,1), NDWI (1,2).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) index_hwc_kernel(const T* __restrict__ src, float* __restrict__ out, long long n,
+                                                        int channels, int hi_c, int lo_c) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const T* px = src + i * channels;
+    out[i] = lars_ratio_clip_f32((float)px[hi_c], (float)px[lo_c]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K9: change detection (process-images.py:908-923, :956): index of two white-balanced uint8
+// frames, diff = late - early in float32, 'bwr' colormap over [-0.5, 0.5].
+// ------------------------------------------------------------------------------------------
+struct ChangeParams {
+  const uint8_t* early;
+  const uint8_t* late;
+  float* early_map;     // optional
+  float* late_map;      // optional
+  float* diff;          // required
+  uint8_t* rgb;         // optional [n][3]
+  const uint32_t* cmap; // bwr, packed
+  long long n;
+  int channels, hi_c, lo_c;
+  float vmin, vmax;
+};
+
+__global__ void __launch_bounds__(256) index_change_u8_kernel(const ChangeParams p) {
+  __shared__ uint32_t cm[256];
+  cm[threadIdx.x] = p.cmap[threadIdx.x];
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
+    const uint8_t* e = p.early + i * p.channels;
+    const uint8_t* l = p.late + i * p.channels;
+    const float xe = lars_ratio_pair_u8((int)e[p.hi_c], (int)e[p.lo_c]);
+    const float xl = lars_ratio_pair_u8((int)l[p.hi_c], (int)l[p.lo_c]);
+    const float d = LARS_FSUB(xl, xe);
+    if (p.early_map) p.early_map[i] = xe;
+    if (p.late_map) p.late_map[i] = xl;
+    p.diff[i] = d;
+    if (p.rgb) {
+      const uint32_t c = cm[lars_cmap_index_range(d, p.vmin, p.vmax)];
+      p.rgb[3 * i + 0] = (uint8_t)c; p.rgb[3 * i + 1] = (uint8_t)(c >> 8); p.rgb[3 * i + 2] = (uint8_t)(c >> 16);
+    }
+  }
+}
+
 }  // namespace lars

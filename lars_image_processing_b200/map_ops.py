@@ -183,3 +183,58 @@ def frame_statistics_rows(image_data_list, index_type: str) -> List[dict]:
                 f"{feature} Coverage (%)": st["coverage_pct"],
             }
     return [r for r in rows if r is not None]
+
+
+def index_generic(img_array, index_type: str) -> np.ndarray:
+    """calculate_index for frames that are not uint8 (process-images.py:456-490 applies
+    astype(float32) to any input).  uint16 / float32 / float64 convert on the GPU; other
+    numeric dtypes are cast to float32 first exactly as the reference's first line does."""
+    img = np.asarray(img_array)
+    if img.ndim != 3:
+        raise IndexError(f"too many indices for array: expected an HxWxC frame, got {img.ndim}-dimensional input")
+    if img.shape[2] < 3:
+        raise IndexError(f"index 2 is out of bounds for axis 2 with size {img.shape[2]}")
+    if img.dtype.name not in ("uint16", "float32", "float64"):
+        img = img.astype(np.float32)                                  # process-images.py:456
+    img = np.ascontiguousarray(img)
+    eng = get_engine()
+    s = eng.stream()
+    n = img.shape[0] * img.shape[1]
+    with torch.cuda.stream(s):
+        dev = torch.empty(img.nbytes, dtype=torch.uint8, device=eng.device)
+        dev.copy_(torch.from_numpy(img.reshape(-1).view(np.uint8)), non_blocking=True)
+        out = torch.empty(n, dtype=torch.float32, device=eng.device)
+        with torch.cuda.device(eng.device):
+            check(eng.lib.lars_index_hwc(dev.data_ptr(), _lib.DTYPE_IDS[img.dtype.name], n, img.shape[2],
+                                         _lib.INDEX_IDS[index_type], out.data_ptr(), s.cuda_stream), "lars_index_hwc")
+        host = out.cpu()
+    s.synchronize()
+    return host.numpy().reshape(img.shape[:2])
+
+
+def index_change(early_wb, late_wb, index_type: str, vmin: float = -0.5, vmax: float = 0.5) -> dict:
+    """Change detection between two white-balanced uint8 frames of equal shape
+    (process-images.py:908-923, :956): {'early', 'late', 'diff', 'rgb'}."""
+    e = np.ascontiguousarray(early_wb)
+    l = np.ascontiguousarray(late_wb)
+    if e.shape != l.shape or e.dtype != np.uint8 or l.dtype != np.uint8 or e.ndim != 3 or e.shape[2] < 3:
+        raise ValueError("change detection needs two uint8 HxWxC frames of equal shape")
+    eng = get_engine()
+    s = eng.stream()
+    n = e.shape[0] * e.shape[1]
+    with torch.cuda.stream(s):
+        de = torch.empty(e.size, dtype=torch.uint8, device=eng.device)
+        dl = torch.empty(l.size, dtype=torch.uint8, device=eng.device)
+        de.copy_(torch.from_numpy(e.reshape(-1)), non_blocking=True)
+        dl.copy_(torch.from_numpy(l.reshape(-1)), non_blocking=True)
+        maps = torch.empty((3, n), dtype=torch.float32, device=eng.device)
+        rgb = torch.empty(n * 3, dtype=torch.uint8, device=eng.device)
+        with torch.cuda.device(eng.device):
+            check(eng.lib.lars_index_change_u8(de.data_ptr(), dl.data_ptr(), n, e.shape[2], _lib.INDEX_IDS[index_type],
+                                               float(vmin), float(vmax), maps[0].data_ptr(), maps[1].data_ptr(),
+                                               maps[2].data_ptr(), rgb.data_ptr(), s.cuda_stream), "lars_index_change_u8")
+        h_maps, h_rgb = maps.cpu(), rgb.cpu()
+    s.synchronize()
+    hw = e.shape[:2]
+    return {"early": h_maps[0].numpy().reshape(hw), "late": h_maps[1].numpy().reshape(hw),
+            "diff": h_maps[2].numpy().reshape(hw), "rgb": h_rgb.numpy().reshape(hw + (3,))}

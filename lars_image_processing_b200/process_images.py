@@ -16,7 +16,8 @@ import numpy as np
 from .engine import (DEFAULT_BINS, INDEX_TYPES, get_engine)
 
 __all__ = ["fix_white_balance", "calculate_index", "analyze_index", "analyze_frame",
-           "calculate_index_statistics_by_timeframe", "create_index_visualization"]
+           "calculate_index_statistics_by_timeframe", "create_index_visualization",
+           "create_change_detection_visualization", "index_change"]
 
 
 def _feature_name(index_type: str) -> str:
@@ -43,6 +44,9 @@ def calculate_index(img_array, index_type):
     if img_array is None or img_array.size == 0:                     # :452-453
         return None
     _check_index_type(index_type)
+    if np.asarray(img_array).dtype != np.uint8:
+        from .map_ops import index_generic                            # astype(float32) chain, any dtype
+        return index_generic(img_array, index_type)
     res = get_engine().analyze_frame(img_array, outputs=("maps",), white_balance=False,
                                      indices=(index_type,))
     return res["maps"][index_type]
@@ -104,3 +108,31 @@ def create_index_visualization(index_array, index_type):
     from .map_ops import colormap_map
     cmap = "RdYlBu" if index_type == "NDWI" else "RdYlGn"
     return Image.fromarray(colormap_map(index_array, cmap, -1.0, 1.0))
+
+
+def index_change(early_img, late_img, index_type, white_balance: bool = True):
+    """Per-pixel products of change detection (process-images.py:885-989): index maps of both
+    dates, ``late - early`` and its 'bwr' image over [-0.5, 0.5].  Frames are white-balanced
+    first unless ``white_balance`` is False (the reference uses the cached 'corrected_array').
+    Image registration (``align_images``, :515-565) is out of scope: pass aligned frames."""
+    _check_index_type(index_type)
+    from .map_ops import index_change as _change
+    if white_balance:
+        wb = get_engine().analyze_batch([early_img, late_img], outputs=("wb",))
+        early_img, late_img = wb[0]["wb"], wb[1]["wb"]
+    return _change(early_img, late_img, index_type)
+
+
+def create_change_detection_visualization(image_pair, index_type):
+    """process-images.py:885-989 -- returns the 'bwr' change image (PIL) instead of the reference's
+    three-panel matplotlib figure; ``None`` for an invalid pair as in the reference (:888-889)."""
+    if not image_pair or len(image_pair) != 2:
+        return None
+    from PIL import Image
+    frames = []
+    for d in image_pair:
+        cached = d.get("corrected_array")
+        frames.append(cached if cached is not None else fix_white_balance(d["array"]))
+    if frames[0] is None or frames[1] is None:
+        return None
+    return Image.fromarray(index_change(frames[0], frames[1], index_type, white_balance=False)["rgb"])

@@ -432,3 +432,42 @@ def test_uint16_batch_config3_shape(engine):
             assert np.array_equal(res[i]["stats"][t]["hist"], want["stats"][t]["hist"])
             std = float(np.std(want["maps"][t]))
             assert moment_close(res[i]["stats"][t]["mean"], float(np.mean(want["maps"][t])), std)
+
+
+# ------------------------------------------------------------------------------------- next rows
+def test_calculate_index_on_non_uint8_frames(engine):
+    from lars_image_processing_b200 import process_images as pi
+    rng = np.random.default_rng(31)
+    u16 = synth.vegetation_frame(400, 61, 83, np.uint16)
+    f32 = rng.uniform(0, 255, (40, 50, 3)).astype(np.float32)
+    f32[0, 0] = 0
+    f64 = rng.uniform(0, 1, (17, 23, 4))
+    i32 = rng.integers(0, 1000, (9, 9, 3)).astype(np.int32)
+    for img in (u16, f32, f64, i32):
+        for t in INDEX_TYPES:
+            got = pi.calculate_index(img, t)
+            want = o.calculate_index(img, t)
+            assert got.dtype == np.float32 and np.array_equal(got.view(np.uint32), want.view(np.uint32)), (img.dtype, t)
+
+
+def test_change_detection(engine):
+    from lars_image_processing_b200 import process_images as pi
+    a = synth.vegetation_frame(410, 90, 120)
+    b = synth.vegetation_frame(411, 90, 120)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        wa, wb_ = o.fix_white_balance_literal(a), o.fix_white_balance_literal(b)
+    for t in ("NDVI", "NDWI"):
+        res = pi.index_change(a, b, t)
+        ea, la = o.calculate_index(wa, t), o.calculate_index(wb_, t)
+        diff = la - ea                                                  # process-images.py:923
+        assert np.array_equal(res["early"].view(np.uint32), ea.view(np.uint32))
+        assert np.array_equal(res["late"].view(np.uint32), la.view(np.uint32))
+        assert np.array_equal(res["diff"].view(np.uint32), diff.view(np.uint32))
+        assert np.array_equal(res["rgb"], o.apply_colormap(diff, name="bwr", vmin=-0.5, vmax=0.5))
+    pair = [{"array": a, "corrected_array": wa}, {"array": b}]
+    img = pi.create_change_detection_visualization(pair, "NDVI")
+    assert img.size == (120, 90)
+    assert np.array_equal(np.array(img), o.apply_colormap(o.calculate_index(wb_, "NDVI") - o.calculate_index(wa, "NDVI"),
+                                                          name="bwr", vmin=-0.5, vmax=0.5))
+    assert pi.create_change_detection_visualization([pair[0]], "NDVI") is None
