@@ -125,17 +125,24 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # CPU side: the oracle port of the reference's NumPy path
 # ------------------------------------------------------------------------------------------
-def _cpu_one_frame(args):
-    seed, h, w = args
-    import warnings
-    import numpy as np  # noqa: F401
-    from oracle import oracle_np as o
+_CPU_FRAME = None
+
+
+def _cpu_worker_init(h, w):
+    """Each worker process builds its synthetic frame ONCE, outside any timed region."""
+    global _CPU_FRAME
     from oracle import synth
-    img = synth.vegetation_frame(seed, h, w)
+    _CPU_FRAME = synth.vegetation_frame(2 + os.getpid() % 1000, h, w)
+
+
+def _cpu_one_frame(_):
+    """The reference's NumPy path (oracle port) on this worker's cached frame."""
+    import warnings
+    from oracle import oracle_np as o
     t0 = time.perf_counter()
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        o.reference_cpu_path(img)
+        o.reference_cpu_path(_CPU_FRAME)
     return time.perf_counter() - t0
 
 
@@ -165,12 +172,12 @@ def run_reference(a):
     workers = max(1, min(cores, 64))
     ctx = mp.get_context("spawn")
     npx = a.height * a.width
-    with ctx.Pool(workers) as pool:
-        for w in range(max(1, min(a.warmup, 1))):
-            pool.map(_cpu_one_frame, [(9000 + i, a.height // 4, a.width // 4) for i in range(workers)])
+    with ctx.Pool(workers, initializer=_cpu_worker_init, initargs=(a.height, a.width)) as pool:
+        for _ in range(max(1, min(a.warmup, 1))):
+            pool.map(_cpu_one_frame, range(workers), chunksize=1)
         t0 = time.perf_counter()
-        for k in range(a.steps):
-            pool.map(_cpu_one_frame, [(2 + k * workers + i, a.height, a.width) for i in range(workers)])
+        for _ in range(a.steps):
+            pool.map(_cpu_one_frame, range(workers), chunksize=1)
         dt = time.perf_counter() - t0
     value = workers * a.steps * npx / dt / 1e6
     line = {

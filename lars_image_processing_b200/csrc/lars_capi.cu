@@ -35,6 +35,9 @@ int fail(int code, const char* fmt, ...) {
                   __FILE__, __LINE__);                                                    \
   } while (0)
 
+#ifndef LARS_L2_KEEP_BYTES
+#define LARS_L2_KEEP_BYTES (40ll << 20)   /* measured: ~one 36 MB frame survives between the passes */
+#endif
 constexpr int kMaxDevices = 64;
 struct DeviceState {
   bool ready = false;
@@ -180,6 +183,7 @@ int lars_wb_hist_u8(const uint8_t* src, int32_t n_frames, int64_t n_pixels, int3
   p.total_units = p.units_per_frame * n_frames;
   p.n_frames = n_frames;
   p.hist_set_stride = shared_hist ? 0 : 768;
+  p.keep_in_l2 = (frame_bytes * n_frames <= (long long)LARS_L2_KEEP_BYTES) ? 1 : 0;
   const long long target_ctas = 2ll * st->sm_count;  // 2 resident CTAs per SM (96 KB smem each)
   const int grid = (int)(p.total_units < target_ctas ? p.total_units : target_ctas);
   if (channels == 3)

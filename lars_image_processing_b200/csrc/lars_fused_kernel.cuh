@@ -6,10 +6,10 @@
 // (process-images.py:492-513, process-ndvi.py:65, :97).
 //
 // CTA = 8 consumer warps + 1 TMA-load warp + 1 TMA-store warp, persistent over a balanced
-// contiguous range of 1024-pixel tiles:
-//   load warp  : cp.async.bulk global->shared into a 4-stage ring (mbarrier full / empty)
-//   consumers  : 4 pixels per thread per tile; fp32 maps leave as coalesced 128-bit streaming
-//                stores; byte outputs (WB, 3 x RGB) are staged in a 3-stage shared ring
+// contiguous range of 2048-pixel tiles:
+//   load warp  : cp.async.bulk global->shared into a 3-stage ring (mbarrier full / empty)
+//   consumers  : 2 x 4 pixels per thread per 2048-pixel tile; fp32 maps leave as coalesced 128-bit streaming
+//                stores; byte outputs (WB, 3 x RGB) are staged in a 2-stage shared ring
 //   store warp : cp.async.bulk shared->global of the staged bytes (mbarrier full / empty), so
 //                no CTA-wide barrier sits on the consumers' critical path
 // Statistics: per-thread registers, lane-private shared histograms (bank == lane, conflict
@@ -26,19 +26,30 @@
 
 namespace lars {
 
-constexpr int K2_TILE_PX = 1024;            // pixels per pipeline tile
-constexpr int K2_CONSUMERS = 256;           // 4 pixels per consumer thread per tile
-constexpr int K2_CONSUMER_WARPS = K2_CONSUMERS / 32;
-constexpr int K2_THREADS = K2_CONSUMERS + 64;  // + TMA load warp + TMA store warp
+#ifndef LARS_K2_STORE_EVICT_FIRST
+#define LARS_K2_STORE_EVICT_FIRST 1   /* outputs carry an L2 evict-first policy (never re-read on the GPU) */
+#endif
+#ifndef LARS_K2_PREFETCH_TILES
+#define LARS_K2_PREFETCH_TILES 0    /* >0: the load warp pulls this many tiles into L2 in one burst */
+#endif
+#ifndef LARS_K2_GROUPS
+#define LARS_K2_GROUPS 2          /* 4-pixel groups per consumer thread per tile */
+#endif
 #ifndef LARS_K2_IN_STAGES
-#define LARS_K2_IN_STAGES 4
+#define LARS_K2_IN_STAGES 3
 #endif
 #ifndef LARS_K2_OUT_STAGES
-#define LARS_K2_OUT_STAGES 3
+#define LARS_K2_OUT_STAGES 2
 #endif
 #ifndef LARS_K2_CTAS_PER_SM
 #define LARS_K2_CTAS_PER_SM 2
 #endif
+constexpr int K2_CONSUMERS = 256;
+constexpr int K2_CONSUMER_WARPS = K2_CONSUMERS / 32;
+constexpr int K2_GROUPS = LARS_K2_GROUPS;
+constexpr int K2_GROUP_PX = 4 * K2_CONSUMERS;            // pixels one pass of the consumers covers
+constexpr int K2_TILE_PX = K2_GROUP_PX * K2_GROUPS;      // pixels per pipeline tile
+constexpr int K2_THREADS = K2_CONSUMERS + 64;            // + TMA load warp + TMA store warp
 constexpr int K2_IN_STAGES = LARS_K2_IN_STAGES;
 constexpr int K2_OUT_STAGES = LARS_K2_OUT_STAGES;
 constexpr int K2_CTAS_PER_SM = LARS_K2_CTAS_PER_SM;
@@ -89,7 +100,9 @@ struct K2Smem {
   static constexpr int OFF_CMAP = (BPS == 1) ? 1024 : 3136;      // 3 x 257 words
   static constexpr int OFF_HIST = OFF_CMAP + 3104;               // 3 x 65 rows x 32 lanes x 4 B
   static constexpr int OFF_IN = OFF_HIST + 3 * K2_HIST_ROWS * 128;
-  static constexpr int OFF_OUT = OFF_IN + K2_IN_STAGES * IN_BYTES;
+  // uint16 tiles are twice as large: two input stages keep two CTAs per SM resident
+  static constexpr int IN_STAGES = (BPS == 2) ? 2 : K2_IN_STAGES;
+  static constexpr int OFF_OUT = OFF_IN + IN_STAGES * IN_BYTES;
   static constexpr int OFF_RED = OFF_OUT + K2_OUT_STAGES * OUT_BYTES;
   static constexpr int RED_BYTES = K2_CONSUMER_WARPS * 16 * 8;
   static constexpr int OFF_BAR = OFF_RED + RED_BYTES;
@@ -122,6 +135,7 @@ struct K2ThreadConst {
   float half_bins, half_bins_bias_m05;
   float kshift[2];
   bool ndwi_by_sign;       // thresholds[2] == 0: count NDWI > 0 from the sign bit of GNDVI
+  uint64_t store_policy;   // L2 evict-first policy for the output streams
 };
 
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
@@ -170,42 +184,62 @@ __device__ __forceinline__ uint32_t stretch_u16(uint32_t v, const lars_stretch_u
   return (uint32_t)g;
 }
 
+// raw words of one 4-pixel group of one thread
+template <int C, int BPS>
+struct K2Raw {
+  uint32_t w[C * BPS];
+};
+
+template <int C, int BPS>
+__device__ __forceinline__ void k2_load_group(const uint8_t* in_group, int tid, K2Raw<C, BPS>& r) {
+  constexpr int NW = C * BPS;                      // 4 pixels * C samples * BPS bytes / 4
+  if (NW == 3) {
+    const uint32_t* in = reinterpret_cast<const uint32_t*>(in_group) + 3 * tid;
+    r.w[0] = in[0]; r.w[1] = in[1]; r.w[2] = in[2];
+  } else if (NW == 4) {
+    const uint4 v = *(reinterpret_cast<const uint4*>(in_group) + tid);
+    r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
+  } else if (NW == 6) {
+    const uint2* in = reinterpret_cast<const uint2*>(in_group) + 3 * tid;
+    const uint2 a = in[0], b = in[1], c = in[2];
+    r.w[0] = a.x; r.w[1] = a.y; r.w[2] = b.x; r.w[3] = b.y; r.w[4] = c.x; r.w[5] = c.y;
+  } else {
+    const uint4* in = reinterpret_cast<const uint4*>(in_group) + 2 * tid;
+    const uint4 a = in[0], b = in[1];
+    r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w; r.w[4] = b.x; r.w[5] = b.y; r.w[6] = b.z; r.w[7] = b.w;
+  }
+}
+
+// fp32 partial sums of one tile of one thread (float64 accumulation happens once per tile)
+struct K2TileSums {
+  float gx[2], gd[2], gdd[2];
+};
+
+// One 4-pixel group of one consumer thread: stretch, indices, fp32 maps, staged bytes, statistics.
+//   out_wb / out_rgb : this thread's slots in the staging buffers of the group
+//   map_dst[i]       : this thread's 4 floats in index map i (nullptr = not requested)
 template <int C, int BPS, bool FULL>
-__device__ __forceinline__ void k2_process_tile(const K2Params& p, uint8_t* smem, uint32_t smem_base,
-                                                int in_stage, int out_stage, int tid, int lane,
-                                                long long frame, long long px0, int nvalid,
-                                                const K2ThreadConst& tc, bool stage_bytes, K2ThreadStats& st) {
+__device__ __forceinline__ void k2_process_group(const K2Params& p, const uint8_t* smem, const K2Raw<C, BPS>& raw,
+                                                 uint32_t* out_wb, uint32_t* out_rgb, int rgb_stride_words,
+                                                 float* const map_dst[3], int first, int nvalid,
+                                                 const K2ThreadConst& tc, bool stage_bytes, K2ThreadStats& st,
+                                                 K2TileSums& ts) {
   using L = K2Smem<C, BPS>;
 
   // ---- white balance: one stretch lookup per sample (process-images.py:438-441) ----
   uint32_t wb[3][4];
   if (BPS == 2) {
     const lars_stretch_u16* st16 = reinterpret_cast<const lars_stretch_u16*>(smem + L::OFF_LUT);
-    uint32_t w[2 * C];
-    if (C == 3) {
-      const uint2* in = reinterpret_cast<const uint2*>(smem + L::OFF_IN + in_stage * L::IN_BYTES) + 3 * tid;
-      const uint2 a = in[0], b = in[1], c = in[2];
-      w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y; w[4] = c.x; w[5] = c.y;
-    } else {
-      const uint4* in = reinterpret_cast<const uint4*>(smem + L::OFF_IN + in_stage * L::IN_BYTES) + 2 * tid;
-      const uint4 a = in[0], b = in[1];
-      w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(smem_base + L::OFF_BAR + 8u * (K2_IN_STAGES + in_stage));  // stage consumed
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const int sidx = j * C + c;                      // sample index within the 4-pixel group
-        const uint32_t word = w[sidx >> 1];
+        const uint32_t word = raw.w[sidx >> 1];
         wb[c][j] = stretch_u16((sidx & 1) ? (word >> 16) : (word & 0xFFFFu), st16 + c);
       }
   } else if (C == 3) {
-    const uint32_t* in = reinterpret_cast<const uint32_t*>(smem + L::OFF_IN + in_stage * L::IN_BYTES) + 3 * tid;
-    const uint32_t w0 = in[0], w1 = in[1], w2 = in[2];
-    __syncwarp();
-    if (lane == 0) mbar_arrive(smem_base + L::OFF_BAR + 8u * (K2_IN_STAGES + in_stage));  // stage consumed
+    const uint32_t w0 = raw.w[0], w1 = raw.w[1], w2 = raw.w[2];
     wb[0][0] = lut_gather<0>(w0, tc.lut_addr[0]); wb[1][0] = lut_gather<1>(w0, tc.lut_addr[1]);
     wb[2][0] = lut_gather<2>(w0, tc.lut_addr[2]); wb[0][1] = lut_gather<3>(w0, tc.lut_addr[0]);
     wb[1][1] = lut_gather<0>(w1, tc.lut_addr[1]); wb[2][1] = lut_gather<1>(w1, tc.lut_addr[2]);
@@ -213,20 +247,15 @@ __device__ __forceinline__ void k2_process_tile(const K2Params& p, uint8_t* smem
     wb[2][2] = lut_gather<0>(w2, tc.lut_addr[2]); wb[0][3] = lut_gather<1>(w2, tc.lut_addr[0]);
     wb[1][3] = lut_gather<2>(w2, tc.lut_addr[1]); wb[2][3] = lut_gather<3>(w2, tc.lut_addr[2]);
   } else {
-    const uint4 v = *(reinterpret_cast<const uint4*>(smem + L::OFF_IN + in_stage * L::IN_BYTES) + tid);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(smem_base + L::OFF_BAR + 8u * (K2_IN_STAGES + in_stage));
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      wb[0][j] = lut_gather<0>(w[j], tc.lut_addr[0]);
-      wb[1][j] = lut_gather<1>(w[j], tc.lut_addr[1]);
-      wb[2][j] = lut_gather<2>(w[j], tc.lut_addr[2]);
+      wb[0][j] = lut_gather<0>(raw.w[j], tc.lut_addr[0]);
+      wb[1][j] = lut_gather<1>(raw.w[j], tc.lut_addr[1]);
+      wb[2][j] = lut_gather<2>(raw.w[j], tc.lut_addr[2]);
     }
   }
-  uint8_t* out_stage_ptr = smem + L::OFF_OUT + out_stage * L::OUT_BYTES;
   if (stage_bytes && p.wb_out) {
-    uint32_t* o = reinterpret_cast<uint32_t*>(out_stage_ptr) + C * tid;
+    uint32_t* o = out_wb;
     if (C == 3) {
       o[0] = pack4(wb[0][0], wb[1][0], wb[2][0], wb[0][1]);
       o[1] = pack4(wb[1][1], wb[2][1], wb[0][2], wb[1][2]);
@@ -247,18 +276,20 @@ __device__ __forceinline__ void k2_process_tile(const K2Params& p, uint8_t* smem
   }
 
   // ---- fp32 maps: one coalesced 128-bit streaming store per index ----
-  const int first = 4 * tid;
   const bool any_valid = FULL || first < nvalid;
   const bool all_valid = FULL || first + 4 <= nvalid;
   {
     const float* vals[3] = {ndvi, gndvi, ndwi};
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      float* mp = p.maps[i];
-      if (mp && any_valid) {
-        float* dst = mp + frame * p.map_frame_stride + px0 + first;
+      float* dst = map_dst[i];
+      if (dst && any_valid) {
         if (all_valid) {
+#if LARS_K2_STORE_EVICT_FIRST
+          stg_v4_policy(dst, vals[i][0], vals[i][1], vals[i][2], vals[i][3], tc.store_policy);
+#else
           stg_stream_v4(dst, vals[i][0], vals[i][1], vals[i][2], vals[i][3]);
+#endif
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -277,7 +308,7 @@ __device__ __forceinline__ void k2_process_tile(const K2Params& p, uint8_t* smem
         uint32_t c[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) c[j] = lds_u32(lars_cmap_slot_bits(vals[i][j]) * 4u + tc.cmap_cst[i]);
-        uint32_t* o = reinterpret_cast<uint32_t*>(out_stage_ptr + L::WB_BYTES + i * L::RGB_BYTES) + 3 * tid;
+        uint32_t* o = out_rgb + i * rgb_stride_words;
         o[0] = prmt(c[0], c[1], 0x4210);  // R0 G0 B0 R1
         o[1] = prmt(c[1], c[2], 0x5421);  // G1 B1 R2 G2
         o[2] = prmt(c[2], c[3], 0x6542);  // B2 R3 G3 B3
@@ -287,7 +318,7 @@ __device__ __forceinline__ void k2_process_tile(const K2Params& p, uint8_t* smem
 
   // ---- statistics + histograms ----
   if (p.partials) {
-    float gx[2] = {0.f, 0.f}, gd[2] = {0.f, 0.f}, gdd[2] = {0.f, 0.f};
+    float* gx = ts.gx; float* gd = ts.gd; float* gdd = ts.gdd;
     if (FULL) {
       st.mn[0] = fmin3(fmin3(st.mn[0], ndvi[0], ndvi[1]), ndvi[2], ndvi[3]);
       st.mx[0] = fmax3(fmax3(st.mx[0], ndvi[0], ndvi[1]), ndvi[2], ndvi[3]);
@@ -314,9 +345,6 @@ __device__ __forceinline__ void k2_process_tile(const K2Params& p, uint8_t* smem
         red_shared_inc(lars_hist_row_bits(x2, tc.half_bins, tc.half_bins_bias_m05) * 128u + tc.hist_cst[2]);
       }
     }
-    // float32 over 4 pixels, float64 across tiles (error analysis in DESIGN.md)
-    st.sx[0] += (double)gx[0]; st.sd[0] += (double)gd[0]; st.sdd[0] += (double)gdd[0];
-    st.sx[1] += (double)gx[1]; st.sd[1] += (double)gd[1]; st.sdd[1] += (double)gdd[1];
   }
 }
 
@@ -377,7 +405,8 @@ __global__ void __launch_bounds__(K2_THREADS, K2_CTAS_PER_SM) fused_index_kernel
       long long frame = t_begin / p.tiles_per_frame;          // one division, then incremental
       long long tile = t_begin - frame * p.tiles_per_frame;
       uint32_t so = 0, phase = 0;
-      uint32_t prev_so = 0;
+      const uint64_t spol = l2_policy_evict_first();
+      (void)spol;
       for (long long t = t_begin; t < t_end; ++t) {
         const long long px0 = tile * K2_TILE_PX;
         const long long rem = p.n_pixels - px0;
@@ -386,18 +415,26 @@ __global__ void __launch_bounds__(K2_THREADS, K2_CTAS_PER_SM) fused_index_kernel
         const uint32_t stage_addr = smem_base + L::OFF_OUT + so * L::OUT_BYTES;
         const uint32_t wb_bytes = (nvalid * C + 15u) & ~15u;
         const uint32_t rgb_bytes = (nvalid * 3u + 15u) & ~15u;
+#if LARS_K2_STORE_EVICT_FIRST
+        if (p.wb_out) tma_store_1d_hint(p.wb_out + frame * p.wb_frame_stride + px0 * C, stage_addr, wb_bytes, spol);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          if (p.rgb[i])
+            tma_store_1d_hint(p.rgb[i] + frame * p.rgb_frame_stride + px0 * 3,
+                              stage_addr + L::WB_BYTES + i * L::RGB_BYTES, rgb_bytes, spol);
+#else
         if (p.wb_out) tma_store_1d(p.wb_out + frame * p.wb_frame_stride + px0 * C, stage_addr, wb_bytes);
 #pragma unroll
         for (int i = 0; i < 3; ++i)
           if (p.rgb[i])
             tma_store_1d(p.rgb[i] + frame * p.rgb_frame_stride + px0 * 3,
                          stage_addr + L::WB_BYTES + i * L::RGB_BYTES, rgb_bytes);
+#endif
         tma_store_commit();
-        if (t > t_begin) {  // the previous tile's stores have finished reading their stage: hand it back
-          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          mbar_arrive(bar_out_empty + 8u * prev_so);
-        }
-        prev_so = so;
+        // this warp has nothing else to do: wait until the bulk engine has read the staging buffer
+        // (~1 us) and hand it straight back, so two buffers keep the consumers a full tile ahead
+        tma_store_wait_read_all();
+        mbar_arrive(bar_out_empty + 8u * so);
         if (++so == K2_OUT_STAGES) { so = 0; phase ^= 1u; }
         if (++tile == p.tiles_per_frame) { tile = 0; ++frame; }
       }
@@ -409,6 +446,10 @@ __global__ void __launch_bounds__(K2_THREADS, K2_CTAS_PER_SM) fused_index_kernel
     // ===================== TMA load warp (one elected lane) =====================
     if (lane == 0 && t_begin < t_end) {
       const uint64_t pol = l2_policy_evict_first();  // raw bytes are dead after this pass
+#if LARS_K2_PREFETCH_TILES > 0
+      const uint64_t pol_last = l2_policy_evict_last();
+      int until_prefetch = 0;
+#endif
       long long frame = t_begin / p.tiles_per_frame;
       long long tile = t_begin - frame * p.tiles_per_frame;
       uint32_t s = 0, phase = 0;
@@ -417,11 +458,26 @@ __global__ void __launch_bounds__(K2_THREADS, K2_CTAS_PER_SM) fused_index_kernel
         const long long rem = p.n_pixels - px0;
         const uint32_t nvalid = rem < K2_TILE_PX ? (uint32_t)rem : (uint32_t)K2_TILE_PX;
         const uint32_t bytes = (nvalid * (C * BPS) + 15u) & ~15u;
+#if LARS_K2_PREFETCH_TILES > 0
+        if (until_prefetch == 0) {
+          // one large DRAM read burst for the next tiles of this frame: fewer read / write
+          // turnarounds than a trickle of tile-sized reads between the output writes
+          long long ntl = p.tiles_per_frame - tile;
+          if (ntl > LARS_K2_PREFETCH_TILES) ntl = LARS_K2_PREFETCH_TILES;
+          if (ntl > t_end - t) ntl = t_end - t;
+          long long pbytes = ntl * (long long)(K2_TILE_PX * C * BPS);
+          const long long left = (p.n_pixels - px0) * (C * BPS);
+          if (pbytes > left) pbytes = left;
+          l2_prefetch_bulk(p.src + frame * p.src_frame_stride + px0 * (C * BPS), (uint32_t)((pbytes + 15) & ~15ll), pol_last);
+          until_prefetch = (int)ntl;
+        }
+        --until_prefetch;
+#endif
         mbar_wait(bar_base + 8u * (K2_IN_STAGES + s), phase ^ 1u);
         mbar_arrive_expect_tx(bar_base + 8u * s, bytes);
         tma_load_1d_hint(smem_base + L::OFF_IN + s * L::IN_BYTES,
                          p.src + frame * p.src_frame_stride + px0 * (C * BPS), bytes, bar_base + 8u * s, pol);
-        if (++s == K2_IN_STAGES) { s = 0; phase ^= 1u; }
+        if (++s == L::IN_STAGES) { s = 0; phase ^= 1u; }
         if (++tile == p.tiles_per_frame) { tile = 0; ++frame; }
       }
     }
@@ -447,6 +503,7 @@ __global__ void __launch_bounds__(K2_THREADS, K2_CTAS_PER_SM) fused_index_kernel
   tc.half_bins = 0.5f * (float)p.bins;
   tc.half_bins_bias_m05 = tc.half_bins + LARS_HIST_BIAS - 0.5f;
   tc.ndwi_by_sign = (p.thresholds[2] == 0.0f);
+  tc.store_policy = l2_policy_evict_first();
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     tc.lut_addr[i] = smem_base + L::OFF_LUT + lut_shift + 256u * i;
@@ -502,17 +559,46 @@ __global__ void __launch_bounds__(K2_THREADS, K2_CTAS_PER_SM) fused_index_kernel
       const int nvalid = rem < K2_TILE_PX ? (int)rem : K2_TILE_PX;
       if (stage_bytes) mbar_wait(bar_out_empty + 8u * s_out, ph_out ^ 1u);  // staging buffer drained
       mbar_wait(bar_base + 8u * s_in, ph_in);                               // tile landed
-      if (nvalid == K2_TILE_PX)
-        k2_process_tile<C, BPS, true>(p, smem, smem_base, s_in, s_out, tid, lane, frame, px0, nvalid, tc, stage_bytes, st);
-      else
-        k2_process_tile<C, BPS, false>(p, smem, smem_base, s_in, s_out, tid, lane, frame, px0, nvalid, tc, stage_bytes, st);
+      // all of this thread's raw words of the tile, then release the input stage
+      K2Raw<C, BPS> raw[K2_GROUPS];
+      const uint8_t* in_tile = smem + L::OFF_IN + s_in * L::IN_BYTES;
+#pragma unroll
+      for (int g = 0; g < K2_GROUPS; ++g) k2_load_group<C, BPS>(in_tile + g * (K2_GROUP_PX * C * BPS), tid, raw[g]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_base + 8u * (K2_IN_STAGES + s_in));
+      uint8_t* out_tile = smem + L::OFF_OUT + s_out * L::OUT_BYTES;
+      K2TileSums ts;
+      ts.gx[0] = ts.gx[1] = ts.gd[0] = ts.gd[1] = ts.gdd[0] = ts.gdd[1] = 0.f;
+      float* map_base[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        map_base[i] = p.maps[i] ? p.maps[i] + frame * p.map_frame_stride + px0 + 4 * tid : nullptr;
+#pragma unroll
+      for (int g = 0; g < K2_GROUPS; ++g) {
+        uint32_t* out_wb = reinterpret_cast<uint32_t*>(out_tile + g * (K2_GROUP_PX * C)) + C * tid;
+        uint32_t* out_rgb = reinterpret_cast<uint32_t*>(out_tile + L::WB_BYTES + g * (K2_GROUP_PX * 3)) + 3 * tid;
+        float* map_dst[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) map_dst[i] = map_base[i] ? map_base[i] + g * K2_GROUP_PX : nullptr;
+        const int first = g * K2_GROUP_PX + 4 * tid;
+        if (nvalid == K2_TILE_PX)
+          k2_process_group<C, BPS, true>(p, smem, raw[g], out_wb, out_rgb, L::RGB_BYTES / 4, map_dst, first, nvalid,
+                                         tc, stage_bytes, st, ts);
+        else
+          k2_process_group<C, BPS, false>(p, smem, raw[g], out_wb, out_rgb, L::RGB_BYTES / 4, map_dst, first, nvalid,
+                                          tc, stage_bytes, st, ts);
+      }
+      if (p.partials) {  // float32 within the tile, float64 across tiles (error analysis in DESIGN.md)
+        st.sx[0] += (double)ts.gx[0]; st.sd[0] += (double)ts.gd[0]; st.sdd[0] += (double)ts.gdd[0];
+        st.sx[1] += (double)ts.gx[1]; st.sd[1] += (double)ts.gd[1]; st.sdd[1] += (double)ts.gdd[1];
+      }
       if (stage_bytes) {
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk-copy engine
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_out_full + 8u * s_out);
         if (++s_out == K2_OUT_STAGES) { s_out = 0; ph_out ^= 1u; }
       }
-      if (++s_in == K2_IN_STAGES) { s_in = 0; ph_in ^= 1u; }
+      if (++s_in == L::IN_STAGES) { s_in = 0; ph_in ^= 1u; }
     }
 
     // ---------------- flush this span into its partial record ----------------

@@ -88,6 +88,11 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
@@ -109,6 +114,33 @@ __device__ __forceinline__ uint4 ldg_stream_v4(const void* p) {
 }
 __device__ __forceinline__ void stg_stream_v4(void* p, float a, float b, float c, float d) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+// 128-bit load / store with an explicit L2 eviction policy (createpolicy result)
+__device__ __forceinline__ uint4 ldg_v4_policy(const void* p, uint64_t policy) {
+  uint4 r;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(policy));
+  return r;
+}
+__device__ __forceinline__ void stg_v4_policy(void* p, float a, float b, float c, float d, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d),
+               "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_1d_hint(void* dst_gmem, uint32_t src_smem, uint32_t bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(
+                   __cvta_generic_to_global(dst_gmem)),
+               "r"(src_smem), "r"(bytes), "l"(policy)
+               : "memory");
+}
+
+// Bulk prefetch of a contiguous global range into L2 (no shared-memory destination).
+__device__ __forceinline__ void l2_prefetch_bulk(const void* src_gmem, uint32_t bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(__cvta_generic_to_global(src_gmem)),
+               "r"(bytes), "l"(policy)
                : "memory");
 }
 
