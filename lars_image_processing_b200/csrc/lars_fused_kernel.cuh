@@ -672,49 +672,64 @@ struct K2fParams {
 __global__ void __launch_bounds__(3 * K2_BINS_PAD) fused_finalize_kernel(const K2fParams p) {
   const int frame = blockIdx.x;
   const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
   const K2Partial* recs = p.partials + (long long)frame * p.slots_per_frame;
   lars_index_stats* out = p.stats + (long long)frame * 3;
-  {  // histograms: thread (index, bin)
+  {  // histograms: thread (index, bin); integer sums, any order is exact
     const int idx = tid / K2_BINS_PAD, bin = tid % K2_BINS_PAD;
     unsigned long long h = 0;
     for (int s = 0; s < p.slots_per_frame; ++s)
       if (recs[s].count) h += recs[s].hist[idx][bin];
     out[idx].hist[bin] = h;
   }
-  if (tid < 3) {
-    const int i = tid;
+  if (warp < 3) {
+    // one warp per index: lane l folds slots l, l + 32, ... in order, then a fixed butterfly --
+    // the summation tree depends only on the launch geometry, so results are reproducible
+    const int i = warp;
     const int g = (i == 0) ? 0 : 1;  // NDWI statistics derive from GNDVI's (x -> 0 - x)
     double sx = 0.0, sd = 0.0, sdd = 0.0;
     float mn = INFINITY, mx = -INFINITY;
     unsigned long long cnt = 0, above = 0;
-    for (int s = 0; s < p.slots_per_frame; ++s) {
+    for (int s = lane; s < p.slots_per_frame; s += 32) {
       const K2Partial& r = recs[s];
       if (!r.count) continue;
       sx += r.sx[g]; sd += r.sd[g]; sdd += r.sdd[g];
       mn = fminf(mn, r.mn[g]); mx = fmaxf(mx, r.mx[g]);
       cnt += r.count; above += r.above[i];
     }
-    lars_index_stats& o = out[i];
-    if (i == 2) {
-      const float t = mn;
-      mn = 0.0f - mx; mx = 0.0f - t;
-      sx = 0.0 - sx; sd = 0.0 - sd;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      sx += __shfl_xor_sync(0xffffffffu, sx, d);
+      sd += __shfl_xor_sync(0xffffffffu, sd, d);
+      sdd += __shfl_xor_sync(0xffffffffu, sdd, d);
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+      above += __shfl_xor_sync(0xffffffffu, above, d);
     }
-    const double n = (double)cnt;
-    const double mean = cnt ? sx / n : 0.0;
-    const double md = cnt ? sd / n : 0.0;
-    double var = cnt ? sdd / n - md * md : 0.0;
-    var = var > 0.0 ? var : 0.0;
-    o.count = cnt;
-    o.count_above = above;
-    o.sum = sx;
-    o.sumsq = cnt ? (var + mean * mean) * n : 0.0;
-    o.mean = mean;
-    o.std = sqrt(var);
-    o.min = cnt ? mn : 0.f;
-    o.max = cnt ? mx : 0.f;
-    o.threshold = p.thresholds[i];
-    o.bins = (uint32_t)p.bins;
+    if (lane == 0) {
+      lars_index_stats& o = out[i];
+      if (i == 2) {
+        const float t = mn;
+        mn = 0.0f - mx; mx = 0.0f - t;
+        sx = 0.0 - sx; sd = 0.0 - sd;
+      }
+      const double n = (double)cnt;
+      const double mean = cnt ? sx / n : 0.0;
+      const double md = cnt ? sd / n : 0.0;
+      double var = cnt ? sdd / n - md * md : 0.0;
+      var = var > 0.0 ? var : 0.0;
+      o.count = cnt;
+      o.count_above = above;
+      o.sum = sx;
+      o.sumsq = cnt ? (var + mean * mean) * n : 0.0;
+      o.mean = mean;
+      o.std = sqrt(var);
+      o.min = cnt ? mn : 0.f;
+      o.max = cnt ? mx : 0.f;
+      o.threshold = p.thresholds[i];
+      o.bins = (uint32_t)p.bins;
+    }
   }
 }
 

@@ -211,21 +211,12 @@ class Engine:
                   "lars_wb_stretch_build_u16")
         return stretch, pct
 
-    def fused(self, frames: DeviceFrames, lut: Optional[torch.Tensor], outputs=ALL_OUTPUTS,
-              indices=INDEX_TYPES, bins: int = DEFAULT_BINS, thresholds=DEFAULT_THRESHOLDS,
-              cmaps=DEFAULT_CMAPS, rgb_indices=None, out: Optional[DeviceOutputs] = None,
-              stream=None) -> DeviceOutputs:
-        """Pass 2 (K2): one read of the raw frames -> every requested product.
-
-        ``lut`` None means identity (``calculate_index`` on an already white-balanced frame).
-        ``indices`` selects which fp32 maps are written; ``rgb_indices`` (default: same)
-        which colormapped images.  Statistics are always produced for all three indices
-        when "stats" is requested (they share the arithmetic).
-        """
-        s = stream or self.stream()
+    def _build_fused_args(self, frames: DeviceFrames, lut, outputs, res: DeviceOutputs, s, indices=INDEX_TYPES,
+                          bins: int = DEFAULT_BINS, thresholds=DEFAULT_THRESHOLDS, cmaps=DEFAULT_CMAPS,
+                          rgb_indices=None) -> FusedArgs:
+        """Fill a ``lars_fused_args`` block (allocating any missing output buffer of ``res``)."""
         F, npx, ch = frames.n_frames, frames.n_pixels, frames.channels
         ppx = _pad_px(npx)
-        res = out or DeviceOutputs(frames=frames)
         res.frames = frames
         res.bins = bins
         rgb_indices = indices if rgb_indices is None else rgb_indices
@@ -266,6 +257,23 @@ class Engine:
             ws = self._alloc((ws_bytes,), torch.uint8, s)
             res._keep = [ws]
             a.stats, a.workspace, a.workspace_bytes = res.stats.data_ptr(), ws.data_ptr(), ws_bytes
+        return a
+
+    def fused(self, frames: DeviceFrames, lut: Optional[torch.Tensor], outputs=ALL_OUTPUTS,
+              indices=INDEX_TYPES, bins: int = DEFAULT_BINS, thresholds=DEFAULT_THRESHOLDS,
+              cmaps=DEFAULT_CMAPS, rgb_indices=None, out: Optional[DeviceOutputs] = None,
+              stream=None) -> DeviceOutputs:
+        """Pass 2 (K2): one read of the raw frames -> every requested product.
+
+        ``lut`` None means identity (``calculate_index`` on an already white-balanced frame).
+        ``indices`` selects which fp32 maps are written; ``rgb_indices`` (default: same)
+        which colormapped images.  Statistics are always produced for all three indices
+        when "stats" is requested (they share the arithmetic).
+        """
+        s = stream or self.stream()
+        res = out or DeviceOutputs(frames=frames)
+        a = self._build_fused_args(frames, lut, outputs, res, s, indices=indices, bins=bins, thresholds=thresholds,
+                                   cmaps=cmaps, rgb_indices=rgb_indices)
         with torch.cuda.device(self.device):
             if frames.sample_bytes == 2:
                 check(self.lib.lars_fused_index_u16(C.byref(a), s.cuda_stream), "lars_fused_index_u16")
@@ -471,6 +479,70 @@ class Engine:
     def analyze_frame(self, img: np.ndarray, outputs=ALL_OUTPUTS, white_balance=True, **kw) -> dict:
         """The fused entry point for one frame: {wb, maps, rgb, stats, percentiles}."""
         return self.analyze_batch([img], outputs=outputs, white_balance=white_balance, **kw)[0]
+
+
+class FramePlan:
+    """Pre-bound execution plan for a fixed batch shape (SURVEY.md section 7 hard part 5: the
+    many-small-frames regime is launch-bound, so nothing may be allocated or re-derived per step).
+
+    All device buffers, the workspace and the C argument block are created once; ``run`` is then
+    four C-ABI calls (Pass 1, LUT build, fused Pass 2 + finalize, optional dataset merge) and
+    ``capture`` records them into a CUDA graph so that a step is a single ``replay``.
+    """
+
+    def __init__(self, engine: "Engine", frames: DeviceFrames, outputs=ALL_OUTPUTS, white_balance: bool = True,
+                 quantiles=DEFAULT_QUANTILES, merge_dataset: bool = False, stream=None, **fused_kw):
+        if frames.sample_bytes != 1:
+            raise LarsError("FramePlan currently covers uint8 frames")
+        self.engine = engine
+        self.frames = frames
+        self.stream = stream or engine.stream()
+        s = self.stream
+        F = frames.n_frames
+        self.white_balance = white_balance
+        self.quantiles = (float(quantiles[0]), float(quantiles[1]))
+        self.out = engine.alloc_outputs(frames, outputs, s)
+        self.hist = engine._alloc((F, 3, 256), torch.int64, s) if white_balance else None
+        self.lut = engine._alloc((F, 3, 256), torch.uint8, s) if white_balance else None
+        self.pct = engine._alloc((F, 3, 2), torch.float64, s) if white_balance else None
+        self.out.wb_hist, self.out.wb_lut, self.out.wb_pct = self.hist, self.lut, self.pct
+        self.merged = engine._alloc((3, INDEX_STATS_DTYPE.itemsize), torch.uint8, s) \
+            if (merge_dataset and "stats" in outputs) else None
+        # one dry run builds the argument block (and the workspace) through the normal path
+        self._args = engine._build_fused_args(frames, self.lut, outputs, self.out, s, **fused_kw)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+
+    def run(self) -> DeviceOutputs:
+        """Enqueue one step on the plan's stream (no allocation, no synchronisation)."""
+        lib, fr, sp = self.engine.lib, self.frames, self.stream.cuda_stream
+        if self.white_balance:
+            check(lib.lars_wb_hist_u8(fr.data.data_ptr(), fr.n_frames, fr.n_pixels, fr.channels, fr.stride_bytes,
+                                      self.hist.data_ptr(), 0, sp), "lars_wb_hist_u8")
+            check(lib.lars_wb_lut_build_u8(self.hist.data_ptr(), fr.n_frames, self.quantiles[0], self.quantiles[1],
+                                           self.lut.data_ptr(), self.pct.data_ptr(), sp), "lars_wb_lut_build_u8")
+        check(lib.lars_fused_index_u8(C.byref(self._args), sp), "lars_fused_index_u8")
+        if self.merged is not None:
+            check(lib.lars_stats_merge(self.out.stats.data_ptr(), fr.n_frames, self.merged.data_ptr(), sp),
+                  "lars_stats_merge")
+        return self.out
+
+    def capture(self) -> "FramePlan":
+        """Record ``run`` into a CUDA graph; afterwards ``replay`` costs one launch."""
+        with torch.cuda.device(self.engine.device):
+            self.run()                                  # warm-up outside capture (module load, attributes)
+            self.stream.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.stream):
+                self.run()
+            self.graph = g
+        return self
+
+    def replay(self) -> DeviceOutputs:
+        if self.graph is None:
+            raise LarsError("FramePlan.capture() has not been called")
+        with torch.cuda.stream(self.stream):
+            self.graph.replay()
+        return self.out
 
 
 _default_engine: Optional[Engine] = None

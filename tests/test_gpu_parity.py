@@ -471,3 +471,56 @@ def test_change_detection(engine):
     assert np.array_equal(np.array(img), o.apply_colormap(o.calculate_index(wb_, "NDVI") - o.calculate_index(wa, "NDVI"),
                                                           name="bwr", vmin=-0.5, vmax=0.5))
     assert pi.create_change_detection_visualization([pair[0]], "NDVI") is None
+
+
+def test_frame_plan_and_cuda_graph(engine):
+    """Pre-bound plan: plain run and CUDA-graph replay give the oracle's results, also after the
+    input buffer is refilled in place (the graph is bound to the buffers, not to their content)."""
+    from lars_image_processing_b200.engine import FramePlan
+    frames = [synth.vegetation_frame(500 + i, 96, 128) for i in range(5)]
+    dev = engine.upload(frames)
+    plan = FramePlan(engine, dev, merge_dataset=True)
+    plan.run()
+    for i, r in enumerate(engine.download(plan.out)):
+        check_frame_result(r, frames[i], label=f"plan.run[{i}]")
+    plan.capture()
+    frames2 = [synth.vegetation_frame(600 + i, 96, 128) for i in range(5)]
+    import torch
+    with torch.cuda.stream(plan.stream):
+        for i, f in enumerate(frames2):
+            dev.data[i, :f.size].copy_(torch.from_numpy(f.reshape(-1)), non_blocking=True)
+    plan.replay()
+    for i, r in enumerate(engine.download(plan.out)):
+        check_frame_result(r, frames2[i], label=f"plan.replay[{i}]")
+    from lars_image_processing_b200 import distributed as ld
+    merged = ld.records_to_numpy(plan.merged)
+    want = sum(int(oracle_frame(f)["stats"]["NDVI"]["count_above"]) for f in frames2)
+    assert int(merged[0]["count_above"]) == want and int(merged[0]["count"]) == 5 * 96 * 128
+
+
+def test_reduced_config4_mosaic_4096(engine):
+    """BASELINE config 4 reduced to 4096 x 4096 (16.8 MP) as 8 row-band tiles with one global
+    white-balance LUT: white-balanced bytes, NDVI map bits and every histogram against the oracle."""
+    from lars_image_processing_b200 import distributed as ld
+    from lars_image_processing_b200.engine import stats_records_to_dicts
+    img = synth.vegetation_frame(4, 4096, 4096)
+    bands = [np.ascontiguousarray(b) for b in np.split(img, 8, axis=0)]
+    dev = engine.upload(bands)
+    res, whole = ld.process_mosaic_tiles(engine, dev, outputs=("wb", "maps", "stats"), indices=("NDVI",))
+    out = engine.download(res)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        wb = o.fix_white_balance_from_hist(img)
+    assert np.array_equal(np.concatenate([o_["wb"] for o_ in out], axis=0), wb)
+    ndvi = o.calculate_index(wb, "NDVI")
+    assert np.array_equal(np.concatenate([o_["maps"]["NDVI"] for o_ in out], axis=0).view(np.uint32), ndvi.view(np.uint32))
+    st = stats_records_to_dicts(ld.records_to_numpy(whole).reshape(1, 3), 50)[0]
+    for t in INDEX_TYPES:
+        m = ndvi if t == "NDVI" else o.calculate_index(wb, t)
+        assert np.array_equal(st[t]["hist"], o.index_histogram(m)), t
+        assert st[t]["count"] == 4096 * 4096
+        assert st[t]["count_above"] == int(np.count_nonzero(m > np.float32(o.coverage_threshold(t))))
+        assert st[t]["min"] == float(m.min()) and st[t]["max"] == float(m.max())
+        std = float(m.astype(np.float64).std())
+        assert moment_close(st[t]["mean"], float(m.astype(np.float64).mean()), std)
+        assert moment_close(st[t]["std"], std, std)
