@@ -74,12 +74,15 @@ typedef struct lars_index_stats {
 
 /* White-balance stretch of one channel of a uint16 frame: the monotone map
  * v -> uint8(clip((v - p_lo) / (p_hi - p_lo) * 255, 0, 255)) (process-images.py:438-441) stored as
- * its 256 step positions, thr[k] = smallest v with LUT(v) >= k (thr[0] = 0, unreachable k and
- * thr[256..257] = 65536), plus the float parameters of a first guess.  1040 bytes. */
+ * its 256 step positions thr[k] = smallest v with LUT(v) >= k (thr[0] = 0, unreachable k = 65536),
+ * laid out as pairs (thr[k], thr[k + 1]) so one 8-byte load brackets a guess, plus the parameters
+ * of that guess: t = ((v - lo_int) - lo_frac) * scale.  2064 bytes. */
 typedef struct lars_stretch_u16 {
-  float lo;          /* p_lo rounded to float32             */
-  float scale;       /* 255 / (p_hi - p_lo), 0 if degenerate */
-  uint32_t thr[258];
+  int32_t lo_int;    /* floor(p_lo)                                         */
+  float lo_frac;     /* p_lo - floor(p_lo)                                  */
+  float scale;       /* 255 / (p_hi - p_lo); 2^20 around the single step if p_hi == p_lo */
+  uint32_t reserved;
+  uint32_t pairs[256][2];
 } lars_stretch_u16;
 
 /* Arguments of the fused Pass 2 (one struct so the ABI can grow without breaking callers). */

@@ -18,7 +18,7 @@ LARS_OK = 0
 NUM_INDICES = 3
 MAX_BINS = 64
 PIXEL_GROUP = 16
-STRETCH_U16_BYTES = 1040   # sizeof(lars_stretch_u16)
+STRETCH_U16_BYTES = 2064   # sizeof(lars_stretch_u16)
 CMAP_IDS = {"RdYlGn": 0, "RdYlBu": 1, "bwr": 2}
 INDEX_IDS = {"NDVI": 0, "GNDVI": 1, "NDWI": 2}
 DTYPE_IDS = {"uint8": 0, "uint16": 1, "float32": 2, "float64": 3}

@@ -18,6 +18,7 @@
 // and a branch-free correctly-rounded division (pixel_math.h).
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "../../include/lars_b200.h"
@@ -95,9 +96,9 @@ struct K2Smem {
   static constexpr int RGB_BYTES = K2_TILE_PX * 3;
   static constexpr int OUT_BYTES = WB_BYTES + 3 * RGB_BYTES;     // one output stage
   // uint8: 3 x 256 B stretch tables, each 256-aligned (1 KB reserved to absorb any base alignment)
-  // uint16: 3 x lars_stretch_u16 (guess parameters + 258 thresholds = 1040 B each)
+  // uint16: 3 x lars_stretch_u16 (guess parameters + 256 threshold pairs = 2064 B each)
   static constexpr int OFF_LUT = 0;
-  static constexpr int OFF_CMAP = (BPS == 1) ? 1024 : 3136;      // 3 x 257 words
+  static constexpr int OFF_CMAP = (BPS == 1) ? 1024 : 6208;      // 3 x 257 words
   static constexpr int OFF_HIST = OFF_CMAP + 3104;               // 3 x 65 rows x 32 lanes x 4 B
   static constexpr int OFF_IN = OFF_HIST + 3 * K2_HIST_ROWS * 128;
   // uint16 tiles are twice as large: two input stages keep two CTAs per SM resident
@@ -172,16 +173,29 @@ __device__ __forceinline__ uint32_t pack4(uint32_t b0, uint32_t b1, uint32_t b2,
   return prmt(prmt(b0, b1, 0x0040), prmt(b2, b3, 0x0040), 0x5410);
 }
 
-// uint16 sample -> white-balanced uint8: float guess of the stretch, then a +-1 correction against
-// the monotone thresholds thr[k] = smallest v with LUT(v) >= k (exact: the thresholds were derived
-// from the reference's fp64 chain on all 65,536 values).
-__device__ __forceinline__ uint32_t stretch_u16(uint32_t v, const lars_stretch_u16* st) {
-  float t = (lars_small_int_to_float((int)v) - st->lo) * st->scale;
-  t = fminf(fmaxf(t, 0.0f), 255.0f);
-  int g = (int)(lars_f2u(t + LARS_MAGIC_F) - LARS_MAGIC_U);   // round to nearest: a guess is enough
-  while (v < st->thr[g]) --g;          // thr[0] == 0 stops the descent
-  while (v >= st->thr[g + 1]) ++g;     // thr[256] == 65536 stops the ascent
-  return (uint32_t)g;
+// uint16 sample -> white-balanced uint8, branch-free: a float guess of the stretch that is provably
+// within +-1 of the reference's value (the difference v - p_lo is formed from an exact integer part,
+// so its error is relative to itself; p_hi - p_lo >= 0.02 whenever it is not zero), then one 8-byte
+// load of the bracketing thresholds (thr[g], thr[g + 1]) and a +-1 correction.  Exact because the
+// thresholds come from the reference's fp64 -> fp32 -> uint8 chain evaluated on all 65,536 values.
+struct U16Guess {
+  int lo_int;
+  float lo_frac, scale;
+};
+__device__ __forceinline__ U16Guess load_guess(const lars_stretch_u16* st) {
+  const uint4 h = *reinterpret_cast<const uint4*>(st);   // lo_int, lo_frac, scale, reserved
+  U16Guess g;
+  g.lo_int = (int)h.x; g.lo_frac = __uint_as_float(h.y); g.scale = __uint_as_float(h.z);
+  return g;
+}
+__device__ __forceinline__ uint32_t stretch_u16(uint32_t v, const U16Guess& st, uint32_t pairs_addr) {
+  const float d = lars_small_int_to_float((int)v - st.lo_int);
+  float t = fmaf(d - st.lo_frac, st.scale, -0.5f);
+  t = fminf(fmaxf(t, -0.5f), 254.5f);
+  const uint32_t gb = lars_f2u(t + LARS_MAGIC_F);              // MAGIC_U + g0, g0 in [0, 255]
+  uint32_t lo, hi;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(gb * 8u + pairs_addr));
+  return (gb - LARS_MAGIC_U) + (v >= hi ? 1u : 0u) - (v < lo ? 1u : 0u);
 }
 
 // raw words of one 4-pixel group of one thread
@@ -230,13 +244,14 @@ __device__ __forceinline__ void k2_process_group(const K2Params& p, const uint8_
   uint32_t wb[3][4];
   if (BPS == 2) {
     const lars_stretch_u16* st16 = reinterpret_cast<const lars_stretch_u16*>(smem + L::OFF_LUT);
+    const U16Guess g16[3] = {load_guess(st16), load_guess(st16 + 1), load_guess(st16 + 2)};
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const int sidx = j * C + c;                      // sample index within the 4-pixel group
         const uint32_t word = raw.w[sidx >> 1];
-        wb[c][j] = stretch_u16((sidx & 1) ? (word >> 16) : (word & 0xFFFFu), st16 + c);
+        wb[c][j] = stretch_u16((sidx & 1) ? (word >> 16) : (word & 0xFFFFu), g16[c], tc.lut_addr[c]);
       }
   } else if (C == 3) {
     const uint32_t w0 = raw.w[0], w1 = raw.w[1], w2 = raw.w[2];
@@ -506,7 +521,10 @@ __global__ void __launch_bounds__(K2_THREADS, K2_CTAS_PER_SM) fused_index_kernel
   tc.store_policy = l2_policy_evict_first();
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    tc.lut_addr[i] = smem_base + L::OFF_LUT + lut_shift + 256u * i;
+    tc.lut_addr[i] = (BPS == 2)
+                         ? smem_base + L::OFF_LUT + (uint32_t)(i * sizeof(lars_stretch_u16) + offsetof(lars_stretch_u16, pairs)) -
+                               (LARS_MAGIC_U << 3)
+                         : smem_base + L::OFF_LUT + lut_shift + 256u * i;
     tc.hist_cst[i] = smem_base + L::OFF_HIST + (uint32_t)(i * K2_HIST_ROWS * 128 + 4 * lane) - (LARS_MAGIC_U << 7);
     tc.cmap_cst[i] = smem_base + L::OFF_CMAP + (uint32_t)(i * K2_CMAP_SLOTS * 4) - (LARS_MAGIC_U << 2);
   }
@@ -539,7 +557,9 @@ __global__ void __launch_bounds__(K2_THREADS, K2_CTAS_PER_SM) fused_index_kernel
       if (BPS == 2) {
         const uint16_t* f0 = reinterpret_cast<const uint16_t*>(p.src + frame * p.src_frame_stride);
         const lars_stretch_u16* st16 = reinterpret_cast<const lars_stretch_u16*>(smem + L::OFF_LUT);
-        r = (int)stretch_u16(f0[0], st16); g = (int)stretch_u16(f0[1], st16 + 1); n = (int)stretch_u16(f0[2], st16 + 2);
+        r = (int)stretch_u16(f0[0], load_guess(st16), tc.lut_addr[0]);
+        g = (int)stretch_u16(f0[1], load_guess(st16 + 1), tc.lut_addr[1]);
+        n = (int)stretch_u16(f0[2], load_guess(st16 + 2), tc.lut_addr[2]);
       } else {
         const uint8_t* f0 = p.src + frame * p.src_frame_stride;
         r = lut_s[f0[0]]; g = lut_s[256 + f0[1]]; n = lut_s[512 + f0[2]];

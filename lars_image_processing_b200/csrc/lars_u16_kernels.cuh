@@ -312,17 +312,30 @@ __global__ void __launch_bounds__(256) wb_stretch_build_u16_kernel(const U16Buil
   const double plo = pcts[0], phi = pcts[1];
   lars_stretch_u16& st = p.stretch[sc];
   // thr[k] = smallest v with LUT(v) >= k; the LUT is monotone, so thresholds sit where it steps
-  for (int k = v; k < 258; k += 256) st.thr[k] = (k == 0) ? 0u : 65536u;
+  __shared__ uint32_t thr[258];
+  for (int k = v; k < 258; k += 256) thr[k] = (k == 0) ? 0u : 65536u;
   __syncthreads();
   for (int val = v; val < 65536; val += 256) {
     const int cur = (int)lars_wb_lut_entry((double)val, plo, phi);
     const int prev = val ? (int)lars_wb_lut_entry((double)(val - 1), plo, phi) : 0;
-    for (int k = prev + 1; k <= cur; ++k) st.thr[k] = (uint32_t)val;
+    for (int k = prev + 1; k <= cur; ++k) thr[k] = (uint32_t)val;
   }
+  __syncthreads();
+  st.pairs[v][0] = thr[v];
+  st.pairs[v][1] = thr[v + 1];
   if (v == 0) {
-    st.lo = (float)plo;
     const double span = LARS_DSUB(phi, plo);
-    st.scale = span > 0.0 ? (float)(255.0 / span) : 0.0f;
+    if (span > 0.0) {
+      const double fl = floor(plo);
+      st.lo_int = (int32_t)fl;
+      st.lo_frac = (float)LARS_DSUB(plo, fl);
+      st.scale = (float)(255.0 / span);
+    } else {  // p_hi == p_lo: one step from 0 to 255 at thr[1]; a steep ramp centred just below it
+      st.lo_int = (int32_t)thr[1] - 1;
+      st.lo_frac = 0.5f;
+      st.scale = 1048576.0f;
+    }
+    st.reserved = 0u;
   }
 }
 
