@@ -524,3 +524,43 @@ def test_reduced_config4_mosaic_4096(engine):
         std = float(m.astype(np.float64).std())
         assert moment_close(st[t]["mean"], float(m.astype(np.float64).mean()), std)
         assert moment_close(st[t]["std"], std, std)
+
+
+def test_no_write_outside_the_frame_slots(engine):
+    """Own bounds check (compute-sanitizer is closed on this pool): every output buffer is carved
+    out of a larger sentinel-filled allocation; after the passes the guard bytes in front of,
+    between and behind the frame slots must be untouched, for ragged sizes and tile boundaries."""
+    import torch
+    from lars_image_processing_b200.engine import DeviceFrames, DeviceOutputs, _pad_px
+    from lars_image_processing_b200._lib import INDEX_STATS_DTYPE
+    GUARD = 4096
+    for (h, w, F, dtype) in ((7, 13, 3, np.uint8), (1, 2049, 2, np.uint8), (33, 65, 4, np.uint8), (1, 1, 5, np.uint8),
+                             (64, 97, 3, np.uint16)):
+        frames = [synth.vegetation_frame(700 + i, h, w, dtype) for i in range(F)]
+        dev = engine.upload(frames)
+        npx, ppx = h * w, _pad_px(h * w)
+        s = engine.stream()
+
+        def guarded(rows, row_bytes, lead=1):
+            flat = torch.full((GUARD + lead * rows * row_bytes + GUARD,), 0xA5, dtype=torch.uint8, device=engine.device)
+            return flat, flat[GUARD:GUARD + lead * rows * row_bytes]
+
+        wb_all, wb_v = guarded(F, ppx * 3)
+        maps_all, maps_v = guarded(F, ppx * 4, lead=3)
+        rgb_all, rgb_v = guarded(F, ppx * 3, lead=3)
+        st_all, st_v = guarded(F, 3 * INDEX_STATS_DTYPE.itemsize)
+        res = DeviceOutputs(frames=dev, wb=wb_v.view(F, ppx * 3), maps=maps_v.view(torch.float32).view(3, F, ppx),
+                            rgb=rgb_v.view(3, F, ppx * 3), stats=st_v.view(F, 3, INDEX_STATS_DTYPE.itemsize))
+        engine.process_device(dev, out=res, stream=s)
+        s.synchronize()
+        for name, flat in (("wb", wb_all), ("maps", maps_all), ("rgb", rgb_all), ("stats", st_all)):
+            host = flat.cpu().numpy()
+            assert (host[:GUARD] == 0xA5).all() and (host[-GUARD:] == 0xA5).all(), (name, h, w, F)
+        # bytes between n_pixels and the 16-pixel padded slot end are scratch; everything past the
+        # slot (the next frame's first bytes) is checked by the parity of the next frame
+        out = engine.download(res)
+        for i in (0, F - 1):
+            want = oracle_frame(frames[i])
+            assert np.array_equal(out[i]["wb"], want["wb"])
+            assert np.array_equal(out[i]["maps"]["NDWI"].view(np.uint32), want["maps"]["NDWI"].view(np.uint32))
+            assert np.array_equal(out[i]["rgb"]["NDVI"], want["rgb"]["NDVI"])
