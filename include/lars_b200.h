@@ -210,6 +210,36 @@ int lars_index_change_u8(const uint8_t* early, const uint8_t* late, int64_t n_pi
                          int32_t index, float vmin, float vmax, float* early_map, float* late_map,
                          float* diff, uint8_t* rgb, void* stream);
 
+/* ---- resize in front of the path -----------------------------
+ * preprocess_large_image(img_array, max_dimension=1024), process-images.py:398-422:
+ * Image.fromarray(img).resize((new_w, new_h), Image.Resampling.LANCZOS).  Bit-identical to Pillow's
+ * src/libImaging/Resample.c for 8-bit channels: horizontal pass into a uint8 intermediate image,
+ * then the vertical pass, 22-bit fixed-point coefficients.  1, 3 or 4 interleaved channels, every
+ * channel filtered independently (Pillow modes L / RGB; RGBA differs: Pillow premultiplies alpha). */
+typedef struct lars_resize_plan {
+  int32_t in_h, in_w, out_h, out_w, channels;
+  int32_t need_h, need_v;         /* which passes run (Resample.c need_horizontal / need_vertical)   */
+  int32_t ksize_h, ksize_v;       /* taps per output column / row                                    */
+  int32_t row_first, row_count;   /* source rows the horizontal pass produces (ybox_first .. last)   */
+  int32_t xo_tile, span_words, out_pitch; /* launch geometry of the horizontal pass                  */
+  uint64_t table_bytes;           /* size of the coefficient block (host and device copies)          */
+  uint64_t temp_frame_bytes;      /* intermediate image bytes per frame (multiple of 16); 0 if unused */
+} lars_resize_plan;
+/* Host only: geometry of a resize.  LARS_ERR_UNSUPPORTED if a single filter window does not fit
+ * in shared memory (down-scaling by more than ~250x). */
+int lars_resize_plan_lanczos(int32_t in_h, int32_t in_w, int32_t out_h, int32_t out_w, int32_t channels,
+                             lars_resize_plan* plan);
+/* Host only: fills plan->table_bytes bytes of HOST memory with the coefficient block
+ * (Resample.c precompute_coeffs + normalize_coeffs_8bpc, double precision + libm sin);
+ * the caller copies it to the device once per geometry. */
+int lars_resize_tables_lanczos(const lars_resize_plan* plan, void* tables_host);
+/* Device: n_frames frames [in_h][in_w][channels] -> [out_h][out_w][channels].  tables_dev is the
+ * device copy of the coefficient block (4-byte aligned); temp holds n_frames * temp_frame_bytes
+ * bytes (may be NULL when temp_frame_bytes == 0).  Frame strides in bytes. */
+int lars_resize_lanczos_u8(const lars_resize_plan* plan, const void* tables_dev, const uint8_t* src,
+                           int64_t src_frame_stride, int32_t n_frames, uint8_t* dst, int64_t dst_frame_stride,
+                           void* temp, size_t temp_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = (
     "lars_stats_merge",
     "lars_wb_u16_workspace_bytes", "lars_wb_stretch_build_u16", "lars_fused_index_u16",
     "lars_index_hwc", "lars_index_change_u8",
+    "lars_resize_plan_lanczos", "lars_resize_tables_lanczos", "lars_resize_lanczos_u8",
 )
 
 
@@ -64,6 +65,14 @@ class FusedArgs(C.Structure):
         ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_size_t),
     ]
+
+
+class ResizePlan(C.Structure):
+    """Mirror of ``lars_resize_plan`` (include/lars_b200.h)."""
+    _fields_ = [(n, C.c_int32) for n in (
+        "in_h", "in_w", "out_h", "out_w", "channels", "need_h", "need_v", "ksize_h", "ksize_v",
+        "row_first", "row_count", "xo_tile", "span_words", "out_pitch")] + [
+        ("table_bytes", C.c_uint64), ("temp_frame_bytes", C.c_uint64)]
 
 
 # numpy view of ``lars_index_stats`` (576 bytes)
@@ -129,6 +138,12 @@ def _declare(lib):
     lib.lars_index_hwc.restype = C.c_int
     lib.lars_index_change_u8.argtypes = [vp, vp, i64, i32, i32, f32, f32, vp, vp, vp, vp, vp]
     lib.lars_index_change_u8.restype = C.c_int
+    lib.lars_resize_plan_lanczos.argtypes = [i32, i32, i32, i32, i32, C.POINTER(ResizePlan)]
+    lib.lars_resize_plan_lanczos.restype = C.c_int
+    lib.lars_resize_tables_lanczos.argtypes = [C.POINTER(ResizePlan), vp]
+    lib.lars_resize_tables_lanczos.restype = C.c_int
+    lib.lars_resize_lanczos_u8.argtypes = [C.POINTER(ResizePlan), vp, vp, i64, i32, vp, i64, vp, C.c_size_t, vp]
+    lib.lars_resize_lanczos_u8.restype = C.c_int
 
 
 def load():
@@ -172,3 +187,14 @@ def histogram_edges(bins: int) -> np.ndarray:
     out = np.empty(bins + 1, np.float32)
     check(load().lars_histogram_edges_f32(bins, out.ctypes.data), "lars_histogram_edges_f32")
     return out
+
+
+def resize_plan(in_h: int, in_w: int, out_h: int, out_w: int, channels: int):
+    """(plan, tables) of a Lanczos resize: geometry + the coefficient block as an int32 array
+    (host-only, no GPU needed)."""
+    lib = load()
+    plan = ResizePlan()
+    check(lib.lars_resize_plan_lanczos(in_h, in_w, out_h, out_w, channels, C.byref(plan)), "lars_resize_plan_lanczos")
+    tables = np.zeros(int(plan.table_bytes) // 4, np.int32)
+    check(lib.lars_resize_tables_lanczos(C.byref(plan), tables.ctypes.data), "lars_resize_tables_lanczos")
+    return plan, tables

@@ -14,6 +14,7 @@
 #include "lars_fused_kernel.cuh"
 #include "lars_map_kernels.cuh"
 #include "lars_u16_kernels.cuh"
+#include "lars_resize_kernels.cuh"
 
 namespace {
 
@@ -588,6 +589,229 @@ int lars_index_change_u8(const uint8_t* early, const uint8_t* late, int64_t n_pi
   if (want < grid) grid = (int)want;
   lars::index_change_u8_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   LARS_CUDA(cudaGetLastError());
+  return LARS_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// Lanczos resize (Pillow Resample.c restated; preprocess_large_image, process-images.py:398-422)
+// ------------------------------------------------------------------------------------------
+namespace {
+
+constexpr double kLanczosSupport = 3.0;
+constexpr int kResizeSmemBudget = 96 * 1024;   // two CTAs per SM
+constexpr int kResizeSmemMax = 200 * 1024;
+
+inline double rs_sinc(double x) {
+  if (x == 0.0) return 1.0;
+  x = x * M_PI;
+  return sin(x) / x;
+}
+inline double rs_lanczos(double x) {
+  if (-3.0 <= x && x < 3.0) return rs_sinc(x) * rs_sinc(x / 3);
+  return 0.0;
+}
+inline int rs_ksize(int in_size, int out_size) {
+  double filterscale = (double)in_size / out_size;
+  if (filterscale < 1.0) filterscale = 1.0;
+  return (int)ceil(kLanczosSupport * filterscale) * 2 + 1;
+}
+// window of output sample xx: first source sample and tap count (Resample.c precompute_coeffs)
+inline void rs_window(int in_size, int out_size, int xx, int* first, int* count) {
+  const double scale = (double)in_size / out_size;
+  double filterscale = scale;
+  if (filterscale < 1.0) filterscale = 1.0;
+  const double support = kLanczosSupport * filterscale;
+  const double center = (xx + 0.5) * scale;
+  int xmin = (int)(center - support + 0.5);
+  if (xmin < 0) xmin = 0;
+  int xmax = (int)(center + support + 0.5);
+  if (xmax > in_size) xmax = in_size;
+  *first = xmin;
+  *count = xmax - xmin;
+}
+// bounds [out][2] and fixed-point coefficients [out][ksize]; `scratch` holds ksize doubles
+void rs_coeffs(int in_size, int out_size, int ksize, int* bounds, int* kk, double* scratch) {
+  const double scale = (double)in_size / out_size;
+  double filterscale = scale;
+  if (filterscale < 1.0) filterscale = 1.0;
+  const double ss = 1.0 / filterscale;
+  for (int xx = 0; xx < out_size; ++xx) {
+    int xmin, cnt;
+    rs_window(in_size, out_size, xx, &xmin, &cnt);
+    const double center = (xx + 0.5) * scale;
+    double ww = 0.0;
+    for (int x = 0; x < cnt; ++x) {
+      const double w = rs_lanczos((x + xmin - center + 0.5) * ss);
+      scratch[x] = w;
+      ww += w;
+    }
+    int* k = kk + (size_t)xx * ksize;
+    for (int x = 0; x < cnt; ++x) {
+      double v = scratch[x];
+      if (ww != 0.0) v /= ww;
+      k[x] = (v < 0) ? (int)(-0.5 + v * (1 << lars::RS_PRECISION_BITS)) : (int)(0.5 + v * (1 << lars::RS_PRECISION_BITS));
+    }
+    for (int x = cnt; x < ksize; ++x) k[x] = 0;
+    bounds[2 * xx] = xmin;
+    bounds[2 * xx + 1] = cnt;
+  }
+}
+// shared bytes of the horizontal pass for `tile` output columns per CTA
+int rs_h_smem(int in_w, int out_w, int channels, int tile, int* span_words, int* out_pitch) {
+  int span_max = 0;
+  for (int xo0 = 0; xo0 < out_w; xo0 += tile) {
+    const int last = (xo0 + tile < out_w ? xo0 + tile : out_w) - 1;
+    int f0, c0, f1, c1;
+    rs_window(in_w, out_w, xo0, &f0, &c0);
+    rs_window(in_w, out_w, last, &f1, &c1);
+    const int span = (f1 + c1 - f0) * channels;
+    if (span > span_max) span_max = span;
+  }
+  *span_words = (span_max + 3) / 4 + 1;
+  int pw = (tile * channels + 3) / 4;
+  if ((pw & 1) == 0) ++pw;                       // odd word pitch: lanes (rows) fall on distinct banks
+  *out_pitch = pw * 4;
+  return *span_words * lars::RS_IN_PITCH * 4 + lars::RS_ROWS * *out_pitch;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lars_resize_plan_lanczos(int32_t in_h, int32_t in_w, int32_t out_h, int32_t out_w, int32_t channels,
+                             lars_resize_plan* plan) {
+  if (!plan) return fail(LARS_ERR_INVALID, "lars_resize_plan_lanczos: NULL plan");
+  if (in_h < 1 || in_w < 1 || out_h < 1 || out_w < 1)
+    return fail(LARS_ERR_INVALID, "lars_resize_plan_lanczos: sizes must be positive");
+  if (channels != 1 && channels != 3 && channels != 4)
+    return fail(LARS_ERR_UNSUPPORTED, "lars_resize_plan_lanczos: %d channels (1, 3 or 4)", channels);
+  if ((long long)in_w * channels > 0x7fffffffll / 2 || (long long)out_w * channels > 0x7fffffffll / 2)
+    return fail(LARS_ERR_UNSUPPORTED, "lars_resize_plan_lanczos: rows longer than 2^30 bytes");
+  memset(plan, 0, sizeof(*plan));
+  plan->in_h = in_h; plan->in_w = in_w; plan->out_h = out_h; plan->out_w = out_w; plan->channels = channels;
+  plan->need_h = (out_w != in_w);
+  plan->need_v = (out_h != in_h);
+  plan->ksize_h = plan->need_h ? rs_ksize(in_w, out_w) : 0;
+  plan->ksize_v = plan->need_v ? rs_ksize(in_h, out_h) : 0;
+  plan->row_first = 0;
+  plan->row_count = in_h;
+  if (plan->need_h && plan->need_v) {
+    int f0, c0, f1, c1;
+    rs_window(in_h, out_h, 0, &f0, &c0);
+    rs_window(in_h, out_h, out_h - 1, &f1, &c1);
+    plan->row_first = f0;                       // Resample.c ybox_first
+    plan->row_count = f1 + c1 - f0;             // ybox_last - ybox_first
+  }
+  if (plan->need_h) {
+    int tile = 64, smem = 0;
+    for (;; tile >>= 1) {
+      smem = rs_h_smem(in_w, out_w, channels, tile, &plan->span_words, &plan->out_pitch);
+      if (smem <= kResizeSmemBudget || tile == 1) break;
+    }
+    if (smem > kResizeSmemMax)
+      return fail(LARS_ERR_UNSUPPORTED, "lars_resize_plan_lanczos: a %d -> %d filter window needs %d bytes of shared memory",
+                  in_w, out_w, smem);
+    plan->xo_tile = tile;
+  }
+  plan->table_bytes = 4ull * ((uint64_t)(plan->need_h ? out_w : 0) * (2 + plan->ksize_h) +
+                              (uint64_t)(plan->need_v ? out_h : 0) * (2 + plan->ksize_v));
+  if (plan->table_bytes == 0) plan->table_bytes = 4;
+  plan->temp_frame_bytes = (plan->need_h && plan->need_v)
+                               ? (((uint64_t)plan->row_count * out_w * channels + 15ull) & ~15ull) : 0;
+  return LARS_OK;
+}
+
+int lars_resize_tables_lanczos(const lars_resize_plan* plan, void* tables_host) {
+  if (!plan || !tables_host) return fail(LARS_ERR_INVALID, "lars_resize_tables_lanczos: NULL pointer");
+  int* t = static_cast<int*>(tables_host);
+  const int kmax = plan->ksize_h > plan->ksize_v ? plan->ksize_h : plan->ksize_v;
+  double* scratch = static_cast<double*>(malloc(sizeof(double) * (size_t)(kmax + 1)));
+  if (!scratch) return fail(LARS_ERR_INVALID, "lars_resize_tables_lanczos: out of host memory");
+  if (plan->need_h) {
+    int* bounds = t;
+    int* kk = t + 2 * (size_t)plan->out_w;
+    rs_coeffs(plan->in_w, plan->out_w, plan->ksize_h, bounds, kk, scratch);
+    t = kk + (size_t)plan->out_w * plan->ksize_h;
+  }
+  if (plan->need_v) {
+    int* bounds = t;
+    int* kk = t + 2 * (size_t)plan->out_h;
+    rs_coeffs(plan->in_h, plan->out_h, plan->ksize_v, bounds, kk, scratch);
+    for (int i = 0; i < plan->out_h; ++i) bounds[2 * i] -= plan->row_first;   // rows of the intermediate image
+  }
+  if (!plan->need_h && !plan->need_v) t[0] = 0;
+  free(scratch);
+  return LARS_OK;
+}
+
+int lars_resize_lanczos_u8(const lars_resize_plan* plan, const void* tables_dev, const uint8_t* src,
+                           int64_t src_frame_stride, int32_t n_frames, uint8_t* dst, int64_t dst_frame_stride,
+                           void* temp, size_t temp_bytes, void* stream) {
+  DeviceState* st = nullptr;
+  int rc = current_state(&st);
+  if (rc != LARS_OK) return rc;
+  if (!plan || !tables_dev || !src || !dst) return fail(LARS_ERR_INVALID, "lars_resize_lanczos_u8: NULL pointer");
+  if (n_frames < 1 || n_frames > 65535) return fail(LARS_ERR_INVALID, "lars_resize_lanczos_u8: n_frames must be 1..65535");
+  if (reinterpret_cast<uintptr_t>(tables_dev) & 3u) return fail(LARS_ERR_INVALID, "lars_resize_lanczos_u8: tables must be 4-byte aligned");
+  const int C = plan->channels;
+  const long long in_frame = (long long)plan->in_h * plan->in_w * C, out_frame = (long long)plan->out_h * plan->out_w * C;
+  if (src_frame_stride < in_frame || dst_frame_stride < out_frame)
+    return fail(LARS_ERR_INVALID, "lars_resize_lanczos_u8: frame strides smaller than a frame");
+  if (plan->temp_frame_bytes && (!temp || temp_bytes < plan->temp_frame_bytes * (uint64_t)n_frames))
+    return fail(LARS_ERR_INVALID, "lars_resize_lanczos_u8: temp must hold %llu bytes",
+                (unsigned long long)(plan->temp_frame_bytes * (uint64_t)n_frames));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int* t = static_cast<const int*>(tables_dev);
+  if (!plan->need_h && !plan->need_v) {          // Image.resize returns a copy
+    LARS_CUDA(cudaMemcpy2DAsync(dst, (size_t)dst_frame_stride, src, (size_t)src_frame_stride, (size_t)in_frame,
+                                (size_t)n_frames, cudaMemcpyDeviceToDevice, s));
+    return LARS_OK;
+  }
+  const uint8_t* v_src = src;
+  long long v_src_stride = src_frame_stride;
+  if (plan->need_h) {
+    lars::ResizeHParams p;
+    p.src = src; p.src_frame_stride = src_frame_stride;
+    p.dst = plan->need_v ? static_cast<uint8_t*>(temp) : dst;
+    p.dst_frame_stride = plan->need_v ? (long long)plan->temp_frame_bytes : dst_frame_stride;
+    p.bounds = t; p.kk = t + 2 * (size_t)plan->out_w;
+    p.in_w = plan->in_w; p.out_w = plan->out_w; p.ksize = plan->ksize_h;
+    p.row_first = plan->row_first; p.row_count = plan->row_count;
+    p.xo_tile = plan->xo_tile; p.span_words = plan->span_words; p.out_pitch = plan->out_pitch;
+    const int smem = plan->span_words * lars::RS_IN_PITCH * 4 + lars::RS_ROWS * plan->out_pitch;
+    if (smem > kResizeSmemMax) return fail(LARS_ERR_INVALID, "lars_resize_lanczos_u8: inconsistent plan");
+    const long long gy = (plan->row_count + lars::RS_ROWS - 1) / lars::RS_ROWS;
+    if (gy > 65535) return fail(LARS_ERR_UNSUPPORTED, "lars_resize_lanczos_u8: more than 2,097,120 rows");
+    dim3 grid((plan->out_w + plan->xo_tile - 1) / plan->xo_tile, (unsigned)gy, n_frames);
+    auto launch = [&](auto kern) -> int {
+      if (smem > 48 * 1024) LARS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      kern<<<grid, lars::RS_THREADS, smem, s>>>(p);
+      return LARS_OK;
+    };
+    rc = (C == 1) ? launch(lars::resize_h_kernel<1>) : (C == 3) ? launch(lars::resize_h_kernel<3>) : launch(lars::resize_h_kernel<4>);
+    if (rc != LARS_OK) return rc;
+    LARS_CUDA(cudaGetLastError());
+    t = p.kk + (size_t)plan->out_w * plan->ksize_h;
+    v_src = static_cast<const uint8_t*>(temp);
+    v_src_stride = (long long)plan->temp_frame_bytes;
+  }
+  if (plan->need_v) {
+    lars::ResizeVParams p;
+    p.src = v_src; p.src_frame_stride = v_src_stride;
+    p.dst = dst; p.dst_frame_stride = dst_frame_stride;
+    p.bounds = t; p.kk = t + 2 * (size_t)plan->out_h;
+    p.row_bytes = plan->out_w * C; p.out_h = plan->out_h; p.ksize = plan->ksize_v;
+    if (plan->out_h > 65535) return fail(LARS_ERR_UNSUPPORTED, "lars_resize_lanczos_u8: more than 65535 output rows");
+    const bool vec4 = (p.row_bytes % 4 == 0) && (v_src_stride % 4 == 0) && (dst_frame_stride % 4 == 0) &&
+                      !(reinterpret_cast<uintptr_t>(v_src) & 3u) && !(reinterpret_cast<uintptr_t>(dst) & 3u);
+    const int per = lars::RS_THREADS * (vec4 ? 4 : 1);
+    dim3 grid((p.row_bytes + per - 1) / per, plan->out_h, n_frames);
+    if (vec4) lars::resize_v_kernel<4><<<grid, lars::RS_THREADS, 0, s>>>(p);
+    else lars::resize_v_kernel<1><<<grid, lars::RS_THREADS, 0, s>>>(p);
+    LARS_CUDA(cudaGetLastError());
+  }
   return LARS_OK;
 }
 

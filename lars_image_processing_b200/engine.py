@@ -116,6 +116,8 @@ class Engine:
             check(self.lib.lars_init(self.device_index), "lars_init")
             self.sm_count = check(self.lib.lars_sm_count(), "lars_sm_count")
         self._tls = threading.local()
+        self._resize_plans: Dict[tuple, tuple] = {}
+        self._resize_lock = threading.Lock()
 
     # ------------------------------------------------------------------ plumbing
     def stream(self) -> torch.cuda.Stream:
@@ -310,6 +312,65 @@ class Engine:
             lut = res.wb_lut
         return self.fused(frames, lut, outputs=outputs, out=res, stream=s, **kw)
 
+    # ------------------------------------------------------------------ resize in front of the path
+    @staticmethod
+    def preprocess_target(height: int, width: int, max_dimension: int = 1024):
+        """process-images.py:404-416: (new_h, new_w), or None when the frame is small enough."""
+        if max(height, width) <= max_dimension:
+            return None
+        if height > width:
+            return max_dimension, int(width * (max_dimension / height))
+        return int(height * (max_dimension / width)), max_dimension
+
+    def _resize_plan(self, in_h, in_w, out_h, out_w, channels):
+        key = (in_h, in_w, out_h, out_w, channels)
+        with self._resize_lock:
+            hit = self._resize_plans.get(key)
+            if hit is None:
+                plan, tables = _lib.resize_plan(in_h, in_w, out_h, out_w, channels)
+                dev = torch.from_numpy(tables).to(self.device)      # synchronous: once per geometry
+                hit = (plan, dev)
+                self._resize_plans[key] = hit
+        return hit
+
+    def resize_device(self, frames: DeviceFrames, out_h: int, out_w: int, stream=None) -> DeviceFrames:
+        """K10: Pillow-exact Lanczos resize of a device-resident uint8 batch (the GPU form of
+        preprocess_large_image, process-images.py:398-422) -> a new padded device batch."""
+        if frames.sample_bytes != 1:
+            raise LarsError("resize covers uint8 frames (Pillow cannot hold multi-channel 16-bit images)")
+        if out_h < 1 or out_w < 1:
+            raise ValueError("height and width must be > 0")         # Pillow's message
+        s = stream or self.stream()
+        in_h, in_w = frames.shape
+        plan, tables = self._resize_plan(in_h, in_w, out_h, out_w, frames.channels)
+        out = self.alloc_frames(frames.n_frames, out_h, out_w, frames.channels, s)
+        temp_bytes = int(plan.temp_frame_bytes) * frames.n_frames
+        temp = self._alloc((max(temp_bytes, 16),), torch.uint8, s)
+        with torch.cuda.device(self.device):
+            check(self.lib.lars_resize_lanczos_u8(C.byref(plan), tables.data_ptr(), frames.data.data_ptr(),
+                                                  frames.stride_bytes, frames.n_frames, out.data.data_ptr(),
+                                                  out.stride_bytes, temp.data_ptr(), temp_bytes, s.cuda_stream),
+                  "lars_resize_lanczos_u8")
+        temp.record_stream(s)
+        return out
+
+    def resize_batch(self, frames: Sequence[np.ndarray], out_h: int, out_w: int) -> List[np.ndarray]:
+        """Host uint8 frames (HxWxC or HxW) in, resized host frames out."""
+        arrs = [np.asarray(f) for f in frames]
+        two_d = arrs[0].ndim == 2
+        if any(a.dtype != np.uint8 for a in arrs):
+            raise TypeError("resize needs uint8 frames")
+        s = self.stream()
+        dev = self.upload([a[:, :, None] if two_d else a for a in arrs], stream=s)
+        out = self.resize_device(dev, out_h, out_w, s)
+        n = out_h * out_w * dev.channels
+        with torch.cuda.stream(s):
+            host = torch.empty((dev.n_frames, n), dtype=torch.uint8, pin_memory=True)
+            host.copy_(out.data[:, :n], non_blocking=True)
+        s.synchronize()
+        shape = (out_h, out_w) if two_d else (out_h, out_w, dev.channels)
+        return [host[i].numpy().reshape(shape).copy() for i in range(dev.n_frames)]
+
     # ------------------------------------------------------------------ host-array API
     def download(self, res: DeviceOutputs, stream=None, pinned: bool = True) -> List[dict]:
         """Copy the requested products of every frame back to host memory -> list of dicts."""
@@ -382,8 +443,9 @@ class Engine:
         return out
 
     def run_host_batch(self, host_frames: torch.Tensor, shape, host_out: Dict[str, torch.Tensor],
-                       chunk: int = 4, white_balance: bool = True, **kw) -> None:
-        """Host frames in (pinned ``[F, H*W*C]`` uint8), host results out, software-pipelined.
+                       chunk: int = 4, white_balance: bool = True, sample_bytes: int = 1, **kw) -> None:
+        """Host frames in (pinned ``[F, H*W*C]`` uint8, or ``[F, H*W*C*2]`` bytes of little-endian
+        uint16 samples with ``sample_bytes=2``), host results out, software-pipelined.
 
         The batch is cut into chunks of ``chunk`` frames; H2D of chunk c+1, the kernels of chunk
         c and D2H of chunk c-1 run concurrently on three streams over double-buffered device
@@ -393,15 +455,17 @@ class Engine:
         h, w, ch = shape
         F = host_frames.shape[0]
         npx = h * w
-        nbytes = npx * ch
+        nbytes = npx * ch * sample_bytes
+        if host_frames.dtype != torch.uint8 or host_frames.shape[1] != nbytes:
+            raise ValueError(f"host_frames must be uint8 [F, {nbytes}] for this shape / sample width")
         outputs = tuple(k for k in ALL_OUTPUTS if k in host_out)
         st = getattr(self._tls, "pipe", None)
-        key = (chunk, h, w, ch, outputs)
+        key = (chunk, h, w, ch, outputs, sample_bytes)
         if st is None or st["key"] != key:
             s_in, s_cmp, s_out = (torch.cuda.Stream(device=self.device) for _ in range(3))
             slots = []
             for _ in range(2):
-                frames = self.alloc_frames(chunk, h, w, ch, s_cmp)
+                frames = self.alloc_frames(chunk, h, w, ch, s_cmp, sample_bytes=sample_bytes)
                 slots.append({"frames": frames, "res": self.alloc_outputs(frames, outputs, s_cmp)})
             st = {"key": key, "streams": (s_in, s_cmp, s_out), "slots": slots}
             self._tls.pipe = st
@@ -416,7 +480,7 @@ class Engine:
             k = b - a
             slot = slots[c & 1]
             fr: DeviceFrames = slot["frames"]
-            view = DeviceFrames(fr.data[:k], fr.n_pixels, fr.channels, fr.shape)
+            view = DeviceFrames(fr.data[:k], fr.n_pixels, fr.channels, fr.shape, fr.sample_bytes)
             with torch.cuda.stream(s_in):
                 if c >= 2:
                     s_in.wait_event(ev_cmp[c - 2])          # slot's input consumed
@@ -438,7 +502,7 @@ class Engine:
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_cmp[c])
                 if "wb" in host_out:
-                    host_out["wb"][a:b].copy_(sub.wb[:k, :nbytes], non_blocking=True)
+                    host_out["wb"][a:b].copy_(sub.wb[:k, :npx * ch], non_blocking=True)
                 if "maps" in host_out:
                     for i in range(3):
                         if sub.map_mask[i]:
@@ -468,11 +532,17 @@ class Engine:
         return img
 
     def analyze_batch(self, frames: Sequence[np.ndarray], outputs=ALL_OUTPUTS, white_balance=True,
-                      **kw) -> List[dict]:
-        """Host frames in, host results out (H2D, Pass 1, LUT, Pass 2, D2H, one sync)."""
+                      max_dimension: Optional[int] = None, **kw) -> List[dict]:
+        """Host frames in, host results out (H2D, [resize,] Pass 1, LUT, Pass 2, D2H, one sync).
+        ``max_dimension``: apply preprocess_large_image (process-images.py:398-422) on the device
+        first, as the app does before every analysis (:1130, :1444)."""
         frames = [self._check_frame(f) for f in frames]
         s = self.stream()
         dev = self.upload(frames, stream=s)
+        if max_dimension is not None:
+            target = self.preprocess_target(dev.shape[0], dev.shape[1], max_dimension)
+            if target is not None:
+                dev = self.resize_device(dev, target[0], target[1], s)
         res = self.process_device(dev, outputs=outputs, white_balance=white_balance, stream=s, **kw)
         return self.download(res, stream=s)
 

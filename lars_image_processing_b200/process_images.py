@@ -13,9 +13,9 @@ from typing import List, Optional
 
 import numpy as np
 
-from .engine import (DEFAULT_BINS, INDEX_TYPES, get_engine)
+from .engine import DEFAULT_BINS, INDEX_TYPES, Engine, get_engine
 
-__all__ = ["fix_white_balance", "calculate_index", "analyze_index", "analyze_frame",
+__all__ = ["preprocess_large_image", "fix_white_balance", "calculate_index", "analyze_index", "analyze_frame",
            "calculate_index_statistics_by_timeframe", "create_index_visualization",
            "create_change_detection_visualization", "index_change"]
 
@@ -27,6 +27,26 @@ def _feature_name(index_type: str) -> str:
 def _check_index_type(index_type: str) -> None:
     if index_type not in INDEX_TYPES:
         raise ValueError(f"Unknown index type: {index_type}")       # process-images.py:485
+
+
+def preprocess_large_image(img_array, max_dimension=1024):
+    """process-images.py:398-422 -- shrink a frame so that max(h, w) == max_dimension with Pillow's
+    LANCZOS filter; frames that are already small enough are returned as they are (same object).
+
+    GPU path: K10h + K10v, bit-identical to ``Image.fromarray(img).resize(..., LANCZOS)``.
+    """
+    if img_array is None or img_array.size == 0:                     # :401-402
+        return None
+    h, w = img_array.shape[:2]
+    target = Engine.preprocess_target(h, w, max_dimension)           # :404-416
+    if target is None:
+        return img_array
+    arr = np.asarray(img_array)
+    if arr.dtype != np.uint8 or arr.ndim not in (2, 3) or (arr.ndim == 3 and arr.shape[2] != 3):
+        # Image.fromarray accepts more layouts (RGBA is resized with premultiplied alpha, float /
+        # int32 single-band images in their own precision); the RGNir path only produces these two
+        raise TypeError(f"Cannot handle this data type: {arr.shape[2:] or (1,)}, {arr.dtype.str}")
+    return get_engine().resize_batch([arr], target[0], target[1])[0]
 
 
 def fix_white_balance(img_array):

@@ -1,0 +1,143 @@
+"""Lanczos resize in front of the path (preprocess_large_image, process-images.py:398-422).
+
+The arithmetic is Pillow's (src/libImaging/Resample.c); Pillow is installed here and on the GPU
+box, so both the NumPy restatement (oracle/resize_np.py) and the CUDA kernels are compared with
+``PIL.Image.resize(..., LANCZOS)`` itself -- bit-exact."""
+import numpy as np
+import pytest
+from PIL import Image
+
+from oracle import resize_np
+from oracle import synth
+
+# (in_h, in_w, out_h, out_w)
+GEOMETRIES = [(37, 53, 11, 20), (300, 400, 75, 100), (123, 77, 150, 200), (64, 64, 32, 64), (64, 64, 64, 32),
+              (5, 7, 2, 3), (1, 100, 1, 10), (100, 1, 10, 1), (50, 50, 50, 50), (960, 1280, 768, 1024),
+              (333, 1001, 97, 255)]
+
+
+def pil_resize(img, out_h, out_w):
+    return np.array(Image.fromarray(img).resize((out_w, out_h), Image.Resampling.LANCZOS))
+
+
+def stripes(h, w, c):
+    img = np.zeros((h, w, c), np.uint8)
+    img[::2] = 255
+    img[:, ::3] = 255
+    return img
+
+
+# --------------------------------------------------------------------------------- CPU (oracle + host tables)
+@pytest.mark.parametrize("geom", GEOMETRIES)
+def test_oracle_matches_pillow(geom):
+    ih, iw, oh, ow = geom
+    rng = np.random.default_rng(ih * 7919 + iw)
+    for img in (rng.integers(0, 256, (ih, iw, 3), dtype=np.uint8), stripes(ih, iw, 3),
+                rng.integers(0, 256, (ih, iw), dtype=np.uint8)):
+        assert np.array_equal(resize_np.resize_lanczos(img, ow, oh), pil_resize(img, oh, ow))
+
+
+def test_oracle_preprocess_large_image_matches_pillow_chain():
+    img = synth.vegetation_frame(31, 1200, 1700)
+    got = resize_np.preprocess_large_image(img, 1024)
+    new_w, new_h = 1024, int(1200 * (1024 / 1700))                 # process-images.py:411-416
+    assert got.shape == (new_h, new_w, 3)
+    assert np.array_equal(got, pil_resize(img, new_h, new_w))
+    small = synth.vegetation_frame(32, 100, 200)
+    assert resize_np.preprocess_large_image(small, 1024) is small  # :407-408 returns the input itself
+    assert resize_np.preprocess_large_image(None) is None
+    tall = synth.vegetation_frame(33, 1500, 700)
+    assert resize_np.preprocess_large_image(tall, 1024).shape == (1024, int(700 * (1024 / 1500)), 3)
+
+
+@pytest.mark.parametrize("geom", GEOMETRIES + [(3000, 4000, 768, 1024), (3648, 5472, 682, 1024),
+                                               (4096, 4096, 1024, 1024)])
+def test_host_coefficient_tables_match_the_oracle(geom):
+    """lars_resize_tables_lanczos (host code of the C ABI, no GPU) == Resample.c restatement."""
+    from lars_image_processing_b200 import _lib
+    ih, iw, oh, ow = geom
+    plan, t = _lib.resize_plan(ih, iw, oh, ow, 3)
+    assert (plan.need_h, plan.need_v) == (int(ow != iw), int(oh != ih))
+    off = 0
+    if plan.need_h:
+        ks, b, k = resize_np.precompute_coeffs(iw, ow)
+        assert ks == plan.ksize_h
+        assert np.array_equal(t[off:off + 2 * ow].reshape(ow, 2), b)
+        off += 2 * ow
+        assert np.array_equal(t[off:off + ow * ks].reshape(ow, ks), k)
+        off += ow * ks
+    if plan.need_v:
+        ks, b, k = resize_np.precompute_coeffs(ih, oh)
+        assert ks == plan.ksize_v
+        b = b.copy()
+        b[:, 0] -= plan.row_first
+        assert np.array_equal(t[off:off + 2 * oh].reshape(oh, 2), b)
+        off += 2 * oh
+        assert np.array_equal(t[off:off + oh * ks].reshape(oh, ks), k)
+    if plan.need_h and plan.need_v:
+        assert plan.row_first + plan.row_count <= ih and plan.temp_frame_bytes >= plan.row_count * ow * 3
+
+
+def test_resize_plan_rejects_bad_arguments():
+    import ctypes as C
+    from lars_image_processing_b200 import _lib
+    lib = _lib.load()
+    plan = _lib.ResizePlan()
+    assert lib.lars_resize_plan_lanczos(0, 10, 5, 5, 3, C.byref(plan)) < 0
+    assert lib.lars_resize_plan_lanczos(10, 10, 5, 5, 2, C.byref(plan)) < 0
+    assert lib.lars_resize_plan_lanczos(10, 10, 5, 5, 3, None) < 0
+    assert b"channels" in lib.lars_last_error() or b"NULL" in lib.lars_last_error()
+    # a window that cannot fit in shared memory is refused, not silently mis-computed
+    assert lib.lars_resize_plan_lanczos(8, 2_000_000, 8, 64, 3, C.byref(plan)) < 0
+
+
+# --------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("geom", GEOMETRIES + [(1500, 2000, 384, 512)])
+def test_gpu_resize_is_bit_identical_to_pillow(engine, geom):
+    ih, iw, oh, ow = geom
+    rng = np.random.default_rng(ih * 31 + iw)
+    frames = [rng.integers(0, 256, (ih, iw, 3), dtype=np.uint8), stripes(ih, iw, 3),
+              synth.vegetation_frame(ih + iw, ih, iw)]
+    got = engine.resize_batch(frames, oh, ow)
+    for g, f in zip(got, frames):
+        assert g.shape == (oh, ow, 3) and g.dtype == np.uint8
+        assert np.array_equal(g, pil_resize(f, oh, ow))
+    gray = rng.integers(0, 256, (ih, iw), dtype=np.uint8)
+    assert np.array_equal(engine.resize_batch([gray], oh, ow)[0], pil_resize(gray, oh, ow))
+
+
+@pytest.mark.gpu
+def test_gpu_preprocess_large_image_drop_in(engine):
+    from lars_image_processing_b200 import process_images as pi
+    assert pi.preprocess_large_image(None) is None
+    assert pi.preprocess_large_image(np.zeros((0, 0, 3), np.uint8)) is None
+    small = synth.vegetation_frame(41, 600, 800)
+    assert pi.preprocess_large_image(small) is small
+    for h, w in ((3000, 4000), (2000, 1100), (1025, 1025)):
+        img = synth.vegetation_frame(h + w, h, w)
+        got = pi.preprocess_large_image(img, 1024)
+        want = resize_np.preprocess_large_image(img, 1024)
+        assert got.shape == want.shape and np.array_equal(got, want)
+        t = resize_np.target_size(h, w, 1024)
+        assert np.array_equal(got, pil_resize(img, t[0], t[1]))
+    with pytest.raises(TypeError):
+        pi.preprocess_large_image(np.zeros((2000, 2000, 3), np.uint16))
+
+
+@pytest.mark.gpu
+def test_gpu_analysis_after_device_side_resize(engine):
+    """The app's order -- preprocess_large_image, then white balance and indices (process-images.py:1130,
+    :1444-1457, :1522) -- in one trip: resize on the device, analysis on the resized frame."""
+    import warnings
+    from oracle import oracle_np as o
+    img = synth.vegetation_frame(77, 1536, 2048)
+    res = engine.analyze_batch([img], max_dimension=1024)[0]
+    small = resize_np.preprocess_large_image(img, 1024)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = o.analyze_frame(small)
+    assert np.array_equal(res["wb"], want["wb"])
+    for t in o.INDEX_TYPES:
+        assert np.array_equal(res["maps"][t].view(np.uint32), want["maps"][t].view(np.uint32))
+        assert np.array_equal(res["stats"][t]["hist"], want["stats"][t]["hist"])
