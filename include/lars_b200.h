@@ -221,7 +221,8 @@ typedef struct lars_resize_plan {
   int32_t need_h, need_v;         /* which passes run (Resample.c need_horizontal / need_vertical)   */
   int32_t ksize_h, ksize_v;       /* taps per output column / row                                    */
   int32_t row_first, row_count;   /* source rows the horizontal pass produces (ybox_first .. last)   */
-  int32_t xo_tile, span_words, out_pitch; /* launch geometry of the horizontal pass                  */
+  int32_t xo_tile, plane_words, out_pitch; /* launch geometry of the horizontal pass                 */
+  int32_t groups_h, groups_v;     /* 4-tap coefficient groups per output column / row                */
   uint64_t table_bytes;           /* size of the coefficient block (host and device copies)          */
   uint64_t temp_frame_bytes;      /* intermediate image bytes per frame (multiple of 16); 0 if unused */
 } lars_resize_plan;

@@ -659,21 +659,40 @@ void rs_coeffs(int in_size, int out_size, int ksize, int* bounds, int* kk, doubl
   }
 }
 // shared bytes of the horizontal pass for `tile` output columns per CTA
-int rs_h_smem(int in_w, int out_w, int channels, int tile, int* span_words, int* out_pitch) {
-  int span_max = 0;
+int rs_h_smem(int in_w, int out_w, int channels, int tile, int* plane_words, int* out_pitch) {
+  int span_max = 0;                              // pixels
   for (int xo0 = 0; xo0 < out_w; xo0 += tile) {
     const int last = (xo0 + tile < out_w ? xo0 + tile : out_w) - 1;
     int f0, c0, f1, c1;
     rs_window(in_w, out_w, xo0, &f0, &c0);
     rs_window(in_w, out_w, last, &f1, &c1);
-    const int span = (f1 + c1 - f0) * channels;
+    const int span = f1 + c1 - f0;
     if (span > span_max) span_max = span;
   }
-  *span_words = (span_max + 3) / 4 + 1;
+  *plane_words = (span_max + 3) / 4 + 4;         // + slack: tile origin rounded down to 4 pixels, last tap group
   int pw = (tile * channels + 3) / 4;
   if ((pw & 1) == 0) ++pw;                       // odd word pitch: lanes (rows) fall on distinct banks
   *out_pitch = pw * 4;
-  return *span_words * lars::RS_IN_PITCH * 4 + lars::RS_ROWS * *out_pitch;
+  return channels * *plane_words * lars::RS_IN_PITCH * 4 + lars::RS_ROWS * *out_pitch;
+}
+// [n][ksize] int coefficients -> [n][groups][3] byte planes of 4 taps (bits 0-7, 8-15 unsigned; 16-23 signed)
+bool rs_pack_planes(const int* kk, int n, int ksize, int groups, uint32_t* out) {
+  for (int i = 0; i < n; ++i)
+    for (int g = 0; g < groups; ++g) {
+      uint32_t w0 = 0, w1 = 0, w2 = 0;
+      for (int t = 0; t < 4; ++t) {
+        const int idx = 4 * g + t;
+        const int k = idx < ksize ? kk[(size_t)i * ksize + idx] : 0;
+        const int hi = k >> 16;                  // arithmetic shift: floor
+        if (hi < -128 || hi > 127) return false;
+        w0 |= (uint32_t)(k & 255) << (8 * t);
+        w1 |= (uint32_t)((k >> 8) & 255) << (8 * t);
+        w2 |= (uint32_t)(hi & 255) << (8 * t);
+      }
+      uint32_t* o = out + ((size_t)i * groups + g) * 3;
+      o[0] = w0; o[1] = w1; o[2] = w2;
+    }
+  return true;
 }
 
 }  // namespace
@@ -707,7 +726,7 @@ int lars_resize_plan_lanczos(int32_t in_h, int32_t in_w, int32_t out_h, int32_t 
   if (plan->need_h) {
     int tile = 64, smem = 0;
     for (;; tile >>= 1) {
-      smem = rs_h_smem(in_w, out_w, channels, tile, &plan->span_words, &plan->out_pitch);
+      smem = rs_h_smem(in_w, out_w, channels, tile, &plan->plane_words, &plan->out_pitch);
       if (smem <= kResizeSmemBudget || tile == 1) break;
     }
     if (smem > kResizeSmemMax)
@@ -715,8 +734,10 @@ int lars_resize_plan_lanczos(int32_t in_h, int32_t in_w, int32_t out_h, int32_t 
                   in_w, out_w, smem);
     plan->xo_tile = tile;
   }
-  plan->table_bytes = 4ull * ((uint64_t)(plan->need_h ? out_w : 0) * (2 + plan->ksize_h) +
-                              (uint64_t)(plan->need_v ? out_h : 0) * (2 + plan->ksize_v));
+  plan->groups_h = (plan->ksize_h + 3) / 4;
+  plan->groups_v = (plan->ksize_v + 3) / 4;
+  plan->table_bytes = 4ull * ((uint64_t)(plan->need_h ? out_w : 0) * (2 + 3 * plan->groups_h) +
+                              (uint64_t)(plan->need_v ? out_h : 0) * (2 + 3 * plan->groups_v));
   if (plan->table_bytes == 0) plan->table_bytes = 4;
   plan->temp_frame_bytes = (plan->need_h && plan->need_v)
                                ? (((uint64_t)plan->row_count * out_w * channels + 15ull) & ~15ull) : 0;
@@ -731,14 +752,24 @@ int lars_resize_tables_lanczos(const lars_resize_plan* plan, void* tables_host) 
   if (!scratch) return fail(LARS_ERR_INVALID, "lars_resize_tables_lanczos: out of host memory");
   if (plan->need_h) {
     int* bounds = t;
-    int* kk = t + 2 * (size_t)plan->out_w;
+    uint32_t* planes = reinterpret_cast<uint32_t*>(t + 2 * (size_t)plan->out_w);
+    int* kk = static_cast<int*>(malloc(sizeof(int) * (size_t)plan->out_w * plan->ksize_h));
+    if (!kk) { free(scratch); return fail(LARS_ERR_INVALID, "lars_resize_tables_lanczos: out of host memory"); }
     rs_coeffs(plan->in_w, plan->out_w, plan->ksize_h, bounds, kk, scratch);
-    t = kk + (size_t)plan->out_w * plan->ksize_h;
+    const bool ok = rs_pack_planes(kk, plan->out_w, plan->ksize_h, plan->groups_h, planes);
+    free(kk);
+    if (!ok) { free(scratch); return fail(LARS_ERR_UNSUPPORTED, "lars_resize_tables_lanczos: coefficient outside 24 bits"); }
+    t = reinterpret_cast<int*>(planes + (size_t)plan->out_w * plan->groups_h * 3);
   }
   if (plan->need_v) {
     int* bounds = t;
-    int* kk = t + 2 * (size_t)plan->out_h;
+    uint32_t* planes = reinterpret_cast<uint32_t*>(t + 2 * (size_t)plan->out_h);
+    int* kk = static_cast<int*>(malloc(sizeof(int) * (size_t)plan->out_h * plan->ksize_v));
+    if (!kk) { free(scratch); return fail(LARS_ERR_INVALID, "lars_resize_tables_lanczos: out of host memory"); }
     rs_coeffs(plan->in_h, plan->out_h, plan->ksize_v, bounds, kk, scratch);
+    const bool ok = rs_pack_planes(kk, plan->out_h, plan->ksize_v, plan->groups_v, planes);
+    free(kk);
+    if (!ok) { free(scratch); return fail(LARS_ERR_UNSUPPORTED, "lars_resize_tables_lanczos: coefficient outside 24 bits"); }
     for (int i = 0; i < plan->out_h; ++i) bounds[2 * i] -= plan->row_first;   // rows of the intermediate image
   }
   if (!plan->need_h && !plan->need_v) t[0] = 0;
@@ -776,11 +807,11 @@ int lars_resize_lanczos_u8(const lars_resize_plan* plan, const void* tables_dev,
     p.src = src; p.src_frame_stride = src_frame_stride;
     p.dst = plan->need_v ? static_cast<uint8_t*>(temp) : dst;
     p.dst_frame_stride = plan->need_v ? (long long)plan->temp_frame_bytes : dst_frame_stride;
-    p.bounds = t; p.kk = t + 2 * (size_t)plan->out_w;
-    p.in_w = plan->in_w; p.out_w = plan->out_w; p.ksize = plan->ksize_h;
+    p.bounds = t; p.kk = reinterpret_cast<const uint32_t*>(t + 2 * (size_t)plan->out_w);
+    p.in_w = plan->in_w; p.out_w = plan->out_w; p.groups = plan->groups_h;
     p.row_first = plan->row_first; p.row_count = plan->row_count;
-    p.xo_tile = plan->xo_tile; p.span_words = plan->span_words; p.out_pitch = plan->out_pitch;
-    const int smem = plan->span_words * lars::RS_IN_PITCH * 4 + lars::RS_ROWS * plan->out_pitch;
+    p.xo_tile = plan->xo_tile; p.plane_words = plan->plane_words; p.out_pitch = plan->out_pitch;
+    const int smem = C * plan->plane_words * lars::RS_IN_PITCH * 4 + lars::RS_ROWS * plan->out_pitch;
     if (smem > kResizeSmemMax) return fail(LARS_ERR_INVALID, "lars_resize_lanczos_u8: inconsistent plan");
     const long long gy = (plan->row_count + lars::RS_ROWS - 1) / lars::RS_ROWS;
     if (gy > 65535) return fail(LARS_ERR_UNSUPPORTED, "lars_resize_lanczos_u8: more than 2,097,120 rows");
@@ -790,10 +821,14 @@ int lars_resize_lanczos_u8(const lars_resize_plan* plan, const void* tables_dev,
       kern<<<grid, lars::RS_THREADS, smem, s>>>(p);
       return LARS_OK;
     };
-    rc = (C == 1) ? launch(lars::resize_h_kernel<1>) : (C == 3) ? launch(lars::resize_h_kernel<3>) : launch(lars::resize_h_kernel<4>);
+    const bool fast = (C == 3) && ((long long)plan->in_w * 3 % 4 == 0) && (src_frame_stride % 4 == 0) &&
+                      !(reinterpret_cast<uintptr_t>(src) & 3u);
+    rc = (C == 1) ? launch(lars::resize_h_kernel<1, false>)
+         : (C == 4) ? launch(lars::resize_h_kernel<4, false>)
+         : fast ? launch(lars::resize_h_kernel<3, true>) : launch(lars::resize_h_kernel<3, false>);
     if (rc != LARS_OK) return rc;
     LARS_CUDA(cudaGetLastError());
-    t = p.kk + (size_t)plan->out_w * plan->ksize_h;
+    t = reinterpret_cast<const int*>(p.kk + (size_t)plan->out_w * plan->groups_h * 3);
     v_src = static_cast<const uint8_t*>(temp);
     v_src_stride = (long long)plan->temp_frame_bytes;
   }
@@ -801,8 +836,9 @@ int lars_resize_lanczos_u8(const lars_resize_plan* plan, const void* tables_dev,
     lars::ResizeVParams p;
     p.src = v_src; p.src_frame_stride = v_src_stride;
     p.dst = dst; p.dst_frame_stride = dst_frame_stride;
-    p.bounds = t; p.kk = t + 2 * (size_t)plan->out_h;
-    p.row_bytes = plan->out_w * C; p.out_h = plan->out_h; p.ksize = plan->ksize_v;
+    p.bounds = t; p.kk = reinterpret_cast<const uint32_t*>(t + 2 * (size_t)plan->out_h);
+    p.row_bytes = plan->out_w * C; p.out_h = plan->out_h; p.groups = plan->groups_v;
+    p.src_rows = plan->row_count;
     if (plan->out_h > 65535) return fail(LARS_ERR_UNSUPPORTED, "lars_resize_lanczos_u8: more than 65535 output rows");
     const bool vec4 = (p.row_bytes % 4 == 0) && (v_src_stride % 4 == 0) && (dst_frame_stride % 4 == 0) &&
                       !(reinterpret_cast<uintptr_t>(v_src) & 3u) && !(reinterpret_cast<uintptr_t>(dst) & 3u);

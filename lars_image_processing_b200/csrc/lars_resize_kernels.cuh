@@ -11,9 +11,10 @@
 //
 //   K10h (horizontal): a warp owns one output column at a time and its 32 lanes are 32 image ROWS, so
 //         window position, tap count and coefficients are warp-uniform.  A CTA stages a
-//         [32 rows] x [input span of its output columns] tile in shared memory TRANSPOSED
-//         (word column major, 33-word pitch): the lanes of a warp then hit 32 different banks for
-//         every tap.  Results go through a second shared tile so the global stores are row-contiguous.
+//         [32 rows] x [input span of its output columns] tile in shared memory DE-INTERLEAVED and
+//         TRANSPOSED (channel plane, word column major, 33-word pitch): one conflict-free 32-bit
+//         load brings four taps of one channel, DP4A applies four coefficients at once.  Results go
+//         through a second shared tile so the global stores are row-contiguous.
 //   K10v (vertical): lanes run along the row (4 consecutive bytes per thread); every tap is one
 //         coalesced 32-bit load of the intermediate image (L2-resident: it is 1/scale of the input).
 #pragma once
@@ -33,24 +34,39 @@ __device__ __forceinline__ uint32_t rs_clip8(int acc) {
   return (uint32_t)min(max(v, 0), 255);
 }
 
+// dp4a with unsigned bytes in `a` and signed bytes in `b`
+__device__ __forceinline__ int rs_dp4a_us(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
 struct ResizeHParams {
   const uint8_t* src;        // [frame][in_h][in_w * C]
   uint8_t* dst;              // [frame][row_count][out_w * C]
   const int* bounds;         // [out_w][2]  (first source column, tap count)
-  const int* kk;             // [out_w][ksize]
+  const uint32_t* kk;        // [out_w][groups][3]: byte planes of 4 coefficients (bits 0-7, 8-15, 16-23 signed)
   long long src_frame_stride, dst_frame_stride;
-  int in_w, out_w, ksize;
+  int in_w, out_w, groups;
   int row_first, row_count;  // source rows to produce
   int xo_tile;               // output columns per CTA
-  int span_words;            // shared words per row of the input tile (max over tiles)
+  int plane_words;           // shared words per row per channel plane of the input tile (max over tiles, + slack)
   int out_pitch;             // bytes per row of the output tile (odd number of words)
 };
 
-template <int C>
+// The 22-bit coefficients are split into three byte planes k = k0 + 2^8 k1 + 2^16 k2 (k0, k1 unsigned,
+// k2 signed), so four taps of one channel cost three DP4A on one gathered word instead of four
+// byte extractions + four IMAD; the three partial sums recombine exactly modulo 2^32 and the true
+// value fits in int32 (Resample.c accumulates in int as well).
+// FAST: C == 3 and every row of every frame starts on a 4-byte boundary (in_w * 3 and the frame
+// stride are multiples of 4, the base pointer is 4-byte aligned).
+template <int C, bool FAST>
 __global__ void __launch_bounds__(RS_THREADS) resize_h_kernel(const ResizeHParams p) {
   extern __shared__ __align__(16) uint8_t rs_smem[];
-  uint8_t* in_s = rs_smem;                                                  // [span_words][33] words
-  uint8_t* out_s = rs_smem + (size_t)p.span_words * RS_IN_PITCH * 4;        // [32][out_pitch] bytes
+  const int PW = p.plane_words;
+  uint32_t* in_w32 = reinterpret_cast<uint32_t*>(rs_smem);                  // [C][PW][33] words (planar, transposed)
+  uint8_t* in_s = rs_smem;
+  uint8_t* out_s = rs_smem + (size_t)C * PW * RS_IN_PITCH * 4;              // [32][out_pitch] bytes
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int xo0 = blockIdx.x * p.xo_tile;
   const int nxo = min(p.xo_tile, p.out_w - xo0);
@@ -60,35 +76,82 @@ __global__ void __launch_bounds__(RS_THREADS) resize_h_kernel(const ResizeHParam
   const uint8_t* src = p.src + blockIdx.z * p.src_frame_stride + (long long)(p.row_first + r0) * in_pitch;
   uint8_t* dst = p.dst + blockIdx.z * p.dst_frame_stride + (long long)r0 * p.out_w * C;
 
-  const int b0 = p.bounds[2 * xo0] * C;                                     // first input byte of the tile
-  const int b1 = (p.bounds[2 * (xo0 + nxo - 1)] + p.bounds[2 * (xo0 + nxo - 1) + 1]) * C;
-  const int span = b1 - b0;
+  // tile origin: the first input pixel of the tile, rounded down to a 4-pixel group when the fast
+  // staging path is used (12 bytes = 3 aligned words per group)
+  const int px_first = p.bounds[2 * xo0];
+  const int px0 = FAST ? (px_first & ~3) : px_first;
+  const int px1 = p.bounds[2 * (xo0 + nxo - 1)] + p.bounds[2 * (xo0 + nxo - 1) + 1];
 
-  // ---- stage: global rows (lanes along the row) -> transposed shared tile ----
-  for (int r = warp; r < nrows; r += RS_WARPS) {
-    const uint8_t* row = src + (long long)r * in_pitch + b0;
-    for (int j = lane; j < span; j += 32) in_s[((j >> 2) * RS_IN_PITCH + r) * 4 + (j & 3)] = row[j];
+  // ---- stage: global rows (lanes along the row) -> de-interleaved, transposed shared tile ----
+  if (FAST) {
+    // C == 3, rows 4-byte aligned: a lane turns three aligned words (4 RGB pixels) into one word per
+    // channel plane with six PRMT; groups past the end of the row read inside the frame slot's padding
+    // or the next row and only feed taps whose coefficients are zero / never read
+    const int ngroups = (px1 - px0 + 3) >> 2;
+    const long long row_words_max = ((long long)p.in_w * 3 + 3) >> 2;       // words of one row
+    for (int r = warp; r < nrows; r += RS_WARPS) {
+      const uint32_t* row = reinterpret_cast<const uint32_t*>(src + (long long)r * in_pitch) + (px0 >> 2) * 3;
+      const long long avail = row_words_max - (long long)(px0 >> 2) * 3;    // words left in this row
+      for (int u = lane; u < ngroups; u += 32) {
+        uint32_t w0 = 0, w1 = 0, w2 = 0;
+        if (3 * u + 0 < avail) w0 = __ldg(row + 3 * u);
+        if (3 * u + 1 < avail) w1 = __ldg(row + 3 * u + 1);
+        if (3 * u + 2 < avail) w2 = __ldg(row + 3 * u + 2);
+        // bytes: w0 = R0 G0 B0 R1, w1 = G1 B1 R2 G2, w2 = B2 R3 G3 B3
+        const uint32_t pr = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);   // R0 R1 R2 R3
+        const uint32_t pg = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);   // G0 G1 G2 G3
+        const uint32_t pb = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);   // B0 B1 B2 B3
+        in_w32[(0 * PW + u) * RS_IN_PITCH + r] = pr;
+        in_w32[(1 * PW + u) * RS_IN_PITCH + r] = pg;
+        in_w32[(2 * PW + u) * RS_IN_PITCH + r] = pb;
+      }
+    }
+  } else {
+    const int span = (px1 - px0) * C;
+    for (int r = warp; r < nrows; r += RS_WARPS) {
+      const uint8_t* row = src + (long long)r * in_pitch + (long long)px0 * C;
+      for (int j = lane; j < span; j += 32) {
+        const int x = j / C, c = j - x * C;
+        in_s[((c * PW + (x >> 2)) * RS_IN_PITCH + r) * 4 + (x & 3)] = row[j];
+      }
+    }
   }
   __syncthreads();
 
   // ---- convolve: warp = output column, lane = row ----
-  const uint8_t* my_in = in_s + lane * 4;
   for (int xl = warp; xl < nxo; xl += RS_WARPS) {
     const int xo = xo0 + xl;
-    const int first = p.bounds[2 * xo], cnt = p.bounds[2 * xo + 1];
-    const int* kk = p.kk + (long long)xo * p.ksize;
-    int acc[C];
+    const int xs = p.bounds[2 * xo] - px0, cnt = p.bounds[2 * xo + 1];
+    const int ng = (cnt + 3) >> 2;
+    const uint32_t* kk = p.kk + (long long)xo * p.groups * 3;
+    const uint32_t sel = 0x3210u + 0x1111u * (uint32_t)(xs & 3);            // realign 4 bytes out of 2 words
+    const uint32_t* base = in_w32 + (xs >> 2) * RS_IN_PITCH + lane;
+    uint32_t a0[C], a1[C];
+    int a2[C];
+    uint32_t prev[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] = 1 << (RS_PRECISION_BITS - 1);
-    int j = first * C - b0;
-    for (int k = 0; k < cnt; ++k) {
-      const int coef = __ldg(kk + k);
+    for (int c = 0; c < C; ++c) {
+      a0[c] = 0u; a1[c] = 0u; a2[c] = 0;
+      prev[c] = base[c * PW * RS_IN_PITCH];
+    }
+    for (int g = 0; g < ng; ++g) {
+      const uint32_t k0 = __ldg(kk + 3 * g), k1 = __ldg(kk + 3 * g + 1), k2 = __ldg(kk + 3 * g + 2);
 #pragma unroll
-      for (int c = 0; c < C; ++c, ++j) acc[c] += (int)my_in[(j >> 2) * (RS_IN_PITCH * 4) + (j & 3)] * coef;
+      for (int c = 0; c < C; ++c) {
+        const uint32_t next = base[(c * PW + g + 1) * RS_IN_PITCH];
+        const uint32_t v = __byte_perm(prev[c], next, sel);
+        prev[c] = next;
+        a0[c] = __dp4a(v, k0, a0[c]);
+        a1[c] = __dp4a(v, k1, a1[c]);
+        a2[c] = rs_dp4a_us(v, k2, a2[c]);
+      }
     }
     uint8_t* o = out_s + lane * p.out_pitch + xl * C;
 #pragma unroll
-    for (int c = 0; c < C; ++c) o[c] = (uint8_t)rs_clip8(acc[c]);
+    for (int c = 0; c < C; ++c) {
+      const uint32_t acc = (1u << (RS_PRECISION_BITS - 1)) + a0[c] + (a1[c] << 8) + ((uint32_t)a2[c] << 16);
+      o[c] = (uint8_t)rs_clip8((int)acc);
+    }
   }
   __syncthreads();
 
@@ -105,42 +168,66 @@ struct ResizeVParams {
   const uint8_t* src;        // [frame][rows][row_bytes]  (intermediate image, or the source when no horizontal pass)
   uint8_t* dst;              // [frame][out_h][row_bytes]
   const int* bounds;         // [out_h][2]  (first row relative to the intermediate image, tap count)
-  const int* kk;             // [out_h][ksize]
+  const uint32_t* kk;        // [out_h][groups][3] byte planes of 4 coefficients, as in ResizeHParams
   long long src_frame_stride, dst_frame_stride;
-  int row_bytes, out_h, ksize;
+  int row_bytes, out_h, groups, src_rows;
 };
 
 // VEC = 4: row_bytes and both frame strides are multiples of 4; VEC = 1: anything.
+// Four taps at a time: four coalesced loads (rows k .. k+3 of the same 4 columns), a 4x4 byte
+// transpose (8 PRMT) and three DP4A per column against the byte planes of the coefficients.
 template <int VEC>
 __global__ void __launch_bounds__(RS_THREADS) resize_v_kernel(const ResizeVParams p) {
   const int yo = blockIdx.y;
   const int xb = (blockIdx.x * RS_THREADS + threadIdx.x) * VEC;
   if (xb >= p.row_bytes) return;
   const int first = p.bounds[2 * yo], cnt = p.bounds[2 * yo + 1];
-  const int* kk = p.kk + (long long)yo * p.ksize;
-  const uint8_t* src = p.src + blockIdx.z * p.src_frame_stride + (long long)first * p.row_bytes + xb;
-  int acc[VEC];
+  const int ng = (cnt + 3) >> 2;
+  const uint32_t* kk = p.kk + (long long)yo * p.groups * 3;
+  const uint8_t* src = p.src + blockIdx.z * p.src_frame_stride + xb;
+  const int last_row = p.src_rows - 1;          // rows past the window carry zero coefficients: clamp the address
+  uint32_t a0[VEC], a1[VEC];
+  int a2[VEC];
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) acc[i] = 1 << (RS_PRECISION_BITS - 1);
-  for (int k = 0; k < cnt; ++k) {
-    const int coef = __ldg(kk + k);
+  for (int i = 0; i < VEC; ++i) { a0[i] = 0u; a1[i] = 0u; a2[i] = 0; }
+  for (int g = 0; g < ng; ++g) {
+    const uint32_t k0 = __ldg(kk + 3 * g), k1 = __ldg(kk + 3 * g + 1), k2 = __ldg(kk + 3 * g + 2);
+    const int r = first + 4 * g;
     if (VEC == 4) {
-      const uint32_t w = *reinterpret_cast<const uint32_t*>(src + (long long)k * p.row_bytes);
-      acc[0] += (int)(w & 255u) * coef;
-      acc[1 % VEC] += (int)((w >> 8) & 255u) * coef;
-      acc[2 % VEC] += (int)((w >> 16) & 255u) * coef;
-      acc[3 % VEC] += (int)(w >> 24) * coef;
+      const uint32_t w0 = *reinterpret_cast<const uint32_t*>(src + (long long)min(r, last_row) * p.row_bytes);
+      const uint32_t w1 = *reinterpret_cast<const uint32_t*>(src + (long long)min(r + 1, last_row) * p.row_bytes);
+      const uint32_t w2 = *reinterpret_cast<const uint32_t*>(src + (long long)min(r + 2, last_row) * p.row_bytes);
+      const uint32_t w3 = *reinterpret_cast<const uint32_t*>(src + (long long)min(r + 3, last_row) * p.row_bytes);
+      const uint32_t t0 = __byte_perm(w0, w1, 0x5140), t1 = __byte_perm(w2, w3, 0x5140);
+      const uint32_t t2 = __byte_perm(w0, w1, 0x7362), t3 = __byte_perm(w2, w3, 0x7362);
+      const uint32_t col[4] = {__byte_perm(t0, t1, 0x5410), __byte_perm(t0, t1, 0x7632),
+                               __byte_perm(t2, t3, 0x5410), __byte_perm(t2, t3, 0x7632)};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        a0[i % VEC] = __dp4a(col[i], k0, a0[i % VEC]);
+        a1[i % VEC] = __dp4a(col[i], k1, a1[i % VEC]);
+        a2[i % VEC] = rs_dp4a_us(col[i], k2, a2[i % VEC]);
+      }
     } else {
-      acc[0] += (int)src[(long long)k * p.row_bytes] * coef;
+      const uint32_t b0 = src[(long long)min(r, last_row) * p.row_bytes];
+      const uint32_t b1 = src[(long long)min(r + 1, last_row) * p.row_bytes];
+      const uint32_t b2 = src[(long long)min(r + 2, last_row) * p.row_bytes];
+      const uint32_t b3 = src[(long long)min(r + 3, last_row) * p.row_bytes];
+      const uint32_t v = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+      a0[0] = __dp4a(v, k0, a0[0]);
+      a1[0] = __dp4a(v, k1, a1[0]);
+      a2[0] = rs_dp4a_us(v, k2, a2[0]);
     }
   }
-  uint8_t* dst = p.dst + blockIdx.z * p.dst_frame_stride + (long long)yo * p.row_bytes + xb;
-  if (VEC == 4) {
-    *reinterpret_cast<uint32_t*>(dst) = rs_clip8(acc[0]) | (rs_clip8(acc[1 % VEC]) << 8) |
-                                        (rs_clip8(acc[2 % VEC]) << 16) | (rs_clip8(acc[3 % VEC]) << 24);
-  } else {
-    dst[0] = (uint8_t)rs_clip8(acc[0]);
+  uint32_t out[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const uint32_t acc = (1u << (RS_PRECISION_BITS - 1)) + a0[i] + (a1[i] << 8) + ((uint32_t)a2[i] << 16);
+    out[i] = rs_clip8((int)acc);
   }
+  uint8_t* dst = p.dst + blockIdx.z * p.dst_frame_stride + (long long)yo * p.row_bytes + xb;
+  if (VEC == 4) *reinterpret_cast<uint32_t*>(dst) = out[0] | (out[1 % VEC] << 8) | (out[2 % VEC] << 16) | (out[3 % VEC] << 24);
+  else dst[0] = (uint8_t)out[0];
 }
 
 }  // namespace lars

@@ -351,7 +351,6 @@ class Engine:
                                                   frames.stride_bytes, frames.n_frames, out.data.data_ptr(),
                                                   out.stride_bytes, temp.data_ptr(), temp_bytes, s.cuda_stream),
                   "lars_resize_lanczos_u8")
-        temp.record_stream(s)
         return out
 
     def resize_batch(self, frames: Sequence[np.ndarray], out_h: int, out_w: int) -> List[np.ndarray]:

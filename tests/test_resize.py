@@ -13,7 +13,7 @@ from oracle import synth
 # (in_h, in_w, out_h, out_w)
 GEOMETRIES = [(37, 53, 11, 20), (300, 400, 75, 100), (123, 77, 150, 200), (64, 64, 32, 64), (64, 64, 64, 32),
               (5, 7, 2, 3), (1, 100, 1, 10), (100, 1, 10, 1), (50, 50, 50, 50), (960, 1280, 768, 1024),
-              (333, 1001, 97, 255)]
+              (333, 1001, 97, 255), (200, 1000, 50, 250), (90, 404, 45, 101)]
 
 
 def pil_resize(img, out_h, out_w):
@@ -50,6 +50,16 @@ def test_oracle_preprocess_large_image_matches_pillow_chain():
     assert resize_np.preprocess_large_image(tall, 1024).shape == (1024, int(700 * (1024 / 1500)), 3)
 
 
+def _unpack_planes(words, n, groups):
+    """[n][groups][3] byte planes of 4 taps -> [n][4 * groups] integer coefficients
+    (k = k0 + 2^8 k1 + 2^16 k2 with k2 signed)."""
+    planes = words.view(np.uint32).reshape(n, groups, 3)
+    shifts = 8 * np.arange(4, dtype=np.uint32)
+    b = [((planes[:, :, i, None] >> shifts) & 255).astype(np.int64).reshape(n, 4 * groups) for i in range(3)]
+    b[2] = np.where(b[2] > 127, b[2] - 256, b[2])
+    return b[0] + (b[1] << 8) + (b[2] << 16)
+
+
 @pytest.mark.parametrize("geom", GEOMETRIES + [(3000, 4000, 768, 1024), (3648, 5472, 682, 1024),
                                                (4096, 4096, 1024, 1024)])
 def test_host_coefficient_tables_match_the_oracle(geom):
@@ -59,21 +69,20 @@ def test_host_coefficient_tables_match_the_oracle(geom):
     plan, t = _lib.resize_plan(ih, iw, oh, ow, 3)
     assert (plan.need_h, plan.need_v) == (int(ow != iw), int(oh != ih))
     off = 0
-    if plan.need_h:
-        ks, b, k = resize_np.precompute_coeffs(iw, ow)
-        assert ks == plan.ksize_h
-        assert np.array_equal(t[off:off + 2 * ow].reshape(ow, 2), b)
-        off += 2 * ow
-        assert np.array_equal(t[off:off + ow * ks].reshape(ow, ks), k)
-        off += ow * ks
-    if plan.need_v:
-        ks, b, k = resize_np.precompute_coeffs(ih, oh)
-        assert ks == plan.ksize_v
+    for need, n_in, n_out, groups, shift in ((plan.need_h, iw, ow, plan.groups_h, 0),
+                                             (plan.need_v, ih, oh, plan.groups_v, plan.row_first)):
+        if not need:
+            continue
+        ks, b, k = resize_np.precompute_coeffs(n_in, n_out)
+        assert groups == (ks + 3) // 4
         b = b.copy()
-        b[:, 0] -= plan.row_first
-        assert np.array_equal(t[off:off + 2 * oh].reshape(oh, 2), b)
-        off += 2 * oh
-        assert np.array_equal(t[off:off + oh * ks].reshape(oh, ks), k)
+        b[:, 0] -= shift                       # vertical windows address rows of the intermediate image
+        assert np.array_equal(t[off:off + 2 * n_out].reshape(n_out, 2), b)
+        off += 2 * n_out
+        unpacked = _unpack_planes(t[off:off + n_out * groups * 3], n_out, groups)
+        off += n_out * groups * 3
+        assert np.array_equal(unpacked[:, :ks], k) and not unpacked[:, ks:].any()
+    assert off * 4 == max(plan.table_bytes, 4) or (off == 0 and plan.table_bytes == 4)
     if plan.need_h and plan.need_v:
         assert plan.row_first + plan.row_count <= ih and plan.temp_frame_bytes >= plan.row_count * ow * 3
 

@@ -14,7 +14,8 @@ for (h, w, F) in ((3000, 4000, 16), (3648, 5472, 8), (960, 1280, 64)):
     t = eng.preprocess_target(h, w, 1024) or (h // 2, w // 2)
     frames = [synth.vegetation_frame(100 + i, h, w) for i in range(min(F, 2))]
     dev = eng.upload([frames[i % len(frames)] for i in range(F)], stream=s)
-    out = eng.resize_device(dev, t[0], t[1], s)          # warm-up + plan
+    for _ in range(3):                                   # warm-up: plan, allocator pools
+        out = eng.resize_device(dev, t[0], t[1], s)
     s.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n = 10
