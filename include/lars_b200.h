@@ -241,6 +241,27 @@ int lars_resize_lanczos_u8(const lars_resize_plan* plan, const void* tables_dev,
                            int64_t src_frame_stride, int32_t n_frames, uint8_t* dst, int64_t dst_frame_stride,
                            void* temp, size_t temp_bytes, void* stream);
 
+/* ---- ingest ---------------------------------------------------
+ * Host-only baseline-TIFF reader: uncompressed, chunky, strips, 8- or 16-bit unsigned samples,
+ * 1 / 3 / 4 samples per pixel, either byte order.  Replaces PIL.Image.open + np.array for such
+ * files (process-images.py:183-193; backend-process.py:52; process-ndvi.py:18; process-rgn.py:18)
+ * and adds the true 16-bit path Pillow cannot deliver (it opens 16-bit RGB as 8-bit): the strips
+ * of a (memory-mapped) file are copied straight into the caller's pinned HWC buffer.  Anything
+ * else (compression, tiles, BigTIFF, planar, float) returns LARS_ERR_UNSUPPORTED and the caller
+ * decodes with Pillow. */
+typedef struct lars_tiff_info {
+  int32_t width, height, samples_per_pixel, bits_per_sample;
+  int32_t big_endian, compression, planar_config, photometric, sample_format;
+  int32_t rows_per_strip, n_strips;
+  int32_t strip_offsets_type, strip_counts_type; /* TIFF field types (3 = SHORT, 4 = LONG)        */
+  int32_t reserved;
+  uint64_t strip_offsets_pos, strip_counts_pos;  /* file positions of the two arrays               */
+  uint64_t frame_bytes;                          /* height * width * samples * bytes per sample    */
+} lars_tiff_info;
+int lars_tiff_probe(const void* file, size_t file_bytes, lars_tiff_info* info);
+/* dst receives height x width x samples, little-endian samples, rows contiguous. */
+int lars_tiff_read(const void* file, size_t file_bytes, const lars_tiff_info* info, void* dst, size_t dst_bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,7 @@ EXPORTED_SYMBOLS = (
     "lars_wb_u16_workspace_bytes", "lars_wb_stretch_build_u16", "lars_fused_index_u16",
     "lars_index_hwc", "lars_index_change_u8",
     "lars_resize_plan_lanczos", "lars_resize_tables_lanczos", "lars_resize_lanczos_u8",
+    "lars_tiff_probe", "lars_tiff_read",
 )
 
 
@@ -73,6 +74,15 @@ class ResizePlan(C.Structure):
         "in_h", "in_w", "out_h", "out_w", "channels", "need_h", "need_v", "ksize_h", "ksize_v",
         "row_first", "row_count", "xo_tile", "plane_words", "out_pitch", "groups_h", "groups_v")] + [
         ("table_bytes", C.c_uint64), ("temp_frame_bytes", C.c_uint64)]
+
+
+class TiffInfo(C.Structure):
+    """Mirror of ``lars_tiff_info`` (include/lars_b200.h)."""
+    _fields_ = [(n, C.c_int32) for n in (
+        "width", "height", "samples_per_pixel", "bits_per_sample", "big_endian", "compression",
+        "planar_config", "photometric", "sample_format", "rows_per_strip", "n_strips",
+        "strip_offsets_type", "strip_counts_type", "reserved")] + [
+        ("strip_offsets_pos", C.c_uint64), ("strip_counts_pos", C.c_uint64), ("frame_bytes", C.c_uint64)]
 
 
 # numpy view of ``lars_index_stats`` (576 bytes)
@@ -138,6 +148,10 @@ def _declare(lib):
     lib.lars_index_hwc.restype = C.c_int
     lib.lars_index_change_u8.argtypes = [vp, vp, i64, i32, i32, f32, f32, vp, vp, vp, vp, vp]
     lib.lars_index_change_u8.restype = C.c_int
+    lib.lars_tiff_probe.argtypes = [vp, C.c_size_t, C.POINTER(TiffInfo)]
+    lib.lars_tiff_probe.restype = C.c_int
+    lib.lars_tiff_read.argtypes = [vp, C.c_size_t, C.POINTER(TiffInfo), vp, C.c_size_t]
+    lib.lars_tiff_read.restype = C.c_int
     lib.lars_resize_plan_lanczos.argtypes = [i32, i32, i32, i32, i32, C.POINTER(ResizePlan)]
     lib.lars_resize_plan_lanczos.restype = C.c_int
     lib.lars_resize_tables_lanczos.argtypes = [C.POINTER(ResizePlan), vp]

@@ -10,6 +10,7 @@
 
 #include "../../include/lars_b200.h"
 #include "host_tables.h"
+#include "tiff_host.h"
 #include "lars_kernels.cuh"
 #include "lars_fused_kernel.cuh"
 #include "lars_map_kernels.cuh"
@@ -848,6 +849,33 @@ int lars_resize_lanczos_u8(const lars_resize_plan* plan, const void* tables_dev,
     else lars::resize_v_kernel<1><<<grid, lars::RS_THREADS, 0, s>>>(p);
     LARS_CUDA(cudaGetLastError());
   }
+  return LARS_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// ingest: baseline TIFF reader (host only)
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int lars_tiff_probe(const void* file, size_t file_bytes, lars_tiff_info* info) {
+  if (!file || !info) return fail(LARS_ERR_INVALID, "lars_tiff_probe: NULL pointer");
+  bool unsupported = false;
+  const char* why = lars_host::tiff_probe(file, file_bytes, info, &unsupported);
+  if (why) return fail(unsupported ? LARS_ERR_UNSUPPORTED : LARS_ERR_INVALID, "lars_tiff_probe: %s", why);
+  return LARS_OK;
+}
+
+int lars_tiff_read(const void* file, size_t file_bytes, const lars_tiff_info* info, void* dst, size_t dst_bytes) {
+  if (!file || !info || !dst) return fail(LARS_ERR_INVALID, "lars_tiff_read: NULL pointer");
+  lars_tiff_info check;
+  bool unsupported = false;
+  const char* why = lars_host::tiff_probe(file, file_bytes, &check, &unsupported);   // never trust a stale info block
+  if (why) return fail(unsupported ? LARS_ERR_UNSUPPORTED : LARS_ERR_INVALID, "lars_tiff_read: %s", why);
+  if (memcmp(&check, info, sizeof(check)) != 0) return fail(LARS_ERR_INVALID, "lars_tiff_read: info does not describe this file");
+  why = lars_host::tiff_read(file, file_bytes, &check, dst, dst_bytes);
+  if (why) return fail(LARS_ERR_INVALID, "lars_tiff_read: %s", why);
   return LARS_OK;
 }
 
