@@ -42,6 +42,9 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1 and not dist.is_initialized():
+        # NCCL writes its version banner / debug log to stdout by default; programs that print results
+        # on stdout (bench.py: one JSON line) must not have them mixed in
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
@@ -86,6 +89,65 @@ def dataset_statistics(engine, per_frame_records: torch.Tensor, group=None, stre
     with torch.cuda.stream(s):
         gathered = gather_records(local, group)       # NCCL runs on the current (= engine) stream
     return merge_records_device(engine, gathered, s)
+
+
+class AsyncDatasetStatistics:
+    """The dataset-statistics exchange taken off the critical path.
+
+    A step's result (3 x 576 bytes per rank) is not an input of the next step, so the all-gather
+    and the final merge run on a side stream while the main stream already works on the next
+    batch: ``submit`` folds the per-frame records into one of ``depth`` rotating local records on
+    the caller's stream (a 5 us kernel), then hands that record to the side stream.  ``result``
+    makes a stream wait for the most recent exchange and returns the dataset-wide records.
+    Ranks no longer meet once per step, so host-side jitter of one rank does not stall the others.
+    """
+
+    def __init__(self, engine, group=None, depth: int = 2):
+        self.engine, self.group, self.depth = engine, group, max(2, int(depth))
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        dev = engine.device
+        self.side = torch.cuda.Stream(device=dev)
+        self.local = [torch.zeros((3, RECORD_BYTES), dtype=torch.uint8, device=dev) for _ in range(self.depth)]
+        self.gathered = [torch.zeros((self.world * 3, RECORD_BYTES), dtype=torch.uint8, device=dev)
+                         for _ in range(self.depth)] if self.world > 1 else None
+        self.out = [torch.zeros((3, RECORD_BYTES), dtype=torch.uint8, device=dev) for _ in range(self.depth)] \
+            if self.world > 1 else self.local
+        self.done = [None] * self.depth
+        self.count = 0
+        torch.cuda.synchronize(dev)
+
+    def submit(self, per_frame_records: torch.Tensor, stream=None) -> None:
+        eng = self.engine
+        s = stream or eng.stream()
+        k = self.count % self.depth
+        self.count += 1
+        if self.done[k] is not None:
+            s.wait_event(self.done[k])                    # slot k's previous exchange has been consumed
+        with torch.cuda.device(eng.device):
+            check(eng.lib.lars_stats_merge(per_frame_records.data_ptr(), per_frame_records.shape[0],
+                                           self.local[k].data_ptr(), s.cuda_stream), "lars_stats_merge")
+        ev = torch.cuda.Event()
+        ev.record(s)
+        if self.world == 1:
+            self.done[k] = ev
+            return
+        self.side.wait_event(ev)
+        with torch.cuda.stream(self.side):
+            dist.all_gather_into_tensor(self.gathered[k], self.local[k], group=self.group)
+            with torch.cuda.device(eng.device):
+                check(eng.lib.lars_stats_merge(self.gathered[k].data_ptr(), self.world, self.out[k].data_ptr(),
+                                               self.side.cuda_stream), "lars_stats_merge")
+            done = torch.cuda.Event()
+            done.record(self.side)
+        self.done[k] = done
+
+    def result(self, stream=None) -> torch.Tensor:
+        """Dataset-wide records of the latest submitted step; ``stream`` waits for them."""
+        if self.count == 0:
+            raise RuntimeError("no statistics have been submitted")
+        k = (self.count - 1) % self.depth
+        (stream or self.engine.stream()).wait_event(self.done[k])
+        return self.out[k]
 
 
 def allreduce_wb_histogram(hist: torch.Tensor, group=None) -> torch.Tensor:

@@ -581,15 +581,20 @@ class FramePlan:
         self._args = engine._build_fused_args(frames, self.lut, outputs, self.out, s, **fused_kw)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
 
-    def run(self) -> DeviceOutputs:
-        """Enqueue one step on the plan's stream (no allocation, no synchronisation)."""
+    def run(self, fused_events=None) -> DeviceOutputs:
+        """Enqueue one step on the plan's stream (no allocation, no synchronisation).
+        ``fused_events``: optional (start, end) CUDA events recorded around the fused Pass 2."""
         lib, fr, sp = self.engine.lib, self.frames, self.stream.cuda_stream
         if self.white_balance:
             check(lib.lars_wb_hist_u8(fr.data.data_ptr(), fr.n_frames, fr.n_pixels, fr.channels, fr.stride_bytes,
                                       self.hist.data_ptr(), 0, sp), "lars_wb_hist_u8")
             check(lib.lars_wb_lut_build_u8(self.hist.data_ptr(), fr.n_frames, self.quantiles[0], self.quantiles[1],
                                            self.lut.data_ptr(), self.pct.data_ptr(), sp), "lars_wb_lut_build_u8")
+        if fused_events is not None:
+            fused_events[0].record(self.stream)
         check(lib.lars_fused_index_u8(C.byref(self._args), sp), "lars_fused_index_u8")
+        if fused_events is not None:
+            fused_events[1].record(self.stream)
         if self.merged is not None:
             check(lib.lars_stats_merge(self.out.stats.data_ptr(), fr.n_frames, self.merged.data_ptr(), sp),
                   "lars_stats_merge")

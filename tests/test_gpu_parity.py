@@ -564,3 +564,21 @@ def test_no_write_outside_the_frame_slots(engine):
             assert np.array_equal(out[i]["wb"], want["wb"])
             assert np.array_equal(out[i]["maps"]["NDWI"].view(np.uint32), want["maps"]["NDWI"].view(np.uint32))
             assert np.array_equal(out[i]["rgb"]["NDVI"], want["rgb"]["NDVI"])
+
+
+def test_async_dataset_statistics_matches_the_synchronous_exchange(engine):
+    """The side-stream exchange (bench / survey path) gives the records of the synchronous one,
+    also when more steps are submitted than it has rotating slots."""
+    from lars_image_processing_b200 import distributed as ld
+    s = engine.stream()
+    ex = ld.AsyncDatasetStatistics(engine, depth=2)
+    batches = [[synth.vegetation_frame(40 + 3 * b + i, 60, 80) for i in range(3)] for b in range(5)]
+    for frames in batches:
+        res = engine.process_device(engine.upload(frames, stream=s), outputs=("stats",), stream=s)
+        ex.submit(res.stats, stream=s)
+        want = ld.records_to_numpy(ld.dataset_statistics(engine, res.stats, stream=s))
+        got = ld.records_to_numpy(ex.result(s))
+        s.synchronize()
+        for name in want.dtype.names:
+            assert np.array_equal(got[name], want[name]), name
+        assert int(got["count"][0]) == 3 * 60 * 80
