@@ -96,6 +96,7 @@ def measured_hbm_peak():
 class ClockSampler:
     def __init__(self, index):
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.recording = False          # the thread runs from before the barrier; samples count only inside the timed region
         self._stop = threading.Event()
         self._thread = None
         try:
@@ -114,6 +115,9 @@ class ClockSampler:
                  "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
                  "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
         while not self._stop.is_set():
+            if not self.recording:
+                time.sleep(0.0005)
+                continue
             try:
                 self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
                 try:
@@ -252,6 +256,17 @@ def run_ours(a):
     if world != a.gpus and rank == 0:
         print(f"[bench] note: --gpus {a.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
     torch.cuda.set_device(local_rank)
+    affinity = "unchanged"
+    if world > 1 and os.environ.get("LARS_BENCH_GPU_LOCAL_CPUS", "1") == "1":
+        # pinned staging buffers should live on the NUMA node the GPU hangs off: bind this rank to the
+        # GPU-local CPUs before anything is allocated (ignored when the container's cpuset forbids it)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+            affinity = f"gpu-local ({len(os.sched_getaffinity(0))} cpus)"
+        except Exception:
+            pass
     eng = Engine(local_rank)
     s = eng.stream()
     F, h, w = a.frames, a.height, a.width
@@ -294,20 +309,26 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(a.warmup):
-        step(False)
-    barrier()
+    # NVML is initialised and the sampling thread started BEFORE the barrier: nvmlInit takes a different
+    # time on every rank, and anything between the barrier and t_start becomes start skew that the last
+    # step's exchange turns into time for every rank
     sampler = ClockSampler(local_rank)
     sampler.start()
+    for _ in range(a.warmup):
+        step(False)
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    host_s[0] = 0.0
+    barrier()
+    sampler.recording = True
     t_start.record(s)
     for _ in range(a.steps):
         step(True)
     dataset = exchange.result(s)                            # every exchange has landed inside the timed region
     t_end.record(s)
     barrier()
+    sampler.recording = False
     clocks = sampler.stop()
-    host_enqueue_ms = host_s[0] / max(1, a.steps + a.warmup) * 1e3
+    host_enqueue_ms = host_s[0] / max(1, a.steps) * 1e3
     ms = t_start.elapsed_time(t_end)
     k2_ms = sum(e0.elapsed_time(e1) for e0, e1 in fused_ms) / len(fused_ms)
     t = torch.tensor([ms, k2_ms], device=eng.device, dtype=torch.float64)
@@ -375,6 +396,7 @@ def run_ours(a):
         "dtype": a.dtype, "data": "synthetic",
         "config": {"workload": workload_name(a), "frames_per_gpu": F, "height": h, "width": w,
                    "l2": f"inputs larger than L2 ({F * npx * 3 * sb / 1e6:.0f} MB raw per GPU per step)",
+                   "cpu_affinity": affinity,
                    "parallelism": f"frames sharded over {world} GPU(s), one dataset-statistics all-gather per step on a side stream (overlaps the next step)"
                    if world > 1 else "single GPU"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
