@@ -66,7 +66,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 extern "C" {
 
 const char* lars_last_error(void) { return g_err; }
-int lars_abi_version(void) { return 2; }
+int lars_abi_version(void) { return 3; }   // 3: + resize, TIFF ingest
 
 int lars_init(int device) {
   std::lock_guard<std::mutex> lock(g_mu);

@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(K2_THREADS, K2_CTAS_PER_SM) fused_index_kernel
         const long long px0 = tile * K2_TILE_PX;
         const long long rem = p.n_pixels - px0;
         const uint32_t nvalid = rem < K2_TILE_PX ? (uint32_t)rem : (uint32_t)K2_TILE_PX;
-        mbar_wait(bar_out_full + 8u * so, phase);
+        mbar_wait_relaxed(bar_out_full + 8u * so, phase);
         const uint32_t stage_addr = smem_base + L::OFF_OUT + so * L::OUT_BYTES;
         const uint32_t wb_bytes = (nvalid * C + 15u) & ~15u;
         const uint32_t rgb_bytes = (nvalid * 3u + 15u) & ~15u;
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(K2_THREADS, K2_CTAS_PER_SM) fused_index_kernel
         }
         --until_prefetch;
 #endif
-        mbar_wait(bar_base + 8u * (K2_IN_STAGES + s), phase ^ 1u);
+        mbar_wait_relaxed(bar_base + 8u * (K2_IN_STAGES + s), phase ^ 1u);
         mbar_arrive_expect_tx(bar_base + 8u * s, bytes);
         tma_load_1d_hint(smem_base + L::OFF_IN + s * L::IN_BYTES,
                          p.src + frame * p.src_frame_stride + px0 * (C * BPS), bytes, bar_base + 8u * s, pol);
