@@ -160,6 +160,22 @@ int lars_wb_stretch_build_u16(const uint16_t* src, int32_t n_frames, int64_t n_p
                               int64_t src_frame_stride, double q_lo, double q_hi, lars_stretch_u16* stretch,
                               double* pct, void* workspace, size_t workspace_bytes, int32_t shared_hist,
                               void* stream);
+/* The same in stages, for an image whose tiles live on several GPUs: the
+ * caller SUM-all-reduces the counters between the stages so that every rank derives identical
+ * thresholds.  Workspace layout: [n_sets][3][256] uint64 high-byte histogram, then
+ * [n_sets][3][4][256] uint64 low-byte histograms, then private selection records.
+ *   LARS_U16_STAGE_HIST_HI  zero the workspace, level A          -> all-reduce the first block
+ *   LARS_U16_STAGE_HIST_LO  bucket selection + level B           -> all-reduce the second block
+ *   LARS_U16_STAGE_BUILD    percentiles + thresholds into stretch / pct
+ *   LARS_U16_STAGE_ALL      everything (= lars_wb_stretch_build_u16) */
+#define LARS_U16_STAGE_ALL 0
+#define LARS_U16_STAGE_HIST_HI 1
+#define LARS_U16_STAGE_HIST_LO 2
+#define LARS_U16_STAGE_BUILD 3
+int lars_wb_stretch_build_u16_staged(const uint16_t* src, int32_t n_frames, int64_t n_pixels, int32_t channels,
+                                     int64_t src_frame_stride, double q_lo, double q_hi, lars_stretch_u16* stretch,
+                                     double* pct, void* workspace, size_t workspace_bytes, int32_t shared_hist,
+                                     int32_t stage, void* stream);
 /* Pass 2 on uint16 frames: same products as lars_fused_index_u8 (WB output is uint8);
  * lut_frame_stride = 3 * sizeof(lars_stretch_u16) or 0 for one shared set. */
 int lars_fused_index_u16(const lars_fused_args* args, void* stream);

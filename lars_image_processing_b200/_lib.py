@@ -31,7 +31,8 @@ EXPORTED_SYMBOLS = (
     "lars_map_stats_workspace_bytes", "lars_map_stats_f32", "lars_select_workspace_bytes",
     "lars_select_f32", "lars_colormap_f32", "lars_ndvi_f64_u8", "lars_index_planes_f32",
     "lars_stats_merge",
-    "lars_wb_u16_workspace_bytes", "lars_wb_stretch_build_u16", "lars_fused_index_u16",
+    "lars_wb_u16_workspace_bytes", "lars_wb_stretch_build_u16", "lars_wb_stretch_build_u16_staged",
+    "lars_fused_index_u16",
     "lars_index_hwc", "lars_index_change_u8",
     "lars_resize_plan_lanczos", "lars_resize_tables_lanczos", "lars_resize_lanczos_u8",
     "lars_tiff_probe", "lars_tiff_read",
@@ -142,6 +143,8 @@ def _declare(lib):
     lib.lars_wb_u16_workspace_bytes.restype = C.c_size_t
     lib.lars_wb_stretch_build_u16.argtypes = [vp, i32, i64, i32, i64, f64, f64, vp, vp, vp, C.c_size_t, i32, vp]
     lib.lars_wb_stretch_build_u16.restype = C.c_int
+    lib.lars_wb_stretch_build_u16_staged.argtypes = [vp, i32, i64, i32, i64, f64, f64, vp, vp, vp, C.c_size_t, i32, i32, vp]
+    lib.lars_wb_stretch_build_u16_staged.restype = C.c_int
     lib.lars_fused_index_u16.argtypes = [C.POINTER(FusedArgs), vp]
     lib.lars_fused_index_u16.restype = C.c_int
     lib.lars_index_hwc.argtypes = [vp, i32, i64, i32, i32, vp, vp]

@@ -481,6 +481,14 @@ int lars_wb_stretch_build_u16(const uint16_t* src, int32_t n_frames, int64_t n_p
                               int64_t src_frame_stride, double q_lo, double q_hi, lars_stretch_u16* stretch,
                               double* pct, void* workspace, size_t workspace_bytes, int32_t shared_hist,
                               void* stream) {
+  return lars_wb_stretch_build_u16_staged(src, n_frames, n_pixels, channels, src_frame_stride, q_lo, q_hi, stretch, pct,
+                                          workspace, workspace_bytes, shared_hist, LARS_U16_STAGE_ALL, stream);
+}
+
+int lars_wb_stretch_build_u16_staged(const uint16_t* src, int32_t n_frames, int64_t n_pixels, int32_t channels,
+                                     int64_t src_frame_stride, double q_lo, double q_hi, lars_stretch_u16* stretch,
+                                     double* pct, void* workspace, size_t workspace_bytes, int32_t shared_hist,
+                                     int32_t stage, void* stream) {
   DeviceState* st = nullptr;
   int rc = current_state(&st);
   if (rc != LARS_OK) return rc;
@@ -499,7 +507,12 @@ int lars_wb_stretch_build_u16(const uint16_t* src, int32_t n_frames, int64_t n_p
   unsigned long long* hist_hi = reinterpret_cast<unsigned long long*>(ws);
   unsigned long long* hist_lo = reinterpret_cast<unsigned long long*>(ws + (size_t)n_sets * 3 * 256 * 8);
   lars::U16Select* select = reinterpret_cast<lars::U16Select*>(ws + (size_t)n_sets * (3 * 256 * 8 + 3 * lars::U16_MAX_BUCKETS * 256 * 8));
-  LARS_CUDA(cudaMemsetAsync(workspace, 0, (size_t)n_sets * kU16SetBytes, s));
+  if (stage < LARS_U16_STAGE_ALL || stage > LARS_U16_STAGE_BUILD)
+    return fail(LARS_ERR_INVALID, "lars_wb_stretch_build_u16: unknown stage %d", stage);
+  const bool do_hi = stage == LARS_U16_STAGE_ALL || stage == LARS_U16_STAGE_HIST_HI;
+  const bool do_lo = stage == LARS_U16_STAGE_ALL || stage == LARS_U16_STAGE_HIST_LO;
+  const bool do_build = stage == LARS_U16_STAGE_ALL || stage == LARS_U16_STAGE_BUILD;
+  if (do_hi) LARS_CUDA(cudaMemsetAsync(workspace, 0, (size_t)n_sets * kU16SetBytes, s));
 
   const long long frame_bytes = (long long)n_pixels * channels * 2;
   const long long unit = (channels == 3) ? lars::U16Unit<3>::BYTES : lars::U16Unit<4>::BYTES;
@@ -513,23 +526,29 @@ int lars_wb_stretch_build_u16(const uint16_t* src, int32_t n_frames, int64_t n_p
   p.n_frames = n_frames; p.lo_pass = 0;
   const long long target = 2ll * st->sm_count;
   const int grid = (int)(p.total_units < target ? p.total_units : target);
-  if (channels == 3) lars::wb_hist_u16_hi_kernel<3><<<grid, lars::K1_THREADS, lars::K1_SMEM_BYTES, s>>>(p);
-  else lars::wb_hist_u16_hi_kernel<4><<<grid, lars::K1_THREADS, lars::K1_SMEM_BYTES, s>>>(p);
-  LARS_CUDA(cudaGetLastError());
-  lars::U16SelectParams sp; sp.hist_hi = hist_hi; sp.select = select; sp.q_lo = q_lo; sp.q_hi = q_hi;
-  lars::wb_u16_select_kernel<<<n_sets * 3, 256, 0, s>>>(sp);
-  LARS_CUDA(cudaGetLastError());
-  for (int pass = 0; pass < 2; ++pass) {
-    p.lo_pass = pass;
-    if (channels == 3) lars::wb_hist_u16_lo_kernel<3><<<grid, lars::K1_THREADS, lars::U16_LO_SMEM_BYTES, s>>>(p);
-    else lars::wb_hist_u16_lo_kernel<4><<<grid, lars::K1_THREADS, lars::U16_LO_SMEM_BYTES, s>>>(p);
+  if (do_hi) {
+    if (channels == 3) lars::wb_hist_u16_hi_kernel<3><<<grid, lars::K1_THREADS, lars::K1_SMEM_BYTES, s>>>(p);
+    else lars::wb_hist_u16_hi_kernel<4><<<grid, lars::K1_THREADS, lars::K1_SMEM_BYTES, s>>>(p);
     LARS_CUDA(cudaGetLastError());
   }
-  lars::U16BuildParams bp;
-  bp.hist_hi = hist_hi; bp.hist_lo = hist_lo; bp.select = select; bp.stretch = stretch; bp.pct = pct;
-  bp.q_lo = q_lo; bp.q_hi = q_hi;
-  lars::wb_stretch_build_u16_kernel<<<n_sets * 3, 256, 0, s>>>(bp);
-  LARS_CUDA(cudaGetLastError());
+  if (do_lo) {
+    lars::U16SelectParams sp; sp.hist_hi = hist_hi; sp.select = select; sp.q_lo = q_lo; sp.q_hi = q_hi;
+    lars::wb_u16_select_kernel<<<n_sets * 3, 256, 0, s>>>(sp);
+    LARS_CUDA(cudaGetLastError());
+    for (int pass = 0; pass < 2; ++pass) {
+      p.lo_pass = pass;
+      if (channels == 3) lars::wb_hist_u16_lo_kernel<3><<<grid, lars::K1_THREADS, lars::U16_LO_SMEM_BYTES, s>>>(p);
+      else lars::wb_hist_u16_lo_kernel<4><<<grid, lars::K1_THREADS, lars::U16_LO_SMEM_BYTES, s>>>(p);
+      LARS_CUDA(cudaGetLastError());
+    }
+  }
+  if (do_build) {
+    lars::U16BuildParams bp;
+    bp.hist_hi = hist_hi; bp.hist_lo = hist_lo; bp.select = select; bp.stretch = stretch; bp.pct = pct;
+    bp.q_lo = q_lo; bp.q_hi = q_hi;
+    lars::wb_stretch_build_u16_kernel<<<n_sets * 3, 256, 0, s>>>(bp);
+    LARS_CUDA(cudaGetLastError());
+  }
   return LARS_OK;
 }
 

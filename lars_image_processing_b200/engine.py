@@ -196,21 +196,36 @@ class Engine:
         return res
 
     def wb_stretch_u16(self, frames: DeviceFrames, quantiles=DEFAULT_QUANTILES, shared: bool = False,
-                       stream=None):
+                       stream=None, hist_hook=None):
         """uint16 Pass 1: two-level radix histogram -> exact percentiles -> per-channel stretch
-        thresholds.  Returns (stretch [S, 3, 1040] uint8, percentiles [S, 3, 2] float64)."""
+        thresholds.  Returns (stretch [S, 3, 2064] uint8, percentiles [S, 3, 2] float64).
+        ``hist_hook(counters)`` (tile-sharded image on several GPUs) is called on the high-byte
+        histogram after level A and on the low-byte histograms after level B -- int64 tensors to be
+        SUM-all-reduced in place."""
         s = stream or self.stream()
         n_sets = 1 if shared else frames.n_frames
         stretch = self._alloc((n_sets, 3, STRETCH_U16_BYTES), torch.uint8, s)
         pct = self._alloc((n_sets, 3, 2), torch.float64, s)
         ws_bytes = int(self.lib.lars_wb_u16_workspace_bytes(n_sets))
         ws = self._alloc((ws_bytes,), torch.uint8, s)
-        with torch.cuda.device(self.device):
-            check(self.lib.lars_wb_stretch_build_u16(frames.data.data_ptr(), frames.n_frames, frames.n_pixels,
-                                                     frames.channels, frames.stride_bytes, float(quantiles[0]),
-                                                     float(quantiles[1]), stretch.data_ptr(), pct.data_ptr(),
-                                                     ws.data_ptr(), ws_bytes, 1 if shared else 0, s.cuda_stream),
-                  "lars_wb_stretch_build_u16")
+        def run(stage):
+            with torch.cuda.device(self.device):
+                check(self.lib.lars_wb_stretch_build_u16_staged(
+                    frames.data.data_ptr(), frames.n_frames, frames.n_pixels, frames.channels, frames.stride_bytes,
+                    float(quantiles[0]), float(quantiles[1]), stretch.data_ptr(), pct.data_ptr(), ws.data_ptr(),
+                    ws_bytes, 1 if shared else 0, stage, s.cuda_stream), "lars_wb_stretch_build_u16")
+
+        if hist_hook is None:
+            run(0)
+            return stretch, pct
+        hi_bytes, lo_bytes = n_sets * 3 * 256 * 8, n_sets * 3 * 4 * 256 * 8
+        run(1)                                              # LARS_U16_STAGE_HIST_HI
+        with torch.cuda.stream(s):
+            hist_hook(ws[:hi_bytes].view(torch.int64).view(n_sets, 3, 256))
+        run(2)                                              # LARS_U16_STAGE_HIST_LO
+        with torch.cuda.stream(s):
+            hist_hook(ws[hi_bytes:hi_bytes + lo_bytes].view(torch.int64).view(n_sets, 3, 4, 256))
+        run(3)                                              # LARS_U16_STAGE_BUILD
         return stretch, pct
 
     def _build_fused_args(self, frames: DeviceFrames, lut, outputs, res: DeviceOutputs, s, indices=INDEX_TYPES,
@@ -299,9 +314,7 @@ class Engine:
             if not white_balance:
                 raise LarsError("uint16 frames go through the white-balance stretch (uint8 out); "
                                 "there is no identity mode for them")
-            if hist_hook is not None:
-                raise LarsError("tile-sharded uint16 mosaics across GPUs are not supported yet")
-            res.wb_lut, res.wb_pct = self.wb_stretch_u16(frames, quantiles, tiles_of_one_image, s)
+            res.wb_lut, res.wb_pct = self.wb_stretch_u16(frames, quantiles, tiles_of_one_image, s, hist_hook=hist_hook)
             return self.fused(frames, res.wb_lut, outputs=outputs, out=res, stream=s, **kw)
         if white_balance:
             res.wb_hist = self.wb_histogram(frames, shared=tiles_of_one_image, stream=s)

@@ -582,3 +582,54 @@ def test_async_dataset_statistics_matches_the_synchronous_exchange(engine):
         for name in want.dtype.names:
             assert np.array_equal(got[name], want[name]), name
         assert int(got["count"][0]) == 3 * 60 * 80
+
+
+def test_uint16_mosaic_sharded_over_two_ranks(engine):
+    """A 16-bit image whose row bands live on two 'ranks' (two threads with their own streams; the
+    all-reduce is emulated by exchanging the counters between them): the staged Pass 1 must give both
+    ranks the percentiles and thresholds of the WHOLE image -- two SUM exchanges, after level A and
+    after level B of the radix histogram."""
+    import torch
+    img = synth.vegetation_frame(310, 512, 640, np.uint16)
+    img[:96] //= 5                                      # bands differ: per-rank percentiles would be wrong
+    bands = [np.ascontiguousarray(b) for b in np.split(img, 8, axis=0)]
+    shards = [bands[:3], bands[3:]]                     # uneven split
+    gate = threading.Barrier(2)
+    box = [None, None]
+    results, errors = [None, None], []
+
+    def run(rank):
+        try:
+            s = engine.stream()
+            dev = engine.upload(shards[rank], stream=s)
+
+            def hook(counters):
+                s.synchronize()
+                box[rank] = counters.clone()
+                torch.cuda.synchronize()
+                gate.wait()
+                other = box[1 - rank].clone()
+                gate.wait()
+                counters.add_(other)
+
+            res = engine.process_device(dev, tiles_of_one_image=True, hist_hook=hook, stream=s)
+            results[rank] = engine.download(res, stream=s)
+        except Exception as exc:                        # pragma: no cover
+            errors.append(exc)
+            gate.abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in (0, 1)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    want = oracle_frame(img)
+    out = results[0] + results[1]
+    assert np.array_equal(np.concatenate([o_["wb"] for o_ in out], axis=0), want["wb"])
+    for t in INDEX_TYPES:
+        got = np.concatenate([o_["maps"][t] for o_ in out], axis=0)
+        assert np.array_equal(got.view(np.uint32), want["maps"][t].view(np.uint32))
+    want_pct = np.array([np.percentile(img[:, :, c].astype(np.float32), (2, 98)) for c in range(3)])
+    assert np.array_equal(results[0][0]["percentiles"], want_pct)
+    assert np.array_equal(results[1][0]["percentiles"], want_pct)
