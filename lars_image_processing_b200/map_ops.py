@@ -25,6 +25,15 @@ def _to_device_f32(eng: Engine, arr: np.ndarray, s) -> torch.Tensor:
     return dev
 
 
+def _to_host(dev: torch.Tensor) -> torch.Tensor:
+    """Device -> pinned host copy on the current stream (the pinned block comes from PyTorch's caching
+    host allocator and returns to it when the NumPy view handed to the caller dies).  Copies into
+    pageable memory run at a fraction of the PCIe rate."""
+    host = torch.empty(dev.shape, dtype=dev.dtype, pin_memory=True)
+    host.copy_(dev, non_blocking=True)
+    return host
+
+
 def device_map_statistics(eng: Engine, dev_map: torch.Tensor, n: int, threshold: float,
                           bins: int = DEFAULT_BINS, median: bool = False, stream=None):
     """Statistics (and optionally the exact median) of one device-resident float32 map.
@@ -90,7 +99,7 @@ def colormap_map(index_array, cmap: str = "RdYlGn", vmin: float = -1.0, vmax: fl
         with torch.cuda.device(eng.device):
             check(lib.lars_colormap_f32(dev.data_ptr(), arr.size, _lib.CMAP_IDS[cmap], float(vmin), float(vmax),
                                         rgb.data_ptr(), s.cuda_stream), "lars_colormap_f32")
-        host = rgb.cpu()
+        host = _to_host(rgb)
     s.synchronize()
     return host.numpy().reshape(arr.shape + (3,))
 
@@ -113,7 +122,7 @@ def ndvi_float64(img_array) -> np.ndarray:
         with torch.cuda.device(eng.device):
             check(lib.lars_ndvi_f64_u8(dev.data_ptr(), n, img.shape[2], out.data_ptr(), s.cuda_stream),
                   "lars_ndvi_f64_u8")
-        host = out.cpu()
+        host = _to_host(out)
     s.synchronize()
     return host.numpy().reshape(img.shape[:2])
 
@@ -133,7 +142,7 @@ def index_from_planes(hi_plane, lo_plane) -> np.ndarray:
         with torch.cuda.device(eng.device):
             check(lib.lars_index_planes_f32(dh.data_ptr(), dl.data_ptr(), hi.size, out.data_ptr(), s.cuda_stream),
                   "lars_index_planes_f32")
-        host = out.cpu()
+        host = _to_host(out)
     s.synchronize()
     return host.numpy().reshape(hi.shape)
 
@@ -207,7 +216,7 @@ def index_generic(img_array, index_type: str) -> np.ndarray:
         with torch.cuda.device(eng.device):
             check(eng.lib.lars_index_hwc(dev.data_ptr(), _lib.DTYPE_IDS[img.dtype.name], n, img.shape[2],
                                          _lib.INDEX_IDS[index_type], out.data_ptr(), s.cuda_stream), "lars_index_hwc")
-        host = out.cpu()
+        host = _to_host(out)
     s.synchronize()
     return host.numpy().reshape(img.shape[:2])
 
@@ -233,7 +242,7 @@ def index_change(early_wb, late_wb, index_type: str, vmin: float = -0.5, vmax: f
             check(eng.lib.lars_index_change_u8(de.data_ptr(), dl.data_ptr(), n, e.shape[2], _lib.INDEX_IDS[index_type],
                                                float(vmin), float(vmax), maps[0].data_ptr(), maps[1].data_ptr(),
                                                maps[2].data_ptr(), rgb.data_ptr(), s.cuda_stream), "lars_index_change_u8")
-        h_maps, h_rgb = maps.cpu(), rgb.cpu()
+        h_maps, h_rgb = _to_host(maps), _to_host(rgb)
     s.synchronize()
     hw = e.shape[:2]
     return {"early": h_maps[0].numpy().reshape(hw), "late": h_maps[1].numpy().reshape(hw),
