@@ -365,7 +365,7 @@ int lars_map_stats_f32(const float* data, int32_t n_maps, int64_t n, int64_t str
   lars::MapFinalizeParams f;
   f.partials = p.partials; f.data = data; f.stride = stride; f.stats = stats;
   f.n_parts = parts; f.bins = bins; f.threshold = threshold;
-  lars::map_stats_finalize_kernel<<<n_maps, lars::MAP_HIST_ROWS, 0, s>>>(f);
+  lars::map_stats_finalize_kernel<<<n_maps, lars::MAP_HIST_ROWS * lars::MAP_FIN_SPLIT, 0, s>>>(f);
   LARS_CUDA(cudaGetLastError());
   return LARS_OK;
 }
@@ -391,7 +391,6 @@ int lars_select_f32(const float* data, int64_t n, uint64_t rank_lo, uint64_t ran
   if (want < grid) grid = (int)(want > 0 ? want : 1);
   for (int pass = 0; pass < 4; ++pass) {
     lars::select_pass_kernel<<<grid, lars::SEL_THREADS, lars::SEL_SMEM_BYTES, s>>>(data, n, state, pass);
-    lars::select_scan_kernel<<<1, 256, 0, s>>>(state, pass);
   }
   LARS_CUDA(cudaGetLastError());
   LARS_CUDA(cudaMemcpyAsync(out3, reinterpret_cast<const char*>(state) + offsetof(lars::SelectState, value),
@@ -574,19 +573,22 @@ int lars_index_hwc(const void* src, int32_t dtype, int64_t n_pixels, int32_t cha
   int grid = st->sm_count * 8;
   if (want < grid) grid = (int)want;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto launch = [&](auto kern, const auto* typed) { kern<<<grid, 256, 0, s>>>(typed, out, n_pixels, channels); };
+#define LARS_HWC_DISPATCH(T)                                                                   \
+  do {                                                                                         \
+    const T* typed = static_cast<const T*>(src);                                               \
+    if (index == LARS_NDVI) launch(lars::index_hwc_kernel<T, 2, 0>, typed);                    \
+    else if (index == LARS_GNDVI) launch(lars::index_hwc_kernel<T, 2, 1>, typed);              \
+    else launch(lars::index_hwc_kernel<T, 1, 2>, typed);                                       \
+  } while (0)
   switch (dtype) {
-    case LARS_DTYPE_U16:
-      lars::index_hwc_kernel<uint16_t><<<grid, 256, 0, s>>>(static_cast<const uint16_t*>(src), out, n_pixels, channels, hi_c, lo_c);
-      break;
-    case LARS_DTYPE_F32:
-      lars::index_hwc_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(src), out, n_pixels, channels, hi_c, lo_c);
-      break;
-    case LARS_DTYPE_F64:
-      lars::index_hwc_kernel<double><<<grid, 256, 0, s>>>(static_cast<const double*>(src), out, n_pixels, channels, hi_c, lo_c);
-      break;
+    case LARS_DTYPE_U16: LARS_HWC_DISPATCH(uint16_t); break;
+    case LARS_DTYPE_F32: LARS_HWC_DISPATCH(float); break;
+    case LARS_DTYPE_F64: LARS_HWC_DISPATCH(double); break;
     default:
       return fail(LARS_ERR_UNSUPPORTED, "lars_index_hwc: dtype %d (uint8 frames go through lars_fused_index_u8)", dtype);
   }
+#undef LARS_HWC_DISPATCH
   LARS_CUDA(cudaGetLastError());
   return LARS_OK;
 }
@@ -607,7 +609,10 @@ int lars_index_change_u8(const uint8_t* early, const uint8_t* late, int64_t n_pi
   long long want = (n_pixels + 255) / 256;
   int grid = st->sm_count * 8;
   if (want < grid) grid = (int)want;
-  lars::index_change_u8_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  if (index == LARS_NDVI) lars::index_change_u8_kernel<2, 0><<<grid, 256, 0, cs>>>(p);
+  else if (index == LARS_GNDVI) lars::index_change_u8_kernel<2, 1><<<grid, 256, 0, cs>>>(p);
+  else lars::index_change_u8_kernel<1, 2><<<grid, 256, 0, cs>>>(p);
   LARS_CUDA(cudaGetLastError());
   return LARS_OK;
 }

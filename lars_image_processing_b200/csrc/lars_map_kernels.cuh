@@ -92,7 +92,24 @@ __global__ void __launch_bounds__(MAP_THREADS) map_stats_f32_kernel(const MapSta
   const long long v0 = (long long)blockIdx.x * per;
   const long long v1 = (v0 + per < nvec) ? v0 + per : nvec;
   const float4* xv = reinterpret_cast<const float4*>(x);
-  for (long long v = v0 + tid; v < v1; v += MAP_THREADS) {
+  // four independent 128-bit loads in flight per thread (one per trip is latency-bound: measured 2.0 TB/s)
+  long long v = v0 + tid;
+  for (; v + 3ll * MAP_THREADS < v1; v += 4ll * MAP_THREADS) {
+    float4 q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) q[u] = __ldg(xv + v + (long long)u * MAP_THREADS);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float gx = 0.f, gd = 0.f, gdd = 0.f;
+      map_stats_accum(q[u].x, k, thr, edges_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
+      map_stats_accum(q[u].y, k, thr, edges_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
+      map_stats_accum(q[u].z, k, thr, edges_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
+      map_stats_accum(q[u].w, k, thr, edges_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
+      sx += (double)gx; sd += (double)gd; sdd += (double)gdd;
+    }
+    count += 16;
+  }
+  for (; v < v1; v += MAP_THREADS) {
     const float4 q = __ldg(xv + v);
     float gx = 0.f, gd = 0.f, gdd = 0.f;
     map_stats_accum(q.x, k, thr, edges_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
@@ -159,38 +176,65 @@ struct MapFinalizeParams {
   float threshold;
 };
 
-__global__ void __launch_bounds__(MAP_HIST_ROWS) map_stats_finalize_kernel(const MapFinalizeParams p) {
+constexpr int MAP_FIN_SPLIT = 8;   // partials are folded by 8 thread groups per bin, then combined in order
+
+__global__ void __launch_bounds__(MAP_HIST_ROWS * MAP_FIN_SPLIT) map_stats_finalize_kernel(const MapFinalizeParams p) {
+  __shared__ unsigned long long hpart[MAP_FIN_SPLIT][MAP_HIST_ROWS];
   const int map = blockIdx.x, tid = threadIdx.x;
   const MapPartial* recs = p.partials + (long long)map * p.n_parts;
   lars_index_stats& o = p.stats[map];
-  if (tid < LARS_MAX_BINS) {
+  {
+    const int bin = tid % MAP_HIST_ROWS, grp = tid / MAP_HIST_ROWS;
     unsigned long long h = 0;
-    if (tid < p.bins)
-      for (int s = 0; s < p.n_parts; ++s) h += recs[s].hist[tid];
+    if (bin < p.bins)
+      for (int s = grp; s < p.n_parts; s += MAP_FIN_SPLIT) h += recs[s].hist[bin];
+    hpart[grp][bin] = h;
+  }
+  __syncthreads();
+  if (tid < MAP_HIST_ROWS) {
+    unsigned long long h = 0;
+#pragma unroll
+    for (int g = 0; g < MAP_FIN_SPLIT; ++g) h += hpart[g][tid];   // integer sums: any order is exact
     o.hist[tid] = h;
   }
-  if (tid == 0) {
+  // moments: lane l of warp 0 folds partials l, l + 32, ... in order, then a fixed butterfly -- the
+  // summation tree depends only on n_parts, so results are reproducible (one thread walking all
+  // partials took 119 us for 592 of them)
+  if (tid < 32) {
     double sx = 0.0, sd = 0.0, sdd = 0.0;
     float mn = INFINITY, mx = -INFINITY;
     unsigned long long cnt = 0, above = 0;
     uint32_t nan = 0;
-    for (int s = 0; s < p.n_parts; ++s) {
+    for (int s = tid; s < p.n_parts; s += 32) {
       const MapPartial& r = recs[s];
       if (!r.count) continue;
       sx += r.sx; sd += r.sd; sdd += r.sdd;
       mn = fminf(mn, r.mn); mx = fmaxf(mx, r.mx);
       cnt += r.count; above += r.above; nan |= r.has_nan;
     }
-    const double n = (double)cnt;
-    const double mean = cnt ? sx / n : 0.0;
-    const double md = cnt ? sd / n : 0.0;
-    double var = cnt ? sdd / n - md * md : 0.0;
-    var = var > 0.0 ? var : 0.0;
-    o.count = cnt; o.count_above = above;
-    o.sum = sx; o.sumsq = cnt ? (var + mean * mean) * n : 0.0;
-    o.mean = nan ? NAN : mean; o.std = nan ? NAN : sqrt(var);
-    o.min = nan ? NAN : mn; o.max = nan ? NAN : mx;
-    o.threshold = p.threshold; o.bins = (uint32_t)p.bins;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      sx += __shfl_xor_sync(0xffffffffu, sx, d);
+      sd += __shfl_xor_sync(0xffffffffu, sd, d);
+      sdd += __shfl_xor_sync(0xffffffffu, sdd, d);
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+      above += __shfl_xor_sync(0xffffffffu, above, d);
+      nan |= __shfl_xor_sync(0xffffffffu, nan, d);
+    }
+    if (tid == 0) {
+      const double n = (double)cnt;
+      const double mean = cnt ? sx / n : 0.0;
+      const double md = cnt ? sd / n : 0.0;
+      double var = cnt ? sdd / n - md * md : 0.0;
+      var = var > 0.0 ? var : 0.0;
+      o.count = cnt; o.count_above = above;
+      o.sum = sx; o.sumsq = cnt ? (var + mean * mean) * n : 0.0;
+      o.mean = nan ? NAN : mean; o.std = nan ? NAN : sqrt(var);
+      o.min = nan ? NAN : mn; o.max = nan ? NAN : mx;
+      o.threshold = p.threshold; o.bins = (uint32_t)p.bins;
+    }
   }
 }
 
@@ -220,6 +264,7 @@ __global__ void select_init_kernel(SelectState* st, unsigned long long r0, unsig
     st->rank[0] = r0; st->rank[1] = r1;
     st->prefix[0] = st->prefix[1] = 0u;
     st->value[0] = st->value[1] = st->median = 0.f;
+    st->pad_ = 0u;                              // arrival counter of the pass kernel
   }
   st->hist[0][t] = 0ull;
   st->hist[1][t] = 0ull;
@@ -228,29 +273,91 @@ __global__ void select_init_kernel(SelectState* st, unsigned long long r0, unsig
 constexpr int SEL_THREADS = 512;
 constexpr int SEL_SMEM_BYTES = 2 * 256 * 32 * 4;
 
+// Digit selection after a pass: scan the 256-bin digit histogram(s), pick the bin that holds each rank,
+// extend the prefixes, clear the histograms.  Called by ALL threads of one CTA (>= 256 threads).
+__device__ __forceinline__ void select_scan(SelectState* st, int pass, unsigned long long* cum, unsigned long long* wtot) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const bool active = t < 256;
+  const bool same = (pass == 0) || (st->prefix[0] == st->prefix[1]);
+  __syncthreads();
+  for (int r = 0; r < 2; ++r) {
+    const int src = same ? 0 : r;
+    unsigned long long x = active ? __ldcg(&st->hist[src][t]) : 0ull;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (active && lane == 31) wtot[warp] = x;
+    __syncthreads();
+    unsigned long long add = 0;
+    if (active)
+      for (int w = 0; w < warp; ++w) add += wtot[w];
+    x += add;
+    if (active) cum[t] = x;
+    __syncthreads();
+    const unsigned long long below = (active && t) ? cum[t - 1] : 0ull;
+    const unsigned long long rk = st->rank[r];
+    __syncthreads();
+    if (active && below <= rk && rk < x) {
+      st->prefix[r] = (st->prefix[r] << 8) | (uint32_t)t;
+      st->rank[r] = rk - below;
+    }
+    __syncthreads();
+  }
+  if (active) {
+    st->hist[0][t] = 0ull;
+    st->hist[1][t] = 0ull;
+  }
+  if (pass == 3 && t == 0) {
+    const float a = float_from_order_key(st->prefix[0]);
+    const float b = float_from_order_key(st->prefix[1]);
+    st->value[0] = a;
+    st->value[1] = b;
+    st->median = LARS_FMUL(LARS_FADD(a, b), 0.5f);  // np.mean of the two middle float32 values
+  }
+}
+
+// One radix pass.  The last CTA to finish (arrival counter) also performs the digit selection, so a
+// select is four launches with nothing in between.
 __global__ void __launch_bounds__(SEL_THREADS) select_pass_kernel(const float* __restrict__ data, long long n,
                                                                    SelectState* st, int pass) {
   extern __shared__ __align__(16) uint32_t sel_hist[];  // [2][256][32] lane-private
+  __shared__ unsigned long long cum[256];
+  __shared__ unsigned long long wtot[8];
+  __shared__ unsigned int is_last;
   const int tid = threadIdx.x, lane = tid & 31;
   for (int i = tid; i < 2 * 256 * 32; i += SEL_THREADS) sel_hist[i] = 0u;
   __syncthreads();
   const uint32_t p0 = st->prefix[0], p1 = st->prefix[1];
   const bool same = (pass == 0) || (p0 == p1);
-  const int hi_shift = 32 - 8 * pass;     // bits above the current digit
   const int dg_shift = 24 - 8 * pass;
-  uint32_t* h0 = sel_hist + lane;
-  uint32_t* h1 = sel_hist + 256 * 32 + lane;
+  // 32-bit shared addresses and RED (no return value); the prefix test is one masked compare:
+  // (key ^ prefix_bits) & hi_mask == 0, with hi_mask = 0 in pass 0
+  const uint32_t hi_mask = pass == 0 ? 0u : (0xFFFFFFFFu << (32 - 8 * pass));
+  const uint32_t want0 = pass == 0 ? 0u : (p0 << (32 - 8 * pass));
+  const uint32_t want1 = pass == 0 ? 0u : (p1 << (32 - 8 * pass));
+  const uint32_t a0 = smem_u32(sel_hist) + 4u * lane, a1 = a0 + 256u * 32u * 4u;
 
   auto visit = [&](float x) {
-    const uint32_t key = float_order_key(x);
-    const uint32_t hi = (pass == 0) ? 0u : (key >> hi_shift);
-    const uint32_t dg = (key >> dg_shift) & 0xFFu;
-    if (hi == p0) atomicAdd(h0 + dg * 32, 1u);
-    if (!same && hi == p1) atomicAdd(h1 + dg * 32, 1u);
+    const uint32_t b = __float_as_uint(x);
+    const uint32_t key = b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);   // order-preserving key
+    const uint32_t off = ((key >> dg_shift) & 0xFFu) << 7;                    // digit * 32 lanes * 4 bytes
+    if (((key ^ want0) & hi_mask) == 0u) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a0 + off) : "memory");
+    if (!same && ((key ^ want1) & hi_mask) == 0u) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a1 + off) : "memory");
   };
   const long long nvec = n / 4;
   const float4* xv = reinterpret_cast<const float4*>(data);
-  for (long long v = (long long)blockIdx.x * SEL_THREADS + tid; v < nvec; v += (long long)gridDim.x * SEL_THREADS) {
+  const long long stride = (long long)gridDim.x * SEL_THREADS;
+  long long v = (long long)blockIdx.x * SEL_THREADS + tid;
+  for (; v + 3 * stride < nvec; v += 4 * stride) {     // four independent 128-bit loads in flight
+    const float4 q0 = __ldg(xv + v), q1 = __ldg(xv + v + stride), q2 = __ldg(xv + v + 2 * stride), q3 = __ldg(xv + v + 3 * stride);
+    visit(q0.x); visit(q0.y); visit(q0.z); visit(q0.w);
+    visit(q1.x); visit(q1.y); visit(q1.z); visit(q1.w);
+    visit(q2.x); visit(q2.y); visit(q2.z); visit(q2.w);
+    visit(q3.x); visit(q3.y); visit(q3.z); visit(q3.w);
+  }
+  for (; v < nvec; v += stride) {
     const float4 q = __ldg(xv + v);
     visit(q.x); visit(q.y); visit(q.z); visit(q.w);
   }
@@ -263,46 +370,18 @@ __global__ void __launch_bounds__(SEL_THREADS) select_pass_kernel(const float* _
     for (int l = 0; l < 32; ++l) s += sel_hist[b * 32 + ((l + tid) & 31)];
     if (s) atomicAdd(&st->hist[b >> 8][b & 255], (unsigned long long)s);
   }
-}
-
-__global__ void __launch_bounds__(256) select_scan_kernel(SelectState* st, int pass) {
-  __shared__ unsigned long long cum[256];
-  __shared__ unsigned long long wtot[8];
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const bool same = (pass == 0) || (st->prefix[0] == st->prefix[1]);
+  // last CTA standing does the selection
+  __threadfence();
   __syncthreads();
-  for (int r = 0; r < 2; ++r) {
-    const int src = same ? 0 : r;
-    unsigned long long x = st->hist[src][t];
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d);
-      if (lane >= d) x += y;
-    }
-    if (lane == 31) wtot[warp] = x;
-    __syncthreads();
-    unsigned long long add = 0;
-    for (int w = 0; w < warp; ++w) add += wtot[w];
-    x += add;
-    cum[t] = x;
-    __syncthreads();
-    const unsigned long long below = t ? cum[t - 1] : 0ull;
-    const unsigned long long rk = st->rank[r];
-    __syncthreads();
-    if (below <= rk && rk < x) {
-      st->prefix[r] = (st->prefix[r] << 8) | (uint32_t)t;
-      st->rank[r] = rk - below;
-    }
-    __syncthreads();
+  if (tid == 0) {
+    const unsigned int ticket = atomicAdd(&st->pad_, 1u);
+    is_last = (ticket == gridDim.x - 1) ? 1u : 0u;
   }
-  st->hist[0][t] = 0ull;
-  st->hist[1][t] = 0ull;
-  if (pass == 3 && t == 0) {
-    const float a = float_from_order_key(st->prefix[0]);
-    const float b = float_from_order_key(st->prefix[1]);
-    st->value[0] = a;
-    st->value[1] = b;
-    st->median = LARS_FMUL(LARS_FADD(a, b), 0.5f);  // np.mean of the two middle float32 values
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    select_scan(st, pass, cum, wtot);
+    if (tid == 0) st->pad_ = 0u;
   }
 }
 
@@ -372,7 +451,25 @@ __global__ void __launch_bounds__(256) colormap_f32_kernel(const ColormapParams 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ndvi_f64_u8_kernel(const uint8_t* __restrict__ src, double* __restrict__ out,
                                                           long long n, int channels) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+  long long done = 0;
+  if (channels == 3 && (reinterpret_cast<uintptr_t>(src) & 3u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+    // 4 pixels per thread: three aligned words in, two 16-byte stores out
+    const long long ngroups = n / 4;
+    const uint32_t* in = reinterpret_cast<const uint32_t*>(src);
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += (long long)gridDim.x * blockDim.x) {
+      const uint32_t w0 = __ldg(in + 3 * g), w1 = __ldg(in + 3 * g + 1), w2 = __ldg(in + 3 * g + 2);
+      // bytes: w0 = R0 G0 N0 R1, w1 = G1 N1 R2 G2, w2 = N2 R3 G3 N3
+      const double x0 = lars_ratio_clip_f64((double)((w0 >> 16) & 255u), (double)(w0 & 255u));
+      const double x1 = lars_ratio_clip_f64((double)((w1 >> 8) & 255u), (double)(w0 >> 24));
+      const double x2 = lars_ratio_clip_f64((double)(w2 & 255u), (double)((w1 >> 16) & 255u));
+      const double x3 = lars_ratio_clip_f64((double)(w2 >> 24), (double)((w2 >> 8) & 255u));
+      double2* o = reinterpret_cast<double2*>(out + 4 * g);
+      o[0] = make_double2(x0, x1);
+      o[1] = make_double2(x2, x3);
+    }
+    done = ngroups * 4;
+  }
+  for (long long i = done + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const uint8_t* px = src + i * channels;
     out[i] = lars_ratio_clip_f64((double)px[2], (double)px[0]);
@@ -441,10 +538,32 @@ __global__ void __launch_bounds__(LARS_MAX_BINS) stats_merge_kernel(const lars_i
 // not uint8, process-images.py:456-490: astype(float32), ratio, clip).  hi_c / lo_c select the
 // channels: NDVI (2,0), GNDVI (2,1), NDWI (1,2).
 // ------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int HI, int LO>
 __global__ void __launch_bounds__(256) index_hwc_kernel(const T* __restrict__ src, float* __restrict__ out, long long n,
-                                                        int channels, int hi_c, int lo_c) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+                                                        int channels) {
+  constexpr int hi_c = HI, lo_c = LO;   // compile-time channels: sample positions resolve to fixed shifts
+  long long done = 0;
+  if (sizeof(T) == 2 && channels == 3 && (reinterpret_cast<uintptr_t>(src) & 7u) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+    // uint16 RGN: 4 pixels = 24 bytes = three 8-byte loads per thread, one float4 out
+    const long long ngroups = n / 4;
+    const uint2* in = reinterpret_cast<const uint2*>(src);
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += (long long)gridDim.x * blockDim.x) {
+      const uint2 a = __ldg(in + 3 * g), b = __ldg(in + 3 * g + 1), c = __ldg(in + 3 * g + 2);
+      const uint32_t w[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+      float x[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int sh = 3 * j + hi_c, sl = 3 * j + lo_c;           // sample indices 0..11
+        const float hi = (float)((w[sh >> 1] >> (16 * (sh & 1))) & 0xFFFFu);
+        const float lo = (float)((w[sl >> 1] >> (16 * (sl & 1))) & 0xFFFFu);
+        x[j] = lars_ratio_clip_f32(hi, lo);
+      }
+      reinterpret_cast<float4*>(out)[g] = make_float4(x[0], x[1], x[2], x[3]);
+    }
+    done = ngroups * 4;
+  }
+  for (long long i = done + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const T* px = src + i * channels;
     out[i] = lars_ratio_clip_f32((float)px[hi_c], (float)px[lo_c]);
   }
@@ -467,15 +586,56 @@ struct ChangeParams {
   float vmin, vmax;
 };
 
+__device__ __forceinline__ uint32_t change_byte(const uint32_t w[3], int idx) {   // byte idx (0..11) of 3 words
+  return (w[idx >> 2] >> (8 * (idx & 3))) & 255u;
+}
+
+template <int HI, int LO>
 __global__ void __launch_bounds__(256) index_change_u8_kernel(const ChangeParams p) {
   __shared__ uint32_t cm[256];
   cm[threadIdx.x] = p.cmap[threadIdx.x];
   __syncthreads();
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
+  long long done = 0;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(p.early) | reinterpret_cast<uintptr_t>(p.late) |
+                         reinterpret_cast<uintptr_t>(p.rgb)) & 3u) == 0 &&
+                       ((reinterpret_cast<uintptr_t>(p.diff) | reinterpret_cast<uintptr_t>(p.early_map) |
+                         reinterpret_cast<uintptr_t>(p.late_map)) & 15u) == 0;
+  if (p.channels == 3 && aligned) {
+    // 4 pixels per thread: three aligned words per frame in, one float4 per map and three words of RGB out
+    const long long ngroups = p.n / 4;
+    const uint32_t* ein = reinterpret_cast<const uint32_t*>(p.early);
+    const uint32_t* lin = reinterpret_cast<const uint32_t*>(p.late);
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += (long long)gridDim.x * blockDim.x) {
+      const uint32_t e[3] = {__ldg(ein + 3 * g), __ldg(ein + 3 * g + 1), __ldg(ein + 3 * g + 2)};
+      const uint32_t l[3] = {__ldg(lin + 3 * g), __ldg(lin + 3 * g + 1), __ldg(lin + 3 * g + 2)};
+      float xe[4], xl[4], d[4];
+      uint32_t c[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // HI / LO are compile-time, so the byte positions 3 j + channel are fixed shifts
+        xe[j] = lars_ratio_pair_u8((int)change_byte(e, 3 * j + HI), (int)change_byte(e, 3 * j + LO));
+        xl[j] = lars_ratio_pair_u8((int)change_byte(l, 3 * j + HI), (int)change_byte(l, 3 * j + LO));
+        d[j] = LARS_FSUB(xl[j], xe[j]);
+      }
+      if (p.early_map) reinterpret_cast<float4*>(p.early_map)[g] = make_float4(xe[0], xe[1], xe[2], xe[3]);
+      if (p.late_map) reinterpret_cast<float4*>(p.late_map)[g] = make_float4(xl[0], xl[1], xl[2], xl[3]);
+      reinterpret_cast<float4*>(p.diff)[g] = make_float4(d[0], d[1], d[2], d[3]);
+      if (p.rgb) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c[j] = cm[lars_cmap_index_range(d[j], p.vmin, p.vmax)];
+        uint32_t* o = reinterpret_cast<uint32_t*>(p.rgb) + 3 * g;
+        o[0] = prmt(c[0], c[1], 0x4210);  // R0 G0 B0 R1
+        o[1] = prmt(c[1], c[2], 0x5421);  // G1 B1 R2 G2
+        o[2] = prmt(c[2], c[3], 0x6542);  // B2 R3 G3 B3
+      }
+    }
+    done = ngroups * 4;
+  }
+  for (long long i = done + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
     const uint8_t* e = p.early + i * p.channels;
     const uint8_t* l = p.late + i * p.channels;
-    const float xe = lars_ratio_pair_u8((int)e[p.hi_c], (int)e[p.lo_c]);
-    const float xl = lars_ratio_pair_u8((int)l[p.hi_c], (int)l[p.lo_c]);
+    const float xe = lars_ratio_pair_u8((int)e[HI], (int)e[LO]);
+    const float xl = lars_ratio_pair_u8((int)l[HI], (int)l[LO]);
     const float d = LARS_FSUB(xl, xe);
     if (p.early_map) p.early_map[i] = xe;
     if (p.late_map) p.late_map[i] = xl;

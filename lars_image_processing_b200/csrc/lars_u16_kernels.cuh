@@ -213,14 +213,12 @@ __global__ void __launch_bounds__(K1_THREADS, 2) wb_hist_u16_lo_kernel(const U16
     const uint8_t* fsrc = p.src + frame * p.frame_stride;
     u = span_end;
     const U16Select* sel = p.select + frame * p.set_stride * 3;
-    int want[3][2];
-    bool any = false;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      want[c][0] = sel[c].buckets[2 * p.lo_pass];
-      want[c][1] = sel[c].buckets[2 * p.lo_pass + 1];
-      any |= want[c][0] >= 0;
-    }
+    // six scalars, not an array: the scalar tail indexes by a run-time channel, and a dynamically
+    // indexed local array would put the selection in local memory for the hot loop as well
+    const int w00 = sel[0].buckets[2 * p.lo_pass], w01 = sel[0].buckets[2 * p.lo_pass + 1];
+    const int w10 = sel[1].buckets[2 * p.lo_pass], w11 = sel[1].buckets[2 * p.lo_pass + 1];
+    const int w20 = sel[2].buckets[2 * p.lo_pass], w21 = sel[2].buckets[2 * p.lo_pass + 1];
+    const bool any = (w00 >= 0) || (w10 >= 0) || (w20 >= 0);
     if (!any) continue;  // uniform per CTA: this pass has nothing to count for this frame
     for (int i = tid; i < 3 * 2 * 256 * 16; i += K1_THREADS) u16_lo[i] = 0u;
     __syncthreads();
@@ -229,9 +227,11 @@ __global__ void __launch_bounds__(K1_THREADS, 2) wb_hist_u16_lo_kernel(const U16
     u16_visit_span<C>(fsrc, b0, b1, tid, [&](int ch, uint32_t v) {
       const int hi = (int)(v >> 8);
       const uint32_t lo = v & 0xFFu;
-      if (hi == want[ch][0])
+      const int want0 = ch == 0 ? w00 : (ch == 1 ? w10 : w20);
+      const int want1 = ch == 0 ? w01 : (ch == 1 ? w11 : w21);
+      if (hi == want0)
         asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(base + (uint32_t)((ch * 2 + 0) * 256 + lo) * 64u) : "memory");
-      else if (hi == want[ch][1])
+      else if (hi == want1)
         asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(base + (uint32_t)((ch * 2 + 1) * 256 + lo) * 64u) : "memory");
     });
     __syncthreads();
