@@ -239,6 +239,9 @@ typedef struct lars_resize_plan {
   int32_t row_first, row_count;   /* source rows the horizontal pass produces (ybox_first .. last)   */
   int32_t xo_tile, plane_words, out_pitch; /* launch geometry of the horizontal pass                 */
   int32_t groups_h, groups_v;     /* 4-tap coefficient groups per output column / row                */
+  int32_t mma_ksteps;             /* > 0: tensor-core horizontal pass available (k-steps of 32 pixels) */
+  int32_t mma_plane_words;        /* its shared words per row per channel plane                      */
+  uint64_t mma_table_offset;      /* byte offset of its block-start / fragment tables in the block   */
   uint64_t table_bytes;           /* size of the coefficient block (host and device copies)          */
   uint64_t temp_frame_bytes;      /* intermediate image bytes per frame (multiple of 16); 0 if unused */
 } lars_resize_plan;

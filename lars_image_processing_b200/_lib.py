@@ -73,8 +73,9 @@ class ResizePlan(C.Structure):
     """Mirror of ``lars_resize_plan`` (include/lars_b200.h)."""
     _fields_ = [(n, C.c_int32) for n in (
         "in_h", "in_w", "out_h", "out_w", "channels", "need_h", "need_v", "ksize_h", "ksize_v",
-        "row_first", "row_count", "xo_tile", "plane_words", "out_pitch", "groups_h", "groups_v")] + [
-        ("table_bytes", C.c_uint64), ("temp_frame_bytes", C.c_uint64)]
+        "row_first", "row_count", "xo_tile", "plane_words", "out_pitch", "groups_h", "groups_v",
+        "mma_ksteps", "mma_plane_words")] + [
+        ("mma_table_offset", C.c_uint64), ("table_bytes", C.c_uint64), ("temp_frame_bytes", C.c_uint64)]
 
 
 class TiffInfo(C.Structure):

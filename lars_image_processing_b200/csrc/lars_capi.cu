@@ -700,6 +700,36 @@ int rs_h_smem(int in_w, int out_w, int channels, int tile, int* plane_words, int
   *out_pitch = pw * 4;
   return channels * *plane_words * lars::RS_IN_PITCH * 4 + lars::RS_ROWS * *out_pitch;
 }
+// Tensor-core horizontal pass: blocks of 8 output columns; block nb starts at input pixel
+// kstart = first(8 nb) rounded down to 4 and spans `ksteps` steps of 32 pixels.
+constexpr int kMmaOutPitch = 196;               // 64 columns x 3 bytes, padded to an odd number of words
+int rs_mma_kstart(int in_w, int out_w, int nb) {
+  int f, c;
+  rs_window(in_w, out_w, nb * 8, &f, &c);
+  return f & ~3;
+}
+// returns ksteps (0 = not usable) and the shared words per row per plane
+int rs_mma_geometry(int in_w, int out_w, int* plane_words) {
+  const int nblocks = (out_w + 7) / 8;
+  int ksteps = 0;
+  for (int nb = 0; nb < nblocks; ++nb) {
+    const int last = (nb * 8 + 8 < out_w ? nb * 8 + 8 : out_w) - 1;
+    int f, c;
+    rs_window(in_w, out_w, last, &f, &c);
+    const int need = (f + c - rs_mma_kstart(in_w, out_w, nb) + 31) / 32;
+    if (need > ksteps) ksteps = need;
+  }
+  int span = 0;                                  // pixels a 64-column tile can touch
+  for (int nb0 = 0; nb0 < nblocks; nb0 += 8) {
+    const int nbl = (nb0 + 8 < nblocks ? nb0 + 8 : nblocks) - 1;
+    const int s = rs_mma_kstart(in_w, out_w, nbl) + ksteps * 32 - rs_mma_kstart(in_w, out_w, nb0);
+    if (s > span) span = s;
+  }
+  *plane_words = span / 4;
+  const long long smem = 3ll * *plane_words * 32 * 4 + 32ll * kMmaOutPitch;
+  return smem <= 100 * 1024 ? ksteps : 0;
+}
+
 // [n][ksize] int coefficients -> [n][groups][3] byte planes of 4 taps (bits 0-7, 8-15 unsigned; 16-23 signed)
 bool rs_pack_planes(const int* kk, int n, int ksize, int groups, uint32_t* out) {
   for (int i = 0; i < n; ++i)
@@ -764,6 +794,15 @@ int lars_resize_plan_lanczos(int32_t in_h, int32_t in_w, int32_t out_h, int32_t 
   plan->table_bytes = 4ull * ((uint64_t)(plan->need_h ? out_w : 0) * (2 + 3 * plan->groups_h) +
                               (uint64_t)(plan->need_v ? out_h : 0) * (2 + 3 * plan->groups_v));
   if (plan->table_bytes == 0) plan->table_bytes = 4;
+  if (plan->need_h && channels == 3) {
+    plan->mma_ksteps = rs_mma_geometry(in_w, out_w, &plan->mma_plane_words);
+    if (plan->mma_ksteps > 0) {
+      const uint64_t nblocks = (uint64_t)(out_w + 7) / 8;
+      plan->mma_table_offset = (plan->table_bytes + 7ull) & ~7ull;
+      plan->table_bytes = plan->mma_table_offset + ((nblocks * 4 + 7ull) & ~7ull) +
+                          nblocks * (uint64_t)plan->mma_ksteps * 3 * 32 * 8;
+    }
+  }
   plan->temp_frame_bytes = (plan->need_h && plan->need_v)
                                ? (((uint64_t)plan->row_count * out_w * channels + 15ull) & ~15ull) : 0;
   return LARS_OK;
@@ -782,6 +821,39 @@ int lars_resize_tables_lanczos(const lars_resize_plan* plan, void* tables_host) 
     if (!kk) { free(scratch); return fail(LARS_ERR_INVALID, "lars_resize_tables_lanczos: out of host memory"); }
     rs_coeffs(plan->in_w, plan->out_w, plan->ksize_h, bounds, kk, scratch);
     const bool ok = rs_pack_planes(kk, plan->out_w, plan->ksize_h, plan->groups_h, planes);
+    if (ok && plan->mma_ksteps > 0) {
+      // B fragments of mma.m16n8k32 (col-major 32 x 8): lane = 4 g + t holds k = 4 t .. 4 t + 3 (b0) and
+      // 16 + 4 t .. (b1) of output column g; one uint2 per (block, k-step, byte plane, lane)
+      char* base = static_cast<char*>(tables_host) + plan->mma_table_offset;
+      const int nblocks = (plan->out_w + 7) / 8;
+      int* kstart = reinterpret_cast<int*>(base);
+      uint32_t* frag = reinterpret_cast<uint32_t*>(base + (((size_t)nblocks * 4 + 7) & ~(size_t)7));
+      for (int nb = 0; nb < nblocks; ++nb) {
+        kstart[nb] = rs_mma_kstart(plan->in_w, plan->out_w, nb);
+        for (int ks = 0; ks < plan->mma_ksteps; ++ks)
+          for (int pl = 0; pl < 3; ++pl)
+            for (int lane = 0; lane < 32; ++lane) {
+              const int g = lane >> 2, t4 = (lane & 3) * 4;
+              const int xo = nb * 8 + g;
+              uint32_t w[2] = {0u, 0u};
+              for (int half = 0; half < 2; ++half)
+                for (int j = 0; j < 4; ++j) {
+                  const int px = kstart[nb] + ks * 32 + half * 16 + t4 + j;
+                  int coef = 0;
+                  if (xo < plan->out_w) {
+                    const int tap = px - bounds[2 * xo];
+                    if (tap >= 0 && tap < bounds[2 * xo + 1]) coef = kk[(size_t)xo * plan->ksize_h + tap];
+                  }
+                  const uint32_t byte = pl == 0 ? (uint32_t)(coef & 255) : pl == 1 ? (uint32_t)((coef >> 8) & 255)
+                                                                                  : (uint32_t)((coef >> 16) & 255);
+                  w[half] |= byte << (8 * j);
+                }
+              uint32_t* o = frag + ((((size_t)nb * plan->mma_ksteps + ks) * 3 + pl) * 32 + lane) * 2;
+              o[0] = w[0];
+              o[1] = w[1];
+            }
+      }
+    }
     free(kk);
     if (!ok) { free(scratch); return fail(LARS_ERR_UNSUPPORTED, "lars_resize_tables_lanczos: coefficient outside 24 bits"); }
     t = reinterpret_cast<int*>(planes + (size_t)plan->out_w * plan->groups_h * 3);
@@ -848,6 +920,32 @@ int lars_resize_lanczos_u8(const lars_resize_plan* plan, const void* tables_dev,
     };
     const bool fast = (C == 3) && ((long long)plan->in_w * 3 % 4 == 0) && (src_frame_stride % 4 == 0) &&
                       !(reinterpret_cast<uintptr_t>(src) & 3u);
+    if (fast && plan->mma_ksteps > 0 && !(plan->mma_table_offset & 7u) && !(reinterpret_cast<uintptr_t>(tables_dev) & 7u)) {
+      const char* mbase = static_cast<const char*>(tables_dev) + plan->mma_table_offset;
+      const size_t nblocks = (size_t)(plan->out_w + 7) / 8;
+      lars::ResizeHMmaParams m;
+      m.src = p.src; m.dst = p.dst; m.bounds = p.bounds;
+      m.kstart = reinterpret_cast<const int*>(mbase);
+      m.bfrag = reinterpret_cast<const uint2*>(mbase + ((nblocks * 4 + 7) & ~(size_t)7));
+      m.src_frame_stride = p.src_frame_stride; m.dst_frame_stride = p.dst_frame_stride;
+      m.in_w = plan->in_w; m.out_w = plan->out_w; m.ksteps = plan->mma_ksteps;
+      m.row_first = plan->row_first; m.row_count = plan->row_count;
+      m.plane_words = plan->mma_plane_words; m.out_pitch = kMmaOutPitch;
+      const int msmem = 3 * plan->mma_plane_words * 32 * 4 + 32 * kMmaOutPitch;
+      dim3 mgrid((plan->out_w + lars::RS_MMA_COLS - 1) / lars::RS_MMA_COLS, (unsigned)gy, n_frames);
+      auto mlaunch = [&](auto kern) -> int {
+        if (msmem > 48 * 1024) LARS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem));
+        kern<<<mgrid, lars::RS_THREADS, msmem, s>>>(m);
+        return LARS_OK;
+      };
+      switch (plan->mma_ksteps) {               // k-step counts of ordinary scale factors keep B in registers
+        case 1: rc = mlaunch(lars::resize_h_mma_kernel<1>); break;
+        case 2: rc = mlaunch(lars::resize_h_mma_kernel<2>); break;
+        case 3: rc = mlaunch(lars::resize_h_mma_kernel<3>); break;
+        case 4: rc = mlaunch(lars::resize_h_mma_kernel<4>); break;
+        default: rc = mlaunch(lars::resize_h_mma_kernel<0>); break;
+      }
+    } else
     rc = (C == 1) ? launch(lars::resize_h_kernel<1, false>)
          : (C == 4) ? launch(lars::resize_h_kernel<4, false>)
          : fast ? launch(lars::resize_h_kernel<3, true>) : launch(lars::resize_h_kernel<3, false>);

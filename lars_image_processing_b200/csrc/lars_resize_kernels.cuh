@@ -164,6 +164,168 @@ __global__ void __launch_bounds__(RS_THREADS) resize_h_kernel(const ResizeHParam
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// K10h on the tensor cores.  The horizontal pass is a banded matrix product
+//   out[row][xo] = sum_x in[row][x] * K[x][xo]
+// -- the one contraction in this code base.  It is exact in integers: the 22-bit coefficients are split
+// into three byte planes (k = k0 + 2^8 k1 + 2^16 k2, k0 / k1 unsigned, k2 signed), each plane is one
+// int8 MMA (mma.sync.m16n8k32, u8 x u8 / u8 x s8 -> s32) and the three accumulators recombine modulo
+// 2^32 to Pillow's 32-bit sum.  A = 16 rows x 32 input pixels of one channel plane (the de-interleaved
+// shared tile, XOR-swizzled so that staging stores and fragment loads are both conflict-free),
+// B = 32 input pixels x 8 output columns of coefficient bytes, prepared on the host in fragment order.
+// One warp owns one block of 8 output columns: it loads the B fragments of a k-step once and applies
+// them to 3 channels x 2 row blocks (6 MMA tiles x 3 planes).
+// ------------------------------------------------------------------------------------------
+struct ResizeHMmaParams {
+  const uint8_t* src;
+  uint8_t* dst;
+  const int* bounds;         // [out_w][2] (tile extents)
+  const int* kstart;         // [n_blocks] first input pixel (multiple of 4) of each 8-column block
+  const uint2* bfrag;        // [n_blocks][ksteps][3 planes][32 lanes] B fragments
+  long long src_frame_stride, dst_frame_stride;
+  int in_w, out_w, ksteps;
+  int row_first, row_count;
+  int plane_words;           // shared words per row per channel plane
+  int out_pitch;             // bytes per row of the output tile
+};
+
+constexpr int RS_MMA_COLS = 64;   // output columns per CTA = 8 warps x 8
+
+__device__ __forceinline__ int rs_swz(int xw) { return ((xw & 3) << 3) | ((xw >> 2) & 7); }
+
+__device__ __forceinline__ void rs_mma_u8u8(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void rs_mma_u8s8(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// KS > 0: the number of k-steps is the compile-time KS and the warp's B fragments (KS x 3 planes) are
+// fetched into registers BEFORE the tile is staged, so their latency hides behind the staging loads and
+// they serve all three channels; KS == 0: any k-step count, fragments re-read per channel.
+#ifndef LARS_RS_MMA_CTAS
+#define LARS_RS_MMA_CTAS 4
+#endif
+template <int KS>
+__global__ void __launch_bounds__(RS_THREADS, LARS_RS_MMA_CTAS) resize_h_mma_kernel(const ResizeHMmaParams p) {
+  extern __shared__ __align__(16) uint8_t rs_smem[];
+  const int PW = p.plane_words;
+  uint32_t* in_w32 = reinterpret_cast<uint32_t*>(rs_smem);                  // [3][PW][32] words, row index swizzled
+  uint8_t* out_s = rs_smem + (size_t)3 * PW * 32 * 4;                       // [32][out_pitch] bytes
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int xo0 = blockIdx.x * RS_MMA_COLS;
+  const int nxo = min(RS_MMA_COLS, p.out_w - xo0);
+  const int r0 = blockIdx.y * RS_ROWS;
+  const int nrows = min(RS_ROWS, p.row_count - r0);
+  const long long in_pitch = (long long)p.in_w * 3;
+  const uint8_t* src = p.src + blockIdx.z * p.src_frame_stride + (long long)(p.row_first + r0) * in_pitch;
+  uint8_t* dst = p.dst + blockIdx.z * p.dst_frame_stride + (long long)r0 * p.out_w * 3;
+  const int nb0 = xo0 >> 3, nbt = (nxo + 7) >> 3;
+  const int ksteps = KS > 0 ? KS : p.ksteps;
+  const int px0 = p.kstart[nb0];                                             // tile origin, multiple of 4
+  const int px1 = p.kstart[nb0 + nbt - 1] + ksteps * 32;                     // everything a fragment can touch
+  const int my_nb = nb0 + (warp < nbt ? warp : 0);
+  const int my_kstart = p.kstart[my_nb];
+  uint2 breg[KS > 0 ? KS * 3 : 1];
+  if (KS > 0) {
+    const uint2* bf = p.bfrag + ((long long)my_nb * KS * 3) * 32 + lane;
+#pragma unroll
+    for (int i = 0; i < KS * 3; ++i) breg[i] = __ldg(bf + i * 32);
+  }
+
+  // ---- stage ----
+  {
+    const int ngroups = (px1 - px0) >> 2;
+    const long long row_words = in_pitch >> 2;                               // rows are whole words (fast path)
+    const long long first_word = (long long)(px0 >> 2) * 3;
+    // a warp stages its four rows (warp, warp + 8, +16, +24) together: 12 independent loads per thread
+    // in flight (one row at a time left ~12 KB in flight per SM and the pass latency-bound)
+    const long long avail_full = row_words - first_word;
+    for (int u = lane; u < ngroups; u += 32) {
+      uint32_t w[4][3];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = warp + q * RS_WARPS;
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(src + (long long)r * in_pitch) + first_word;
+        const long long avail = (r < nrows) ? avail_full : 0;                  // rows past the image: zeros
+#pragma unroll
+        for (int k = 0; k < 3; ++k) w[q][k] = (3 * u + k < avail) ? __ldg(row + 3 * u + k) : 0u;
+      }
+      const int sw = rs_swz(u);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int sr = (warp + q * RS_WARPS) ^ sw;
+        in_w32[(0 * PW + u) * 32 + sr] = __byte_perm(__byte_perm(w[q][0], w[q][1], 0x0630), w[q][2], 0x5210);
+        in_w32[(1 * PW + u) * 32 + sr] = __byte_perm(__byte_perm(w[q][0], w[q][1], 0x0741), w[q][2], 0x6210);
+        in_w32[(2 * PW + u) * 32 + sr] = __byte_perm(__byte_perm(w[q][0], w[q][1], 0x0052), w[q][2], 0x7410);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- contract: warp = block of 8 output columns ----
+  if (warp < nbt) {
+    const int nb = my_nb;
+    const int g = lane >> 2, t = lane & 3;
+    const int xw_base = (my_kstart - px0) >> 2;
+    const uint2* bf = p.bfrag + ((long long)nb * ksteps * 3) * 32 + lane;
+    // one channel at a time keeps the accumulators at 24 registers (the B fragments are re-read from L1
+    // per channel; all three channels at once needed 123 registers and halved the occupancy)
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {
+      int acc[2][3][4];                                                      // [row block][plane][fragment]
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[mb][pl][i] = 0;
+#pragma unroll
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint2 b_lo = KS > 0 ? breg[(KS > 0 ? ks : 0) * 3 + 0] : __ldg(bf + (ks * 3 + 0) * 32);
+        const uint2 b_mid = KS > 0 ? breg[(KS > 0 ? ks : 0) * 3 + 1] : __ldg(bf + (ks * 3 + 1) * 32);
+        const uint2 b_hi = KS > 0 ? breg[(KS > 0 ? ks : 0) * 3 + 2] : __ldg(bf + (ks * 3 + 2) * 32);
+        const int xa = xw_base + ks * 8 + t, xb = xa + 4;
+        const int sa = rs_swz(xa), sb = rs_swz(xb);
+        const uint32_t* pa = in_w32 + (c * PW + xa) * 32;
+        const uint32_t* pb = in_w32 + (c * PW + xb) * 32;
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+          const int row = mb * 16 + g;
+          const uint32_t a[4] = {pa[row ^ sa], pa[(row + 8) ^ sa], pb[row ^ sb], pb[(row + 8) ^ sb]};
+          rs_mma_u8u8(acc[mb][0], a, b_lo.x, b_lo.y);
+          rs_mma_u8u8(acc[mb][1], a, b_mid.x, b_mid.y);
+          rs_mma_u8s8(acc[mb][2], a, b_hi.x, b_hi.y);
+        }
+      }
+      // epilogue: thread holds rows g, g + 8 and columns 2 t, 2 t + 1 of every 16 x 8 tile
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = mb * 16 + g + ((i >> 1) << 3);
+          const int col = warp * 8 + 2 * t + (i & 1);
+          const uint32_t v = (1u << (RS_PRECISION_BITS - 1)) + (uint32_t)acc[mb][0][i] +
+                             ((uint32_t)acc[mb][1][i] << 8) + ((uint32_t)acc[mb][2][i] << 16);
+          out_s[row * p.out_pitch + col * 3 + c] = (uint8_t)rs_clip8((int)v);
+        }
+    }
+  }
+  __syncthreads();
+
+  // ---- write: row-contiguous stores ----
+  const int out_bytes = nxo * 3;
+  for (int r = warp; r < nrows; r += RS_WARPS) {
+    uint8_t* row = dst + (long long)r * p.out_w * 3 + (long long)xo0 * 3;
+    const uint8_t* s = out_s + r * p.out_pitch;
+    for (int j = lane; j < out_bytes; j += 32) row[j] = s[j];
+  }
+}
+
 struct ResizeVParams {
   const uint8_t* src;        // [frame][rows][row_bytes]  (intermediate image, or the source when no horizontal pass)
   uint8_t* dst;              // [frame][out_h][row_bytes]

@@ -82,7 +82,37 @@ def test_host_coefficient_tables_match_the_oracle(geom):
         unpacked = _unpack_planes(t[off:off + n_out * groups * 3], n_out, groups)
         off += n_out * groups * 3
         assert np.array_equal(unpacked[:, :ks], k) and not unpacked[:, ks:].any()
-    assert off * 4 == max(plan.table_bytes, 4) or (off == 0 and plan.table_bytes == 4)
+    if plan.mma_ksteps == 0:
+        assert off * 4 == max(plan.table_bytes, 4) or (off == 0 and plan.table_bytes == 4)
+    else:
+        # tensor-core horizontal pass: block starts + B fragments of mma.m16n8k32 must encode the same
+        # coefficients (byte planes) at the right (input pixel, output column) positions
+        assert plan.mma_table_offset == (off * 4 + 7) // 8 * 8
+        ks_h, b_h, k_h = resize_np.precompute_coeffs(iw, ow)
+        nblocks = (ow + 7) // 8
+        m0 = plan.mma_table_offset // 4
+        kstart = t[m0:m0 + nblocks]
+        f0 = m0 + (nblocks + 1) // 2 * 2
+        frag = t[f0:f0 + nblocks * plan.mma_ksteps * 3 * 32 * 2].view(np.uint32).reshape(nblocks, plan.mma_ksteps, 3, 32, 2)
+        assert (f0 + frag.size) * 4 == plan.table_bytes
+        for nb in sorted({0, min(1, nblocks - 1), nblocks // 2, nblocks - 1}):
+            assert kstart[nb] == (b_h[nb * 8, 0] & ~3)
+            dense = np.zeros((8, plan.mma_ksteps * 32), np.int64)          # [column][k]
+            for ks in range(plan.mma_ksteps):
+                for lane in range(32):
+                    g, t4 = lane >> 2, (lane & 3) * 4
+                    for half in range(2):
+                        for j in range(4):
+                            b = [(int(frag[nb, ks, pl, lane, half]) >> (8 * j)) & 255 for pl in range(3)]
+                            hi = b[2] - 256 if b[2] > 127 else b[2]
+                            dense[g, ks * 32 + half * 16 + t4 + j] = b[0] + (b[1] << 8) + (hi << 16)
+            for g in range(8):
+                xo = nb * 8 + g
+                want = np.zeros(plan.mma_ksteps * 32, np.int64)
+                if xo < ow:
+                    first, cnt = int(b_h[xo, 0]), int(b_h[xo, 1])
+                    want[first - kstart[nb]:first - kstart[nb] + cnt] = k_h[xo, :cnt]
+                assert np.array_equal(dense[g], want), (nb, g)
     if plan.need_h and plan.need_v:
         assert plan.row_first + plan.row_count <= ih and plan.temp_frame_bytes >= plan.row_count * ow * 3
 
