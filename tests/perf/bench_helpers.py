@@ -2,7 +2,7 @@
 memory, one frame per call -- exactly how the Streamlit app calls them) next to the NumPy oracle
 port of the same helper on one host core.  BASELINE config 2 frame (4000x3000 uint8) by default."""
 import os, sys, time, warnings
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from PIL import Image
 from oracle import oracle_np as o, resize_np, synth

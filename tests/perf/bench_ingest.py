@@ -3,7 +3,7 @@ statistics back.  BASELINE config 5 shape (1280x960 uint8) as uncompressed TIFF 
 config 3 shape (5472x3648 uint16 TIFF, which Pillow cannot deliver), next to the reference's serial
 loop (np.array(Image.open(f)) + the NumPy port of its per-frame path) on a sample of the same files."""
 import os, sys, tempfile, time, warnings
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from PIL import Image
 from oracle import oracle_np as o, synth

@@ -1,7 +1,7 @@
 """K10 timing: Pillow-exact Lanczos resize of C2 frames to the app's 1024-pixel working size,
 CUDA events on the launching stream, next to Pillow on one host core."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 from PIL import Image
