@@ -192,7 +192,7 @@ int lars_map_stats_f32(const float* data, int32_t n_maps, int64_t n, int64_t str
 
 /* Exact order statistics of a float32 map (np.median, process-images.py:508, :654;
  * process-ndvi.py:62): out3 (device) = { x[rank_lo], x[rank_hi], float32 mean of the two }
- * of the sorted data.  4-pass radix select, no sort, no host round trip. */
+ * of the sorted data.  3-pass (11 + 11 + 10 bit) radix select, no sort, no host round trip. */
 size_t lars_select_workspace_bytes(void);
 int lars_select_f32(const float* data, int64_t n, uint64_t rank_lo, uint64_t rank_hi, float* out3,
                     void* workspace, size_t workspace_bytes, void* stream);

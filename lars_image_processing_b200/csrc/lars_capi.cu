@@ -387,9 +387,9 @@ int lars_select_f32(const float* data, int64_t n, uint64_t rank_lo, uint64_t ran
   lars::SelectState* state = static_cast<lars::SelectState*>(workspace);
   lars::select_init_kernel<<<1, 256, 0, s>>>(state, rank_lo, rank_hi);
   long long want = (n / 4 + lars::SEL_THREADS - 1) / lars::SEL_THREADS;
-  int grid = st->sm_count * 2;
+  int grid = st->sm_count * (lars::SEL_SMEM_BYTES <= 100 * 1024 ? 2 : 1);   // co-resident CTAs by shared counters
   if (want < grid) grid = (int)(want > 0 ? want : 1);
-  for (int pass = 0; pass < 4; ++pass) {
+  for (int pass = 0; pass < 3; ++pass) {      // 11 + 11 + 10 key bits
     lars::select_pass_kernel<<<grid, lars::SEL_THREADS, lars::SEL_SMEM_BYTES, s>>>(data, n, state, pass);
   }
   LARS_CUDA(cudaGetLastError());

@@ -1,6 +1,6 @@
 // Kernels over float maps / raw frames that sit next to the fused pass:
 //
-//   K3  select_*            exact order statistics (median) of a float32 map: 4-pass 8-bit
+//   K3  select_*            exact order statistics (median) of a float32 map: 3-pass (11 + 11 + 10 bit)
 //                           radix select on order-preserving keys (np.median,
 //                           process-images.py:508, :654; process-ndvi.py:62)
 //   K4  map_stats_f32       statistics + np.histogram of an arbitrary float32 map
@@ -241,13 +241,22 @@ __global__ void __launch_bounds__(MAP_HIST_ROWS * MAP_FIN_SPLIT) map_stats_final
 // ------------------------------------------------------------------------------------------
 // K3: exact order statistics by radix select
 // ------------------------------------------------------------------------------------------
+// Three passes over 11 + 11 + 10 key bits (a fourth 8-bit pass costs another full read of the map).
+constexpr int SEL_BINS = 2048;                 // bins of the widest digit
+#ifndef LARS_SEL_LANES
+#define LARS_SEL_LANES 4
+#endif
+constexpr int SEL_LANES = LARS_SEL_LANES;      // lane copies of each counter (lanes congruent modulo this share one)
+__host__ __device__ constexpr int sel_digit_bits(int pass) { return pass == 2 ? 10 : 11; }
+__host__ __device__ constexpr int sel_digit_shift(int pass) { return pass == 0 ? 21 : (pass == 1 ? 10 : 0); }
+
 struct SelectState {
   unsigned long long rank[2];   // remaining rank inside the current prefix bucket
   uint32_t prefix[2];           // selected high digits so far
   float value[2];               // the two order statistics (written after the last pass)
   float median;                 // float32 mean of the two (np.median for even n)
-  uint32_t pad_;
-  unsigned long long hist[2][256];
+  uint32_t pad_;                // arrival counter of the pass kernel
+  unsigned long long hist[2][SEL_BINS];
 };
 
 __device__ __forceinline__ uint32_t float_order_key(float x) {
@@ -264,52 +273,59 @@ __global__ void select_init_kernel(SelectState* st, unsigned long long r0, unsig
     st->rank[0] = r0; st->rank[1] = r1;
     st->prefix[0] = st->prefix[1] = 0u;
     st->value[0] = st->value[1] = st->median = 0.f;
-    st->pad_ = 0u;                              // arrival counter of the pass kernel
+    st->pad_ = 0u;
   }
-  st->hist[0][t] = 0ull;
-  st->hist[1][t] = 0ull;
+  for (int b = t; b < SEL_BINS; b += blockDim.x) {
+    st->hist[0][b] = 0ull;
+    st->hist[1][b] = 0ull;
+  }
 }
 
 constexpr int SEL_THREADS = 512;
-constexpr int SEL_SMEM_BYTES = 2 * 256 * 32 * 4;
+constexpr int SEL_SMEM_BYTES = 2 * SEL_BINS * SEL_LANES * 4;   // 128 KB: [2][2048][8]
 
-// Digit selection after a pass: scan the 256-bin digit histogram(s), pick the bin that holds each rank,
-// extend the prefixes, clear the histograms.  Called by ALL threads of one CTA (>= 256 threads).
-__device__ __forceinline__ void select_scan(SelectState* st, int pass, unsigned long long* cum, unsigned long long* wtot) {
+// Digit selection after a pass: scan the digit histogram(s), pick the bin that holds each rank, extend
+// the prefixes, clear the histograms.  Called by ALL 512 threads of one CTA; thread t owns bins 4 t .. 4 t + 3.
+__device__ __forceinline__ void select_scan(SelectState* st, int pass, unsigned long long* wtot) {
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const bool active = t < 256;
+  const int bits = sel_digit_bits(pass);
+  const int nb = 1 << bits;
   const bool same = (pass == 0) || (st->prefix[0] == st->prefix[1]);
   __syncthreads();
   for (int r = 0; r < 2; ++r) {
     const int src = same ? 0 : r;
-    unsigned long long x = active ? __ldcg(&st->hist[src][t]) : 0ull;
+    unsigned long long c[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[j] = (4 * t + j < nb) ? __ldcg(&st->hist[src][4 * t + j]) : 0ull;
+    unsigned long long x = c[0] + c[1] + c[2] + c[3];       // inclusive scan over threads of the 4-bin sums
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d);
       if (lane >= d) x += y;
     }
-    if (active && lane == 31) wtot[warp] = x;
+    if (lane == 31) wtot[warp] = x;
     __syncthreads();
     unsigned long long add = 0;
-    if (active)
-      for (int w = 0; w < warp; ++w) add += wtot[w];
+    for (int w = 0; w < warp; ++w) add += wtot[w];
     x += add;
-    if (active) cum[t] = x;
-    __syncthreads();
-    const unsigned long long below = (active && t) ? cum[t - 1] : 0ull;
     const unsigned long long rk = st->rank[r];
     __syncthreads();
-    if (active && below <= rk && rk < x) {
-      st->prefix[r] = (st->prefix[r] << 8) | (uint32_t)t;
-      st->rank[r] = rk - below;
+    unsigned long long below = x - (c[0] + c[1] + c[2] + c[3]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (below <= rk && rk < below + c[j]) {
+        st->prefix[r] = (st->prefix[r] << bits) | (uint32_t)(4 * t + j);
+        st->rank[r] = rk - below;
+      }
+      below += c[j];
     }
     __syncthreads();
   }
-  if (active) {
-    st->hist[0][t] = 0ull;
-    st->hist[1][t] = 0ull;
+  for (int b = t; b < SEL_BINS; b += SEL_THREADS) {
+    st->hist[0][b] = 0ull;
+    st->hist[1][b] = 0ull;
   }
-  if (pass == 3 && t == 0) {
+  if (pass == 2 && t == 0) {
     const float a = float_from_order_key(st->prefix[0]);
     const float b = float_from_order_key(st->prefix[1]);
     st->value[0] = a;
@@ -319,30 +335,32 @@ __device__ __forceinline__ void select_scan(SelectState* st, int pass, unsigned 
 }
 
 // One radix pass.  The last CTA to finish (arrival counter) also performs the digit selection, so a
-// select is four launches with nothing in between.
+// select is three launches with nothing in between.
 __global__ void __launch_bounds__(SEL_THREADS) select_pass_kernel(const float* __restrict__ data, long long n,
                                                                    SelectState* st, int pass) {
-  extern __shared__ __align__(16) uint32_t sel_hist[];  // [2][256][32] lane-private
-  __shared__ unsigned long long cum[256];
-  __shared__ unsigned long long wtot[8];
+  extern __shared__ __align__(16) uint32_t sel_hist[];  // [2][SEL_BINS][SEL_LANES]
+  __shared__ unsigned long long wtot[SEL_THREADS / 32];
   __shared__ unsigned int is_last;
   const int tid = threadIdx.x, lane = tid & 31;
-  for (int i = tid; i < 2 * 256 * 32; i += SEL_THREADS) sel_hist[i] = 0u;
+  const int bits = sel_digit_bits(pass), dg_shift = sel_digit_shift(pass);
+  const int nb = 1 << bits;
+  for (int i = tid; i < 2 * SEL_BINS * SEL_LANES; i += SEL_THREADS) sel_hist[i] = 0u;
   __syncthreads();
   const uint32_t p0 = st->prefix[0], p1 = st->prefix[1];
   const bool same = (pass == 0) || (p0 == p1);
-  const int dg_shift = 24 - 8 * pass;
   // 32-bit shared addresses and RED (no return value); the prefix test is one masked compare:
   // (key ^ prefix_bits) & hi_mask == 0, with hi_mask = 0 in pass 0
-  const uint32_t hi_mask = pass == 0 ? 0u : (0xFFFFFFFFu << (32 - 8 * pass));
-  const uint32_t want0 = pass == 0 ? 0u : (p0 << (32 - 8 * pass));
-  const uint32_t want1 = pass == 0 ? 0u : (p1 << (32 - 8 * pass));
-  const uint32_t a0 = smem_u32(sel_hist) + 4u * lane, a1 = a0 + 256u * 32u * 4u;
+  const int hi_shift = dg_shift + bits;                   // 32 in pass 0
+  const uint32_t hi_mask = pass == 0 ? 0u : (0xFFFFFFFFu << hi_shift);
+  const uint32_t want0 = pass == 0 ? 0u : (p0 << hi_shift);
+  const uint32_t want1 = pass == 0 ? 0u : (p1 << hi_shift);
+  const uint32_t dg_mask = (uint32_t)nb - 1u;
+  const uint32_t a0 = smem_u32(sel_hist) + 4u * (lane & (SEL_LANES - 1)), a1 = a0 + (uint32_t)SEL_BINS * SEL_LANES * 4u;
 
   auto visit = [&](float x) {
     const uint32_t b = __float_as_uint(x);
     const uint32_t key = b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);   // order-preserving key
-    const uint32_t off = ((key >> dg_shift) & 0xFFu) << 7;                    // digit * 32 lanes * 4 bytes
+    const uint32_t off = ((key >> dg_shift) & dg_mask) * (SEL_LANES * 4u);
     if (((key ^ want0) & hi_mask) == 0u) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a0 + off) : "memory");
     if (!same && ((key ^ want1) & hi_mask) == 0u) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a1 + off) : "memory");
   };
@@ -364,11 +382,13 @@ __global__ void __launch_bounds__(SEL_THREADS) select_pass_kernel(const float* _
   if (blockIdx.x == 0)
     for (long long i = nvec * 4 + tid; i < n; i += SEL_THREADS) visit(data[i]);
   __syncthreads();
-  for (int b = tid; b < 2 * 256; b += SEL_THREADS) {
-    if (same && b >= 256) break;
+  for (int b = tid; b < 2 * nb; b += SEL_THREADS) {
+    const int set = b >= nb ? 1 : 0, bin = b - set * nb;
+    if (same && set) break;
     uint32_t s = 0;
-    for (int l = 0; l < 32; ++l) s += sel_hist[b * 32 + ((l + tid) & 31)];
-    if (s) atomicAdd(&st->hist[b >> 8][b & 255], (unsigned long long)s);
+#pragma unroll
+    for (int l = 0; l < SEL_LANES; ++l) s += sel_hist[(set * SEL_BINS + bin) * SEL_LANES + ((l + tid) & (SEL_LANES - 1))];
+    if (s) atomicAdd(&st->hist[set][bin], (unsigned long long)s);
   }
   // last CTA standing does the selection
   __threadfence();
@@ -380,7 +400,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_pass_kernel(const float* _
   __syncthreads();
   if (is_last) {
     __threadfence();
-    select_scan(st, pass, cum, wtot);
+    select_scan(st, pass, wtot);
     if (tid == 0) st->pad_ = 0u;
   }
 }

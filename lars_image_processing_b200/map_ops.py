@@ -58,6 +58,21 @@ def device_map_statistics(eng: Engine, dev_map: torch.Tensor, n: int, threshold:
     return stats, med
 
 
+def device_map_median(eng: Engine, dev_map: torch.Tensor, n: int, stream=None) -> torch.Tensor:
+    """Exact np.median of one device-resident float32 map -> [3] float32 tensor
+    (x[(n-1)//2], x[n//2], their float32 mean); nothing is synced."""
+    lib = eng.lib
+    s = stream or eng.stream()
+    with torch.cuda.stream(s):
+        med = torch.empty(3, dtype=torch.float32, device=eng.device)
+        sel_bytes = int(lib.lars_select_workspace_bytes())
+        sel_ws = torch.empty(sel_bytes, dtype=torch.uint8, device=eng.device)
+        with torch.cuda.device(eng.device):
+            check(lib.lars_select_f32(dev_map.data_ptr(), n, (n - 1) // 2, n // 2, med.data_ptr(),
+                                      sel_ws.data_ptr(), sel_bytes, s.cuda_stream), "lars_select_f32")
+    return med
+
+
 def map_statistics(index_array, threshold: float = 0.2, bins: int = DEFAULT_BINS, median: bool = True) -> dict:
     """mean / std / min / max / coverage / histogram (/ exact median) of a host float map."""
     arr = np.asarray(index_array)
@@ -172,9 +187,8 @@ def frame_statistics_rows(image_data_list, index_type: str) -> List[dict]:
                                  indices=(index_type,), stream=s)
         n = dev.n_pixels
         meds = []
-        for k in range(len(members)):
-            _, med = device_map_statistics(eng, res.maps[i_idx, k], n, thr, median=True, stream=s)
-            meds.append(med)
+        for k in range(len(members)):       # the fused pass already produced every other statistic
+            meds.append(device_map_median(eng, res.maps[i_idx, k], n, stream=s))
         with torch.cuda.stream(s):
             h_stats = res.stats.cpu()
             h_meds = torch.stack(meds).cpu()

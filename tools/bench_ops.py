@@ -46,7 +46,7 @@ def timed(label, bytes_per_el, fn, reps=5):
 
 timed("K4 map_stats_f32 (stats + hist(50) of a float map)", 4,
       lambda: check(lib.lars_map_stats_f32(maps.data_ptr(), M, n, n, 50, 0.2, stats.data_ptr(), ws.data_ptr(), ws.numel(), sp)))
-timed("K3 select_f32 (exact median, 4 radix passes)", 16,
+timed("K3 select_f32 (exact median, 3 radix passes)", 12,
       lambda: [check(lib.lars_select_f32(maps[i].data_ptr(), n, (n - 1) // 2, n // 2, med[i].data_ptr(), sel_ws.data_ptr(), sel_ws.numel(), sp)) for i in range(M)])
 timed("K5 colormap_f32 (float map -> RGB)", 7,
       lambda: [check(lib.lars_colormap_f32(maps[i].data_ptr(), n, 0, -1.0, 1.0, rgb[i].data_ptr(), sp)) for i in range(M)])
