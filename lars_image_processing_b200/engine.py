@@ -140,8 +140,41 @@ class Engine:
         data = self._alloc((n_frames, _pad_px(n_px) * channels * sample_bytes), torch.uint8, stream)
         return DeviceFrames(data, n_px, channels, (height, width), sample_bytes)
 
+    # pageable host arrays reach the device through a per-thread pinned staging buffer filled by a few
+    # copy threads (NumPy releases the GIL for large copies) while the previous piece is already on the
+    # wire; a plain cudaMemcpy from pageable memory is staged by one driver thread at ~12 GB/s
+    _STAGE_PIECE = 4 << 20
+    _STAGE_MIN = 8 << 20
+
+    def _staged_h2d(self, dst: torch.Tensor, src: np.ndarray, s: torch.cuda.Stream) -> None:
+        """dst: 1-D uint8 device view, src: 1-D uint8 host array (pageable), same length."""
+        n = src.size
+        src_t = torch.from_numpy(src)
+        if n < self._STAGE_MIN or src_t.is_pinned():     # small, or already page-locked (e.g. a result of ours)
+            dst.copy_(src_t, non_blocking=True)
+            return
+        st = getattr(self._tls, "stage", None)
+        if st is None or st["buf"].numel() < n:
+            from concurrent.futures import ThreadPoolExecutor
+            if st is not None:
+                st["done"].synchronize()
+            st = {"buf": torch.empty(n, dtype=torch.uint8, pin_memory=True), "done": torch.cuda.Event(),
+                  "pool": st["pool"] if st is not None else ThreadPoolExecutor(4)}
+            st["done"].record(s)
+            self._tls.stage = st
+        st["done"].synchronize()                      # the previous upload has left the staging buffer
+        buf_np = st["buf"].numpy()
+        piece = self._STAGE_PIECE
+        futs = [st["pool"].submit(np.copyto, buf_np[a:min(n, a + piece)], src[a:min(n, a + piece)])
+                for a in range(0, n, piece)]
+        for k, f in enumerate(futs):
+            f.result()
+            a, b = k * piece, min(n, (k + 1) * piece)
+            dst[a:b].copy_(st["buf"][a:b], non_blocking=True)
+        st["done"].record(s)
+
     def upload(self, frames: Sequence[np.ndarray], stream: Optional[torch.cuda.Stream] = None) -> DeviceFrames:
-        """Copy equally-shaped HWC uint8 host frames into a padded device batch."""
+        """Copy equally-shaped HWC uint8 / uint16 host frames into a padded device batch."""
         first = np.asarray(frames[0])
         h, w, c = first.shape
         s = stream or self.stream()
@@ -153,8 +186,7 @@ class Engine:
                 fr = np.ascontiguousarray(fr)
                 if fr.shape != first.shape or fr.dtype != first.dtype:
                     raise ValueError("all frames of a batch must share shape and dtype")
-                src = torch.from_numpy(fr.reshape(-1).view(np.uint8))
-                dev.data[i, :nbytes].copy_(src, non_blocking=True)
+                self._staged_h2d(dev.data[i, :nbytes], fr.reshape(-1).view(np.uint8), s)
         return dev
 
     def wb_histogram(self, frames: DeviceFrames, shared: bool = False, stream=None) -> torch.Tensor:

@@ -21,7 +21,7 @@ def _to_device_f32(eng: Engine, arr: np.ndarray, s) -> torch.Tensor:
     flat = np.ascontiguousarray(arr, dtype=np.float32).reshape(-1)
     with torch.cuda.stream(s):
         dev = torch.empty(flat.size, dtype=torch.float32, device=eng.device)
-        dev.copy_(torch.from_numpy(flat), non_blocking=True)
+        eng._staged_h2d(dev.view(torch.uint8), flat.view(np.uint8), s)
     return dev
 
 
