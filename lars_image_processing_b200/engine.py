@@ -375,6 +375,8 @@ class Engine:
                 plan, tables = _lib.resize_plan(in_h, in_w, out_h, out_w, channels)
                 dev = torch.from_numpy(tables).to(self.device)      # synchronous: once per geometry
                 hit = (plan, dev)
+                if len(self._resize_plans) >= 64:                   # bounded: drop the oldest geometry
+                    self._resize_plans.pop(next(iter(self._resize_plans)))
                 self._resize_plans[key] = hit
         return hit
 
@@ -388,6 +390,7 @@ class Engine:
         s = stream or self.stream()
         in_h, in_w = frames.shape
         plan, tables = self._resize_plan(in_h, in_w, out_h, out_w, frames.channels)
+        tables.record_stream(s)                  # the plan cache may drop the block while this launch still reads it
         out = self.alloc_frames(frames.n_frames, out_h, out_w, frames.channels, s)
         temp_bytes = int(plan.temp_frame_bytes) * frames.n_frames
         temp = self._alloc((max(temp_bytes, 16),), torch.uint8, s)

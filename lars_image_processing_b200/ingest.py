@@ -48,9 +48,12 @@ def _tiff_probe(buf) -> Optional[_lib.TiffInfo]:
     lib = _lib.load()
     info = _lib.TiffInfo()
     view = np.frombuffer(buf, dtype=np.uint8)
-    if view.size < 4 or bytes(view[:2]) not in (b"II", b"MM"):
-        return None
-    rc = lib.lars_tiff_probe(view.ctypes.data, view.size, C.byref(info))
+    try:        # no view of a memory-mapped file may outlive this call (closing the map would fail)
+        if view.size < 4 or bytes(view[:2]) not in (b"II", b"MM"):
+            return None
+        rc = lib.lars_tiff_probe(view.ctypes.data, view.size, C.byref(info))
+    finally:
+        del view
     if rc == LARS_ERR_UNSUPPORTED:
         return None
     check(rc, "lars_tiff_probe")
@@ -90,9 +93,11 @@ def _decode_buffer(buf, out: Optional[np.ndarray]) -> np.ndarray:
         if dst.dtype != dtype or dst.size != int(np.prod(shape)) or not dst.flags.c_contiguous:
             raise ValueError(f"destination must be a contiguous {np.dtype(dtype).name} array of {shape}")
         view = np.frombuffer(buf, dtype=np.uint8)
-        check(_lib.load().lars_tiff_read(view.ctypes.data, view.size, C.byref(info), dst.ctypes.data, dst.nbytes),
-              "lars_tiff_read")
-        del view
+        try:
+            rc = _lib.load().lars_tiff_read(view.ctypes.data, view.size, C.byref(info), dst.ctypes.data, dst.nbytes)
+        finally:
+            del view
+        check(rc, "lars_tiff_read")
         return dst.reshape(shape)
     from PIL import Image
     data = buf if isinstance(buf, (bytes, bytearray)) else bytes(buf)
@@ -109,14 +114,20 @@ def frame_info(source: Source) -> tuple:
     """(shape, dtype) of a frame without decoding the pixels where the format allows it."""
     if isinstance(source, np.ndarray):
         return tuple(source.shape), source.dtype
-    if isinstance(source, (bytes, bytearray, memoryview)):
-        buf = source
-    else:
-        with open(os.fspath(source), "rb") as fh:
-            buf = fh.read()
-    info = _tiff_probe(buf)
+    if not isinstance(source, (bytes, bytearray, memoryview)):
+        with open(os.fspath(source), "rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+            return frame_info(memoryview(mm)) if _is_tiff(mm) else _info_via_pillow(bytes(mm))
+    info = _tiff_probe(source)
     if info is not None:
         return _tiff_shape(info), np.dtype(np.uint8 if info.bits_per_sample == 8 else np.uint16)
+    return _info_via_pillow(source)
+
+
+def _is_tiff(buf) -> bool:
+    return len(buf) >= 4 and bytes(buf[:2]) in (b"II", b"MM")
+
+
+def _info_via_pillow(buf) -> tuple:
     arr = _decode_buffer(buf, None)
     return tuple(arr.shape), arr.dtype
 

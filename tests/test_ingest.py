@@ -97,8 +97,12 @@ def test_corrupt_tiff_is_rejected_not_read_out_of_bounds(tmp_path):
     # not a TIFF at all
     junk = (C.c_uint8 * 16)(*([1] * 16))
     assert lib.lars_tiff_probe(junk, 16, C.byref(info)) < 0
-    with pytest.raises(Exception):
+    from lars_image_processing_b200._lib import LarsError
+    with pytest.raises(LarsError, match="strip"):
         ingest.read_frame(bytes(raw[:len(raw) - 100]))
+    p.write_bytes(bytes(raw[:len(raw) - 100]))                      # the same through a path (memory-mapped file)
+    with pytest.raises(LarsError, match="strip"):
+        ingest.read_frame(p)
 
 
 # --------------------------------------------------------------------------------- GPU: streaming pipeline
