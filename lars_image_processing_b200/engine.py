@@ -609,8 +609,6 @@ class FramePlan:
 
     def __init__(self, engine: "Engine", frames: DeviceFrames, outputs=ALL_OUTPUTS, white_balance: bool = True,
                  quantiles=DEFAULT_QUANTILES, merge_dataset: bool = False, stream=None, **fused_kw):
-        if frames.sample_bytes != 1:
-            raise LarsError("FramePlan currently covers uint8 frames")
         self.engine = engine
         self.frames = frames
         self.stream = stream or engine.stream()
@@ -619,9 +617,19 @@ class FramePlan:
         self.white_balance = white_balance
         self.quantiles = (float(quantiles[0]), float(quantiles[1]))
         self.out = engine.alloc_outputs(frames, outputs, s)
-        self.hist = engine._alloc((F, 3, 256), torch.int64, s) if white_balance else None
-        self.lut = engine._alloc((F, 3, 256), torch.uint8, s) if white_balance else None
-        self.pct = engine._alloc((F, 3, 2), torch.float64, s) if white_balance else None
+        self.u16 = frames.sample_bytes == 2
+        if self.u16:
+            if not white_balance:
+                raise LarsError("uint16 frames go through the white-balance stretch; there is no identity mode")
+            self.hist = None
+            self.lut = engine._alloc((F, 3, STRETCH_U16_BYTES), torch.uint8, s)       # lars_stretch_u16 records
+            self.pct = engine._alloc((F, 3, 2), torch.float64, s)
+            self._u16_ws_bytes = int(engine.lib.lars_wb_u16_workspace_bytes(F))
+            self._u16_ws = engine._alloc((self._u16_ws_bytes,), torch.uint8, s)
+        else:
+            self.hist = engine._alloc((F, 3, 256), torch.int64, s) if white_balance else None
+            self.lut = engine._alloc((F, 3, 256), torch.uint8, s) if white_balance else None
+            self.pct = engine._alloc((F, 3, 2), torch.float64, s) if white_balance else None
         self.out.wb_hist, self.out.wb_lut, self.out.wb_pct = self.hist, self.lut, self.pct
         self.merged = engine._alloc((3, INDEX_STATS_DTYPE.itemsize), torch.uint8, s) \
             if (merge_dataset and "stats" in outputs) else None
@@ -633,14 +641,22 @@ class FramePlan:
         """Enqueue one step on the plan's stream (no allocation, no synchronisation).
         ``fused_events``: optional (start, end) CUDA events recorded around the fused Pass 2."""
         lib, fr, sp = self.engine.lib, self.frames, self.stream.cuda_stream
-        if self.white_balance:
+        if self.u16:
+            check(lib.lars_wb_stretch_build_u16(fr.data.data_ptr(), fr.n_frames, fr.n_pixels, fr.channels, fr.stride_bytes,
+                                                self.quantiles[0], self.quantiles[1], self.lut.data_ptr(),
+                                                self.pct.data_ptr(), self._u16_ws.data_ptr(), self._u16_ws_bytes, 0, sp),
+                  "lars_wb_stretch_build_u16")
+        elif self.white_balance:
             check(lib.lars_wb_hist_u8(fr.data.data_ptr(), fr.n_frames, fr.n_pixels, fr.channels, fr.stride_bytes,
                                       self.hist.data_ptr(), 0, sp), "lars_wb_hist_u8")
             check(lib.lars_wb_lut_build_u8(self.hist.data_ptr(), fr.n_frames, self.quantiles[0], self.quantiles[1],
                                            self.lut.data_ptr(), self.pct.data_ptr(), sp), "lars_wb_lut_build_u8")
         if fused_events is not None:
             fused_events[0].record(self.stream)
-        check(lib.lars_fused_index_u8(C.byref(self._args), sp), "lars_fused_index_u8")
+        if self.u16:
+            check(lib.lars_fused_index_u16(C.byref(self._args), sp), "lars_fused_index_u16")
+        else:
+            check(lib.lars_fused_index_u8(C.byref(self._args), sp), "lars_fused_index_u8")
         if fused_events is not None:
             fused_events[1].record(self.stream)
         if self.merged is not None:

@@ -633,3 +633,20 @@ def test_uint16_mosaic_sharded_over_two_ranks(engine):
     want_pct = np.array([np.percentile(img[:, :, c].astype(np.float32), (2, 98)) for c in range(3)])
     assert np.array_equal(results[0][0]["percentiles"], want_pct)
     assert np.array_equal(results[1][0]["percentiles"], want_pct)
+
+
+def test_frame_plan_uint16_and_cuda_graph(engine):
+    """The pre-bound plan / CUDA-graph replay on 16-bit frames (two-level histogram, threshold stretch)."""
+    from lars_image_processing_b200.engine import FramePlan
+    frames = [synth.vegetation_frame(700 + i, 80, 112, np.uint16) for i in range(3)]
+    dev = engine.upload(frames)
+    plan = FramePlan(engine, dev)
+    plan.run()
+    for i, r in enumerate(engine.download(plan.out)):
+        check_frame_result(r, frames[i], label=f"u16 plan.run[{i}]")
+    plan.capture()
+    plan.replay()
+    for i, r in enumerate(engine.download(plan.out)):
+        check_frame_result(r, frames[i], label=f"u16 plan.replay[{i}]")
+    want_pct = np.array([np.percentile(frames[0][:, :, c].astype(np.float32), (2, 98)) for c in range(3)])
+    assert np.array_equal(plan.pct[0].cpu().numpy(), want_pct)
