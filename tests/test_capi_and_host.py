@@ -44,6 +44,17 @@ def test_struct_layouts_match_header(tmp_path):
     assert b == _lib.INDEX_STATS_DTYPE.itemsize == 576
     assert c == _lib.FusedArgs.maps.offset and d == _lib.FusedArgs.stats.offset
     assert e == _lib.INDEX_STATS_DTYPE.fields["hist"][1]
+    # the structs of the rows next to the path: resize plan, TIFF info, uint16 stretch record
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "lars_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(lars_resize_plan), offsetof(lars_resize_plan, table_bytes),'
+                   'offsetof(lars_resize_plan, mma_table_offset), sizeof(lars_tiff_info), offsetof(lars_tiff_info, frame_bytes),'
+                   'sizeof(lars_stretch_u16));return 0;}\n')
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    a, b, c, d, e, f = map(int, subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split())
+    assert a == C.sizeof(_lib.ResizePlan) and b == _lib.ResizePlan.table_bytes.offset
+    assert c == _lib.ResizePlan.mma_table_offset.offset
+    assert d == C.sizeof(_lib.TiffInfo) and e == _lib.TiffInfo.frame_bytes.offset
+    assert f == _lib.STRETCH_U16_BYTES
 
 
 def test_host_tables_match_oracle():
