@@ -650,3 +650,56 @@ def test_frame_plan_uint16_and_cuda_graph(engine):
         check_frame_result(r, frames[i], label=f"u16 plan.replay[{i}]")
     want_pct = np.array([np.percentile(frames[0][:, :, c].astype(np.float32), (2, 98)) for c in range(3)])
     assert np.array_equal(plan.pct[0].cpu().numpy(), want_pct)
+
+
+def test_single_frame_beyond_2_gib(engine):
+    """One frame whose byte offsets exceed 2^31 (28,000 x 28,000 x 3 = 2.35 GB): Pass 1 counts every
+    sample, the white-balanced output equals the LUT applied to the input everywhere (checked on the
+    device with torch as plumbing), and the statistics equal those of the same image processed as
+    row-band tiles with one shared histogram (a size-independent property: tiling must not matter)."""
+    import torch
+    from lars_image_processing_b200 import distributed as ld
+    h = w = 28000
+    s = engine.stream()
+    frames = engine.alloc_frames(1, h, w, 3, s)
+    n = h * w
+    g = torch.Generator(device=engine.device)
+    g.manual_seed(5)
+    with torch.cuda.stream(s):
+        step = 1 << 28
+        for a in range(0, n * 3, step):                 # vegetation-like bytes, generated in place
+            b = min(n * 3, a + step)
+            frames.data[0, a:b] = (torch.randn(b - a, generator=g, device=engine.device) * 40 + 120).clamp_(0, 255).to(torch.uint8)
+    res = engine.process_device(frames, outputs=("wb", "stats"), stream=s)
+    s.synchronize()
+    hist = res.wb_hist.cpu().numpy()
+    assert hist.shape == (1, 3, 256) and all(int(hist[0, c].sum()) == n for c in range(3))
+    lut = res.wb_lut[0].to(torch.int64)                   # [3, 256]
+    with torch.cuda.stream(s):
+        ok = True
+        px_step = 1 << 26
+        for a in range(0, n, px_step):                  # includes the region past byte 2^31
+            b = min(n, a + px_step)
+            src = frames.data[0, a * 3:b * 3].view(-1, 3).to(torch.int64)
+            want = torch.stack([lut[c][src[:, c]] for c in range(3)], dim=1).to(torch.uint8)
+            ok = ok and bool(torch.equal(res.wb[0, a * 3:b * 3].view(-1, 3), want))
+    assert ok
+    whole = ld.records_to_numpy(res.stats)[0]
+    assert int(whole["count"][0]) == n and int(whole["hist"][0].sum()) == n
+    # the same image as 8 row bands of 3,500 rows with one shared histogram
+    tiles = engine.alloc_frames(8, h // 8, w, 3, s)
+    tb = (h // 8) * w * 3
+    with torch.cuda.stream(s):
+        for t in range(8):
+            tiles.data[t, :tb].copy_(frames.data[0, t * tb:(t + 1) * tb])
+    del res
+    res_t, merged = ld.process_mosaic_tiles(engine, tiles, outputs=("stats",), stream=s)
+    m = ld.records_to_numpy(merged)
+    s.synchronize()
+    for i in range(3):
+        assert int(m["count"][i]) == int(whole["count"][i]) and int(m["count_above"][i]) == int(whole["count_above"][i])
+        assert np.array_equal(m["hist"][i], whole["hist"][i])
+        assert m["min"][i] == whole["min"][i] and m["max"][i] == whole["max"][i]
+        std = float(whole["std"][i])                  # moments: the stated 1e-6 tolerance (different summation trees)
+        assert moment_close(float(m["mean"][i]), float(whole["mean"][i]), std)
+        assert moment_close(float(m["std"][i]), std, std)
