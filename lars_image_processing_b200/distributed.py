@@ -172,4 +172,8 @@ def process_mosaic_tiles(engine, tiles, outputs=("wb", "maps", "rgb", "stats"), 
 
 
 def records_to_numpy(records: torch.Tensor) -> np.ndarray:
+    """Device records -> structured NumPy array.  Synchronises the device first: the records are
+    usually produced on an engine stream, and ``.cpu()`` only orders against the current one."""
+    if records.is_cuda:
+        torch.cuda.synchronize(records.device)
     return records.cpu().numpy().view(INDEX_STATS_DTYPE).reshape(records.shape[:-1])
