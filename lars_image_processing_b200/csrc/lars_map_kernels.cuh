@@ -419,47 +419,59 @@ struct ColormapParams {
 
 __global__ void __launch_bounds__(256) colormap_f32_kernel(const ColormapParams p) {
   __shared__ uint32_t cm[256];
-  __shared__ uint32_t stage[8][96];
+  __shared__ uint32_t stage[8][2][96];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   cm[tid] = p.cmap[tid];
   __syncthreads();
-  // each warp iteration: 128 pixels in (32 x float4), 384 bytes out (3 x 32 words)
+  // each warp iteration: two groups of 128 pixels (2 x 32 float4 in flight), 2 x 384 bytes out
   const long long ngroups = (p.n + 127) / 128;
   uint32_t* out32 = reinterpret_cast<uint32_t*>(p.rgb);
-  for (long long g = (long long)blockIdx.x * 8 + warp; g < ngroups; g += (long long)gridDim.x * 8) {
-    const long long px = g * 128 + 4 * lane;
-    float v[4];
-    if (px + 4 <= p.n) {
-      const float4 q = __ldg(reinterpret_cast<const float4*>(p.data + px));
-      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-    } else {
+  const long long total_bytes = p.n * 3;
+  const long long stride = (long long)gridDim.x * 8;
+  for (long long g0 = (long long)blockIdx.x * 8 + warp; g0 < ngroups; g0 += 2 * stride) {
+    float v[2][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = (px + j < p.n) ? p.data[px + j] : 0.f;
-    }
-    uint32_t c[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float x = v[j];
-      if (x != x) { c[j] = 0u; continue; }  // matplotlib "bad" colour: transparent black
-      // out-of-range values saturate to the first / last slot (matplotlib under / over colours)
-      const int k = p.unit_range ? lars_cmap_index(x) : lars_cmap_index_range(x, p.vmin, p.vmax);
-      c[j] = cm[k];
-    }
-    stage[warp][3 * lane + 0] = prmt(c[0], c[1], 0x4210);
-    stage[warp][3 * lane + 1] = prmt(c[1], c[2], 0x5421);
-    stage[warp][3 * lane + 2] = prmt(c[2], c[3], 0x6542);
-    __syncwarp();
-    const long long wbase = g * 96;                 // output word index of this group
-    const long long total_bytes = p.n * 3;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const long long w = wbase + r * 32 + lane;
-      const uint32_t val = stage[warp][r * 32 + lane];
-      if (w * 4 + 4 <= total_bytes) {
-        out32[w] = val;
+    for (int u = 0; u < 2; ++u) {
+      const long long px = (g0 + u * stride) * 128 + 4 * lane;
+      if (px + 4 <= p.n) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(p.data + px));
+        v[u][0] = q.x; v[u][1] = q.y; v[u][2] = q.z; v[u][3] = q.w;
       } else {
-        for (int b = 0; b < 4; ++b)
-          if (w * 4 + b < total_bytes) p.rgb[w * 4 + b] = (uint8_t)(val >> (8 * b));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[u][j] = (px + j < p.n) ? p.data[px + j] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      uint32_t c[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float x = v[u][j];
+        // NaN -> matplotlib "bad" colour (transparent black); out-of-range values saturate to the
+        // first / last slot (matplotlib under / over colours)
+        const int k = p.unit_range ? lars_cmap_index(x) : lars_cmap_index_range(x, p.vmin, p.vmax);
+        c[j] = (x != x) ? 0u : cm[k];
+      }
+      stage[warp][u][3 * lane + 0] = prmt(c[0], c[1], 0x4210);
+      stage[warp][u][3 * lane + 1] = prmt(c[1], c[2], 0x5421);
+      stage[warp][u][3 * lane + 2] = prmt(c[2], c[3], 0x6542);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long g = g0 + u * stride;
+      if (g >= ngroups) break;
+      const long long wbase = g * 96;               // output word index of this group
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const long long w = wbase + r * 32 + lane;
+        const uint32_t val = stage[warp][u][r * 32 + lane];
+        if (w * 4 + 4 <= total_bytes) {
+          out32[w] = val;
+        } else {
+          for (int b = 0; b < 4; ++b)
+            if (w * 4 + b < total_bytes) p.rgb[w * 4 + b] = (uint8_t)(val >> (8 * b));
+        }
       }
     }
     __syncwarp();
