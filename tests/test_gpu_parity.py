@@ -703,3 +703,42 @@ def test_single_frame_beyond_2_gib(engine):
         std = float(whole["std"][i])                  # moments: the stated 1e-6 tolerance (different summation trees)
         assert moment_close(float(m["mean"][i]), float(whole["mean"][i]), std)
         assert moment_close(float(m["std"][i]), std, std)
+
+
+def test_random_frames_sweep(engine):
+    """Seeded sweep: 48 frames of random shape (1..260 pixels a side, so every tile / vector tail is hit),
+    sample width, channel count and content class (noise, narrow band, two levels, gradient, saturated
+    tails) through the whole path against the oracle -- bit-exact bytes, maps, histograms and counts."""
+    rng = np.random.default_rng(424242)
+    for case in range(48):
+        h, w = int(rng.integers(1, 260)), int(rng.integers(1, 260))
+        dtype = np.uint16 if case % 4 == 3 else np.uint8
+        top = 65535 if dtype == np.uint16 else 255
+        ch = 4 if case % 5 == 4 else 3
+        kind = case % 6
+        if kind == 0:
+            img = rng.integers(0, top + 1, (h, w, ch))
+        elif kind == 1:                                   # narrow band: percentiles a few counts apart
+            base = int(rng.integers(0, top - 8))
+            img = base + rng.integers(0, 6, (h, w, ch))
+        elif kind == 2:                                   # two levels
+            lo, hi = sorted(int(v) for v in rng.integers(0, top + 1, 2))
+            img = np.where(rng.random((h, w, ch)) < 0.3, lo, hi)
+        elif kind == 3:                                   # gradient along the row, different slope per channel
+            x = np.arange(w)[None, :, None] * np.array([1, 2, 3, 1][:ch])[None, None, :]
+            img = (x + np.arange(h)[:, None, None]) % (top + 1)
+        elif kind == 4:                                   # heavy saturated tails
+            img = np.clip(rng.normal(top / 2, top, (h, w, ch)), 0, top)
+        else:                                             # constant channels
+            img = np.ones((h, w, ch)) * rng.integers(0, top + 1, ch)[None, None, :]
+        img = np.ascontiguousarray(img.astype(dtype))
+        res = engine.analyze_frame(img)
+        want = oracle_frame(img)
+        label = f"case {case} {h}x{w}x{ch} {np.dtype(dtype).name} kind {kind}"
+        assert np.array_equal(res["wb"], want["wb"]), label
+        for t in INDEX_TYPES:
+            assert np.array_equal(res["maps"][t].view(np.uint32), want["maps"][t].view(np.uint32)), label
+            assert np.array_equal(res["rgb"][t], want["rgb"][t]), label
+            assert np.array_equal(res["stats"][t]["hist"], want["stats"][t]["hist"]), label
+            assert res["stats"][t]["count_above"] == want["stats"][t]["count_above"], label
+            assert res["stats"][t]["min"] == want["stats"][t]["min"] and res["stats"][t]["max"] == want["stats"][t]["max"], label

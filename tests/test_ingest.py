@@ -188,3 +188,24 @@ def test_survey_pipeline_surfaces_decode_errors(engine, tmp_path):
         pipe.run([good, synth.vegetation_frame(2, 40, 48)])        # wrong shape in the stream
     assert pipe.run([good])["frames"] == 1                          # the pipeline is still usable
     assert pipe.run([])["frames"] == 0
+
+
+def test_tiff_round_trip_sweep(tmp_path):
+    """Seeded sweep of the writer / native reader pair: shapes, sample widths, channel counts, byte
+    orders and strip heights; 8-bit 1/3/4-channel and 16-bit 1-channel files are also handed to Pillow."""
+    from lars_image_processing_b200 import ingest
+    rng = np.random.default_rng(77)
+    p = tmp_path / "s.tif"
+    for case in range(40):
+        h, w = int(rng.integers(1, 90)), int(rng.integers(1, 90))
+        ch = (None, 3, 4)[case % 3]
+        dtype = np.uint16 if case % 2 else np.uint8
+        shape = (h, w) if ch is None else (h, w, ch)
+        img = rng.integers(0, np.iinfo(dtype).max + 1, shape).astype(dtype)
+        rps = None if case % 4 == 0 else int(rng.integers(1, h + 1))
+        ingest.write_tiff(p, img, big_endian=bool(case % 5 < 2), rows_per_strip=rps)
+        got = ingest.read_frame(p)
+        assert got.dtype == dtype and got.shape == shape and np.array_equal(got, img), (case, shape, dtype)
+        assert ingest.frame_info(p) == (shape, np.dtype(dtype))
+        if dtype == np.uint8 or ch is None:
+            assert np.array_equal(np.array(Image.open(p)), img), (case, "pillow")

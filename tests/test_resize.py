@@ -180,3 +180,23 @@ def test_gpu_analysis_after_device_side_resize(engine):
     for t in o.INDEX_TYPES:
         assert np.array_equal(res["maps"][t].view(np.uint32), want["maps"][t].view(np.uint32))
         assert np.array_equal(res["stats"][t]["hist"], want["stats"][t]["hist"])
+
+
+@pytest.mark.gpu
+def test_gpu_resize_random_geometries(engine):
+    """Seeded sweep over 60 random geometries (down- and up-scaling, partial 8-column blocks, widths
+    that take the tensor-core path (row bytes divisible by 4) and widths that take the DP4A fallback,
+    1 to 5 k-steps, single rows / columns): always bit-identical to Pillow."""
+    rng = np.random.default_rng(20261018)
+    for case in range(60):
+        ih, iw = int(rng.integers(1, 420)), int(rng.integers(1, 420))
+        if case % 3 == 0:
+            iw = max(4, iw // 4 * 4)                        # aligned rows -> tensor-core horizontal pass
+        if case % 7 == 0:
+            oh, ow = int(rng.integers(1, 40)), int(rng.integers(1, 40))      # strong down-scaling: many k-steps
+        else:
+            oh, ow = int(rng.integers(1, 500)), int(rng.integers(1, 500))
+        img = rng.integers(0, 256, (ih, iw, 3), dtype=np.uint8)
+        got = engine.resize_batch([img, stripes(ih, iw, 3)], oh, ow)
+        assert np.array_equal(got[0], pil_resize(img, oh, ow)), (case, ih, iw, oh, ow)
+        assert np.array_equal(got[1], pil_resize(stripes(ih, iw, 3), oh, ow)), (case, ih, iw, oh, ow)
