@@ -293,7 +293,8 @@ static int fused_index_impl(const lars_fused_args* a, void* stream, int BPS) {
   p.wb_frame_stride = a->wb_frame_stride;
   p.map_frame_stride = a->map_frame_stride;
   p.rgb_frame_stride = a->rgb_frame_stride;
-  p.tiles_per_frame = (a->n_pixels + lars::K2_TILE_PX - 1) / lars::K2_TILE_PX;
+  const int tile_px = lars::k2_tile_px(BPS);
+  p.tiles_per_frame = (a->n_pixels + tile_px - 1) / tile_px;
   p.total_tiles = p.tiles_per_frame * a->n_frames;
   p.n_frames = a->n_frames;
   p.bins = a->bins;

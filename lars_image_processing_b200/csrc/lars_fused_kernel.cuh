@@ -6,9 +6,9 @@
 // (process-images.py:492-513, process-ndvi.py:65, :97).
 //
 // CTA = 8 consumer warps + 1 TMA-load warp + 1 TMA-store warp, persistent over a balanced
-// contiguous range of 2048-pixel tiles:
+// contiguous range of pipeline tiles (1024 pixels for uint8 frames, 2048 for uint16):
 //   load warp  : cp.async.bulk global->shared into a 3-stage ring (mbarrier full / empty)
-//   consumers  : 2 x 4 pixels per thread per 2048-pixel tile; fp32 maps leave as coalesced 128-bit streaming
+//   consumers  : one (uint8) or two (uint16) 4-pixel groups per thread per tile; fp32 maps leave as coalesced 128-bit streaming
 //                stores; byte outputs (WB, 3 x RGB) are staged in a 2-stage shared ring
 //   store warp : cp.async.bulk shared->global of the staged bytes (mbarrier full / empty), so
 //                no CTA-wide barrier sits on the consumers' critical path
@@ -34,10 +34,17 @@ namespace lars {
 #define LARS_K2_PREFETCH_TILES 0    /* >0: the load warp pulls this many tiles into L2 in one burst */
 #endif
 #ifndef LARS_K2_GROUPS
-#define LARS_K2_GROUPS 2          /* 4-pixel groups per consumer thread per tile */
+#define LARS_K2_GROUPS 1          /* 4-pixel groups per consumer thread per tile, uint8 frames: 1024-pixel tiles
+                                     (measured: 0.876 of the HBM peak against 0.829 with 2048-pixel tiles) */
+#endif
+#ifndef LARS_K2_GROUPS_U16
+#define LARS_K2_GROUPS_U16 2      /* uint16 frames keep 2048-pixel tiles (1024: 0.72 against 0.78) */
 #endif
 #ifndef LARS_K2_IN_STAGES
 #define LARS_K2_IN_STAGES 3
+#endif
+#ifndef LARS_K2_U16_STAGES
+#define LARS_K2_U16_STAGES 2      /* input stages of the uint16 variant (tiles are twice as large) */
 #endif
 #ifndef LARS_K2_OUT_STAGES
 #define LARS_K2_OUT_STAGES 2
@@ -47,9 +54,9 @@ namespace lars {
 #endif
 constexpr int K2_CONSUMERS = 256;
 constexpr int K2_CONSUMER_WARPS = K2_CONSUMERS / 32;
-constexpr int K2_GROUPS = LARS_K2_GROUPS;
+__host__ __device__ constexpr int k2_groups(int bps) { return bps == 2 ? LARS_K2_GROUPS_U16 : LARS_K2_GROUPS; }
 constexpr int K2_GROUP_PX = 4 * K2_CONSUMERS;            // pixels one pass of the consumers covers
-constexpr int K2_TILE_PX = K2_GROUP_PX * K2_GROUPS;      // pixels per pipeline tile
+__host__ __device__ constexpr int k2_tile_px(int bps) { return K2_GROUP_PX * k2_groups(bps); }   // pixels per pipeline tile
 constexpr int K2_THREADS = K2_CONSUMERS + 64;            // + TMA load warp + TMA store warp
 constexpr int K2_IN_STAGES = LARS_K2_IN_STAGES;
 constexpr int K2_OUT_STAGES = LARS_K2_OUT_STAGES;
@@ -91,9 +98,11 @@ struct K2Params {
 
 template <int C, int BPS>
 struct K2Smem {
-  static constexpr int IN_BYTES = K2_TILE_PX * C * BPS;
-  static constexpr int WB_BYTES = K2_TILE_PX * C;
-  static constexpr int RGB_BYTES = K2_TILE_PX * 3;
+  static constexpr int GROUPS = k2_groups(BPS);
+  static constexpr int TILE_PX = k2_tile_px(BPS);
+  static constexpr int IN_BYTES = TILE_PX * C * BPS;
+  static constexpr int WB_BYTES = TILE_PX * C;
+  static constexpr int RGB_BYTES = TILE_PX * 3;
   static constexpr int OUT_BYTES = WB_BYTES + 3 * RGB_BYTES;     // one output stage
   // uint8: 3 x 256 B stretch tables, each 256-aligned (1 KB reserved to absorb any base alignment)
   // uint16: 3 x lars_stretch_u16 (guess parameters + 256 threshold pairs = 2064 B each)
@@ -102,7 +111,8 @@ struct K2Smem {
   static constexpr int OFF_HIST = OFF_CMAP + 3104;               // 3 x 65 rows x 32 lanes x 4 B
   static constexpr int OFF_IN = OFF_HIST + 3 * K2_HIST_ROWS * 128;
   // uint16 tiles are twice as large: two input stages keep two CTAs per SM resident
-  static constexpr int IN_STAGES = (BPS == 2) ? 2 : K2_IN_STAGES;
+  static constexpr int IN_STAGES = (BPS == 2) ? LARS_K2_U16_STAGES : K2_IN_STAGES;
+  static_assert(IN_STAGES <= K2_IN_STAGES, "the barrier block is sized for K2_IN_STAGES");
   static constexpr int OFF_OUT = OFF_IN + IN_STAGES * IN_BYTES;
   static constexpr int OFF_RED = OFF_OUT + K2_OUT_STAGES * OUT_BYTES;
   static constexpr int RED_BYTES = K2_CONSUMER_WARPS * 16 * 8;
@@ -423,9 +433,9 @@ __global__ void __launch_bounds__(K2_THREADS, K2_CTAS_PER_SM) fused_index_kernel
       const uint64_t spol = l2_policy_evict_first();
       (void)spol;
       for (long long t = t_begin; t < t_end; ++t) {
-        const long long px0 = tile * K2_TILE_PX;
+        const long long px0 = tile * L::TILE_PX;
         const long long rem = p.n_pixels - px0;
-        const uint32_t nvalid = rem < K2_TILE_PX ? (uint32_t)rem : (uint32_t)K2_TILE_PX;
+        const uint32_t nvalid = rem < L::TILE_PX ? (uint32_t)rem : (uint32_t)L::TILE_PX;
         mbar_wait_relaxed(bar_out_full + 8u * so, phase);
         const uint32_t stage_addr = smem_base + L::OFF_OUT + so * L::OUT_BYTES;
         const uint32_t wb_bytes = (nvalid * C + 15u) & ~15u;
@@ -469,9 +479,9 @@ __global__ void __launch_bounds__(K2_THREADS, K2_CTAS_PER_SM) fused_index_kernel
       long long tile = t_begin - frame * p.tiles_per_frame;
       uint32_t s = 0, phase = 0;
       for (long long t = t_begin; t < t_end; ++t) {
-        const long long px0 = tile * K2_TILE_PX;
+        const long long px0 = tile * L::TILE_PX;
         const long long rem = p.n_pixels - px0;
-        const uint32_t nvalid = rem < K2_TILE_PX ? (uint32_t)rem : (uint32_t)K2_TILE_PX;
+        const uint32_t nvalid = rem < L::TILE_PX ? (uint32_t)rem : (uint32_t)L::TILE_PX;
         const uint32_t bytes = (nvalid * (C * BPS) + 15u) & ~15u;
 #if LARS_K2_PREFETCH_TILES > 0
         if (until_prefetch == 0) {
@@ -480,7 +490,7 @@ __global__ void __launch_bounds__(K2_THREADS, K2_CTAS_PER_SM) fused_index_kernel
           long long ntl = p.tiles_per_frame - tile;
           if (ntl > LARS_K2_PREFETCH_TILES) ntl = LARS_K2_PREFETCH_TILES;
           if (ntl > t_end - t) ntl = t_end - t;
-          long long pbytes = ntl * (long long)(K2_TILE_PX * C * BPS);
+          long long pbytes = ntl * (long long)(L::TILE_PX * C * BPS);
           const long long left = (p.n_pixels - px0) * (C * BPS);
           if (pbytes > left) pbytes = left;
           l2_prefetch_bulk(p.src + frame * p.src_frame_stride + px0 * (C * BPS), (uint32_t)((pbytes + 15) & ~15ll), pol_last);
@@ -574,16 +584,16 @@ __global__ void __launch_bounds__(K2_THREADS, K2_CTAS_PER_SM) fused_index_kernel
     st.above[0] = st.above[1] = st.above[2] = 0u;
 
     for (; t < span_end; ++t) {
-      const long long px0 = (t - frame_t0) * K2_TILE_PX;
+      const long long px0 = (t - frame_t0) * L::TILE_PX;
       const long long rem = p.n_pixels - px0;
-      const int nvalid = rem < K2_TILE_PX ? (int)rem : K2_TILE_PX;
+      const int nvalid = rem < L::TILE_PX ? (int)rem : L::TILE_PX;
       if (stage_bytes) mbar_wait(bar_out_empty + 8u * s_out, ph_out ^ 1u);  // staging buffer drained
       mbar_wait(bar_base + 8u * s_in, ph_in);                               // tile landed
       // all of this thread's raw words of the tile, then release the input stage
-      K2Raw<C, BPS> raw[K2_GROUPS];
+      K2Raw<C, BPS> raw[L::GROUPS];
       const uint8_t* in_tile = smem + L::OFF_IN + s_in * L::IN_BYTES;
 #pragma unroll
-      for (int g = 0; g < K2_GROUPS; ++g) k2_load_group<C, BPS>(in_tile + g * (K2_GROUP_PX * C * BPS), tid, raw[g]);
+      for (int g = 0; g < L::GROUPS; ++g) k2_load_group<C, BPS>(in_tile + g * (K2_GROUP_PX * C * BPS), tid, raw[g]);
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_base + 8u * (K2_IN_STAGES + s_in));
       uint8_t* out_tile = smem + L::OFF_OUT + s_out * L::OUT_BYTES;
@@ -594,14 +604,14 @@ __global__ void __launch_bounds__(K2_THREADS, K2_CTAS_PER_SM) fused_index_kernel
       for (int i = 0; i < 3; ++i)
         map_base[i] = p.maps[i] ? p.maps[i] + frame * p.map_frame_stride + px0 + 4 * tid : nullptr;
 #pragma unroll
-      for (int g = 0; g < K2_GROUPS; ++g) {
+      for (int g = 0; g < L::GROUPS; ++g) {
         uint32_t* out_wb = reinterpret_cast<uint32_t*>(out_tile + g * (K2_GROUP_PX * C)) + C * tid;
         uint32_t* out_rgb = reinterpret_cast<uint32_t*>(out_tile + L::WB_BYTES + g * (K2_GROUP_PX * 3)) + 3 * tid;
         float* map_dst[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) map_dst[i] = map_base[i] ? map_base[i] + g * K2_GROUP_PX : nullptr;
         const int first = g * K2_GROUP_PX + 4 * tid;
-        if (nvalid == K2_TILE_PX)
+        if (nvalid == L::TILE_PX)
           k2_process_group<C, BPS, true>(p, smem, raw[g], out_wb, out_rgb, L::RGB_BYTES / 4, map_dst, first, nvalid,
                                          tc, stage_bytes, st, ts);
         else
@@ -670,8 +680,8 @@ __global__ void __launch_bounds__(K2_THREADS, K2_CTAS_PER_SM) fused_index_kernel
         rec->mn[0] = (float)acc[6]; rec->mn[1] = (float)acc[7];
         rec->mx[0] = (float)acc[8]; rec->mx[1] = (float)acc[9];
         rec->above[0] = (uint32_t)acc[10]; rec->above[1] = (uint32_t)acc[11]; rec->above[2] = (uint32_t)acc[12];
-        const long long first_px = (t_begin > frame_t0 ? t_begin - frame_t0 : 0) * K2_TILE_PX;
-        long long last_px = (span_end - frame_t0) * K2_TILE_PX;
+        const long long first_px = (t_begin > frame_t0 ? t_begin - frame_t0 : 0) * L::TILE_PX;
+        long long last_px = (span_end - frame_t0) * L::TILE_PX;
         if (last_px > p.n_pixels) last_px = p.n_pixels;
         rec->count = (uint32_t)(last_px - first_px);
       }
