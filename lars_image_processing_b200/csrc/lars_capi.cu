@@ -100,8 +100,8 @@ int lars_init(int device) {
                                  lars::K2Smem<3, 2>::TOTAL));
   LARS_CUDA(cudaFuncSetAttribute(lars::fused_index_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  lars::K2Smem<4, 2>::TOTAL));
-  LARS_CUDA(cudaFuncSetAttribute(lars::wb_hist_u16_hi_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lars::K1_SMEM_BYTES));
-  LARS_CUDA(cudaFuncSetAttribute(lars::wb_hist_u16_hi_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lars::K1_SMEM_BYTES));
+  LARS_CUDA(cudaFuncSetAttribute(lars::wb_hist_u16_hi_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lars::U16_HI_SMEM_BYTES));
+  LARS_CUDA(cudaFuncSetAttribute(lars::wb_hist_u16_hi_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lars::U16_HI_SMEM_BYTES));
   LARS_CUDA(cudaFuncSetAttribute(lars::wb_hist_u16_lo_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lars::U16_LO_SMEM_BYTES));
   LARS_CUDA(cudaFuncSetAttribute(lars::wb_hist_u16_lo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lars::U16_LO_SMEM_BYTES));
   LARS_CUDA(cudaFuncSetAttribute(lars::select_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -186,7 +186,7 @@ int lars_wb_hist_u8(const uint8_t* src, int32_t n_frames, int64_t n_pixels, int3
   p.n_frames = n_frames;
   p.hist_set_stride = shared_hist ? 0 : 768;
   p.keep_in_l2 = (frame_bytes * n_frames <= (long long)LARS_L2_KEEP_BYTES) ? 1 : 0;
-  const long long target_ctas = 2ll * st->sm_count;  // 2 resident CTAs per SM (96 KB smem each)
+  const long long target_ctas = (long long)lars::K1_CTAS_PER_SM * st->sm_count;  // resident CTAs per SM
   const int grid = (int)(p.total_units < target_ctas ? p.total_units : target_ctas);
   if (channels == 3)
     lars::wb_hist_u8_kernel<3><<<grid, lars::K1_THREADS, lars::K1_SMEM_BYTES, s>>>(p);
@@ -527,8 +527,8 @@ int lars_wb_stretch_build_u16_staged(const uint16_t* src, int32_t n_frames, int6
   const long long target = 2ll * st->sm_count;
   const int grid = (int)(p.total_units < target ? p.total_units : target);
   if (do_hi) {
-    if (channels == 3) lars::wb_hist_u16_hi_kernel<3><<<grid, lars::K1_THREADS, lars::K1_SMEM_BYTES, s>>>(p);
-    else lars::wb_hist_u16_hi_kernel<4><<<grid, lars::K1_THREADS, lars::K1_SMEM_BYTES, s>>>(p);
+    if (channels == 3) lars::wb_hist_u16_hi_kernel<3><<<grid, lars::K1_THREADS, lars::U16_HI_SMEM_BYTES, s>>>(p);
+    else lars::wb_hist_u16_hi_kernel<4><<<grid, lars::K1_THREADS, lars::U16_HI_SMEM_BYTES, s>>>(p);
     LARS_CUDA(cudaGetLastError());
   }
   if (do_lo) {

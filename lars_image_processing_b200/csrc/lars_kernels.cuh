@@ -25,9 +25,18 @@ namespace lars {
 // Shared layout hist[channel][bin][lane] (u32): a lane only ever touches bank == lane, so
 // every shared atomic of a warp is conflict-free whatever the image content (natural images
 // have long runs of equal values, the worst case for a plain 256-bin shared histogram).
+#ifndef LARS_K1_LANES
+#define LARS_K1_LANES 32          /* lane copies of every counter (32: bank == lane, never a conflict) */
+#endif
+#ifndef LARS_K1_CTAS
+#define LARS_K1_CTAS 2
+#endif
 constexpr int K1_THREADS = 512;
 constexpr int K1_WARPS = K1_THREADS / 32;
-constexpr int K1_SMEM_BYTES = 3 * 256 * 32 * 4;  // 96 KB -> 2 CTAs / SM
+constexpr int K1_LANES = LARS_K1_LANES;
+constexpr int K1_CTAS_PER_SM = LARS_K1_CTAS;
+constexpr int K1_BIN_SHIFT = (K1_LANES == 32) ? 7 : (K1_LANES == 16 ? 6 : 5);   // log2(bytes per bin)
+constexpr int K1_SMEM_BYTES = 3 * 256 * K1_LANES * 4;  // 96 KB -> 2 CTAs / SM
 constexpr int K1_WARP_BYTES = 3 * 512;           // one warp iteration: 3 coalesced 512-byte rows
 constexpr int K1_CTA_BYTES = K1_WARPS * K1_WARP_BYTES;
 
@@ -45,8 +54,9 @@ struct K1Params {
 
 template <int SHIFT>
 __device__ __forceinline__ void k1_count_byte(uint32_t word, uint32_t lane_base) {
-  // address = lane_base + byte * 128  (bin stride = 32 lanes * 4 bytes)
-  const uint32_t off = (SHIFT == 0) ? ((word << 7) & 0x7F80u) : ((word >> (SHIFT - 7)) & 0x7F80u);
+  // address = lane_base + byte * (lanes * 4)
+  constexpr uint32_t MASK = 0xFFu << K1_BIN_SHIFT;
+  const uint32_t off = (SHIFT < K1_BIN_SHIFT) ? ((word << (K1_BIN_SHIFT - SHIFT)) & MASK) : ((word >> (SHIFT - K1_BIN_SHIFT)) & MASK);
   asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(lane_base + off) : "memory");
 }
 
@@ -84,13 +94,14 @@ struct K1Unit {
 // sequence of work units (frame-major), so the load is balanced to +-1 unit for any batch
 // shape; a range that crosses a frame boundary flushes its shared histogram in between.
 template <int C>
-__global__ void __launch_bounds__(K1_THREADS, 2) wb_hist_u8_kernel(const K1Params p) {
-  extern __shared__ __align__(16) uint32_t k1_hist[];  // [3][256][32]
+__global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) wb_hist_u8_kernel(const K1Params p) {
+  extern __shared__ __align__(16) uint32_t k1_hist[];  // [3][256][K1_LANES]
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
   const long long frame_bytes = p.n_pixels * C;
-  const uint32_t a0 = smem_u32(k1_hist) + 4u * lane, a1 = a0 + 32768u, a2 = a0 + 65536u;
+  const int hl = lane & (K1_LANES - 1);
+  const uint32_t a0 = smem_u32(k1_hist) + 4u * hl, a1 = a0 + 256u * K1_LANES * 4u, a2 = a1 + 256u * K1_LANES * 4u;
   const long long G = gridDim.x;
   long long u = ((long long)blockIdx.x * p.total_units) / G;
   const long long u_end = ((long long)(blockIdx.x + 1) * p.total_units) / G;
@@ -109,7 +120,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) wb_hist_u8_kernel(const K1Param
     const uint8_t* fsrc = p.src + frame * p.frame_stride;
     u = span_end;
 
-    for (int i = tid; i < 3 * 256 * 32; i += K1_THREADS) k1_hist[i] = 0u;
+    for (int i = tid; i < 3 * 256 * K1_LANES; i += K1_THREADS) k1_hist[i] = 0u;
     __syncthreads();
 
     if (C == 3) {
@@ -143,14 +154,14 @@ __global__ void __launch_bounds__(K1_THREADS, 2) wb_hist_u8_kernel(const K1Param
       }
       // scalar tail (< 1536 bytes, only at the end of a frame)
       for (long long o = vec_end + tid; o < b1; o += K1_THREADS)
-        atomicAdd(&k1_hist[((int)(o % 3) * 256 + (int)fsrc[o]) * 32 + lane], 1u);
+        atomicAdd(&k1_hist[((int)(o % 3) * 256 + (int)fsrc[o]) * K1_LANES + hl], 1u);
     } else {
       const long long vec_end = b0 + ((b1 - b0) / 16) * 16;  // frame_bytes is a multiple of 4
       for (long long off = b0 + 16ll * tid; off + 16 <= vec_end; off += 16ll * K1_THREADS)
         k1_count_vec4(K1_LOAD(fsrc + off), a0, a1, a2);
       for (long long o = vec_end + tid; o < b1; o += K1_THREADS) {
         const int ch = (int)(o & 3);
-        if (ch < 3) atomicAdd(&k1_hist[(ch * 256 + (int)fsrc[o]) * 32 + lane], 1u);
+        if (ch < 3) atomicAdd(&k1_hist[(ch * 256 + (int)fsrc[o]) * K1_LANES + hl], 1u);
       }
     }
     __syncthreads();
@@ -159,7 +170,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) wb_hist_u8_kernel(const K1Param
     for (int b = tid; b < 3 * 256; b += K1_THREADS) {
       uint32_t sum = 0;
 #pragma unroll 8
-      for (int l = 0; l < 32; ++l) sum += k1_hist[b * 32 + ((l + tid) & 31)];
+      for (int l = 0; l < K1_LANES; ++l) sum += k1_hist[b * K1_LANES + ((l + tid) & (K1_LANES - 1))];
       if (sum) atomicAdd(&p.hist[frame * p.hist_set_stride + b], (unsigned long long)sum);
     }
     __syncthreads();

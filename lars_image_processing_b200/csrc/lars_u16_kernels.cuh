@@ -90,6 +90,7 @@ __device__ __forceinline__ void u16_visit_span(const uint8_t* fsrc, long long b0
 }
 
 // ---- level A ------------------------------------------------------------------------------
+constexpr int U16_HI_SMEM_BYTES = 3 * 256 * 32 * 4;   // [3][256][32] lane-private, 96 KB
 template <int C>
 __global__ void __launch_bounds__(K1_THREADS, 2) wb_hist_u16_hi_kernel(const U16HistParams p) {
   extern __shared__ __align__(16) uint32_t u16_hist[];  // [3][256][32] lane-private
