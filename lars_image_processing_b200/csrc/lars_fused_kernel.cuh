@@ -708,8 +708,8 @@ __global__ void __launch_bounds__(3 * K2_BINS_PAD) fused_finalize_kernel(const K
   {  // histograms: thread (index, bin); integer sums, any order is exact
     const int idx = tid / K2_BINS_PAD, bin = tid % K2_BINS_PAD;
     unsigned long long h = 0;
-    for (int s = 0; s < p.slots_per_frame; ++s)
-      if (recs[s].count) h += recs[s].hist[idx][bin];
+#pragma unroll 4
+    for (int s = 0; s < p.slots_per_frame; ++s) h += recs[s].hist[idx][bin];   // unwritten slots are zero (memset)
     out[idx].hist[bin] = h;
   }
   if (warp < 3) {
@@ -722,9 +722,10 @@ __global__ void __launch_bounds__(3 * K2_BINS_PAD) fused_finalize_kernel(const K
     unsigned long long cnt = 0, above = 0;
     for (int s = lane; s < p.slots_per_frame; s += 32) {
       const K2Partial& r = recs[s];
-      if (!r.count) continue;
+      const bool used = r.count != 0;              // unwritten slots are all zero: sums take them as they are,
       sx += r.sx[g]; sd += r.sd[g]; sdd += r.sdd[g];
-      mn = fminf(mn, r.mn[g]); mx = fmaxf(mx, r.mx[g]);
+      mn = used ? fminf(mn, r.mn[g]) : mn;         // only min / max must skip them (select, no branch: loads pipeline)
+      mx = used ? fmaxf(mx, r.mx[g]) : mx;
       cnt += r.count; above += r.above[i];
     }
 #pragma unroll

@@ -538,30 +538,48 @@ __global__ void __launch_bounds__(LARS_MAX_BINS) stats_merge_kernel(const lars_i
   const int idx = blockIdx.x;   // index 0..2
   const int tid = threadIdx.x;  // histogram bin
   unsigned long long h = 0;
+#pragma unroll 4
   for (int s = 0; s < n_sets; ++s) h += in[(long long)s * 3 + idx].hist[tid];
   out[idx].hist[tid] = h;
-  if (tid == 0) {
+  if (tid < 32) {
+    // lane l folds sets l, l + 32, ... in order, then a fixed butterfly: the summation tree depends only on
+    // n_sets (reproducible), and the loads of a lane are independent (one thread walking all sets was a
+    // chain of dependent loads)
     unsigned long long cnt = 0, above = 0;
     double sum = 0.0, sumsq = 0.0;
     float mn = INFINITY, mx = -INFINITY, thr = 0.f;
     uint32_t bins = 0;
-    for (int s = 0; s < n_sets; ++s) {
+    for (int s = tid; s < n_sets; s += 32) {
       const lars_index_stats& r = in[(long long)s * 3 + idx];
-      if (!r.count) continue;
+      const bool used = r.count != 0;
       cnt += r.count; above += r.count_above;
-      sum += r.sum; sumsq += r.sumsq;
-      mn = fminf(mn, r.min); mx = fmaxf(mx, r.max);
-      thr = r.threshold; bins = r.bins;
+      sum += used ? r.sum : 0.0; sumsq += used ? r.sumsq : 0.0;
+      mn = used ? fminf(mn, r.min) : mn; mx = used ? fmaxf(mx, r.max) : mx;
+      thr = used ? r.threshold : thr; bins = used ? r.bins : bins;
     }
-    const double n = (double)cnt;
-    const double mean = cnt ? sum / n : 0.0;
-    double var = cnt ? sumsq / n - mean * mean : 0.0;
-    var = var > 0.0 ? var : 0.0;
-    lars_index_stats& o = out[idx];
-    o.count = cnt; o.count_above = above; o.sum = sum; o.sumsq = sumsq;
-    o.mean = mean; o.std = sqrt(var);
-    o.min = cnt ? mn : 0.f; o.max = cnt ? mx : 0.f;
-    o.threshold = thr; o.bins = bins;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+      above += __shfl_xor_sync(0xffffffffu, above, d);
+      sum += __shfl_xor_sync(0xffffffffu, sum, d);
+      sumsq += __shfl_xor_sync(0xffffffffu, sumsq, d);
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+      const float othr = __shfl_xor_sync(0xffffffffu, thr, d);
+      const uint32_t obins = __shfl_xor_sync(0xffffffffu, bins, d);
+      if (bins == 0) { thr = othr; bins = obins; }        // any used record carries the same threshold / bins
+    }
+    if (tid == 0) {
+      const double n = (double)cnt;
+      const double mean = cnt ? sum / n : 0.0;
+      double var = cnt ? sumsq / n - mean * mean : 0.0;
+      var = var > 0.0 ? var : 0.0;
+      lars_index_stats& o = out[idx];
+      o.count = cnt; o.count_above = above; o.sum = sum; o.sumsq = sumsq;
+      o.mean = mean; o.std = sqrt(var);
+      o.min = cnt ? mn : 0.f; o.max = cnt ? mx : 0.f;
+      o.threshold = thr; o.bins = bins;
+    }
   }
 }
 

@@ -36,7 +36,7 @@ def _records_for(frames):
 
 
 def _merge_numpy(rec):
-    """Same arithmetic as stats_merge_kernel, in set order."""
+    """Same sums as stats_merge_kernel (the kernel folds sets lane-strided with a fixed butterfly; sums agree to rounding)."""
     out = np.zeros(3, rec.dtype)
     for i in range(3):
         for s in range(rec.shape[0]):
