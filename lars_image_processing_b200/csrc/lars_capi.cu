@@ -703,7 +703,7 @@ int rs_h_smem(int in_w, int out_w, int channels, int tile, int* plane_words, int
 }
 // Tensor-core horizontal pass: blocks of 8 output columns; block nb starts at input pixel
 // kstart = first(8 nb) rounded down to 4 and spans `ksteps` steps of 32 pixels.
-constexpr int kMmaOutPitch = 196;               // 64 columns x 3 bytes, padded to an odd number of words
+constexpr int kMmaOutPitch = lars::RS_MMA_OUT_PITCH * 4;   // bytes per row of the output tile: one packed pixel per word
 int rs_mma_kstart(int in_w, int out_w, int nb) {
   int f, c;
   rs_window(in_w, out_w, nb * 8, &f, &c);

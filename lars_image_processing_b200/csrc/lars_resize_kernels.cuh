@@ -190,6 +190,7 @@ struct ResizeHMmaParams {
 };
 
 constexpr int RS_MMA_COLS = 64;   // output columns per CTA = 8 warps x 8
+constexpr int RS_MMA_OUT_PITCH = RS_MMA_COLS + 1;   // words per row of the output tile (one packed pixel per word)
 
 __device__ __forceinline__ int rs_swz(int xw) { return ((xw & 3) << 3) | ((xw >> 2) & 7); }
 
@@ -208,14 +209,14 @@ __device__ __forceinline__ void rs_mma_u8s8(int (&d)[4], const uint32_t (&a)[4],
 // fetched into registers BEFORE the tile is staged, so their latency hides behind the staging loads and
 // they serve all three channels; KS == 0: any k-step count, fragments re-read per channel.
 #ifndef LARS_RS_MMA_CTAS
-#define LARS_RS_MMA_CTAS 4
+#define LARS_RS_MMA_CTAS 3
 #endif
 template <int KS>
 __global__ void __launch_bounds__(RS_THREADS, LARS_RS_MMA_CTAS) resize_h_mma_kernel(const ResizeHMmaParams p) {
   extern __shared__ __align__(16) uint8_t rs_smem[];
   const int PW = p.plane_words;
   uint32_t* in_w32 = reinterpret_cast<uint32_t*>(rs_smem);                  // [3][PW][32] words, row index swizzled
-  uint8_t* out_s = rs_smem + (size_t)3 * PW * 32 * 4;                       // [32][out_pitch] bytes
+  uint32_t* out_w32 = in_w32 + (size_t)3 * PW * 32;                         // [32][RS_MMA_OUT_PITCH] words: R | G << 8 | B << 16
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int xo0 = blockIdx.x * RS_MMA_COLS;
   const int nxo = min(RS_MMA_COLS, p.out_w - xo0);
@@ -275,6 +276,11 @@ __global__ void __launch_bounds__(RS_THREADS, LARS_RS_MMA_CTAS) resize_h_mma_ker
     const uint2* bf = p.bfrag + ((long long)nb * ksteps * 3) * 32 + lane;
     // one channel at a time keeps the accumulators at 24 registers (the B fragments are re-read from L1
     // per channel; all three channels at once needed 123 registers and halved the occupancy)
+    uint32_t pix[2][4];                                                      // packed R | G << 8 | B << 16 of this thread's 8 outputs
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pix[mb][i] = 0u;
 #pragma unroll 1
     for (int c = 0; c < 3; ++c) {
       int acc[2][3][4];                                                      // [row block][plane][fragment]
@@ -302,27 +308,47 @@ __global__ void __launch_bounds__(RS_THREADS, LARS_RS_MMA_CTAS) resize_h_mma_ker
           rs_mma_u8s8(acc[mb][2], a, b_hi.x, b_hi.y);
         }
       }
-      // epilogue: thread holds rows g, g + 8 and columns 2 t, 2 t + 1 of every 16 x 8 tile
 #pragma unroll
       for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int row = mb * 16 + g + ((i >> 1) << 3);
-          const int col = warp * 8 + 2 * t + (i & 1);
           const uint32_t v = (1u << (RS_PRECISION_BITS - 1)) + (uint32_t)acc[mb][0][i] +
                              ((uint32_t)acc[mb][1][i] << 8) + ((uint32_t)acc[mb][2][i] << 16);
-          out_s[row * p.out_pitch + col * 3 + c] = (uint8_t)rs_clip8((int)v);
+          pix[mb][i] |= rs_clip8((int)v) << (8 * c);
         }
     }
+    // thread holds rows g, g + 8 and columns 2 t, 2 t + 1 of every 16 x 8 tile: one word per pixel
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = mb * 16 + g + ((i >> 1) << 3);
+        const int col = warp * 8 + 2 * t + (i & 1);
+        out_w32[row * RS_MMA_OUT_PITCH + col] = pix[mb][i];
+      }
   }
   __syncthreads();
 
-  // ---- write: row-contiguous stores ----
-  const int out_bytes = nxo * 3;
-  for (int r = warp; r < nrows; r += RS_WARPS) {
+  // ---- write: four packed pixels -> three output words, row-contiguous 32-bit stores ----
+  const bool words_ok = (p.out_w & 3) == 0 && (p.dst_frame_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dst) & 3u) == 0;
+  const int nquads = words_ok ? (nxo >> 2) : 0;                              // whole 4-pixel groups of this tile
+  for (int r = warp * 2 + (lane >> 4); r < nrows; r += RS_WARPS * 2) {       // half a warp per row
+    const int q = lane & 15;
+    if (q < nquads) {
+      const uint32_t* s4 = out_w32 + r * RS_MMA_OUT_PITCH + 4 * q;
+      const uint32_t p0 = s4[0], p1 = s4[1], p2 = s4[2], p3 = s4[3];
+      uint32_t* o = reinterpret_cast<uint32_t*>(dst + (long long)r * p.out_w * 3 + (long long)xo0 * 3) + 3 * q;
+      o[0] = __byte_perm(p0, p1, 0x4210);   // R0 G0 B0 R1
+      o[1] = __byte_perm(p1, p2, 0x5421);   // G1 B1 R2 G2
+      o[2] = __byte_perm(p2, p3, 0x6542);   // B2 R3 G3 B3
+    }
+  }
+  for (int r = warp; r < nrows; r += RS_WARPS) {                             // leftover pixels (or everything, unaligned)
     uint8_t* row = dst + (long long)r * p.out_w * 3 + (long long)xo0 * 3;
-    const uint8_t* s = out_s + r * p.out_pitch;
-    for (int j = lane; j < out_bytes; j += 32) row[j] = s[j];
+    for (int x = 4 * nquads + lane; x < nxo; x += 32) {
+      const uint32_t px = out_w32[r * RS_MMA_OUT_PITCH + x];
+      row[3 * x] = (uint8_t)px; row[3 * x + 1] = (uint8_t)(px >> 8); row[3 * x + 2] = (uint8_t)(px >> 16);
+    }
   }
 }
 
