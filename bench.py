@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--cpu-frames", type=int, default=3, help="frames of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-single", action="store_true", help="skip the one-frame-per-pass leg (profiling runs)")
     ap.add_argument("--chunk", type=int, default=2, help="frames per pipeline chunk in the e2e path")
     ap.add_argument("--dtype", default="u8", choices=["u8", "u16"],
                     help="sample type of the synthetic frames (u16: 16-bit frames as in BASELINE config 3)")
@@ -337,7 +338,7 @@ def run_ours(a):
     # ---- BASELINE config 2 read literally: ONE frame per pass (latency-bound: ~60 us of traffic per frame),
     # the whole pass replayed as a CUDA graph
     single = None
-    if sb == 1 and rank == 0:
+    if sb == 1 and rank == 0 and not a.no_single:
         one = synth_frames_device(eng, 1, h, w, seed=99, sample_bytes=1)
         plan1 = FramePlan(eng, one, ALL_OUTPUTS, stream=s).capture()
         for _ in range(5):

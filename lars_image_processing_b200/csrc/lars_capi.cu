@@ -323,7 +323,7 @@ static int fused_index_impl(const lars_fused_args* a, void* stream, int BPS) {
     f.slots_per_frame = p.slots_per_frame;
     f.bins = a->bins;
     for (int i = 0; i < 3; ++i) f.thresholds[i] = a->thresholds[i];
-    lars::fused_finalize_kernel<<<a->n_frames, 3 * lars::K2_BINS_PAD, 0, s>>>(f);
+    lars::fused_finalize_kernel<<<a->n_frames, 3 * lars::K2_BINS_PAD * lars::K2F_SPLIT, 0, s>>>(f);
     LARS_CUDA(cudaGetLastError());
   }
   return LARS_OK;

@@ -699,18 +699,29 @@ struct K2fParams {
   float thresholds[3];
 };
 
-__global__ void __launch_bounds__(3 * K2_BINS_PAD) fused_finalize_kernel(const K2fParams p) {
+constexpr int K2F_SPLIT = 4;   // slot groups per histogram bin (a single frame per launch has ~300 slots to fold)
+
+__global__ void __launch_bounds__(3 * K2_BINS_PAD * K2F_SPLIT) fused_finalize_kernel(const K2fParams p) {
+  __shared__ unsigned long long hpart[K2F_SPLIT][3 * K2_BINS_PAD];
   const int frame = blockIdx.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const K2Partial* recs = p.partials + (long long)frame * p.slots_per_frame;
   lars_index_stats* out = p.stats + (long long)frame * 3;
-  {  // histograms: thread (index, bin); integer sums, any order is exact
-    const int idx = tid / K2_BINS_PAD, bin = tid % K2_BINS_PAD;
+  {  // histograms: thread (slot group, index, bin); integer sums, any order is exact
+    const int grp = tid / (3 * K2_BINS_PAD), rem = tid % (3 * K2_BINS_PAD);
+    const int idx = rem / K2_BINS_PAD, bin = rem % K2_BINS_PAD;
     unsigned long long h = 0;
-#pragma unroll 4
-    for (int s = 0; s < p.slots_per_frame; ++s) h += recs[s].hist[idx][bin];   // unwritten slots are zero (memset)
-    out[idx].hist[bin] = h;
+#pragma unroll 16
+    for (int s = grp; s < p.slots_per_frame; s += K2F_SPLIT) h += recs[s].hist[idx][bin];   // unwritten slots are zero (memset)
+    hpart[grp][rem] = h;
+  }
+  __syncthreads();
+  if (tid < 3 * K2_BINS_PAD) {
+    unsigned long long h = 0;
+#pragma unroll
+    for (int g = 0; g < K2F_SPLIT; ++g) h += hpart[g][tid];
+    out[tid / K2_BINS_PAD].hist[tid % K2_BINS_PAD] = h;
   }
   if (warp < 3) {
     // one warp per index: lane l folds slots l, l + 32, ... in order, then a fixed butterfly --
@@ -720,6 +731,7 @@ __global__ void __launch_bounds__(3 * K2_BINS_PAD) fused_finalize_kernel(const K
     double sx = 0.0, sd = 0.0, sdd = 0.0;
     float mn = INFINITY, mx = -INFINITY;
     unsigned long long cnt = 0, above = 0;
+#pragma unroll 4
     for (int s = lane; s < p.slots_per_frame; s += 32) {
       const K2Partial& r = recs[s];
       const bool used = r.count != 0;              // unwritten slots are all zero: sums take them as they are,
