@@ -742,3 +742,37 @@ def test_random_frames_sweep(engine):
             assert np.array_equal(res["stats"][t]["hist"], want["stats"][t]["hist"]), label
             assert res["stats"][t]["count_above"] == want["stats"][t]["count_above"], label
             assert res["stats"][t]["min"] == want["stats"][t]["min"] and res["stats"][t]["max"] == want["stats"][t]["max"], label
+
+
+def test_run_host_batch_pipeline_parity(engine):
+    """The pinned, software-pipelined host path that bench.py times as `e2e`: ragged chunking (5 frames in
+    chunks of 2), both sample widths, every product compared with the oracle, and a second call on the same
+    buffers (the double-buffered device slots and the three streams are reused)."""
+    import torch
+    from lars_image_processing_b200._lib import INDEX_STATS_DTYPE
+    from lars_image_processing_b200.engine import stats_records_to_dicts
+    for dtype, sb in ((np.uint8, 1), (np.uint16, 2)):
+        h, w, F = 70, 93, 5
+        host_in = torch.empty((F, h * w * 3 * sb), dtype=torch.uint8, pin_memory=True)
+        host_out = engine.alloc_host_outputs(F, h, w, 3)
+        for rep in range(2):
+            frames = [synth.vegetation_frame(800 + 10 * rep + i, h, w, dtype) for i in range(F)]
+            for i, f in enumerate(frames):
+                host_in[i].copy_(torch.from_numpy(f.reshape(-1).view(np.uint8)))
+            engine.run_host_batch(host_in, (h, w, 3), host_out, chunk=2, sample_bytes=sb)
+            rec = host_out["stats"].numpy().view(INDEX_STATS_DTYPE).reshape(F, 3)
+            stats = stats_records_to_dicts(rec, 50)
+            for i, f in enumerate(frames):
+                want = oracle_frame(f)
+                label = f"{np.dtype(dtype).name} rep {rep} frame {i}"
+                assert np.array_equal(host_out["wb"][i].numpy().reshape(h, w, 3), want["wb"]), label
+                for k, t in enumerate(INDEX_TYPES):
+                    got_map = host_out["maps"][k, i].numpy().reshape(h, w)
+                    assert np.array_equal(got_map.view(np.uint32), want["maps"][t].view(np.uint32)), label
+                    assert np.array_equal(host_out["rgb"][k, i].numpy().reshape(h, w, 3), want["rgb"][t]), label
+                    assert np.array_equal(stats[i][t]["hist"], want["stats"][t]["hist"]), label
+                    assert stats[i][t]["count_above"] == want["stats"][t]["count_above"], label
+    # statistics-only leg (survey mode)
+    only = engine.alloc_host_outputs(F, h, w, 3, ("stats",))
+    engine.run_host_batch(host_in, (h, w, 3), only, chunk=4, sample_bytes=2)
+    assert np.array_equal(only["stats"].numpy(), host_out["stats"].numpy())
