@@ -104,6 +104,7 @@ inline const char* tiff_probe(const void* file, size_t file_bytes, lars_tiff_inf
     }
   }
   if (info->width < 1 || info->height < 1) return "missing ImageWidth / ImageLength";
+  if (info->width > (1 << 24) || info->height > (1 << 24)) return "implausible image dimensions";   // keeps all byte counts far below 2^64
   if (info->compression != 1) { *unsupported = true; return "compressed TIFF: decode it with Pillow"; }
   if (bits_mixed || (info->bits_per_sample != 8 && info->bits_per_sample != 16)) {
     *unsupported = true;

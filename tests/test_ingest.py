@@ -209,3 +209,43 @@ def test_tiff_round_trip_sweep(tmp_path):
         assert ingest.frame_info(p) == (shape, np.dtype(dtype))
         if dtype == np.uint8 or ch is None:
             assert np.array_equal(np.array(Image.open(p)), img), (case, "pillow")
+
+
+def test_tiff_reader_survives_corrupted_files(tmp_path):
+    """Robustness of the native reader: 600 randomly corrupted copies of valid files (byte flips in the
+    header / IFD / tag values, truncations) must each either decode to the right shape or be rejected with
+    an error -- never read out of bounds (a crash would take the test process down)."""
+    import ctypes as C
+    from lars_image_processing_b200 import ingest
+    L = _lib()
+    lib = L.load()
+    rng = np.random.default_rng(99)
+    seeds = []
+    for big in (False, True):
+        for dtype in (np.uint8, np.uint16):
+            p = tmp_path / "seed.tif"
+            ingest.write_tiff(p, rng.integers(0, 256, (19, 23, 3)).astype(dtype), big_endian=big, rows_per_strip=5)
+            seeds.append(p.read_bytes())
+    ok = rejected = 0
+    for it in range(600):
+        raw = bytearray(seeds[it % len(seeds)])
+        header_len = min(len(raw), 8 + 2 + 12 * 12 + 64)
+        for _ in range(int(rng.integers(1, 4))):
+            pos = int(rng.integers(0, header_len))
+            raw[pos] = int(rng.integers(0, 256))
+        if it % 5 == 0:
+            raw = raw[:int(rng.integers(1, len(raw)))]
+        buf = (C.c_uint8 * len(raw)).from_buffer(raw)
+        info = L.TiffInfo()
+        rc = lib.lars_tiff_probe(buf, len(raw), C.byref(info))
+        if rc == 0:
+            assert 0 < info.width and 0 < info.height
+            assert info.frame_bytes == info.width * info.height * info.samples_per_pixel * (info.bits_per_sample // 8)
+            if info.frame_bytes <= 1 << 24:
+                dst = np.empty(int(info.frame_bytes), np.uint8)
+                assert lib.lars_tiff_read(buf, len(raw), C.byref(info), dst.ctypes.data, dst.nbytes) == 0
+            ok += 1
+        else:
+            assert lib.lars_last_error()
+            rejected += 1
+    assert ok + rejected == 600 and rejected > 50
