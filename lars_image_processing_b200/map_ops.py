@@ -172,7 +172,6 @@ def frame_statistics_rows(image_data_list, index_type: str) -> List[dict]:
     eng = get_engine()
     i_idx = INDEX_TYPES.index(index_type)
     feature = "Water" if index_type == "NDWI" else "Vegetation"
-    thr = 0.0 if index_type == "NDWI" else 0.2
     rows: List[Optional[dict]] = [None] * len(image_data_list)
     groups: Dict[tuple, list] = {}
     for pos, img_data in enumerate(image_data_list):

@@ -9,7 +9,7 @@ module does not need a GPU; calling a helper without one raises (no CPU fallback
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import Optional
 
 import numpy as np
 
@@ -110,7 +110,8 @@ def calculate_index_statistics_by_timeframe(image_data_list, index_type):
     """
     import pandas as pd
     from .map_ops import frame_statistics_rows
-    _check_index_type(index_type) if image_data_list else None
+    if image_data_list:                      # the reference only meets an unknown index inside its per-frame loop
+        _check_index_type(index_type)
     rows = frame_statistics_rows(image_data_list, index_type)
     return pd.DataFrame(rows)
 
