@@ -200,3 +200,32 @@ def test_gpu_resize_random_geometries(engine):
         got = engine.resize_batch([img, stripes(ih, iw, 3)], oh, ow)
         assert np.array_equal(got[0], pil_resize(img, oh, ow)), (case, ih, iw, oh, ow)
         assert np.array_equal(got[1], pil_resize(stripes(ih, iw, 3), oh, ow)), (case, ih, iw, oh, ow)
+
+
+# --------------------------------------------------------------------------------- committed golden vectors
+def _golden_cases(golden):
+    g = golden["resize"]
+    i = 0
+    while f"in_{i}" in g:
+        yield g[f"in_{i}"], g[f"out_{i}"]
+        i += 1
+
+
+def test_oracle_against_committed_pillow_vectors(golden):
+    """tests/golden/resize.npz holds Pillow's own outputs (oracle/gen_golden_resize.py)."""
+    n = 0
+    for img, want in _golden_cases(golden):
+        assert np.array_equal(resize_np.resize_lanczos(img, want.shape[1], want.shape[0]), want)
+        n += 1
+    assert n >= 5
+    g = golden["resize"]
+    assert np.array_equal(resize_np.preprocess_large_image(g["pre_in"], 1024), g["pre_out"])
+
+
+@pytest.mark.gpu
+def test_gpu_resize_against_committed_pillow_vectors(engine, golden):
+    from lars_image_processing_b200 import process_images as pi
+    for img, want in _golden_cases(golden):
+        assert np.array_equal(engine.resize_batch([img], want.shape[0], want.shape[1])[0], want)
+    g = golden["resize"]
+    assert np.array_equal(pi.preprocess_large_image(g["pre_in"], 1024), g["pre_out"])
