@@ -261,25 +261,35 @@ int lars_resize_lanczos_u8(const lars_resize_plan* plan, const void* tables_dev,
                            void* temp, size_t temp_bytes, void* stream);
 
 /* ---- ingest ---------------------------------------------------
- * Host-only baseline-TIFF reader: uncompressed, chunky, strips, 8- or 16-bit unsigned samples,
- * 1 / 3 / 4 samples per pixel, either byte order.  Replaces PIL.Image.open + np.array for such
- * files (process-images.py:183-193; backend-process.py:52; process-ndvi.py:18; process-rgn.py:18)
- * and adds the true 16-bit path Pillow cannot deliver (it opens 16-bit RGB as 8-bit): the strips
- * of a (memory-mapped) file are copied straight into the caller's pinned HWC buffer.  Anything
- * else (compression, tiles, BigTIFF, planar, float) returns LARS_ERR_UNSUPPORTED and the caller
- * decodes with Pillow. */
+ * Host-only TIFF 6.0 / BigTIFF reader: chunky 8- or 16-bit unsigned samples, 1 / 3 / 4 samples per
+ * pixel, either byte order; strips or tiles; uncompressed, LZW (5), Deflate (8 / 32946; needs the
+ * system zlib at run time) or PackBits (32773), predictor 1 or 2.  Replaces PIL.Image.open +
+ * np.array for such files (process-images.py:183-193; backend-process.py:52; process-ndvi.py:18;
+ * process-rgn.py:18) and adds the true 16-bit path Pillow cannot deliver (it opens 16-bit RGB as
+ * 8-bit): the strips / tiles of a (memory-mapped) file go straight into the caller's pinned HWC
+ * buffer.  lars_tiff_read_region reads only the chunks that touch a rectangle -- the tiles or row
+ * bands one rank owns of an orthomosaic (BASELINE config 4) -- with n_threads host threads decoding
+ * independent chunks side by side.  Anything else (JPEG-in-TIFF, planar, float, 1-bit, WhiteIsZero)
+ * returns LARS_ERR_UNSUPPORTED and the caller decodes with Pillow. */
 typedef struct lars_tiff_info {
   int32_t width, height, samples_per_pixel, bits_per_sample;
   int32_t big_endian, compression, planar_config, photometric, sample_format;
-  int32_t rows_per_strip, n_strips;
-  int32_t strip_offsets_type, strip_counts_type; /* TIFF field types (3 = SHORT, 4 = LONG)        */
-  int32_t reserved;
-  uint64_t strip_offsets_pos, strip_counts_pos;  /* file positions of the two arrays               */
+  int32_t rows_per_strip, n_strips;              /* tiled files: tile_length, number of tiles      */
+  int32_t strip_offsets_type, strip_counts_type; /* TIFF field types (3 SHORT, 4 LONG, 16 LONG8)   */
+  int32_t predictor;                             /* 1 = none, 2 = horizontal differencing          */
+  uint64_t strip_offsets_pos, strip_counts_pos;  /* file positions of the strip / tile arrays      */
   uint64_t frame_bytes;                          /* height * width * samples * bytes per sample    */
+  int32_t tile_width, tile_length;               /* 0 = the image is stored in strips              */
+  int32_t tiles_across, tiles_down;
+  int32_t bigtiff, reserved;
 } lars_tiff_info;
 int lars_tiff_probe(const void* file, size_t file_bytes, lars_tiff_info* info);
-/* dst receives height x width x samples, little-endian samples, rows contiguous. */
+/* dst receives height x width x samples, little-endian samples, rows contiguous (one thread). */
 int lars_tiff_read(const void* file, size_t file_bytes, const lars_tiff_info* info, void* dst, size_t dst_bytes);
+/* dst receives rows [row0, row1) x columns [col0, col1) as one contiguous block. */
+int lars_tiff_read_region(const void* file, size_t file_bytes, const lars_tiff_info* info, int32_t row0,
+                          int32_t row1, int32_t col0, int32_t col1, void* dst, size_t dst_bytes,
+                          int32_t n_threads);
 
 #ifdef __cplusplus
 }

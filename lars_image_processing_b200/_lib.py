@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = (
     "lars_fused_index_u16",
     "lars_index_hwc", "lars_index_change_u8",
     "lars_resize_plan_lanczos", "lars_resize_tables_lanczos", "lars_resize_lanczos_u8",
-    "lars_tiff_probe", "lars_tiff_read",
+    "lars_tiff_probe", "lars_tiff_read", "lars_tiff_read_region",
 )
 
 
@@ -83,8 +83,9 @@ class TiffInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "width", "height", "samples_per_pixel", "bits_per_sample", "big_endian", "compression",
         "planar_config", "photometric", "sample_format", "rows_per_strip", "n_strips",
-        "strip_offsets_type", "strip_counts_type", "reserved")] + [
-        ("strip_offsets_pos", C.c_uint64), ("strip_counts_pos", C.c_uint64), ("frame_bytes", C.c_uint64)]
+        "strip_offsets_type", "strip_counts_type", "predictor")] + [
+        ("strip_offsets_pos", C.c_uint64), ("strip_counts_pos", C.c_uint64), ("frame_bytes", C.c_uint64)] + [
+        (n, C.c_int32) for n in ("tile_width", "tile_length", "tiles_across", "tiles_down", "bigtiff", "reserved")]
 
 
 # numpy view of ``lars_index_stats`` (576 bytes)
@@ -156,6 +157,8 @@ def _declare(lib):
     lib.lars_tiff_probe.restype = C.c_int
     lib.lars_tiff_read.argtypes = [vp, C.c_size_t, C.POINTER(TiffInfo), vp, C.c_size_t]
     lib.lars_tiff_read.restype = C.c_int
+    lib.lars_tiff_read_region.argtypes = [vp, C.c_size_t, C.POINTER(TiffInfo), i32, i32, i32, i32, vp, C.c_size_t, i32]
+    lib.lars_tiff_read_region.restype = C.c_int
     lib.lars_resize_plan_lanczos.argtypes = [i32, i32, i32, i32, i32, C.POINTER(ResizePlan)]
     lib.lars_resize_plan_lanczos.restype = C.c_int
     lib.lars_resize_tables_lanczos.argtypes = [C.POINTER(ResizePlan), vp]

@@ -13,8 +13,9 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     # exact arithmetic: no fast-math anywhere; host tables must not contract to FMA either
-    "-Xcompiler", "-fPIC,-ffp-contract=off,-O2",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-O2,-pthread",
     "-shared",
+    "-ldl",         # the TIFF reader binds the system zlib at run time (dlopen), nothing is linked against it
 ]
 
 

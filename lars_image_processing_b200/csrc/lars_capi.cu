@@ -66,7 +66,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 extern "C" {
 
 const char* lars_last_error(void) { return g_err; }
-int lars_abi_version(void) { return 3; }   // 3: + resize, TIFF ingest
+int lars_abi_version(void) { return 4; }   // 3: + resize, TIFF ingest; 4: lars_tiff_info grew (tiles, predictor, BigTIFF), lars_tiff_read_region
 
 int lars_init(int device) {
   std::lock_guard<std::mutex> lock(g_mu);
@@ -978,7 +978,7 @@ int lars_resize_lanczos_u8(const lars_resize_plan* plan, const void* tables_dev,
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------
-// ingest: baseline TIFF reader (host only)
+// ingest: TIFF reader (host only)
 // ------------------------------------------------------------------------------------------
 extern "C" {
 
@@ -990,16 +990,23 @@ int lars_tiff_probe(const void* file, size_t file_bytes, lars_tiff_info* info) {
   return LARS_OK;
 }
 
-int lars_tiff_read(const void* file, size_t file_bytes, const lars_tiff_info* info, void* dst, size_t dst_bytes) {
+int lars_tiff_read_region(const void* file, size_t file_bytes, const lars_tiff_info* info, int32_t row0,
+                          int32_t row1, int32_t col0, int32_t col1, void* dst, size_t dst_bytes,
+                          int32_t n_threads) {
   if (!file || !info || !dst) return fail(LARS_ERR_INVALID, "lars_tiff_read: NULL pointer");
   lars_tiff_info check;
   bool unsupported = false;
   const char* why = lars_host::tiff_probe(file, file_bytes, &check, &unsupported);   // never trust a stale info block
   if (why) return fail(unsupported ? LARS_ERR_UNSUPPORTED : LARS_ERR_INVALID, "lars_tiff_read: %s", why);
   if (memcmp(&check, info, sizeof(check)) != 0) return fail(LARS_ERR_INVALID, "lars_tiff_read: info does not describe this file");
-  why = lars_host::tiff_read(file, file_bytes, &check, dst, dst_bytes);
+  why = lars_host::tiff_read_region(file, file_bytes, &check, row0, row1, col0, col1, dst, dst_bytes, n_threads);
   if (why) return fail(LARS_ERR_INVALID, "lars_tiff_read: %s", why);
   return LARS_OK;
+}
+
+int lars_tiff_read(const void* file, size_t file_bytes, const lars_tiff_info* info, void* dst, size_t dst_bytes) {
+  if (!info) return fail(LARS_ERR_INVALID, "lars_tiff_read: NULL pointer");
+  return lars_tiff_read_region(file, file_bytes, info, 0, info->height, 0, info->width, dst, dst_bytes, 1);
 }
 
 }  // extern "C"

@@ -6,9 +6,12 @@ backend-process.py:52; process-ndvi.py:18; process-rgn.py:18) inside a serial pe
 (backend-process.py:92-97; process-images.py:633-663).  Here:
 
 * :func:`read_frame` keeps that behaviour for every format Pillow decodes, and adds a native
-  baseline-TIFF reader (``lars_tiff_probe`` / ``lars_tiff_read``, host side of the C ABI) that
-  copies the strips of a memory-mapped file straight into a pinned buffer -- including 16-bit
-  RGB TIFFs, which Pillow opens as 8-bit (SURVEY.md 8(c));
+  TIFF reader (``lars_tiff_probe`` / ``lars_tiff_read_region``, host side of the C ABI: strips or
+  tiles, uncompressed / LZW / Deflate / PackBits, predictor, BigTIFF) that moves the chunks of a
+  memory-mapped file straight into a pinned buffer, compressed chunks decoded by several host
+  threads -- including 16-bit RGB TIFFs, which Pillow opens as 8-bit (SURVEY.md 8(c));
+* :func:`read_region` / :func:`read_mosaic_tiles` read only the strips / tiles that touch a
+  rectangle: every rank of a tile-sharded orthomosaic (BASELINE config 4) reads its own tiles;
 * :class:`SurveyPipeline` streams any number of equally-shaped frames through the GPU path:
   host threads decode into a ring of pinned chunk buffers, one stream copies H2D, one runs
   Pass 1 + LUT + Pass 2, one copies results back, and the dataset-wide statistics are folded on
@@ -65,26 +68,43 @@ def _tiff_shape(info) -> tuple:
     return (info.height, info.width) if spp == 1 else (info.height, info.width, spp)
 
 
-def read_frame(source: Source, out: Optional[np.ndarray] = None) -> np.ndarray:
+def default_decode_threads() -> int:
+    return max(1, min(8, os.cpu_count() or 1))
+
+
+def read_frame(source: Source, out: Optional[np.ndarray] = None, threads: Optional[int] = None) -> np.ndarray:
     """One frame as the array ``np.array(Image.open(source))`` would give -- except that 16-bit
     TIFFs keep their 16 bits.  ``source``: path, encoded bytes, or an array (returned as is).
-    ``out``: optional destination (e.g. a row of a pinned buffer) of the right size and dtype."""
+    ``out``: optional destination (e.g. a row of a pinned buffer) of the right size and dtype.
+    ``threads``: host threads decoding the strips / tiles of a compressed TIFF (default: up to 8)."""
     if isinstance(source, np.ndarray):
         if out is not None:
             np.copyto(out.reshape(source.shape), source)
             return out.reshape(source.shape)
         return source
     if isinstance(source, (bytes, bytearray, memoryview)):
-        return _decode_buffer(source, out)
+        return _decode_buffer(source, out, threads)
     with open(os.fspath(source), "rb") as fh:
         size = os.fstat(fh.fileno()).st_size
         if size == 0:
             raise ValueError(f"{source}: empty file")
         with mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
-            return _decode_buffer(mm, out)
+            return _decode_buffer(mm, out, threads)
 
 
-def _decode_buffer(buf, out: Optional[np.ndarray]) -> np.ndarray:
+def _tiff_read_into(buf, info, region, dst: np.ndarray, threads: Optional[int]) -> None:
+    r0, r1, c0, c1 = region
+    view = np.frombuffer(buf, dtype=np.uint8)
+    try:        # no view of a memory-mapped file may outlive this call (closing the map would fail)
+        rc = _lib.load().lars_tiff_read_region(view.ctypes.data, view.size, C.byref(info), r0, r1, c0, c1,
+                                               dst.ctypes.data, dst.nbytes,
+                                               default_decode_threads() if threads is None else int(threads))
+    finally:
+        del view
+    check(rc, "lars_tiff_read_region")
+
+
+def _decode_buffer(buf, out: Optional[np.ndarray], threads: Optional[int] = None) -> np.ndarray:
     info = _tiff_probe(buf)
     if info is not None:
         dtype = np.uint8 if info.bits_per_sample == 8 else np.uint16
@@ -92,12 +112,7 @@ def _decode_buffer(buf, out: Optional[np.ndarray]) -> np.ndarray:
         dst = out if out is not None else np.empty(shape, dtype)
         if dst.dtype != dtype or dst.size != int(np.prod(shape)) or not dst.flags.c_contiguous:
             raise ValueError(f"destination must be a contiguous {np.dtype(dtype).name} array of {shape}")
-        view = np.frombuffer(buf, dtype=np.uint8)
-        try:
-            rc = _lib.load().lars_tiff_read(view.ctypes.data, view.size, C.byref(info), dst.ctypes.data, dst.nbytes)
-        finally:
-            del view
-        check(rc, "lars_tiff_read")
+        _tiff_read_into(buf, info, (0, info.height, 0, info.width), dst, threads)
         return dst.reshape(shape)
     from PIL import Image
     data = buf if isinstance(buf, (bytes, bytearray)) else bytes(buf)
@@ -108,6 +123,108 @@ def _decode_buffer(buf, out: Optional[np.ndarray]) -> np.ndarray:
         np.copyto(out.reshape(arr.shape), arr)
         return out.reshape(arr.shape)
     return arr
+
+
+def read_region(source: Source, rows: Sequence[int], cols: Optional[Sequence[int]] = None,
+                out: Optional[np.ndarray] = None, threads: Optional[int] = None) -> np.ndarray:
+    """Rows ``[rows[0], rows[1])`` x columns ``[cols[0], cols[1])`` (default: every column) of a frame.
+    For TIFF files only the strips / tiles that touch the rectangle are read and decoded, so a rank can
+    fetch its share of an orthomosaic far larger than its host memory; every other format is decoded
+    as a whole (Pillow) and cropped."""
+    if isinstance(source, np.ndarray):
+        shape = source.shape
+    elif isinstance(source, (bytes, bytearray, memoryview)):
+        return _region_of_buffer(source, rows, cols, out, threads)
+    else:
+        with open(os.fspath(source), "rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+            return _region_of_buffer(mm, rows, cols, out, threads)
+    r0, r1, c0, c1 = _check_region(shape, rows, cols)
+    return _crop_into(source, (r0, r1, c0, c1), out)
+
+
+def _check_region(shape, rows, cols) -> tuple:
+    h, w = shape[:2]
+    r0, r1 = int(rows[0]), int(rows[1])
+    c0, c1 = (0, w) if cols is None else (int(cols[0]), int(cols[1]))
+    if not (0 <= r0 < r1 <= h and 0 <= c0 < c1 <= w):
+        raise ValueError(f"region rows [{r0}, {r1}) x columns [{c0}, {c1}) is empty or outside the {h} x {w} frame")
+    return r0, r1, c0, c1
+
+
+def _crop_into(arr: np.ndarray, region, out: Optional[np.ndarray]) -> np.ndarray:
+    r0, r1, c0, c1 = region
+    crop = arr[r0:r1, c0:c1]
+    if out is None:
+        return np.ascontiguousarray(crop)
+    if out.dtype != crop.dtype or out.size != crop.size:
+        raise ValueError(f"destination must hold {crop.shape} {crop.dtype}, got {out.shape} {out.dtype}")
+    np.copyto(out.reshape(crop.shape), crop)
+    return out.reshape(crop.shape)
+
+
+def _region_of_buffer(buf, rows, cols, out, threads) -> np.ndarray:
+    info = _tiff_probe(buf)
+    if info is None:
+        whole = _decode_buffer(buf, None)
+        return _crop_into(whole, _check_region(whole.shape, rows, cols), out)
+    dtype = np.uint8 if info.bits_per_sample == 8 else np.uint16
+    full = _tiff_shape(info)
+    r0, r1, c0, c1 = _check_region(full, rows, cols)
+    shape = (r1 - r0, c1 - c0) + tuple(full[2:])
+    dst = out if out is not None else np.empty(shape, dtype)
+    if dst.dtype != dtype or dst.size != int(np.prod(shape)) or not dst.flags.c_contiguous:
+        raise ValueError(f"destination must be a contiguous {np.dtype(dtype).name} array of {shape}")
+    _tiff_read_into(buf, info, (r0, r1, c0, c1), dst, threads)
+    return dst.reshape(shape)
+
+
+def mosaic_tile_grid(height: int, width: int, tile_h: int, tile_w: int) -> List[tuple]:
+    """Row-major (row0, col0) origins of the equally-sized tiles of a mosaic.  The device batch holds
+    equally-sized frames and the white-balance percentiles count every pixel exactly once, so the tile
+    size has to divide the image size (pick a divisor, e.g. with :func:`largest_divisor`)."""
+    if tile_h < 1 or tile_w < 1 or height % tile_h or width % tile_w:
+        raise ValueError(f"{tile_h} x {tile_w} tiles do not divide a {height} x {width} mosaic")
+    return [(r, c) for r in range(0, height, tile_h) for c in range(0, width, tile_w)]
+
+
+def largest_divisor(n: int, at_most: int) -> int:
+    """Largest divisor of ``n`` that is <= ``at_most`` (a tile edge for :func:`mosaic_tile_grid`)."""
+    for d in range(max(1, min(n, int(at_most))), 0, -1):
+        if n % d == 0:
+            return d
+    return 1
+
+
+def read_mosaic_tiles(source: Source, tile_h: int, tile_w: int, rank: int = 0, world: int = 1,
+                      out: Optional[np.ndarray] = None, threads: Optional[int] = None):
+    """The tiles rank ``rank`` of ``world`` owns of one huge image (contiguous block of the row-major
+    tile grid, :func:`..distributed.shard_range`), read straight from the file: ``(tiles, origins)`` with
+    ``tiles`` of shape [n, tile_h, tile_w(, C)] -- what ``Engine.upload`` and
+    ``distributed.process_mosaic_tiles`` take -- and ``origins`` the (row0, col0) of each.  ``out``:
+    optional (pinned) destination of that shape."""
+    from .distributed import shard_range
+    shape, dtype = frame_info(source)
+    grid = mosaic_tile_grid(shape[0], shape[1], tile_h, tile_w)
+    a, b = shard_range(len(grid), rank, world)
+    mine = grid[a:b]
+    tshape = (len(mine), tile_h, tile_w) + tuple(shape[2:])
+    tiles = out if out is not None else np.empty(tshape, dtype)
+    if tiles.dtype != dtype or tiles.size != int(np.prod(tshape)) or not tiles.flags.c_contiguous:
+        raise ValueError(f"destination must be a contiguous {np.dtype(dtype).name} array of {tshape}")
+    tiles = tiles.reshape(tshape)
+    if isinstance(source, (np.ndarray, bytes, bytearray, memoryview)):
+        for k, (r, c) in enumerate(mine):
+            read_region(source, (r, r + tile_h), (c, c + tile_w), out=tiles[k], threads=threads)
+    elif mine:
+        with open(os.fspath(source), "rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+            if _is_tiff(mm):
+                for k, (r, c) in enumerate(mine):
+                    _region_of_buffer(mm, (r, r + tile_h), (c, c + tile_w), tiles[k], threads)
+            else:                                   # decoded once, cropped per tile
+                whole = _decode_buffer(mm, None)
+                for k, (r, c) in enumerate(mine):
+                    _crop_into(whole, (r, r + tile_h, c, c + tile_w), tiles[k])
+    return tiles, mine
 
 
 def frame_info(source: Source) -> tuple:
@@ -132,64 +249,171 @@ def _info_via_pillow(buf) -> tuple:
     return tuple(arr.shape), arr.dtype
 
 
-def write_tiff(path, array: np.ndarray, big_endian: bool = False, rows_per_strip: Optional[int] = None) -> None:
-    """Baseline TIFF writer for HxW / HxWx3 / HxWx4 uint8 or uint16 frames (uncompressed, chunky).
-    Pillow cannot write 16-bit RGB; survey frames of BASELINE config 3 are stored with this."""
+TIFF_COMPRESSION = {None: 1, "none": 1, "lzw": 5, "deflate": 8, "packbits": 32773}
+
+
+def _packbits_encode(data: bytes) -> bytes:
+    """TIFF 6.0 section 9, literal runs only (valid PackBits; a writer needs no more)."""
+    out = bytearray()
+    for a in range(0, len(data), 128):
+        piece = data[a:a + 128]
+        out.append(len(piece) - 1)
+        out += piece
+    return bytes(out)
+
+
+def _lzw_encode(data: bytes) -> bytes:
+    """TIFF 6.0 section 13 (MSB-first 9..12-bit codes, early width change).  Plain Python: meant for the
+    modest files a test or an export writes, not for bulk storage -- use "deflate" there."""
+    out = bytearray()
+    acc = nb = 0
+
+    def put(code, width):
+        nonlocal acc, nb
+        acc = (acc << width) | code
+        nb += width
+        while nb >= 8:
+            nb -= 8
+            out.append((acc >> nb) & 0xFF)
+        acc &= (1 << nb) - 1
+
+    table = {bytes([i]): i for i in range(256)}
+    next_code, width = 258, 9
+    put(256, width)
+    w = b""
+    for byte in data:
+        wc = w + bytes([byte])
+        if wc in table:
+            w = wc
+            continue
+        put(table[w], width)
+        table[wc] = next_code
+        next_code += 1
+        if next_code == 4094:                       # table full: emit Clear and start over
+            put(256, width)
+            table = {bytes([i]): i for i in range(256)}
+            next_code, width = 258, 9
+        elif next_code == (1 << width):             # the decoder, one entry behind, switches "one code early"
+            width += 1
+        w = bytes([byte])
+    if w:
+        put(table[w], width)
+        next_code += 1                              # the decoder adds an entry for this code, too
+        if next_code == 4094:
+            put(256, width)
+            width = 9
+        elif next_code == (1 << width):
+            width += 1
+    put(257, width)
+    if nb:
+        out.append((acc << (8 - nb)) & 0xFF)
+    return bytes(out)
+
+
+def write_tiff(path, array: np.ndarray, big_endian: bool = False, rows_per_strip: Optional[int] = None,
+               compression: Optional[str] = None, predictor: bool = False, tile: Optional[Sequence[int]] = None,
+               bigtiff: bool = False) -> None:
+    """TIFF writer for HxW / HxWx3 / HxWx4 uint8 or uint16 frames (chunky).  Pillow cannot write 16-bit
+    RGB; survey frames of BASELINE config 3 and mosaics of config 4 are stored with this.
+    ``compression``: None, "deflate", "lzw" or "packbits"; ``predictor``: horizontal differencing in
+    front of the compressor; ``tile``: (tile_length, tile_width) for a tiled layout instead of strips;
+    ``bigtiff``: 64-bit offsets (files beyond 4 GB)."""
+    import zlib
     a = np.ascontiguousarray(array)
     if a.dtype not in (np.uint8, np.uint16) or a.ndim not in (2, 3):
         raise ValueError("write_tiff needs a uint8 / uint16 HxW or HxWxC array")
+    if compression not in TIFF_COMPRESSION:
+        raise ValueError(f"compression must be one of {sorted(k for k in TIFF_COMPRESSION if k)} or None")
+    comp = TIFF_COMPRESSION[compression]
+    if predictor and comp not in (5, 8):
+        raise ValueError("the differencing predictor belongs to the LZW / Deflate codecs (libtiff ignores it elsewhere)")
     h, w = a.shape[:2]
     spp = 1 if a.ndim == 2 else a.shape[2]
+    a3 = a.reshape(h, w, spp)
     bits = a.dtype.itemsize * 8
     e = ">" if big_endian else "<"
-    data = a.astype(a.dtype.newbyteorder(e)).tobytes()
-    rps = h if not rows_per_strip else max(1, min(h, int(rows_per_strip)))
-    n_strips = (h + rps - 1) // rps
-    row_bytes = w * spp * a.dtype.itemsize
-    entries = []
+    file_dtype = a.dtype.newbyteorder(e)
+
+    def encode(block: np.ndarray) -> bytes:
+        """[rows, cols, spp] samples -> the bytes of one strip / tile."""
+        if predictor:
+            d = block.copy()
+            d[:, 1:] = block[:, 1:] - block[:, :-1]          # modulo 2^bits, per sample (TIFF 6.0 section 14)
+            block = d
+        raw = block.astype(file_dtype).tobytes()
+        if comp == 8:
+            return zlib.compress(raw, 6)
+        if comp == 5:
+            return _lzw_encode(raw)
+        if comp == 32773:
+            return _packbits_encode(raw)
+        return raw
+
+    if tile is not None:
+        tl, tw = int(tile[0]), int(tile[1])
+        if tl < 1 or tw < 1:
+            raise ValueError("tile sizes must be positive")
+        chunks = []
+        for r in range(0, h, tl):
+            for c in range(0, w, tw):
+                block = np.zeros((tl, tw, spp), a.dtype)
+                part = a3[r:r + tl, c:c + tw]
+                block[:part.shape[0], :part.shape[1]] = part
+                chunks.append(encode(block))
+        rps = tl
+    else:
+        rps = h if not rows_per_strip else max(1, min(h, int(rows_per_strip)))
+        chunks = [encode(a3[r:r + rps]) for r in range(0, h, rps)]
+    sizes = [len(ch) for ch in chunks]
+
+    off_fmt, off_type = ("Q", 16) if bigtiff else ("I", 4)
+    header_len, entry_len, inline = (16, 20, 8) if bigtiff else (8, 12, 4)
+    entries: List[bytes] = []
     extra = b""
-    header_len = 8
-    n_tags = 10 + (1 if spp == 4 else 0)
-    ifd_len = 2 + 12 * n_tags + 4
-    extra_base = header_len + ifd_len
 
-    def put_extra(blob: bytes) -> int:
-        nonlocal extra
-        pos = extra_base + len(extra)
-        extra += blob + (b"\0" if len(blob) & 1 else b"")
-        return pos
-
-    def entry(tag, typ, values):
-        fmt = {3: "H", 4: "I"}[typ]
-        blob = struct.pack(e + fmt * len(values), *values)
-        if len(blob) <= 4:
-            entries.append(struct.pack(e + "HHI", tag, typ, len(values)) + blob.ljust(4, b"\0"))
-        else:
-            entries.append(struct.pack(e + "HHII", tag, typ, len(values), put_extra(blob)))
-
-    # strip offsets depend on the size of the extra block: lay out twice
-    offsets = [0] * n_strips
-    for _ in range(2):
+    def layout(offsets):
+        nonlocal entries, extra
         entries, extra = [], b""
-        entry(256, 4, [w])
-        entry(257, 4, [h])
-        entry(258, 3, [bits] * spp)
-        entry(259, 3, [1])
-        entry(262, 3, [2 if spp >= 3 else 1])
-        entry(273, 4, offsets)
-        entry(277, 3, [spp])
-        entry(278, 4, [rps])
-        entry(279, 4, [min(rps, h - s * rps) * row_bytes for s in range(n_strips)])
-        entry(284, 3, [1])
+        tags = [(256, 4, [w]), (257, 4, [h]), (258, 3, [bits] * spp), (259, 3, [comp]),
+                (262, 3, [2 if spp >= 3 else 1]), (277, 3, [spp]), (284, 3, [1])]
+        if tile is None:
+            tags += [(273, off_type, offsets), (278, 4, [rps]), (279, off_type, sizes)]
+        else:
+            tags += [(322, 4, [tw]), (323, 4, [tl]), (324, off_type, offsets), (325, off_type, sizes)]
+        if predictor:
+            tags.append((317, 3, [2]))
         if spp == 4:
-            entry(338, 3, [2])
-        data_base = extra_base + len(extra)
-        offsets = [data_base + s * rps * row_bytes for s in range(n_strips)]
+            tags.append((338, 3, [2]))
+        tags.sort()
+        ifd_len = (8 if bigtiff else 2) + entry_len * len(tags) + (8 if bigtiff else 4)
+        extra_base = header_len + ifd_len
+        for tag, typ, values in tags:
+            blob = struct.pack(e + {3: "H", 4: "I", 16: "Q"}[typ] * len(values), *values)
+            head = struct.pack(e + ("HHQ" if bigtiff else "HHI"), tag, typ, len(values))
+            if len(blob) <= inline:
+                entries.append(head + blob.ljust(inline, b"\0"))
+            else:
+                entries.append(head + struct.pack(e + off_fmt, extra_base + len(extra)))
+                extra += blob + (b"\0" if len(blob) & 1 else b"")
+        return extra_base + len(extra)
+
+    # the chunk offsets depend on the size of the extra block: lay out twice
+    data_base = layout([0] * len(chunks))
+    offsets = list(np.cumsum([data_base] + sizes[:-1]).tolist())
+    if layout(offsets) != data_base:
+        raise AssertionError("TIFF layout did not converge")
+    if not bigtiff and data_base + sum(sizes) > 0xFFFFFFFF:
+        raise ValueError("the file would exceed 4 GB: pass bigtiff=True")
     with open(os.fspath(path), "wb") as fh:
-        fh.write((b"MM" if big_endian else b"II") + struct.pack(e + "HI", 42, header_len))
-        fh.write(struct.pack(e + "H", len(entries)) + b"".join(entries) + struct.pack(e + "I", 0))
+        if bigtiff:
+            fh.write((b"MM" if big_endian else b"II") + struct.pack(e + "HHHQ", 43, 8, 0, header_len))
+            fh.write(struct.pack(e + "Q", len(entries)) + b"".join(entries) + struct.pack(e + "Q", 0))
+        else:
+            fh.write((b"MM" if big_endian else b"II") + struct.pack(e + "HI", 42, header_len))
+            fh.write(struct.pack(e + "H", len(entries)) + b"".join(entries) + struct.pack(e + "I", 0))
         fh.write(extra)
-        fh.write(data)
+        for ch in chunks:
+            fh.write(ch)
 
 
 # ------------------------------------------------------------------------------------------
@@ -245,7 +469,7 @@ class SurveyPipeline:
     def _decode_into(self, source: Source, dst_row: torch.Tensor) -> None:
         shape = (self.h, self.w, self.c)
         dst = dst_row.numpy().view(self.dtype).reshape(shape)
-        arr = read_frame(source, out=None if isinstance(source, np.ndarray) else dst)
+        arr = read_frame(source, out=None if isinstance(source, np.ndarray) else dst, threads=1)   # frames decode side by side already
         if arr.shape != shape and not (self.c == 1 and arr.shape == shape[:2]):
             raise ValueError(f"frame of shape {arr.shape} in a pipeline built for {shape}")
         if arr.dtype != self.dtype:
