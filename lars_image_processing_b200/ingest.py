@@ -446,6 +446,9 @@ class SurveyPipeline:
         self.on_chunk = on_chunk
         self.fused_kw = fused_kw
         self.decode_threads = max(1, int(decode_threads))
+        # frames of a chunk decode side by side; when a chunk has fewer frames than there are decode threads
+        # (large frames), the strips / tiles inside each compressed frame share the remaining threads
+        self.frame_threads = max(1, self.decode_threads // max(1, min(int(chunk), self.decode_threads)))
         eng = self.eng
         self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(device=eng.device) for _ in range(3))
         self.frame_bytes = self.h * self.w * self.c * self.sb
@@ -469,7 +472,7 @@ class SurveyPipeline:
     def _decode_into(self, source: Source, dst_row: torch.Tensor) -> None:
         shape = (self.h, self.w, self.c)
         dst = dst_row.numpy().view(self.dtype).reshape(shape)
-        arr = read_frame(source, out=None if isinstance(source, np.ndarray) else dst, threads=1)   # frames decode side by side already
+        arr = read_frame(source, out=None if isinstance(source, np.ndarray) else dst, threads=self.frame_threads)
         if arr.shape != shape and not (self.c == 1 and arr.shape == shape[:2]):
             raise ValueError(f"frame of shape {arr.shape} in a pipeline built for {shape}")
         if arr.dtype != self.dtype:
