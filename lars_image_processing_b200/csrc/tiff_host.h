@@ -110,55 +110,63 @@ inline size_t packbits_chunk(const uint8_t* in, size_t n_in, uint8_t* out, size_
 }
 
 // TIFF 6.0 section 13: MSB-first codes of 9..12 bits, 256 = Clear, 257 = EndOfInformation, the width
-// grows one code early (after entry 510 / 1022 / 2046 has been added).
+// grows one code early (after entry 510 / 1022 / 2046 has been added).  Every string the table ever
+// holds already stands in the output: the entry made when `code` follows `old` is old's string plus
+// the next byte, i.e. the bytes written for old and the first one written for code.  The table therefore
+// stores (position, length) into the output and a string is emitted by copying from there -- no
+// prefix chains to walk.
 inline size_t lzw_chunk(const uint8_t* in, size_t n_in, uint8_t* out, size_t cap) {
-  struct Entry { uint16_t prefix; uint16_t length; uint8_t suffix; uint8_t first; };
-  std::vector<Entry> table(4096);
-  for (int i = 0; i < 256; ++i) table[i] = Entry{0, 1, (uint8_t)i, (uint8_t)i};
+  struct Entry { uint32_t pos; uint32_t len; };    // 32 KB: the table stays in L1
+  Entry table[4096];
+  if (cap > 0xffffffffull) return 0;               // one strip / tile of 4 GB: not a frame of this path
   const uint8_t* end = in + n_in;
   uint64_t acc = 0;
   int have = 0, nbits = 9, next_code = 258, old = -1;
-  size_t op = 0;
-  // writes the string of `code` (length len) at out + op, clipped to the capacity
-  auto emit = [&](int code, size_t len) {
-    size_t keep = len;
-    if (keep > cap - op) {                         // drop the tail that does not fit
-      keep = cap - op;
-      for (size_t t = len; t > keep; --t) code = table[code].prefix;
-    }
-    uint8_t* w = out + op + keep;
-    for (size_t t = keep; t > 0; --t) {
-      *--w = table[code].suffix;
-      code = table[code].prefix;
-    }
-    op += keep;
-  };
+  size_t op = 0, old_pos = 0, old_len = 0;
   while (op < cap) {
-    while (have < nbits && in < end) { acc = (acc << 8) | *in++; have += 8; }
-    if (have < nbits) break;                       // ran out of input: treat as EndOfInformation
+    if (have < nbits) {                            // refill: several codes' worth of bits at a time
+      while (have <= 56 && in < end) { acc = (acc << 8) | *in++; have += 8; }
+      if (have < nbits) break;                     // ran out of input: treat as EndOfInformation
+    }
     const int code = (int)((acc >> (have - nbits)) & ((1u << nbits) - 1));
     have -= nbits;
     if (code == 256) { nbits = 9; next_code = 258; old = -1; continue; }
     if (code == 257) break;
-    if (old < 0) {                                 // first code after a Clear must be a literal
-      if (code > 255) return 0;
+    const size_t at = op;
+    size_t len;
+    if (code < 256) {                              // a literal
       out[op++] = (uint8_t)code;
-      old = code;
-      continue;
-    }
-    if (code < next_code) {                        // known string; new entry = old + first(code)
-      emit(code, table[code].length);
-      if (next_code < 4096)
-        table[next_code] = Entry{(uint16_t)old, (uint16_t)(table[old].length + 1), table[code].first, table[old].first};
-    } else if (code == next_code && next_code < 4096) {   // the string being defined: old + first(old)
-      table[next_code] = Entry{(uint16_t)old, (uint16_t)(table[old].length + 1), table[old].first, table[old].first};
-      emit(code, table[code].length);
+      len = 1;
+    } else if (old < 0) {
+      return 0;                                    // the first code after a Clear must be a literal
+    } else if (code < next_code) {                 // a string made earlier: it ends before `op`
+      len = table[code].len;
+      const size_t pos = table[code].pos;
+      if (len <= 8 && op + 8 <= cap) {             // most strings are short: one 8-byte move, the excess is
+        uint64_t w;                                // scratch that later output overwrites (pos + 8 <= op + 8 <= cap)
+        memcpy(&w, out + pos, 8);
+        memcpy(out + op, &w, 8);
+        op += len;
+      } else {
+        const size_t keep = len < cap - op ? len : cap - op;
+        memcpy(out + op, out + pos, keep);
+        op += keep;
+      }
+    } else if (code == next_code && next_code < 4096) {   // the string being defined: old + first(old); it
+      len = old_len + 1;                                   // overlaps its own source, so byte by byte
+      const size_t keep = len < cap - op ? len : cap - op;
+      for (size_t i = 0; i < keep; ++i) out[op + i] = out[old_pos + i];
+      op += keep;
     } else {
       return 0;                                    // a code the table cannot hold yet: corrupt stream
     }
-    if (next_code < 4096) ++next_code;
-    if (next_code >= (1 << nbits) - 1 && nbits < 12) ++nbits;
+    if (old >= 0) {
+      if (next_code < 4096) table[next_code++] = Entry{(uint32_t)old_pos, (uint32_t)(old_len + 1)};
+      if (next_code >= (1 << nbits) - 1 && nbits < 12) ++nbits;
+    }
     old = code;
+    old_pos = at;
+    old_len = len;
   }
   return op;
 }
