@@ -291,6 +291,22 @@ int lars_tiff_read_region(const void* file, size_t file_bytes, const lars_tiff_i
                           int32_t row1, int32_t col0, int32_t col1, void* dst, size_t dst_bytes,
                           int32_t n_threads);
 
+/* Host-only PNG reader: non-interlaced grayscale / RGB / RGBA, 8- or 16-bit samples (BASELINE config 1
+ * is a uint8 RGNir PNG).  One call per frame -- chunk walk, one zlib inflate (bound at run time), the
+ * five row filters -- into the caller's pinned HWC buffer; 16-bit samples arrive as little-endian
+ * uint16 (Pillow reduces 16-bit RGB to 8 bits).  Palette, gray + alpha, sub-byte depths, tRNS and Adam7
+ * return LARS_ERR_UNSUPPORTED and the caller decodes with Pillow.  Same reference call sites as the
+ * TIFF reader above. */
+typedef struct lars_png_info {
+  int32_t width, height, channels, bit_depth;
+  int32_t color_type, interlace, n_idat, reserved;
+  uint64_t idat_bytes;                           /* compressed bytes over all IDAT chunks           */
+  uint64_t frame_bytes;                          /* height * width * channels * bytes per sample    */
+} lars_png_info;
+int lars_png_probe(const void* file, size_t file_bytes, lars_png_info* info);
+/* dst receives height x width x channels, little-endian samples, rows contiguous. */
+int lars_png_read(const void* file, size_t file_bytes, const lars_png_info* info, void* dst, size_t dst_bytes);
+
 #ifdef __cplusplus
 }
 #endif

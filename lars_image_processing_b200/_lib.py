@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = (
     "lars_fused_index_u16",
     "lars_index_hwc", "lars_index_change_u8",
     "lars_resize_plan_lanczos", "lars_resize_tables_lanczos", "lars_resize_lanczos_u8",
-    "lars_tiff_probe", "lars_tiff_read", "lars_tiff_read_region",
+    "lars_tiff_probe", "lars_tiff_read", "lars_tiff_read_region", "lars_png_probe", "lars_png_read",
 )
 
 
@@ -86,6 +86,13 @@ class TiffInfo(C.Structure):
         "strip_offsets_type", "strip_counts_type", "predictor")] + [
         ("strip_offsets_pos", C.c_uint64), ("strip_counts_pos", C.c_uint64), ("frame_bytes", C.c_uint64)] + [
         (n, C.c_int32) for n in ("tile_width", "tile_length", "tiles_across", "tiles_down", "bigtiff", "reserved")]
+
+
+class PngInfo(C.Structure):
+    """Mirror of ``lars_png_info`` (include/lars_b200.h)."""
+    _fields_ = [(n, C.c_int32) for n in (
+        "width", "height", "channels", "bit_depth", "color_type", "interlace", "n_idat", "reserved")] + [
+        ("idat_bytes", C.c_uint64), ("frame_bytes", C.c_uint64)]
 
 
 # numpy view of ``lars_index_stats`` (576 bytes)
@@ -159,6 +166,10 @@ def _declare(lib):
     lib.lars_tiff_read.restype = C.c_int
     lib.lars_tiff_read_region.argtypes = [vp, C.c_size_t, C.POINTER(TiffInfo), i32, i32, i32, i32, vp, C.c_size_t, i32]
     lib.lars_tiff_read_region.restype = C.c_int
+    lib.lars_png_probe.argtypes = [vp, C.c_size_t, C.POINTER(PngInfo)]
+    lib.lars_png_probe.restype = C.c_int
+    lib.lars_png_read.argtypes = [vp, C.c_size_t, C.POINTER(PngInfo), vp, C.c_size_t]
+    lib.lars_png_read.restype = C.c_int
     lib.lars_resize_plan_lanczos.argtypes = [i32, i32, i32, i32, i32, C.POINTER(ResizePlan)]
     lib.lars_resize_plan_lanczos.restype = C.c_int
     lib.lars_resize_tables_lanczos.argtypes = [C.POINTER(ResizePlan), vp]

@@ -11,6 +11,7 @@
 #include "../../include/lars_b200.h"
 #include "host_tables.h"
 #include "tiff_host.h"
+#include "png_host.h"
 #include "lars_kernels.cuh"
 #include "lars_fused_kernel.cuh"
 #include "lars_map_kernels.cuh"
@@ -1007,6 +1008,26 @@ int lars_tiff_read_region(const void* file, size_t file_bytes, const lars_tiff_i
 int lars_tiff_read(const void* file, size_t file_bytes, const lars_tiff_info* info, void* dst, size_t dst_bytes) {
   if (!info) return fail(LARS_ERR_INVALID, "lars_tiff_read: NULL pointer");
   return lars_tiff_read_region(file, file_bytes, info, 0, info->height, 0, info->width, dst, dst_bytes, 1);
+}
+
+int lars_png_probe(const void* file, size_t file_bytes, lars_png_info* info) {
+  if (!file || !info) return fail(LARS_ERR_INVALID, "lars_png_probe: NULL pointer");
+  bool unsupported = false;
+  const char* why = lars_host::png_probe(file, file_bytes, info, &unsupported);
+  if (why) return fail(unsupported ? LARS_ERR_UNSUPPORTED : LARS_ERR_INVALID, "lars_png_probe: %s", why);
+  return LARS_OK;
+}
+
+int lars_png_read(const void* file, size_t file_bytes, const lars_png_info* info, void* dst, size_t dst_bytes) {
+  if (!file || !info || !dst) return fail(LARS_ERR_INVALID, "lars_png_read: NULL pointer");
+  lars_png_info check;
+  bool unsupported = false;
+  const char* why = lars_host::png_probe(file, file_bytes, &check, &unsupported);   // never trust a stale info block
+  if (why) return fail(unsupported ? LARS_ERR_UNSUPPORTED : LARS_ERR_INVALID, "lars_png_read: %s", why);
+  if (memcmp(&check, info, sizeof(check)) != 0) return fail(LARS_ERR_INVALID, "lars_png_read: info does not describe this file");
+  why = lars_host::png_read(file, file_bytes, &check, dst, dst_bytes);
+  if (why) return fail(LARS_ERR_INVALID, "lars_png_read: %s", why);
+  return LARS_OK;
 }
 
 }  // extern "C"

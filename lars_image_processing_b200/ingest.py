@@ -10,6 +10,9 @@ backend-process.py:52; process-ndvi.py:18; process-rgn.py:18) inside a serial pe
   tiles, uncompressed / LZW / Deflate / PackBits, predictor, BigTIFF) that moves the chunks of a
   memory-mapped file straight into a pinned buffer, compressed chunks decoded by several host
   threads -- including 16-bit RGB TIFFs, which Pillow opens as 8-bit (SURVEY.md 8(c));
+* PNG frames (BASELINE config 1; gray / RGB / RGBA, 8- or 16-bit, non-interlaced) decode natively as well
+  (``lars_png_probe`` / ``lars_png_read``: one C call per frame, so decode threads do not queue on the
+  interpreter lock as they do inside Pillow);
 * :func:`read_region` / :func:`read_mosaic_tiles` read only the strips / tiles that touch a
   rectangle: every rank of a tile-sharded orthomosaic (BASELINE config 4) reads its own tiles;
 * :class:`SurveyPipeline` streams any number of equally-shaped frames through the GPU path:
@@ -63,6 +66,29 @@ def _tiff_probe(buf) -> Optional[_lib.TiffInfo]:
     return info
 
 
+PNG_SIGNATURE = b"\x89PNG\r\n\x1a\n"
+
+
+def _png_probe(buf) -> Optional[_lib.PngInfo]:
+    """PngInfo if the native reader handles this buffer, None if Pillow has to; raises on a corrupt PNG."""
+    view = np.frombuffer(buf, dtype=np.uint8)
+    try:
+        if view.size < 8 or bytes(view[:8]) != PNG_SIGNATURE:
+            return None
+        info = _lib.PngInfo()
+        rc = _lib.load().lars_png_probe(view.ctypes.data, view.size, C.byref(info))
+    finally:
+        del view
+    if rc == LARS_ERR_UNSUPPORTED:
+        return None
+    check(rc, "lars_png_probe")
+    return info
+
+
+def _png_shape(info) -> tuple:
+    return (info.height, info.width) if info.channels == 1 else (info.height, info.width, info.channels)
+
+
 def _tiff_shape(info) -> tuple:
     spp = info.samples_per_pixel
     return (info.height, info.width) if spp == 1 else (info.height, info.width, spp)
@@ -113,6 +139,20 @@ def _decode_buffer(buf, out: Optional[np.ndarray], threads: Optional[int] = None
         if dst.dtype != dtype or dst.size != int(np.prod(shape)) or not dst.flags.c_contiguous:
             raise ValueError(f"destination must be a contiguous {np.dtype(dtype).name} array of {shape}")
         _tiff_read_into(buf, info, (0, info.height, 0, info.width), dst, threads)
+        return dst.reshape(shape)
+    png = _png_probe(buf)
+    if png is not None:
+        dtype = np.uint8 if png.bit_depth == 8 else np.uint16
+        shape = _png_shape(png)
+        dst = out if out is not None else np.empty(shape, dtype)
+        if dst.dtype != dtype or dst.size != int(np.prod(shape)) or not dst.flags.c_contiguous:
+            raise ValueError(f"destination must be a contiguous {np.dtype(dtype).name} array of {shape}")
+        view = np.frombuffer(buf, dtype=np.uint8)
+        try:
+            rc = _lib.load().lars_png_read(view.ctypes.data, view.size, C.byref(png), dst.ctypes.data, dst.nbytes)
+        finally:
+            del view
+        check(rc, "lars_png_read")
         return dst.reshape(shape)
     from PIL import Image
     data = buf if isinstance(buf, (bytes, bytearray)) else bytes(buf)
@@ -233,10 +273,13 @@ def frame_info(source: Source) -> tuple:
         return tuple(source.shape), source.dtype
     if not isinstance(source, (bytes, bytearray, memoryview)):
         with open(os.fspath(source), "rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
-            return frame_info(memoryview(mm)) if _is_tiff(mm) else _info_via_pillow(bytes(mm))
+            return frame_info(memoryview(mm)) if (_is_tiff(mm) or bytes(mm[:8]) == PNG_SIGNATURE) else _info_via_pillow(bytes(mm))
     info = _tiff_probe(source)
     if info is not None:
         return _tiff_shape(info), np.dtype(np.uint8 if info.bits_per_sample == 8 else np.uint16)
+    png = _png_probe(source)
+    if png is not None:
+        return _png_shape(png), np.dtype(np.uint8 if png.bit_depth == 8 else np.uint16)
     return _info_via_pillow(source)
 
 
