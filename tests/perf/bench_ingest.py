@@ -57,7 +57,7 @@ p8, _ = make_files(512, 960, 1280, np.uint8, "tif")
 run("C5 shape, uncompressed TIFF", p8, 960, 1280, np.uint8, 64, 8, 4)
 run("C5 shape, uncompressed TIFF, 16 thr", p8, 960, 1280, np.uint8, 64, 16, 0)
 pp, _ = make_files(128, 960, 1280, np.uint8, "png")
-run("C5 shape, PNG (Pillow decode)", pp, 960, 1280, np.uint8, 32, 16, 4)
+run("C5 shape, PNG (native decode)", pp, 960, 1280, np.uint8, 32, 16, 4)
 pl, _ = make_files(128, 960, 1280, np.uint8, "lzw.tif")
 run("C5 shape, LZW TIFF (native decode)", pl, 960, 1280, np.uint8, 32, 16, 4)
 p16, _ = make_files(16, 3648, 5472, np.uint16, "tif")
