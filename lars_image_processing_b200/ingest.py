@@ -235,6 +235,21 @@ def largest_divisor(n: int, at_most: int) -> int:
     return 1
 
 
+def read_mosaic_band(source: Source, rank: int = 0, world: int = 1, out: Optional[np.ndarray] = None,
+                     threads: Optional[int] = None):
+    """The full-width row band rank ``rank`` of ``world`` owns of one huge image: ``(band, row0)``.
+    Nothing in the path is two-dimensional, so a band of any height is simply one frame of
+    ``rows * width`` pixels -- this is the sharding for mosaics whose sizes have no convenient divisor
+    (``Engine.upload([band])`` then ``distributed.process_mosaic_tiles``: the bands of different ranks
+    may differ in height, the white-balance counters are all-reduced as for tiles)."""
+    from .distributed import shard_range
+    shape, _ = frame_info(source)
+    if world > shape[0]:
+        raise ValueError(f"{world} ranks for a mosaic of {shape[0]} rows")
+    r0, r1 = shard_range(shape[0], rank, world)
+    return read_region(source, (r0, r1), None, out=out, threads=threads), r0
+
+
 def read_mosaic_tiles(source: Source, tile_h: int, tile_w: int, rank: int = 0, world: int = 1,
                       out: Optional[np.ndarray] = None, threads: Optional[int] = None):
     """The tiles rank ``rank`` of ``world`` owns of one huge image (contiguous block of the row-major

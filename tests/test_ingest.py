@@ -253,6 +253,15 @@ def test_mosaic_tiles_partition_the_image_across_ranks(tmp_path):
     assert origins == [(0, 0), (0, 60)] and np.array_equal(tiles[1], (img >> 8).astype(np.uint8)[:48, 60:])
     with pytest.raises(ValueError, match="do not divide"):
         ingest.read_mosaic_tiles(p, 25, 40)
+    # row bands need no divisor: 96 rows over 7 ranks -> 14,14,14,14,14,13,13 rows, each one frame
+    rows = []
+    for rank in range(7):
+        band, r0 = ingest.read_mosaic_band(p, rank, 7, threads=2)
+        assert band.dtype == np.uint16 and band.shape[1:] == (120, 3) and np.array_equal(band, img[r0:r0 + band.shape[0]])
+        rows.append((r0, band.shape[0]))
+    assert rows[0] == (0, 14) and rows[-1] == (83, 13) and sum(n for _, n in rows) == 96
+    with pytest.raises(ValueError, match="ranks"):
+        ingest.read_mosaic_band(p, 0, 97)
     assert ingest.largest_divisor(32768, 5000) == 4096 and ingest.largest_divisor(97, 50) == 1
     assert len(ingest.mosaic_tile_grid(32768, 32768, 4096, 4096)) == 64                  # BASELINE config 4
 
@@ -501,6 +510,37 @@ def test_mosaic_file_to_tiles_to_gpu_matches_the_oracle_on_the_whole_image(engin
         assert np.array_equal(st[t]["hist"], want["stats"][t]["hist"]) and st[t]["count"] == 256 * 320
         assert st[t]["count_above"] == want["stats"][t]["count_above"]
         assert st[t]["min"] == want["stats"][t]["min"] and st[t]["max"] == want["stats"][t]["max"]
+
+
+@pytest.mark.gpu
+def test_ragged_mosaic_bands_on_two_emulated_ranks(engine, tmp_path):
+    """A mosaic whose height has no useful divisor (811 rows, prime): two 'ranks' own row bands of different
+    heights (406 / 405 rows), each band is ONE frame of its own size; the white-balance counters of the two
+    bands are summed (the all-reduce), both ranks build the same LUT, and the stitched products equal the
+    oracle's on the whole image."""
+    from lars_image_processing_b200 import ingest
+    from oracle import oracle_np as o
+    img = synth.vegetation_frame(91, 811, 613)
+    img[:300] //= 2                                      # the bands differ: per-band percentiles would be wrong
+    p = tmp_path / "ragged.tif"
+    ingest.write_tiff(p, img, rows_per_strip=37, compression="lzw")
+    s = engine.stream()
+    bands = [ingest.read_mosaic_band(p, rank, 2) for rank in range(2)]
+    assert [b.shape[0] for b, _ in bands] == [406, 405] and bands[1][1] == 406
+    devs = [engine.upload([b], stream=s) for b, _ in bands]
+    hists = [engine.wb_histogram(d, shared=True, stream=s) for d in devs]
+    import torch
+    with torch.cuda.stream(s):                           # same stream as the kernels that wrote the counters
+        total = hists[0] + hists[1]                      # what dist.all_reduce(SUM) leaves on every rank
+    lut, pct = engine.wb_lut(total, stream=s)
+    outs = [engine.download(engine.fused(d, lut, stream=s), stream=s)[0] for d in devs]
+    want = _oracle(img)
+    assert np.array_equal(np.concatenate([x["wb"] for x in outs]), want["wb"])
+    for t in o.INDEX_TYPES:
+        got = np.concatenate([x["maps"][t] for x in outs])
+        assert np.array_equal(got.view(np.uint32), want["maps"][t].view(np.uint32)), t
+        assert np.array_equal(np.concatenate([x["rgb"][t] for x in outs]), want["rgb"][t]), t
+        assert np.array_equal(outs[0]["stats"][t]["hist"] + outs[1]["stats"][t]["hist"], want["stats"][t]["hist"]), t
 
 
 def test_tiff_round_trip_sweep(tmp_path):
