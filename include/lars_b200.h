@@ -291,6 +291,28 @@ int lars_tiff_read_region(const void* file, size_t file_bytes, const lars_tiff_i
                           int32_t row1, int32_t col0, int32_t col1, void* dst, size_t dst_bytes,
                           int32_t n_threads);
 
+/* Device-side decode of LZW TIFF strips: the compressed file bytes go to the GPU as they are and one warp
+ * decodes each strip straight into the frame slot (thousands of independent streams per batch).
+ * lars_tiff_lzw_chunks (host) fills one descriptor per strip of a file lars_tiff_probe accepted -- offsets
+ * relative to the start of the file and of the frame; the caller adds the file's / frame's position in its
+ * batch buffers -- and fails with LARS_ERR_UNSUPPORTED unless the file is LZW-compressed, stored in strips of
+ * at most 1 MB decoded.  lars_lzw_decode_device launches the decode; `counters` is two zeroed uint32 on the
+ * device: [0] receives the number of corrupt / short strips, [1] is the work counter.
+ * lars_tiff_post_device undoes the differencing predictor and big-endian 16-bit samples in place. */
+typedef struct lars_lzw_chunk {
+  uint64_t src_offset;   /* compressed bytes: offset from `src`                       */
+  uint64_t dst_offset;   /* decoded bytes: offset from `dst`                           */
+  uint32_t src_bytes;
+  uint32_t dst_bytes;    /* bytes this strip must produce (rows x width x samples)     */
+} lars_lzw_chunk;
+int lars_tiff_lzw_chunks(const void* file, size_t file_bytes, const lars_tiff_info* info, lars_lzw_chunk* chunks,
+                         int32_t max_chunks);
+int lars_lzw_decode_device(const uint8_t* src, const lars_lzw_chunk* chunks, int32_t n_chunks, uint8_t* dst,
+                           uint32_t* counters, void* stream);
+int lars_tiff_post_device(uint8_t* dst, int32_t n_frames, int64_t frame_stride, int32_t rows, int32_t width,
+                          int32_t samples_per_pixel, int32_t sample_bytes, int32_t predictor, int32_t swap16,
+                          void* stream);
+
 /* Host-only PNG reader: non-interlaced grayscale / RGB / RGBA, 8- or 16-bit samples (BASELINE config 1
  * is a uint8 RGNir PNG).  One call per frame -- chunk walk, one zlib inflate (bound at run time), the
  * five row filters -- into the caller's pinned HWC buffer; 16-bit samples arrive as little-endian

@@ -36,6 +36,7 @@ EXPORTED_SYMBOLS = (
     "lars_index_hwc", "lars_index_change_u8",
     "lars_resize_plan_lanczos", "lars_resize_tables_lanczos", "lars_resize_lanczos_u8",
     "lars_tiff_probe", "lars_tiff_read", "lars_tiff_read_region", "lars_png_probe", "lars_png_read",
+    "lars_tiff_lzw_chunks", "lars_lzw_decode_device", "lars_tiff_post_device",
 )
 
 
@@ -94,6 +95,10 @@ class PngInfo(C.Structure):
         "width", "height", "channels", "bit_depth", "color_type", "interlace", "n_idat", "reserved")] + [
         ("idat_bytes", C.c_uint64), ("frame_bytes", C.c_uint64)]
 
+
+# numpy view of ``lars_lzw_chunk`` (24 bytes)
+LZW_CHUNK_DTYPE = np.dtype([("src_offset", "<u8"), ("dst_offset", "<u8"), ("src_bytes", "<u4"), ("dst_bytes", "<u4")])
+assert LZW_CHUNK_DTYPE.itemsize == 24
 
 # numpy view of ``lars_index_stats`` (576 bytes)
 INDEX_STATS_DTYPE = np.dtype([
@@ -170,6 +175,12 @@ def _declare(lib):
     lib.lars_png_probe.restype = C.c_int
     lib.lars_png_read.argtypes = [vp, C.c_size_t, C.POINTER(PngInfo), vp, C.c_size_t]
     lib.lars_png_read.restype = C.c_int
+    lib.lars_tiff_lzw_chunks.argtypes = [vp, C.c_size_t, C.POINTER(TiffInfo), vp, i32]
+    lib.lars_tiff_lzw_chunks.restype = C.c_int
+    lib.lars_lzw_decode_device.argtypes = [vp, vp, i32, vp, vp, vp]
+    lib.lars_lzw_decode_device.restype = C.c_int
+    lib.lars_tiff_post_device.argtypes = [vp, i32, i64, i32, i32, i32, i32, i32, i32, vp]
+    lib.lars_tiff_post_device.restype = C.c_int
     lib.lars_resize_plan_lanczos.argtypes = [i32, i32, i32, i32, i32, C.POINTER(ResizePlan)]
     lib.lars_resize_plan_lanczos.restype = C.c_int
     lib.lars_resize_tables_lanczos.argtypes = [C.POINTER(ResizePlan), vp]

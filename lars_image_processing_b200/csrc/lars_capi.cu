@@ -17,6 +17,7 @@
 #include "lars_map_kernels.cuh"
 #include "lars_u16_kernels.cuh"
 #include "lars_resize_kernels.cuh"
+#include "lars_lzw_kernels.cuh"
 
 namespace {
 
@@ -67,7 +68,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 extern "C" {
 
 const char* lars_last_error(void) { return g_err; }
-int lars_abi_version(void) { return 4; }   // 3: + resize, TIFF ingest; 4: lars_tiff_info grew (tiles, predictor, BigTIFF), lars_tiff_read_region
+int lars_abi_version(void) { return 5; }   // 3: + resize, TIFF ingest; 4: lars_tiff_info grew (tiles, predictor, BigTIFF), lars_tiff_read_region; 5: PNG reader, device-side LZW
 
 int lars_init(int device) {
   std::lock_guard<std::mutex> lock(g_mu);
@@ -107,6 +108,8 @@ int lars_init(int device) {
   LARS_CUDA(cudaFuncSetAttribute(lars::wb_hist_u16_lo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lars::U16_LO_SMEM_BYTES));
   LARS_CUDA(cudaFuncSetAttribute(lars::select_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  lars::SEL_SMEM_BYTES));
+  LARS_CUDA(cudaFuncSetAttribute(lars::lzw_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 lars::LZW_SMEM_BYTES));
 
   // colormap tables: 3 x 256 packed R | G << 8 | B << 16
   static uint32_t packed[3 * 256];
@@ -1027,6 +1030,77 @@ int lars_png_read(const void* file, size_t file_bytes, const lars_png_info* info
   if (memcmp(&check, info, sizeof(check)) != 0) return fail(LARS_ERR_INVALID, "lars_png_read: info does not describe this file");
   why = lars_host::png_read(file, file_bytes, &check, dst, dst_bytes);
   if (why) return fail(LARS_ERR_INVALID, "lars_png_read: %s", why);
+  return LARS_OK;
+}
+
+int lars_tiff_lzw_chunks(const void* file, size_t file_bytes, const lars_tiff_info* info, lars_lzw_chunk* chunks,
+                         int32_t max_chunks) {
+  if (!file || !info || !chunks) return fail(LARS_ERR_INVALID, "lars_tiff_lzw_chunks: NULL pointer");
+  lars_tiff_info check;
+  bool unsupported = false;
+  const char* why = lars_host::tiff_probe(file, file_bytes, &check, &unsupported);
+  if (why) return fail(unsupported ? LARS_ERR_UNSUPPORTED : LARS_ERR_INVALID, "lars_tiff_lzw_chunks: %s", why);
+  if (memcmp(&check, info, sizeof(check)) != 0) return fail(LARS_ERR_INVALID, "lars_tiff_lzw_chunks: info does not describe this file");
+  if (check.compression != 5 || check.tile_width > 0)
+    return fail(LARS_ERR_UNSUPPORTED, "lars_tiff_lzw_chunks: the device decoder takes LZW-compressed strips");
+  if (check.n_strips > max_chunks) return fail(LARS_ERR_INVALID, "lars_tiff_lzw_chunks: %d strips, room for %d", check.n_strips, max_chunks);
+  lars_host::TiffCursor c{static_cast<const uint8_t*>(file), file_bytes, check.big_endian != 0};
+  const uint64_t row_bytes = (uint64_t)check.width * check.samples_per_pixel * (check.bits_per_sample / 8);
+  for (int32_t s = 0; s < check.n_strips; ++s) {
+    const int64_t left = (int64_t)check.height - (int64_t)s * check.rows_per_strip;
+    const uint64_t rows = (uint64_t)(left < check.rows_per_strip ? left : check.rows_per_strip);
+    const uint64_t need = rows * row_bytes;
+    const uint64_t off = lars_host::tiff_value(c, check.strip_offsets_pos, check.strip_offsets_type, (uint64_t)s);
+    const uint64_t cnt = lars_host::tiff_value(c, check.strip_counts_pos, check.strip_counts_type, (uint64_t)s);
+    if (need > LARS_LZW_MAX_CHUNK || cnt > 0xffffffffull)
+      return fail(LARS_ERR_UNSUPPORTED, "lars_tiff_lzw_chunks: a strip decodes to more than 1 MB");
+    chunks[s].src_offset = off;
+    chunks[s].dst_offset = (uint64_t)s * check.rows_per_strip * row_bytes;
+    chunks[s].src_bytes = (uint32_t)cnt;
+    chunks[s].dst_bytes = (uint32_t)need;
+  }
+  return check.n_strips;
+}
+
+int lars_lzw_decode_device(const uint8_t* src, const lars_lzw_chunk* chunks, int32_t n_chunks, uint8_t* dst,
+                           uint32_t* counters, void* stream) {
+  DeviceState* st = nullptr;
+  int rc = current_state(&st);
+  if (rc != LARS_OK) return rc;
+  if (!src || !chunks || !dst || !counters) return fail(LARS_ERR_INVALID, "lars_lzw_decode_device: NULL pointer");
+  if (n_chunks < 1) return fail(LARS_ERR_INVALID, "lars_lzw_decode_device: n_chunks=%d", n_chunks);
+  if (reinterpret_cast<uintptr_t>(chunks) & 7u) return fail(LARS_ERR_INVALID, "lars_lzw_decode_device: chunks must be 8-byte aligned");
+  lars::LzwParams p;
+  p.src = src; p.chunks = chunks; p.dst = dst; p.status = counters; p.next = counters + 1; p.n_chunks = n_chunks;
+  const int want = (n_chunks + lars::LZW_WARPS - 1) / lars::LZW_WARPS;
+  const int full = st->sm_count * 3;
+  lars::lzw_decode_kernel<<<want < full ? want : full, lars::LZW_WARPS * 32, lars::LZW_SMEM_BYTES,
+                            static_cast<cudaStream_t>(stream)>>>(p);
+  LARS_CUDA(cudaGetLastError());
+  return LARS_OK;
+}
+
+int lars_tiff_post_device(uint8_t* dst, int32_t n_frames, int64_t frame_stride, int32_t rows, int32_t width,
+                          int32_t samples_per_pixel, int32_t sample_bytes, int32_t predictor, int32_t swap16,
+                          void* stream) {
+  DeviceState* st = nullptr;
+  int rc = current_state(&st);
+  if (rc != LARS_OK) return rc;
+  if (!dst) return fail(LARS_ERR_INVALID, "lars_tiff_post_device: NULL pointer");
+  if (n_frames < 1 || rows < 1 || width < 1 || samples_per_pixel < 1 || samples_per_pixel > 4 ||
+      (sample_bytes != 1 && sample_bytes != 2) || (predictor != 1 && predictor != 2))
+    return fail(LARS_ERR_INVALID, "lars_tiff_post_device: bad geometry");
+  if (sample_bytes == 2 && ((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)frame_stride) & 1u))
+    return fail(LARS_ERR_INVALID, "lars_tiff_post_device: 16-bit frames must be 2-byte aligned");
+  if (predictor == 1 && !(swap16 && sample_bytes == 2)) return LARS_OK;      // nothing to undo
+  lars::TiffPostParams p;
+  p.dst = dst; p.frame_stride = frame_stride;
+  p.row_bytes = (long long)width * samples_per_pixel * sample_bytes;
+  p.n_frames = n_frames; p.rows = rows; p.width = width; p.spp = samples_per_pixel; p.sample_bytes = sample_bytes;
+  p.predictor = predictor; p.swap16 = swap16 ? 1 : 0;
+  const long long threads = (long long)n_frames * rows * samples_per_pixel;
+  lars::tiff_post_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  LARS_CUDA(cudaGetLastError());
   return LARS_OK;
 }
 

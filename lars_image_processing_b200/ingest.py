@@ -475,6 +475,94 @@ def write_tiff(path, array: np.ndarray, big_endian: bool = False, rows_per_strip
 
 
 # ------------------------------------------------------------------------------------------
+# device-side decode of LZW TIFF frames
+# ------------------------------------------------------------------------------------------
+def device_decodable(source: Source) -> bool:
+    """True if :func:`decode_tiff_batch_on_device` takes this file: an LZW-compressed TIFF stored in strips
+    of at most 1 MB decoded (what libtiff / Pillow / GDAL write by default for LZW)."""
+    def probe(buf):
+        info = _tiff_probe(buf)
+        if info is None or info.compression != 5 or info.tile_width > 0:
+            return False
+        rows = min(info.rows_per_strip, info.height)
+        return rows * info.width * info.samples_per_pixel * (info.bits_per_sample // 8) <= (1 << 20)
+    if isinstance(source, np.ndarray):
+        return False
+    try:
+        if isinstance(source, (bytes, bytearray, memoryview)):
+            return probe(source)
+        with open(os.fspath(source), "rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+            return probe(mm)
+    except (LarsError, OSError, ValueError):
+        return False
+
+
+def decode_tiff_batch_on_device(sources: Sequence[Source], engine: Optional[Engine] = None, stream=None) -> DeviceFrames:
+    """Equally-shaped LZW TIFF frames -> a device-resident frame batch, decoded ON the GPU: the compressed
+    file bytes are uploaded as they are (one pinned staging buffer, one H2D copy), one warp decodes each strip
+    straight into its frame slot (``lars_lzw_decode_device``), a second kernel undoes the differencing
+    predictor / big-endian samples.  The host only parses the IFDs.  Raises ``LarsError`` for a file outside
+    :func:`device_decodable` or a corrupt strip (the call synchronises once to read the strip verdict)."""
+    eng = engine or get_engine()
+    lib = eng.lib
+    s = stream or eng.stream()
+    blobs, infos, tables = [], [], []
+    for src in sources:
+        if isinstance(src, (bytes, bytearray, memoryview)):
+            raw = np.frombuffer(src, dtype=np.uint8)
+        else:
+            raw = np.fromfile(os.fspath(src), dtype=np.uint8)
+        info = _lib.TiffInfo()
+        check(lib.lars_tiff_probe(raw.ctypes.data, raw.size, C.byref(info)), "lars_tiff_probe")
+        chunks = np.zeros(info.n_strips, _lib.LZW_CHUNK_DTYPE)
+        check(lib.lars_tiff_lzw_chunks(raw.ctypes.data, raw.size, C.byref(info), chunks.ctypes.data, chunks.size),
+              "lars_tiff_lzw_chunks")
+        blobs.append(raw)
+        infos.append(info)
+        tables.append(chunks)
+    if not blobs:
+        raise ValueError("no frames")
+    first = infos[0]
+    key = lambda i: (i.height, i.width, i.samples_per_pixel, i.bits_per_sample, i.predictor, i.big_endian)
+    if any(key(i) != key(first) for i in infos):
+        raise ValueError("all frames of a batch must share shape, sample width, predictor and byte order")
+    sb = first.bits_per_sample // 8
+    frames = eng.alloc_frames(len(blobs), first.height, first.width, first.samples_per_pixel, s, sample_bytes=sb)
+    # one staging buffer: the files back to back (8-byte aligned), then the strip table of the whole batch
+    starts, pos = [], 0
+    for raw in blobs:
+        starts.append(pos)
+        pos += (raw.size + 7) & ~7
+    n_chunks = sum(t.size for t in tables)
+    table_at = pos
+    total = table_at + n_chunks * _lib.LZW_CHUNK_DTYPE.itemsize
+    host = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+    host_np = host.numpy()
+    k = 0
+    all_chunks = host_np[table_at:].view(_lib.LZW_CHUNK_DTYPE)
+    for f, (raw, t) in enumerate(zip(blobs, tables)):
+        host_np[starts[f]:starts[f] + raw.size] = raw
+        t["src_offset"] += starts[f]
+        t["dst_offset"] += f * frames.stride_bytes
+        all_chunks[k:k + t.size] = t
+        k += t.size
+    with torch.cuda.stream(s), torch.cuda.device(eng.device):
+        dev = torch.empty(total, dtype=torch.uint8, device=eng.device)
+        dev.copy_(host, non_blocking=True)
+        counters = torch.zeros(2, dtype=torch.int32, device=eng.device)
+        check(lib.lars_lzw_decode_device(dev.data_ptr(), dev.data_ptr() + table_at, n_chunks, frames.data.data_ptr(),
+                                         counters.data_ptr(), s.cuda_stream), "lars_lzw_decode_device")
+        check(lib.lars_tiff_post_device(frames.data.data_ptr(), frames.n_frames, frames.stride_bytes, first.height,
+                                        first.width, first.samples_per_pixel, sb, first.predictor,
+                                        1 if (first.big_endian and sb == 2) else 0, s.cuda_stream),
+              "lars_tiff_post_device")
+        bad = int(counters[0].item())                 # synchronises the stream: the verdict of every strip
+    if bad:
+        raise LarsError(f"{bad} LZW strip(s) of the batch are corrupt or shorter than their rows")
+    return frames
+
+
+# ------------------------------------------------------------------------------------------
 # streaming runner
 # ------------------------------------------------------------------------------------------
 class SurveyPipeline:

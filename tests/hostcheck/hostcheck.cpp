@@ -6,6 +6,8 @@
 #include <string.h>
 
 #include "../../lars_image_processing_b200/csrc/pixel_math.h"
+#include "../../lars_image_processing_b200/csrc/lzw_warp.h"
+#include "../../lars_image_processing_b200/csrc/tiff_host.h"
 
 extern "C" {
 
@@ -64,5 +66,14 @@ void hc_pair_tables_fast(int bins, float* value, int32_t* row, int32_t* slot) {
       row[65536 + k] = (int32_t)(lars_hist_row_bits(xn, half, bias) - LARS_MAGIC_U);
       slot[65536 + k] = (int32_t)(lars_cmap_slot_bits(xn) - LARS_MAGIC_U);
     }
+}
+
+// The warp LZW decoder of the device-side TIFF path (lzw_warp.h) with its 32 lanes run one after the other.
+uint32_t hc_lzw_chunk_host(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t cap) {
+  return (uint32_t)lars_host::lzw_chunk(in, n_in, out, cap);       // the product's host decoder, for comparison
+}
+uint32_t hc_lzw_decode_warp(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t cap) {
+  static thread_local uint32_t table[4096];
+  return lars_lzw_decode_warp(in, n_in, out, cap, table);
 }
 }

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in include/lars_b200.h but not exported"
     assert set(_lib.EXPORTED_SYMBOLS) == set(declared)
-    assert lib.lars_abi_version() == 4
+    assert lib.lars_abi_version() == 5
 
 
 def test_struct_layouts_match_header(tmp_path):
@@ -50,15 +50,17 @@ def test_struct_layouts_match_header(tmp_path):
                    'offsetof(lars_resize_plan, mma_table_offset), sizeof(lars_tiff_info), offsetof(lars_tiff_info, frame_bytes),'
                    'sizeof(lars_stretch_u16));'
                    'printf("%zu %zu %zu %zu\\n", offsetof(lars_tiff_info, tile_width), offsetof(lars_tiff_info, bigtiff),'
-                   'sizeof(lars_png_info), offsetof(lars_png_info, frame_bytes));return 0;}\n')
+                   'sizeof(lars_png_info), offsetof(lars_png_info, frame_bytes));'
+                   'printf("%zu %zu\\n", sizeof(lars_lzw_chunk), offsetof(lars_lzw_chunk, dst_bytes));return 0;}\n')
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
-    a, b, c, d, e, f, g, h, i, j = map(int, subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split())
+    a, b, c, d, e, f, g, h, i, j, k, l = map(int, subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split())
     assert a == C.sizeof(_lib.ResizePlan) and b == _lib.ResizePlan.table_bytes.offset
     assert c == _lib.ResizePlan.mma_table_offset.offset
     assert d == C.sizeof(_lib.TiffInfo) and e == _lib.TiffInfo.frame_bytes.offset
     assert f == _lib.STRETCH_U16_BYTES
     assert g == _lib.TiffInfo.tile_width.offset and h == _lib.TiffInfo.bigtiff.offset
     assert i == C.sizeof(_lib.PngInfo) and j == _lib.PngInfo.frame_bytes.offset
+    assert k == _lib.LZW_CHUNK_DTYPE.itemsize and l == _lib.LZW_CHUNK_DTYPE.fields["dst_bytes"][1]
 
 
 def test_host_tables_match_oracle():

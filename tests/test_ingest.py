@@ -543,6 +543,70 @@ def test_ragged_mosaic_bands_on_two_emulated_ranks(engine, tmp_path):
         assert np.array_equal(outs[0]["stats"][t]["hist"] + outs[1]["stats"][t]["hist"], want["stats"][t]["hist"]), t
 
 
+@pytest.mark.gpu
+def test_lzw_tiff_frames_decoded_on_the_device(engine, tmp_path):
+    """decode_tiff_batch_on_device: compressed file bytes in, frames decoded by the GPU (one warp per LZW
+    strip, then predictor / byte-order kernel) -- identical to the host reader for Pillow-written 8-bit files
+    (with and without predictor) and for 16-bit RGB files of either byte order; a damaged strip raises; the
+    analysis of a device-decoded batch equals that of the uploaded frames."""
+    import torch
+    from lars_image_processing_b200 import ingest
+    from lars_image_processing_b200._lib import LarsError
+    rng = np.random.default_rng(41)
+
+    def frames_to_host(dev, shape, dtype):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        torch.cuda.synchronize()
+        return [dev.data[i, :n].cpu().numpy().view(dtype).reshape(shape) for i in range(dev.n_frames)]
+
+    # Pillow / libtiff files: 8-bit RGB, several strips, table-full Clears inside the noisy strips
+    imgs = [_textured(rng, (211, 333, 3), np.uint8) for _ in range(3)]
+    for kw in ({}, {"tiffinfo": {317: 2}}):
+        paths = []
+        for i, img in enumerate(imgs):
+            p = tmp_path / f"p{i}.tif"
+            Image.fromarray(img).save(p, compression="tiff_lzw", **kw)
+            assert ingest.device_decodable(p)
+            paths.append(p)
+        dev = ingest.decode_tiff_batch_on_device(paths, engine)
+        for got, img, p in zip(frames_to_host(dev, img.shape, np.uint8), imgs, paths):
+            assert np.array_equal(got, img) and np.array_equal(got, ingest.read_frame(p))
+    # 16-bit RGB and gray, our writer: predictor on / off, both byte orders, one-row strips and large strips
+    for k, (shape, kw) in enumerate((((97, 120, 3), dict(predictor=True, rows_per_strip=1)),
+                                     ((97, 120, 3), dict(big_endian=True, predictor=True, rows_per_strip=16)),
+                                     ((64, 50), dict(big_endian=True, rows_per_strip=7)),
+                                     ((40, 33, 4), dict(rows_per_strip=40)))):
+        batch = [_textured(rng, shape, np.uint16) for _ in range(2)]
+        paths = []
+        for i, img in enumerate(batch):
+            p = tmp_path / f"w{k}_{i}.tif"
+            ingest.write_tiff(p, img, compression="lzw", **kw)
+            paths.append(p.read_bytes() if i else p)               # bytes and paths both work
+        dev = ingest.decode_tiff_batch_on_device(paths, engine)
+        assert dev.sample_bytes == 2 and dev.n_frames == 2
+        for got, img in zip(frames_to_host(dev, shape, np.uint16), batch):
+            assert np.array_equal(got, img), (shape, kw)
+    # the analysis path runs on the decoded batch as on uploaded frames
+    p = tmp_path / "a.tif"
+    Image.fromarray(imgs[0]).save(p, compression="tiff_lzw")
+    res_a = engine.download(engine.process_device(ingest.decode_tiff_batch_on_device([p], engine)))[0]
+    res_b = engine.analyze_frame(imgs[0])
+    assert np.array_equal(res_a["wb"], res_b["wb"])
+    assert np.array_equal(res_a["stats"]["NDVI"]["hist"], res_b["stats"]["NDVI"]["hist"])
+    # not eligible / damaged
+    q = tmp_path / "z.tif"
+    ingest.write_tiff(q, imgs[0], compression="deflate")
+    assert not ingest.device_decodable(q) and not ingest.device_decodable(imgs[0])
+    with pytest.raises(LarsError, match="LZW"):
+        ingest.decode_tiff_batch_on_device([q], engine)
+    raw = bytearray(p.read_bytes())
+    info = ingest._tiff_probe(bytes(raw))
+    off = int(np.frombuffer(bytes(raw), "<u4", info.n_strips, info.strip_offsets_pos)[3])
+    raw[off: off + 4] = b"\xff" * 4                                # strip 3 now opens with code 511: no such string yet
+    with pytest.raises(LarsError, match="corrupt"):
+        ingest.decode_tiff_batch_on_device([bytes(raw)], engine)
+
+
 def test_tiff_round_trip_sweep(tmp_path):
     """Seeded sweep of the writer / native reader pair: shapes, sample widths, channel counts, byte
     orders and strip heights; 8-bit 1/3/4-channel and 16-bit 1-channel files are also handed to Pillow."""
@@ -610,3 +674,57 @@ def test_tiff_reader_survives_corrupted_files(tmp_path):
             assert lib.lars_last_error()
             rejected += 1
     assert ok + rejected == 1200 and rejected > 100 and read_rejected > 10
+
+
+def test_warp_lzw_decoder_equals_the_host_decoder(hostcheck):
+    """lzw_warp.h (what the device-side TIFF path runs, one warp per strip) compiled for the host with its 32
+    lanes run in sequence: identical output to the host decoder on valid streams of every texture (9- to
+    12-bit codes, table-full Clears, KwKwK strings, chunk capacities that cut a string) and identical
+    verdicts / prefixes on 3,000 corrupted or truncated streams."""
+    import ctypes as C
+    from lars_image_processing_b200 import ingest
+    hostcheck.hc_lzw_decode_warp.restype = C.c_uint32
+    hostcheck.hc_lzw_chunk_host.restype = C.c_uint32
+    for fn in (hostcheck.hc_lzw_decode_warp, hostcheck.hc_lzw_chunk_host):
+        fn.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+    rng = np.random.default_rng(21)
+
+    def both(blob, cap):
+        src = np.frombuffer(blob, np.uint8)
+        a, b = np.full(cap + 64, 0xAA, np.uint8), np.full(cap + 64, 0xAA, np.uint8)
+        ra = hostcheck.hc_lzw_decode_warp(src.ctypes.data, src.size, a.ctypes.data, cap)
+        rb = hostcheck.hc_lzw_chunk_host(src.ctypes.data, src.size, b.ctypes.data, cap)
+        assert ra == rb and np.array_equal(a[:ra], b[:rb])
+        assert (a[cap:] == 0xAA).all() and (b[cap:] == 0xAA).all()       # nothing written past the capacity
+        if ra:
+            assert (a[ra:] == 0xAA).all()                                # ... nor past what was produced
+        return ra, a
+
+    streams = []
+    for n, kind in ((1, "noise"), (300, "noise"), (70000, "noise"), (70000, "ramp"), (40000, "const"), (120000, "mixed"),
+                    (9000, "pairs")):
+        if kind == "noise":
+            d = rng.integers(0, 256, n, dtype=np.uint8)
+        elif kind == "ramp":
+            d = (np.arange(n) // 7 % 256).astype(np.uint8)
+        elif kind == "const":
+            d = np.full(n, 77, np.uint8)                                 # KwKwK on every code
+        elif kind == "pairs":
+            d = np.tile(np.array([5, 5, 9], np.uint8), n // 3)
+        else:
+            d = np.concatenate([rng.integers(0, 4, n // 2, dtype=np.uint8), (np.arange(n // 2) % 256).astype(np.uint8)])
+        blob = ingest._lzw_encode(d.tobytes())
+        streams.append(blob)
+        for cap in (len(d), max(1, len(d) - 1), max(1, len(d) // 2), len(d) + 100):
+            produced, out = both(blob, cap)
+            assert produced == min(cap, len(d)) and np.array_equal(out[:produced], d[:produced]), (kind, n, cap)
+    rejected = 0
+    for it in range(3000):
+        raw = bytearray(streams[2 + it % 5])
+        for _ in range(int(rng.integers(1, 4))):
+            raw[int(rng.integers(0, len(raw)))] = int(rng.integers(0, 256))
+        if it % 5 == 4:
+            raw = raw[:int(rng.integers(1, len(raw)))]
+        produced, _ = both(bytes(raw), int(rng.integers(1, 200000)))
+        rejected += produced == 0
+    assert rejected > 300
