@@ -497,66 +497,99 @@ def device_decodable(source: Source) -> bool:
         return False
 
 
-def decode_tiff_batch_on_device(sources: Sequence[Source], engine: Optional[Engine] = None, stream=None) -> DeviceFrames:
+def decode_tiff_batch_on_device(sources: Sequence[Source], engine: Optional[Engine] = None, stream=None,
+                                threads: Optional[int] = None, timings: Optional[dict] = None) -> DeviceFrames:
     """Equally-shaped LZW TIFF frames -> a device-resident frame batch, decoded ON the GPU: the compressed
-    file bytes are uploaded as they are (one pinned staging buffer, one H2D copy), one warp decodes each strip
-    straight into its frame slot (``lars_lzw_decode_device``), a second kernel undoes the differencing
-    predictor / big-endian samples.  The host only parses the IFDs.  Raises ``LarsError`` for a file outside
-    :func:`device_decodable` or a corrupt strip (the call synchronises once to read the strip verdict)."""
+    file bytes are uploaded as they are (memory-mapped files copied by ``threads`` host threads into one pinned
+    staging buffer, one H2D copy), one warp decodes each strip straight into its frame slot
+    (``lars_lzw_decode_device``), a second kernel undoes the differencing predictor / big-endian samples.
+    The host only parses the IFDs.  Raises ``LarsError`` for a file outside :func:`device_decodable` or a
+    corrupt strip (the call synchronises once to read the strip verdict).  ``timings``: optional dict that
+    receives ``kernel_ms`` (CUDA events around the two kernels) and ``h2d_bytes``."""
     eng = engine or get_engine()
     lib = eng.lib
     s = stream or eng.stream()
-    blobs, infos, tables = [], [], []
-    for src in sources:
-        if isinstance(src, (bytes, bytearray, memoryview)):
-            raw = np.frombuffer(src, dtype=np.uint8)
-        else:
-            raw = np.fromfile(os.fspath(src), dtype=np.uint8)
-        info = _lib.TiffInfo()
-        check(lib.lars_tiff_probe(raw.ctypes.data, raw.size, C.byref(info)), "lars_tiff_probe")
-        chunks = np.zeros(info.n_strips, _lib.LZW_CHUNK_DTYPE)
-        check(lib.lars_tiff_lzw_chunks(raw.ctypes.data, raw.size, C.byref(info), chunks.ctypes.data, chunks.size),
-              "lars_tiff_lzw_chunks")
-        blobs.append(raw)
-        infos.append(info)
-        tables.append(chunks)
-    if not blobs:
+    if not len(sources):
         raise ValueError("no frames")
-    first = infos[0]
-    key = lambda i: (i.height, i.width, i.samples_per_pixel, i.bits_per_sample, i.predictor, i.big_endian)
-    if any(key(i) != key(first) for i in infos):
-        raise ValueError("all frames of a batch must share shape, sample width, predictor and byte order")
-    sb = first.bits_per_sample // 8
-    frames = eng.alloc_frames(len(blobs), first.height, first.width, first.samples_per_pixel, s, sample_bytes=sb)
-    # one staging buffer: the files back to back (8-byte aligned), then the strip table of the whole batch
-    starts, pos = [], 0
-    for raw in blobs:
-        starts.append(pos)
-        pos += (raw.size + 7) & ~7
-    n_chunks = sum(t.size for t in tables)
-    table_at = pos
-    total = table_at + n_chunks * _lib.LZW_CHUNK_DTYPE.itemsize
-    host = torch.empty(total, dtype=torch.uint8, pin_memory=True)
-    host_np = host.numpy()
-    k = 0
-    all_chunks = host_np[table_at:].view(_lib.LZW_CHUNK_DTYPE)
-    for f, (raw, t) in enumerate(zip(blobs, tables)):
-        host_np[starts[f]:starts[f] + raw.size] = raw
-        t["src_offset"] += starts[f]
-        t["dst_offset"] += f * frames.stride_bytes
-        all_chunks[k:k + t.size] = t
-        k += t.size
+    opened = []                                   # (file handle, mmap) of path sources, closed at the end
+    views: List[Optional[np.ndarray]] = []
+    try:
+        infos, tables = [], []
+        for src in sources:
+            if isinstance(src, (bytes, bytearray, memoryview)):
+                raw = np.frombuffer(src, dtype=np.uint8)
+            else:
+                fh = open(os.fspath(src), "rb")
+                opened.append(fh)
+                mm = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
+                opened.append(mm)
+                raw = np.frombuffer(mm, dtype=np.uint8)
+            views.append(raw)
+            info = _lib.TiffInfo()
+            check(lib.lars_tiff_probe(raw.ctypes.data, raw.size, C.byref(info)), "lars_tiff_probe")
+            chunks = np.zeros(info.n_strips, _lib.LZW_CHUNK_DTYPE)
+            check(lib.lars_tiff_lzw_chunks(raw.ctypes.data, raw.size, C.byref(info), chunks.ctypes.data, chunks.size),
+                  "lars_tiff_lzw_chunks")
+            infos.append(info)
+            tables.append(chunks)
+        first = infos[0]
+        key = lambda i: (i.height, i.width, i.samples_per_pixel, i.bits_per_sample, i.predictor, i.big_endian)
+        if any(key(i) != key(first) for i in infos):
+            raise ValueError("all frames of a batch must share shape, sample width, predictor and byte order")
+        sb = first.bits_per_sample // 8
+        frames = eng.alloc_frames(len(views), first.height, first.width, first.samples_per_pixel, s, sample_bytes=sb)
+        # one staging buffer: the files back to back (8-byte aligned), then the strip table of the whole batch
+        starts, pos = [], 0
+        for raw in views:
+            starts.append(pos)
+            pos += (raw.size + 7) & ~7
+        n_chunks = sum(t.size for t in tables)
+        table_at = pos
+        total = table_at + n_chunks * _lib.LZW_CHUNK_DTYPE.itemsize
+        host = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+        host_np = host.numpy()
+        all_chunks = host_np[table_at:].view(_lib.LZW_CHUNK_DTYPE)
+        k = 0
+        for f, t in enumerate(tables):
+            t["src_offset"] += starts[f]
+            t["dst_offset"] += f * frames.stride_bytes
+            all_chunks[k:k + t.size] = t
+            k += t.size
+
+        def stage(f):                             # page cache -> pinned memory; NumPy releases the GIL for the copy
+            np.copyto(host_np[starts[f]:starts[f] + views[f].size], views[f])
+        n_thr = default_decode_threads() if threads is None else max(1, int(threads))
+        if n_thr > 1 and len(views) > 1:
+            with ThreadPoolExecutor(min(n_thr, len(views))) as pool:
+                list(pool.map(stage, range(len(views))))
+        else:
+            for f in range(len(views)):
+                stage(f)
+    finally:
+        views.clear()                             # no view of a mapped file may outlive its map
+        raw = None
+        for h in reversed(opened):
+            h.close()
     with torch.cuda.stream(s), torch.cuda.device(eng.device):
         dev = torch.empty(total, dtype=torch.uint8, device=eng.device)
         dev.copy_(host, non_blocking=True)
         counters = torch.zeros(2, dtype=torch.int32, device=eng.device)
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if timings is not None else None
+        if ev:
+            ev[0].record(s)
         check(lib.lars_lzw_decode_device(dev.data_ptr(), dev.data_ptr() + table_at, n_chunks, frames.data.data_ptr(),
                                          counters.data_ptr(), s.cuda_stream), "lars_lzw_decode_device")
         check(lib.lars_tiff_post_device(frames.data.data_ptr(), frames.n_frames, frames.stride_bytes, first.height,
                                         first.width, first.samples_per_pixel, sb, first.predictor,
                                         1 if (first.big_endian and sb == 2) else 0, s.cuda_stream),
               "lars_tiff_post_device")
+        if ev:
+            ev[1].record(s)
         bad = int(counters[0].item())                 # synchronises the stream: the verdict of every strip
+    if timings is not None:
+        timings["kernel_ms"] = ev[0].elapsed_time(ev[1])
+        timings["h2d_bytes"] = total
+        timings["strips"] = n_chunks
     if bad:
         raise LarsError(f"{bad} LZW strip(s) of the batch are corrupt or shorter than their rows")
     return frames
