@@ -129,3 +129,43 @@ def test_oracle_is_not_imported_by_the_product():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "/root/reference" not in text.replace("``/root/reference/process-images.py``", ""), f
+
+
+def _run_bench(*args, env_extra=None):
+    env = dict(os.environ)
+    env.update(env_extra or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True,
+                          env=env, timeout=600)
+
+
+def test_bench_reference_arm_contract_on_cpu():
+    """`bench.py --impl reference` needs no GPU: one JSON line with the contract's keys, the CPU numbers
+    described (kind / cores / sample), no device traffic claimed; ranks other than 0 print nothing."""
+    import json
+    r = _run_bench("--impl", "reference", "--steps", "1", "--warmup", "1", "--height", "96", "--width", "128")
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "Mpix/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["vs_baseline"] is None
+    assert d["metric"].startswith("RGNir Mpix/s") and "workload" in d["config"] and d["data"] == "synthetic"
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "frames" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0
+    quiet = _run_bench("--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--height", "96", "--width", "128",
+                       env_extra={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert quiet.returncode == 0 and quiet.stdout.strip() == ""
+
+
+def test_bench_gpu_arm_fails_loudly_without_a_gpu():
+    """No CPU fallback anywhere on the product path: without CUDA the GPU arm exits non-zero and prints no
+    bench line (a silent fallback would put a CPU number on the record)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this check is for the CPU-only container")
+    r = _run_bench("--steps", "1", "--warmup", "1", "--height", "96", "--width", "128", "--frames", "1")
+    assert r.returncode != 0
+    assert not any(ln.lstrip().startswith("{") for ln in r.stdout.splitlines())
+    assert "no CPU fallback" in r.stderr or "CUDA" in r.stderr or "NVIDIA" in r.stderr
