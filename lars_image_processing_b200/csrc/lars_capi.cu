@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -45,6 +46,7 @@ int fail(int code, const char* fmt, ...) {
 constexpr int kMaxDevices = 64;
 struct DeviceState {
   bool ready = false;
+  bool lzw_v2 = false;        // the opt-in LZW kernel got its shared memory
   int sm_count = 0;
   uint32_t* cmaps = nullptr;  // [3][256] packed RGB, device
 };
@@ -110,6 +112,10 @@ int lars_init(int device) {
                                  lars::SEL_SMEM_BYTES));
   LARS_CUDA(cudaFuncSetAttribute(lars::lzw_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  lars::LZW_SMEM_BYTES));
+  // opt-in variant: never let it stand in the way of the library coming up
+  st.lzw_v2 = cudaFuncSetAttribute(lars::lzw_decode_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   lars::LZW2_SMEM_BYTES) == cudaSuccess;
+  if (!st.lzw_v2) cudaGetLastError();
 
   // colormap tables: 3 x 256 packed R | G << 8 | B << 16
   static uint32_t packed[3 * 256];
@@ -1072,10 +1078,20 @@ int lars_lzw_decode_device(const uint8_t* src, const lars_lzw_chunk* chunks, int
   if (reinterpret_cast<uintptr_t>(chunks) & 7u) return fail(LARS_ERR_INVALID, "lars_lzw_decode_device: chunks must be 8-byte aligned");
   lars::LzwParams p;
   p.src = src; p.chunks = chunks; p.dst = dst; p.status = counters; p.next = counters + 1; p.n_chunks = n_chunks;
-  const int want = (n_chunks + lars::LZW_WARPS - 1) / lars::LZW_WARPS;
-  const int full = st->sm_count * 3;
-  lars::lzw_decode_kernel<<<want < full ? want : full, lars::LZW_WARPS * 32, lars::LZW_SMEM_BYTES,
-                            static_cast<cudaStream_t>(stream)>>>(p);
+  static const int variant = [] {
+    const char* e = getenv("LARS_LZW_VARIANT");     // 2 = shared-memory ring kernel (experimental)
+    return (e && e[0] == '2') ? 2 : 1;
+  }();
+  if (variant == 2 && st->lzw_v2) {
+    const int want = (n_chunks + lars::LZW2_WARPS - 1) / lars::LZW2_WARPS;
+    lars::lzw_decode_v2_kernel<<<want < st->sm_count ? want : st->sm_count, lars::LZW2_WARPS * 32,
+                                 lars::LZW2_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(p);
+  } else {
+    const int want = (n_chunks + lars::LZW_WARPS - 1) / lars::LZW_WARPS;
+    const int full = st->sm_count * 3;
+    lars::lzw_decode_kernel<<<want < full ? want : full, lars::LZW_WARPS * 32, lars::LZW_SMEM_BYTES,
+                              static_cast<cudaStream_t>(stream)>>>(p);
+  }
   LARS_CUDA(cudaGetLastError());
   return LARS_OK;
 }

@@ -43,6 +43,28 @@ __global__ void __launch_bounds__(LZW_WARPS * 32) lzw_decode_kernel(const LzwPar
   }
 }
 
+// Variant 2 (opt-in through LARS_LZW_VARIANT=2, see lzw_warp.h): table + 16 KB output ring per warp.
+constexpr int LZW2_WARPS = 7;                                              // per CTA, one CTA per SM
+constexpr int LZW2_SMEM_BYTES = LZW2_WARPS * (4096 * 4 + (int)LARS_LZW_RING);   // 224 KB
+
+__global__ void __launch_bounds__(LZW2_WARPS * 32, 1) lzw_decode_v2_kernel(const LzwParams p) {
+  extern __shared__ __align__(16) uint32_t lzw_tables[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* table = lzw_tables + warp * 4096;
+  uint8_t* ring = reinterpret_cast<uint8_t*>(lzw_tables + LZW2_WARPS * 4096) + warp * LARS_LZW_RING;
+  for (;;) {
+    unsigned int k = 0;
+    if (lane == 0) k = atomicAdd(p.next, 1u);
+    k = __shfl_sync(0xffffffffu, k, 0);
+    if (k >= (unsigned int)p.n_chunks) break;
+    const lars_lzw_chunk c = p.chunks[k];
+    const uint32_t produced = lars_lzw_decode_warp_v2(p.src + c.src_offset, c.src_bytes, p.dst + c.dst_offset,
+                                                      c.dst_bytes, table, ring);
+    if (lane == 0 && produced < c.dst_bytes) atomicAdd(p.status, 1u);
+    __syncwarp();
+  }
+}
+
 struct TiffPostParams {
   uint8_t* dst;
   long long frame_stride;          // bytes between frames

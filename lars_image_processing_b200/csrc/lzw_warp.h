@@ -84,3 +84,86 @@ LARS_LZW_FN uint32_t lars_lzw_decode_warp(const uint8_t* in, uint32_t n_in, uint
   }
   return op;
 }
+
+// ---- variant 2 (opt-in, LARS_LZW_VARIANT=2; not yet measured on hardware) --------------------------------
+// Variant 1 pays one L2 round trip per code: the source of every string copy is output the same warp wrote a
+// moment ago, but it is read back through global memory.  Here the most recent LARS_LZW_RING bytes of output
+// are mirrored in a shared-memory ring; a string whose source starts no further back than
+// LARS_LZW_RING - 4096 bytes (4096 > any string length, so the bytes written for this string can never land
+// on ring slots it still has to read) is copied out of the ring, older ones still come from global memory.
+// Between two table-full Clears a noisy strip produces ~9 KB, so nearly every copy stays on chip.  The bit
+// buffer is refilled four bytes at a time with independent loads.
+#define LARS_LZW_RING 16384u
+
+LARS_LZW_FN uint32_t lars_lzw_decode_warp_v2(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t cap,
+                                             uint32_t* table, uint8_t* ring) {
+  uint64_t acc = 0;
+  int have = 0, nbits = 9, next_code = 258, old = -1;
+  uint32_t ip = 0, op = 0, old_pos = 0, old_len = 0;
+  while (op < cap) {
+    if (have < nbits) {
+      while (have <= 32 && ip + 4 <= n_in) {          // four independent loads, one latency
+        const uint32_t b0 = LARS_LZW_LOAD(in + ip), b1 = LARS_LZW_LOAD(in + ip + 1), b2 = LARS_LZW_LOAD(in + ip + 2),
+                       b3 = LARS_LZW_LOAD(in + ip + 3);
+        acc = (acc << 32) | (uint64_t)((b0 << 24) | (b1 << 16) | (b2 << 8) | b3);
+        ip += 4;
+        have += 32;
+      }
+      while (have <= 56 && ip < n_in) { acc = (acc << 8) | (uint64_t)LARS_LZW_LOAD(in + ip); ++ip; have += 8; }
+      if (have < nbits) break;
+    }
+    const int code = (int)((acc >> (have - nbits)) & ((1u << nbits) - 1u));
+    have -= nbits;
+    if (code == 256) { nbits = 9; next_code = 258; old = -1; continue; }
+    if (code == 257) break;
+    const uint32_t at = op;
+    uint32_t len;
+    if (code < 256) {
+      LARS_LZW_FOR_LANES(lane) {
+        if (lane == 0) { out[op] = (uint8_t)code; ring[op & (LARS_LZW_RING - 1u)] = (uint8_t)code; }
+      }
+      op += 1;
+      len = 1;
+    } else if (old < 0) {
+      return 0;
+    } else if (code < next_code || (code == next_code && next_code < 4096)) {
+      uint32_t pos, wrap;                             // string = out[pos, pos + wrap) followed by out[pos] again
+      if (code < next_code) {
+        const uint32_t e = table[code];
+        pos = e & 0xFFFFFu;
+        len = e >> 20;
+        wrap = len;
+      } else {                                        // the string being defined: old + first(old)
+        pos = old_pos;
+        len = old_len + 1;
+        wrap = old_len;
+      }
+      const uint32_t keep = len < cap - op ? len : cap - op;
+      const bool near = op - pos <= LARS_LZW_RING - 4096u;
+      LARS_LZW_SYNC();                                // the bytes other lanes wrote (ring and global) are visible
+      LARS_LZW_FOR_LANES(lane) {
+        for (uint32_t i = (uint32_t)lane; i < keep; i += 32u) {
+          const uint32_t from = pos + (i < wrap ? i : 0u);
+          const uint8_t b = near ? ring[from & (LARS_LZW_RING - 1u)] : out[from];
+          out[op + i] = b;
+          ring[(op + i) & (LARS_LZW_RING - 1u)] = b;
+        }
+      }
+      op += keep;
+    } else {
+      return 0;
+    }
+    if (old >= 0) {
+      if (next_code < 4096) {
+        table[next_code] = old_pos | ((old_len + 1u) << 20);
+        ++next_code;
+      }
+      if (next_code >= (1 << nbits) - 1 && nbits < 12) ++nbits;
+    }
+    old = code;
+    old_pos = at;
+    old_len = len;
+  }
+  return op;
+}
+

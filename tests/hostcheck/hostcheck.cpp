@@ -72,6 +72,11 @@ void hc_pair_tables_fast(int bins, float* value, int32_t* row, int32_t* slot) {
 uint32_t hc_lzw_chunk_host(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t cap) {
   return (uint32_t)lars_host::lzw_chunk(in, n_in, out, cap);       // the product's host decoder, for comparison
 }
+uint32_t hc_lzw_decode_warp_v2(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t cap) {
+  static thread_local uint32_t table[4096];
+  static thread_local uint8_t ring[LARS_LZW_RING];
+  return lars_lzw_decode_warp_v2(in, n_in, out, cap, table, ring);
+}
 uint32_t hc_lzw_decode_warp(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t cap) {
   static thread_local uint32_t table[4096];
   return lars_lzw_decode_warp(in, n_in, out, cap, table);

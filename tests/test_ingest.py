@@ -683,9 +683,8 @@ def test_warp_lzw_decoder_equals_the_host_decoder(hostcheck):
     verdicts / prefixes on 3,000 corrupted or truncated streams."""
     import ctypes as C
     from lars_image_processing_b200 import ingest
-    hostcheck.hc_lzw_decode_warp.restype = C.c_uint32
-    hostcheck.hc_lzw_chunk_host.restype = C.c_uint32
-    for fn in (hostcheck.hc_lzw_decode_warp, hostcheck.hc_lzw_chunk_host):
+    for fn in (hostcheck.hc_lzw_decode_warp, hostcheck.hc_lzw_decode_warp_v2, hostcheck.hc_lzw_chunk_host):
+        fn.restype = C.c_uint32
         fn.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
     rng = np.random.default_rng(21)
 
@@ -695,6 +694,9 @@ def test_warp_lzw_decoder_equals_the_host_decoder(hostcheck):
         ra = hostcheck.hc_lzw_decode_warp(src.ctypes.data, src.size, a.ctypes.data, cap)
         rb = hostcheck.hc_lzw_chunk_host(src.ctypes.data, src.size, b.ctypes.data, cap)
         assert ra == rb and np.array_equal(a[:ra], b[:rb])
+        a2 = np.full(cap + 64, 0xAA, np.uint8)                           # variant 2 (shared-memory ring), same verdicts
+        assert hostcheck.hc_lzw_decode_warp_v2(src.ctypes.data, src.size, a2.ctypes.data, cap) == ra
+        assert np.array_equal(a2[:ra], a[:ra]) and (a2[cap:] == 0xAA).all()
         assert (a[cap:] == 0xAA).all() and (b[cap:] == 0xAA).all()       # nothing written past the capacity
         if ra:
             assert (a[ra:] == 0xAA).all()                                # ... nor past what was produced
