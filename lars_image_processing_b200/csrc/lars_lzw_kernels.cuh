@@ -43,15 +43,18 @@ __global__ void __launch_bounds__(LZW_WARPS * 32) lzw_decode_kernel(const LzwPar
   }
 }
 
-// Variant 2 (opt-in through LARS_LZW_VARIANT=2, see lzw_warp.h): table + 16 KB output ring per warp.
-constexpr int LZW2_WARPS = 7;                                              // per CTA, one CTA per SM
-constexpr int LZW2_SMEM_BYTES = LZW2_WARPS * (4096 * 4 + (int)LARS_LZW_RING);   // 224 KB
+// Variant 2 (opt-in through LARS_LZW_VARIANT=2, see lzw_warp.h): per warp a table, a 16 KB output ring and a
+// 512-byte ring of the compressed stream.
+constexpr int LZW2_WARPS = 6;                                              // per CTA, one CTA per SM
+constexpr int LZW2_WARP_SMEM = 4096 * 4 + (int)LARS_LZW_RING + (int)LARS_LZW_INBUF_WORDS * 4;   // 33,280 B
+constexpr int LZW2_SMEM_BYTES = LZW2_WARPS * LZW2_WARP_SMEM;               // 195 KB
 
 __global__ void __launch_bounds__(LZW2_WARPS * 32, 1) lzw_decode_v2_kernel(const LzwParams p) {
   extern __shared__ __align__(16) uint32_t lzw_tables[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t* table = lzw_tables + warp * 4096;
-  uint8_t* ring = reinterpret_cast<uint8_t*>(lzw_tables + LZW2_WARPS * 4096) + warp * LARS_LZW_RING;
+  uint32_t* table = lzw_tables + warp * (LZW2_WARP_SMEM / 4);
+  uint32_t* inbuf = table + 4096;
+  uint8_t* ring = reinterpret_cast<uint8_t*>(inbuf + LARS_LZW_INBUF_WORDS);
   for (;;) {
     unsigned int k = 0;
     if (lane == 0) k = atomicAdd(p.next, 1u);
@@ -59,7 +62,7 @@ __global__ void __launch_bounds__(LZW2_WARPS * 32, 1) lzw_decode_v2_kernel(const
     if (k >= (unsigned int)p.n_chunks) break;
     const lars_lzw_chunk c = p.chunks[k];
     const uint32_t produced = lars_lzw_decode_warp_v2(p.src + c.src_offset, c.src_bytes, p.dst + c.dst_offset,
-                                                      c.dst_bytes, table, ring);
+                                                      c.dst_bytes, table, ring, inbuf);
     if (lane == 0 && produced < c.dst_bytes) atomicAdd(p.status, 1u);
     __syncwarp();
   }

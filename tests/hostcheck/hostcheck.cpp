@@ -72,10 +72,15 @@ void hc_pair_tables_fast(int bins, float* value, int32_t* row, int32_t* slot) {
 uint32_t hc_lzw_chunk_host(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t cap) {
   return (uint32_t)lars_host::lzw_chunk(in, n_in, out, cap);       // the product's host decoder, for comparison
 }
-uint32_t hc_lzw_decode_warp_v2(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t cap) {
+uint32_t hc_lzw_decode_warp_v2(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t cap, uint32_t skew) {
   static thread_local uint32_t table[4096];
   static thread_local uint8_t ring[LARS_LZW_RING];
-  return lars_lzw_decode_warp_v2(in, n_in, out, cap, table, ring);
+  static thread_local uint32_t inbuf[LARS_LZW_INBUF_WORDS];
+  // the decoder reads whole aligned words around the stream: give it a padded, aligned copy at byte offset `skew`
+  std::vector<uint32_t> padded((n_in + 16) / 4 + 2, 0xA5A5A5A5u);
+  uint8_t* base = reinterpret_cast<uint8_t*>(padded.data()) + 4 + (skew & 3u);
+  memcpy(base, in, n_in);
+  return lars_lzw_decode_warp_v2(base, n_in, out, cap, table, ring, inbuf);
 }
 uint32_t hc_lzw_decode_warp(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t cap) {
   static thread_local uint32_t table[4096];

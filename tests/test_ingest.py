@@ -686,6 +686,8 @@ def test_warp_lzw_decoder_equals_the_host_decoder(hostcheck):
     for fn in (hostcheck.hc_lzw_decode_warp, hostcheck.hc_lzw_decode_warp_v2, hostcheck.hc_lzw_chunk_host):
         fn.restype = C.c_uint32
         fn.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+    hostcheck.hc_lzw_decode_warp_v2.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]
+    calls = [0]
     rng = np.random.default_rng(21)
 
     def both(blob, cap):
@@ -694,9 +696,13 @@ def test_warp_lzw_decoder_equals_the_host_decoder(hostcheck):
         ra = hostcheck.hc_lzw_decode_warp(src.ctypes.data, src.size, a.ctypes.data, cap)
         rb = hostcheck.hc_lzw_chunk_host(src.ctypes.data, src.size, b.ctypes.data, cap)
         assert ra == rb and np.array_equal(a[:ra], b[:rb])
-        a2 = np.full(cap + 64, 0xAA, np.uint8)                           # variant 2 (shared-memory ring), same verdicts
-        assert hostcheck.hc_lzw_decode_warp_v2(src.ctypes.data, src.size, a2.ctypes.data, cap) == ra
-        assert np.array_equal(a2[:ra], a[:ra]) and (a2[cap:] == 0xAA).all()
+        # variant 2 (stream and output staged in shared-memory rings): same verdicts, whatever the alignment
+        # of the stream (skew) and of the destination (dskew)
+        calls[0] += 1
+        skew, dskew = calls[0] & 3, (calls[0] >> 2) & 3
+        a2 = np.full(cap + 72, 0xAA, np.uint8)
+        assert hostcheck.hc_lzw_decode_warp_v2(src.ctypes.data, src.size, a2.ctypes.data + dskew, cap, skew) == ra
+        assert np.array_equal(a2[dskew:dskew + ra], a[:ra]) and (a2[dskew + cap:] == 0xAA).all() and (a2[:dskew] == 0xAA).all()
         assert (a[cap:] == 0xAA).all() and (b[cap:] == 0xAA).all()       # nothing written past the capacity
         if ra:
             assert (a[ra:] == 0xAA).all()                                # ... nor past what was produced
