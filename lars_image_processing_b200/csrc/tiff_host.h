@@ -234,6 +234,7 @@ inline const char* tiff_probe(const void* file, size_t file_bytes, lars_tiff_inf
         break;
       case 259: info->compression = v31; break;
       case 262: info->photometric = v31; break;
+      case 266: if (v0 == 2) { *unsupported = true; return "FillOrder 2 (bit-reversed data): decode it with Pillow"; } break;
       case 273: strip_pos[0] = pos; strip_type[0] = type; strip_cnt[0] = count; break;
       case 277: info->samples_per_pixel = v31; break;
       case 278: info->rows_per_strip = v31; break;
@@ -277,6 +278,12 @@ inline const char* tiff_probe(const void* file, size_t file_bytes, lars_tiff_inf
     return "planar (separate-plane) TIFF is not supported";
   }
   if (info->photometric == 0) { *unsupported = true; return "WhiteIsZero TIFF: decode it with Pillow (it inverts the samples)"; }
+  // BlackIsZero, RGB, palette indices and CMYK are handed over as stored (as np.array(Image.open()) does);
+  // YCbCr, CIELab, CFA ... are converted or re-interpreted by Pillow
+  if (info->photometric != 1 && info->photometric != 2 && info->photometric != 3 && info->photometric != 5) {
+    *unsupported = true;
+    return "this PhotometricInterpretation is left to Pillow";
+  }
 
   const uint64_t px_bytes = (uint64_t)info->samples_per_pixel * (info->bits_per_sample / 8);
   info->frame_bytes = (uint64_t)info->width * px_bytes * (uint64_t)info->height;

@@ -70,6 +70,14 @@ def test_other_formats_fall_back_to_pillow(tmp_path):
     assert np.array_equal(ingest.read_frame(jpg_tif), np.array(Image.open(jpg_tif)))
     assert np.array_equal(ingest.read_frame(png.read_bytes()), img)
     assert ingest.read_frame(img) is img
+    # other Pillow modes stored as TIFF: CMYK / palette indices / gray are handed over as stored by either
+    # reader, bilevel goes to Pillow -- the arrays always equal np.array(Image.open(...))
+    t = tmp_path / "m.tif"
+    for mode, native in (("CMYK", True), ("P", True), ("L", True), ("1", False)):
+        Image.fromarray(img).convert(mode).save(t)
+        assert (ingest._tiff_probe(t.read_bytes()) is not None) == native, mode
+        got, want = ingest.read_frame(t), np.array(Image.open(t))
+        assert got.dtype == want.dtype and np.array_equal(got, want), mode
 
 
 def test_corrupt_tiff_is_rejected_not_read_out_of_bounds(tmp_path):
