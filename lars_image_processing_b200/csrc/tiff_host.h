@@ -117,8 +117,14 @@ inline size_t packbits_chunk(const uint8_t* in, size_t n_in, uint8_t* out, size_
 // prefix chains to walk.
 inline size_t lzw_chunk(const uint8_t* in, size_t n_in, uint8_t* out, size_t cap) {
   struct Entry { uint32_t pos; uint32_t len; };    // 32 KB: the table stays in L1
+  // Literals are table entries as well -- they point into a page holding the bytes 0..255 (bit 31 of pos) --
+  // so that noisy data, where literals and strings alternate unpredictably, takes no branch on the kind of code.
+  static const struct LiteralPage { uint8_t b[256 + 8]; LiteralPage() { for (int i = 0; i < 264; ++i) b[i] = (uint8_t)i; } } page;
+  constexpr uint32_t kLiteral = 0x80000000u;
   Entry table[4096];
-  if (cap > 0xffffffffull) return 0;               // one strip / tile of 4 GB: not a frame of this path
+  if (cap > 0x7fffffffull) return 0;               // one strip / tile of 2 GB: not a frame of this path
+  for (uint32_t i = 0; i < 256; ++i) table[i] = Entry{kLiteral | i, 1};
+  table[256] = table[257] = Entry{kLiteral, 1};
   const uint8_t* end = in + n_in;
   uint64_t acc = 0;
   int have = 0, nbits = 9, next_code = 258, old = -1;
@@ -134,26 +140,23 @@ inline size_t lzw_chunk(const uint8_t* in, size_t n_in, uint8_t* out, size_t cap
     if (code == 257) break;
     const size_t at = op;
     size_t len;
-    if (code < 256) {                              // a literal
-      out[op++] = (uint8_t)code;
-      len = 1;
-    } else if (old < 0) {
-      return 0;                                    // the first code after a Clear must be a literal
-    } else if (code < next_code) {                 // a string made earlier: it ends before `op`
-      len = table[code].len;
-      const size_t pos = table[code].pos;
+    if (code < next_code) {                        // a literal or a string made earlier (it ends before `op`)
+      if (old < 0 && code > 255) return 0;         // the first code after a Clear must be a literal
+      const Entry e = table[code];
+      len = e.len;
+      const uint8_t* src = (e.pos & kLiteral) ? page.b + (e.pos & 0xFFu) : out + e.pos;
       if (len <= 8 && op + 8 <= cap) {             // most strings are short: one 8-byte move, the excess is
-        uint64_t w;                                // scratch that later output overwrites (pos + 8 <= op + 8 <= cap)
-        memcpy(&w, out + pos, 8);
+        uint64_t w;                                // scratch that later output overwrites (never past cap)
+        memcpy(&w, src, 8);
         memcpy(out + op, &w, 8);
         op += len;
       } else {
         const size_t keep = len < cap - op ? len : cap - op;
-        memcpy(out + op, out + pos, keep);
+        memcpy(out + op, src, keep);
         op += keep;
       }
-    } else if (code == next_code && next_code < 4096) {   // the string being defined: old + first(old); it
-      len = old_len + 1;                                   // overlaps its own source, so byte by byte
+    } else if (code == next_code && next_code < 4096 && old >= 0) {   // the string being defined: old + first(old);
+      len = old_len + 1;                                               // it overlaps its own source, so byte by byte
       const size_t keep = len < cap - op ? len : cap - op;
       for (size_t i = 0; i < keep; ++i) out[op + i] = out[old_pos + i];
       op += keep;
