@@ -138,3 +138,44 @@ def test_oracle_against_live_reference():
         o.calculate_index(frames["c1_like"], "EVI")
     assert R["fix_white_balance"](None) is None and o.fix_white_balance_literal(None) is None
     assert R["analyze_index"](None, "NDVI") == {} and o.analyze_index(None, "NDVI") == {}
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference checkout not present on this box")
+def test_oracle_against_live_reference_random_sweep():
+    """240 seeded frames against the reference's own functions: ragged shapes, uint8 / uint16, RGB / RGBA,
+    dense noise and few-valued content (percentiles that fall between two distinct values, p2 == p98 with its
+    inf / NaN arithmetic) -- the histogram formulation the GPU uses must reproduce the reference byte for
+    byte, and the index maps and statistics computed from its output bit for bit."""
+    R = ref_loader.load("process-images.py")
+    rng = np.random.default_rng(2025)
+    degenerate = 0
+    for it in range(240):
+        h, w = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+        ch = 4 if it % 7 == 0 else 3
+        dtype = np.uint16 if it % 3 == 0 else np.uint8
+        top = np.iinfo(dtype).max
+        kind = it % 4
+        if kind == 0:
+            img = rng.integers(0, top + 1, (h, w, ch))
+        elif kind == 1:                                   # a handful of levels: lerp between distinct values
+            levels = rng.integers(0, top + 1, int(rng.integers(1, 5)))
+            img = levels[rng.integers(0, len(levels), (h, w, ch))]
+        elif kind == 2:                                   # one channel constant: p98 == p2
+            img = rng.integers(0, top + 1, (h, w, ch))
+            img[:, :, int(rng.integers(0, 3))] = int(rng.integers(0, top + 1))
+        else:                                             # narrow band around a random level
+            c = int(rng.integers(0, top + 1))
+            img = np.clip(c + rng.integers(-3, 4, (h, w, ch)), 0, top)
+        img = img.astype(dtype)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = R["fix_white_balance"](img)
+            got = o.fix_white_balance_from_hist(img)
+        assert ref.dtype == np.uint8 and np.array_equal(got, ref), (it, img.shape, dtype, kind)
+        pcts, _ = o.wb_luts_from_hist(o.channel_histograms(img))
+        degenerate += int((pcts[:, 0] == pcts[:, 1]).any())
+        t = INDEX_TYPES[it % 3]
+        mr = R["calculate_index"](ref, t)
+        assert np.array_equal(mr.view(np.uint32), o.calculate_index(got, t).view(np.uint32)), (it, t)
+        assert R["analyze_index"](mr, t) == o.analyze_index(mr, t), (it, t)
+    assert degenerate > 40
