@@ -744,3 +744,63 @@ def test_warp_lzw_decoder_equals_the_host_decoder(hostcheck):
         produced, _ = both(bytes(raw), int(rng.integers(1, 200000)))
         rejected += produced == 0
     assert rejected > 300
+
+
+def test_device_decode_plan_on_the_cpu(hostcheck, tmp_path):
+    """What the device-side decode is made of, without a GPU: lars_tiff_lzw_chunks (the per-strip table) plus the
+    warp decoder of lzw_warp.h (both variants, run on the host through hostcheck) plus the predictor / byte-order
+    step reproduce the frame for Pillow-written and self-written LZW files; files outside the device path are
+    refused with LARS_ERR_UNSUPPORTED."""
+    import ctypes as C
+    from lars_image_processing_b200 import ingest
+    L = _lib()
+    lib = L.load()
+    for fn in (hostcheck.hc_lzw_decode_warp, hostcheck.hc_lzw_decode_warp_v2):
+        fn.restype = C.c_uint32
+    hostcheck.hc_lzw_decode_warp.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+    hostcheck.hc_lzw_decode_warp_v2.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]
+    rng = np.random.default_rng(51)
+    p = tmp_path / "d.tif"
+
+    def plan(raw):
+        info = L.TiffInfo()
+        assert lib.lars_tiff_probe(raw.ctypes.data, raw.size, C.byref(info)) == 0
+        chunks = np.zeros(max(info.n_strips, 1), L.LZW_CHUNK_DTYPE)
+        return info, chunks, lib.lars_tiff_lzw_chunks(raw.ctypes.data, raw.size, C.byref(info), chunks.ctypes.data, chunks.size)
+
+    cases = []
+    img8 = _textured(rng, (211, 333, 3), np.uint8)
+    Image.fromarray(img8).save(p, compression="tiff_lzw", tiffinfo={317: 2})
+    cases.append((img8, np.fromfile(p, np.uint8)))
+    for shape, kw in (((97, 120, 3), dict(predictor=True, rows_per_strip=1)), ((64, 50), dict(big_endian=True, rows_per_strip=7)),
+                      ((40, 33, 4), dict(big_endian=True, predictor=True, rows_per_strip=40))):
+        img = _textured(rng, shape, np.uint16)
+        ingest.write_tiff(p, img, compression="lzw", **kw)
+        cases.append((img, np.fromfile(p, np.uint8)))
+    for variant, (img, raw) in enumerate(cases * 2):
+        info, chunks, n = plan(raw)
+        assert n == info.n_strips and ingest.device_decodable(raw.tobytes())
+        sb, spp = info.bits_per_sample // 8, info.samples_per_pixel
+        row_bytes = info.width * spp * sb
+        assert int(chunks["dst_bytes"].sum()) == img.nbytes and chunks["dst_offset"][0] == 0
+        assert np.array_equal(chunks["dst_offset"][1:], np.cumsum(chunks["dst_bytes"])[:-1])
+        out = np.zeros(img.nbytes + 8, np.uint8)
+        for c in chunks:
+            args = (raw.ctypes.data + int(c["src_offset"]), int(c["src_bytes"]), out.ctypes.data + int(c["dst_offset"]), int(c["dst_bytes"]))
+            produced = (hostcheck.hc_lzw_decode_warp(*args) if variant < len(cases)
+                        else hostcheck.hc_lzw_decode_warp_v2(*args, int(c["src_offset"]) & 3))
+            assert produced == c["dst_bytes"]
+        # what tiff_post_kernel does: byte order, then the running sum along each row per sample of the pixel
+        samples = out[:img.nbytes].view(">u2" if (sb == 2 and info.big_endian) else ("<u2" if sb == 2 else np.uint8))
+        rows = samples.astype(np.uint32).reshape(info.height, info.width, spp)
+        if info.predictor == 2:
+            rows = np.cumsum(rows, axis=1) & (0xFFFF if sb == 2 else 0xFF)
+        assert np.array_equal(rows.astype(img.dtype).reshape(img.shape), img)
+    # refused: Deflate, tiles, strips beyond 1 MB
+    for kw in (dict(compression="deflate"), dict(compression="lzw", tile=(16, 16)), dict()):
+        ingest.write_tiff(p, img8, **kw)
+        raw = np.fromfile(p, np.uint8)
+        assert plan(raw)[2] == -3 and not ingest.device_decodable(p)
+    big = np.zeros((600, 700, 3), np.uint8)
+    ingest.write_tiff(p, big, compression="lzw")                   # one strip of 1.26 MB
+    assert plan(np.fromfile(p, np.uint8))[2] == -3 and not ingest.device_decodable(p)
