@@ -152,3 +152,57 @@ def test_conversion_free_forms_of_the_fused_kernel(hostcheck, bins):
     assert np.array_equal(np.minimum(slot[:65536], 255).reshape(256, 256), o.colormap_index(v))
     assert np.array_equal(np.minimum(slot[65536:], 255).reshape(256, 256), o.colormap_index(vw))
     assert slot.min() >= 0 and slot.max() <= 256
+
+
+def test_uint16_stretch_guess_is_within_one_step_for_every_sample_value(hostcheck):
+    """The uint16 fused pass maps a sample with a float guess of the stretch plus a +-1 correction against the
+    bracketing thresholds (lars_fused_kernel.cuh: stretch_u16).  That is exact iff the guess is never more than
+    one step away from the reference chain (fp64 -> fp32 -> uint8, pixel_math.h: lars_wb_lut_entry).  Checked
+    here for ALL 65,536 sample values under 300 percentile pairs: integral and interpolated percentiles, spans
+    from 0.02 to 65,535, and p2 == p98 (one step from 0 to 255 through the inf / NaN arithmetic)."""
+    import ctypes as C
+    rng = np.random.default_rng(16)
+    hostcheck.hc_wb_lut.argtypes = [C.c_double, C.c_double, C.c_int, C.c_void_p]
+    v = np.arange(65536, dtype=np.int64)
+    worst = 0
+    for it in range(300):
+        kind = it % 6
+        a = float(rng.integers(0, 65536))
+        if kind == 0:                                     # integral percentiles, any span
+            lo, hi = sorted((a, float(rng.integers(0, 65536))))
+        elif kind == 1:                                   # interpolated (multiples of 0.02), any span
+            lo = a + round(float(rng.integers(0, 50)) * 0.02, 2)
+            hi = lo + float(rng.integers(0, 3000)) + round(float(rng.integers(1, 50)) * 0.02, 2)
+        elif kind == 2:                                   # the narrowest non-zero spans
+            lo = a
+            hi = a + round(float(rng.integers(1, 6)) * 0.02, 2)
+        elif kind == 3:                                   # degenerate: p2 == p98
+            lo = hi = a if it % 12 == 3 else a + round(float(rng.integers(0, 50)) * 0.02, 2)
+        elif kind == 4:                                   # full range and near it
+            lo, hi = float(rng.integers(0, 3)), 65535.0 - float(rng.integers(0, 3))
+        else:                                             # generic doubles
+            lo = float(rng.uniform(0, 60000))
+            hi = lo + float(rng.uniform(0.02, 65535 - lo))
+        hi = min(hi, 65535.0)
+        lo = min(lo, hi)
+        lut = np.empty(65536, np.uint8)
+        hostcheck.hc_wb_lut(lo, hi, 65536, lut.ctypes.data)
+        assert (np.diff(lut.astype(np.int32)) >= 0).all()                 # monotone: thresholds are well defined
+        thr = np.full(258, 65536, np.int64)
+        thr[0] = 0
+        thr[1:256] = np.searchsorted(lut, np.arange(1, 256), side="left")  # smallest v with LUT(v) >= k
+        # the guess parameters as wb_stretch_build_u16_kernel stores them
+        if hi - lo > 0.0:
+            lo_int, lo_frac, scale = int(np.floor(lo)), np.float32(lo - np.floor(lo)), np.float32(255.0 / (hi - lo))
+        else:
+            lo_int, lo_frac, scale = int(thr[1]) - 1, np.float32(0.5), np.float32(1048576.0)
+        d = (v - lo_int).astype(np.float32)                               # exact: |v - lo_int| < 2^24
+        x = (d - lo_frac).astype(np.float32)
+        t = (x.astype(np.float64) * np.float64(scale) - 0.5).astype(np.float32)   # fmaf: exact product, one rounding
+        t = np.minimum(np.maximum(t, np.float32(-0.5)), np.float32(254.5))
+        g = np.rint(t).astype(np.int64)                                   # the magic-number add rounds to nearest even
+        assert g.min() >= 0 and g.max() <= 255
+        worst = max(worst, int(np.abs(g - lut).max()))
+        got = g + (v >= thr[g + 1]) - (v < thr[g])
+        assert np.array_equal(got, lut), (it, lo, hi)
+    assert worst == 1                                                     # the correction is needed, and one step suffices
