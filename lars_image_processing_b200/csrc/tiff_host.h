@@ -1,5 +1,5 @@
 // Host-side ingest: TIFF 6.0 / BigTIFF reader for the frame formats of the path -- chunky 8- or 16-bit
-// unsigned samples, 1 / 3 / 4 samples per pixel, either byte order; strips or tiles; uncompressed, LZW,
+// unsigned samples, 1 / 3 / 4 samples per pixel, chunky or planar, either byte order; strips or tiles; uncompressed, LZW,
 // Deflate or PackBits, with or without the horizontal-differencing predictor; whole frames or a
 // rectangular region (the tiles / row bands one rank owns of an orthomosaic, BASELINE config 4).
 //
@@ -276,10 +276,8 @@ inline const char* tiff_probe(const void* file, size_t file_bytes, lars_tiff_inf
     *unsupported = true;
     return "only 1, 3 or 4 samples per pixel are supported";
   }
-  if (info->planar_config != 1 && info->samples_per_pixel != 1) {
-    *unsupported = true;
-    return "planar (separate-plane) TIFF is not supported";
-  }
+  if (info->planar_config != 1 && info->planar_config != 2) return "unknown PlanarConfiguration";
+  if (info->samples_per_pixel == 1) info->planar_config = 1;      // one sample per pixel: the two layouts coincide
   if (info->photometric == 0) { *unsupported = true; return "WhiteIsZero TIFF: decode it with Pillow (it inverts the samples)"; }
   // BlackIsZero, RGB, palette indices and CMYK are handed over as stored (as np.array(Image.open()) does);
   // YCbCr, CIELab, CFA ... are converted or re-interpreted by Pillow
@@ -291,6 +289,10 @@ inline const char* tiff_probe(const void* file, size_t file_bytes, lars_tiff_inf
   const uint64_t px_bytes = (uint64_t)info->samples_per_pixel * (info->bits_per_sample / 8);
   info->frame_bytes = (uint64_t)info->width * px_bytes * (uint64_t)info->height;
   const bool tiled = tile_pos[0] != 0 || info->tile_width > 0 || info->tile_length > 0;
+  // PlanarConfiguration 2: every sample of the pixel has its own run of strips / tiles (plane after plane),
+  // each chunk holding one sample per pixel
+  const uint64_t planes = info->planar_config == 2 ? (uint64_t)info->samples_per_pixel : 1;
+  const uint64_t file_px_bytes = px_bytes / planes;
   uint64_t n_chunks;
   if (tiled) {
     if (!tile_pos[0]) return "missing TileOffsets";
@@ -298,7 +300,7 @@ inline const char* tiff_probe(const void* file, size_t file_bytes, lars_tiff_inf
       return "missing or implausible TileWidth / TileLength";
     info->tiles_across = (info->width + info->tile_width - 1) / info->tile_width;
     info->tiles_down = (info->height + info->tile_length - 1) / info->tile_length;
-    n_chunks = (uint64_t)info->tiles_across * (uint64_t)info->tiles_down;
+    n_chunks = (uint64_t)info->tiles_across * (uint64_t)info->tiles_down * planes;
     info->rows_per_strip = info->tile_length;
     info->strip_offsets_pos = tile_pos[0]; info->strip_offsets_type = tile_type[0];
     info->strip_counts_pos = tile_pos[1]; info->strip_counts_type = tile_type[1];
@@ -308,7 +310,7 @@ inline const char* tiff_probe(const void* file, size_t file_bytes, lars_tiff_inf
   } else {
     if (!strip_pos[0]) return "missing StripOffsets";
     if (info->rows_per_strip < 1 || info->rows_per_strip > info->height) info->rows_per_strip = info->height;
-    n_chunks = (uint64_t)((info->height + info->rows_per_strip - 1) / info->rows_per_strip);
+    n_chunks = (uint64_t)((info->height + info->rows_per_strip - 1) / info->rows_per_strip) * planes;
     info->strip_offsets_pos = strip_pos[0]; info->strip_offsets_type = strip_type[0];
     info->strip_counts_pos = strip_pos[1]; info->strip_counts_type = strip_type[1];
     if (strip_cnt[0] != n_chunks) return "StripOffsets count does not match the image height";
@@ -322,10 +324,12 @@ inline const char* tiff_probe(const void* file, size_t file_bytes, lars_tiff_inf
   if (info->strip_counts_pos && !index_type_ok(info->strip_counts_type)) return "strip / tile byte counts must be SHORT, LONG or LONG8";
 
   // every chunk must lie inside the file; uncompressed ones must hold their rows
-  const uint64_t chunk_row_bytes = (uint64_t)(tiled ? info->tile_width : info->width) * px_bytes;
+  const uint64_t chunk_row_bytes = (uint64_t)(tiled ? info->tile_width : info->width) * file_px_bytes;
+  const uint64_t per_plane = n_chunks / planes;
   for (uint64_t s = 0; s < n_chunks; ++s) {
     const uint64_t off = tiff_value(c, info->strip_offsets_pos, info->strip_offsets_type, s);
-    const uint64_t cy = tiled ? s / (uint64_t)info->tiles_across : s;
+    const uint64_t in_plane = s % per_plane;
+    const uint64_t cy = tiled ? in_plane / (uint64_t)info->tiles_across : in_plane;
     const uint64_t left = (uint64_t)info->height - cy * (uint64_t)info->rows_per_strip;
     const uint64_t rows = tiled ? (uint64_t)info->tile_length : (left < (uint64_t)info->rows_per_strip ? left : (uint64_t)info->rows_per_strip);
     const uint64_t need = chunk_row_bytes * rows;
@@ -370,15 +374,19 @@ inline const char* tiff_read_region(const void* file, size_t file_bytes, const l
   if (row0 < 0 || col0 < 0 || row1 > info->height || col1 > info->width || row0 >= row1 || col0 >= col1)
     return "region outside the image";
   const int spp = info->samples_per_pixel, sb = info->bits_per_sample / 8;
-  const uint64_t px_bytes = (uint64_t)spp * sb;
+  const uint64_t px_bytes = (uint64_t)spp * sb;                 // of the destination (always interleaved)
+  const int planes = info->planar_config == 2 ? spp : 1;
+  const int file_spp = spp / planes;                            // samples per pixel inside one chunk
+  const uint64_t file_px_bytes = (uint64_t)file_spp * sb;
   const uint64_t out_row_bytes = (uint64_t)(col1 - col0) * px_bytes;
   if ((uint64_t)dst_bytes < out_row_bytes * (uint64_t)(row1 - row0)) return "destination buffer smaller than the region";
   const bool tiled = info->tile_width > 0;
   const int64_t chunk_w = tiled ? info->tile_width : info->width, chunk_h = info->rows_per_strip;
   const int64_t across = tiled ? info->tiles_across : 1;
-  const uint64_t chunk_row_bytes = (uint64_t)chunk_w * px_bytes;
+  const int64_t per_plane = info->n_strips / planes;
+  const uint64_t chunk_row_bytes = (uint64_t)chunk_w * file_px_bytes;
   const int64_t cy0 = row0 / chunk_h, cy1 = (row1 - 1) / chunk_h, cx0 = col0 / chunk_w, cx1 = (col1 - 1) / chunk_w;
-  const int64_t n_cx = cx1 - cx0 + 1, n_work = (cy1 - cy0 + 1) * n_cx;
+  const int64_t n_cx = cx1 - cx0 + 1, n_grid = (cy1 - cy0 + 1) * n_cx, n_work = n_grid * planes;
   const bool compressed = tiff_compressed(info->compression);
   const bool direct = !compressed && info->predictor == 1;     // no scratch: copy out of the file
   const bool file_swap = sb == 2 && info->big_endian;
@@ -393,8 +401,9 @@ inline const char* tiff_read_region(const void* file, size_t file_bytes, const l
     for (;;) {
       const int64_t k = next.fetch_add(1);
       if (k >= n_work || error.load() != nullptr) break;
-      const int64_t cy = cy0 + k / n_cx, cx = cx0 + k % n_cx;
-      const uint64_t idx = (uint64_t)(cy * across + cx);
+      const int64_t plane = k / n_grid, kg = k % n_grid;
+      const int64_t cy = cy0 + kg / n_cx, cx = cx0 + kg % n_cx;
+      const uint64_t idx = (uint64_t)(plane * per_plane + cy * across + cx);
       if (idx >= (uint64_t)info->n_strips) { error = "corrupt info block"; break; }
       const int64_t valid_rows = (info->height - cy * chunk_h < chunk_h) ? info->height - cy * chunk_h : chunk_h;
       const uint64_t need = chunk_row_bytes * (uint64_t)valid_rows;                       // bytes the image uses
@@ -429,7 +438,7 @@ inline const char* tiff_read_region(const void* file, size_t file_bytes, const l
         if (produced < need) { error = "a compressed strip / tile is corrupt or shorter than its rows"; break; }
         if (swap) { swap16_inplace(scratch, need); swap = false; }
         if (info->predictor == 2)
-          for (int64_t r = 0; r < valid_rows; ++r) undo_predictor_row(scratch + (uint64_t)r * chunk_row_bytes, (uint64_t)chunk_w, spp, sb);
+          for (int64_t r = 0; r < valid_rows; ++r) undo_predictor_row(scratch + (uint64_t)r * chunk_row_bytes, (uint64_t)chunk_w, file_spp, sb);
         base = scratch;
       }
       // the part of this chunk that lies inside the region
@@ -438,10 +447,23 @@ inline const char* tiff_read_region(const void* file, size_t file_bytes, const l
       const int64_t c_lo = col0 > cx * chunk_w ? col0 : cx * chunk_w;
       int64_t c_hi = (cx + 1) * chunk_w < info->width ? (cx + 1) * chunk_w : info->width;
       if (col1 < c_hi) c_hi = col1;
-      const uint64_t run = (uint64_t)(c_hi - c_lo) * px_bytes;
-      const uint8_t* src = base + (uint64_t)(r_lo - cy * chunk_h) * chunk_row_bytes + (uint64_t)(c_lo - cx * chunk_w) * px_bytes;
+      const uint64_t run = (uint64_t)(c_hi - c_lo) * file_px_bytes;
+      const uint8_t* src = base + (uint64_t)(r_lo - cy * chunk_h) * chunk_row_bytes + (uint64_t)(c_lo - cx * chunk_w) * file_px_bytes;
       uint8_t* o = out + (uint64_t)(r_lo - row0) * out_row_bytes + (uint64_t)(c_lo - col0) * px_bytes;
-      if (run == chunk_row_bytes && run == out_row_bytes) {      // full-width rows on both sides: one run
+      if (planes > 1) {                                          // one sample of every pixel: interleave on the way out
+        o += (uint64_t)plane * sb;
+        for (int64_t r = r_lo; r < r_hi; ++r, src += chunk_row_bytes, o += out_row_bytes) {
+          const int64_t n_px = c_hi - c_lo;
+          if (sb == 1) {
+            for (int64_t x = 0; x < n_px; ++x) o[(uint64_t)x * px_bytes] = src[x];
+          } else {
+            for (int64_t x = 0; x < n_px; ++x) {
+              o[(uint64_t)x * px_bytes] = src[2 * x + (swap ? 1 : 0)];
+              o[(uint64_t)x * px_bytes + 1] = src[2 * x + (swap ? 0 : 1)];
+            }
+          }
+        }
+      } else if (run == chunk_row_bytes && run == out_row_bytes) {   // full-width rows on both sides: one run
         copy_samples(o, src, run * (uint64_t)(r_hi - r_lo), swap);
       } else {
         for (int64_t r = r_lo; r < r_hi; ++r, src += chunk_row_bytes, o += out_row_bytes) copy_samples(o, src, run, swap);

@@ -370,12 +370,13 @@ def _lzw_encode(data: bytes) -> bytes:
 
 def write_tiff(path, array: np.ndarray, big_endian: bool = False, rows_per_strip: Optional[int] = None,
                compression: Optional[str] = None, predictor: bool = False, tile: Optional[Sequence[int]] = None,
-               bigtiff: bool = False) -> None:
+               bigtiff: bool = False, planar: bool = False) -> None:
     """TIFF writer for HxW / HxWx3 / HxWx4 uint8 or uint16 frames (chunky).  Pillow cannot write 16-bit
     RGB; survey frames of BASELINE config 3 and mosaics of config 4 are stored with this.
     ``compression``: None, "deflate", "lzw" or "packbits"; ``predictor``: horizontal differencing in
     front of the compressor; ``tile``: (tile_length, tile_width) for a tiled layout instead of strips;
-    ``bigtiff``: 64-bit offsets (files beyond 4 GB)."""
+    ``bigtiff``: 64-bit offsets (files beyond 4 GB); ``planar``: PlanarConfiguration 2, one run of strips / tiles
+    per sample of the pixel (band-interleaved, as GDAL writes with INTERLEAVE=BAND)."""
     import zlib
     a = np.ascontiguousarray(array)
     if a.dtype not in (np.uint8, np.uint16) or a.ndim not in (2, 3):
@@ -407,21 +408,25 @@ def write_tiff(path, array: np.ndarray, big_endian: bool = False, rows_per_strip
             return _packbits_encode(raw)
         return raw
 
+    planar = bool(planar) and spp > 1
+    layers = [a3[:, :, k:k + 1] for k in range(spp)] if planar else [a3]
+    chunks = []
     if tile is not None:
         tl, tw = int(tile[0]), int(tile[1])
         if tl < 1 or tw < 1:
             raise ValueError("tile sizes must be positive")
-        chunks = []
-        for r in range(0, h, tl):
-            for c in range(0, w, tw):
-                block = np.zeros((tl, tw, spp), a.dtype)
-                part = a3[r:r + tl, c:c + tw]
-                block[:part.shape[0], :part.shape[1]] = part
-                chunks.append(encode(block))
+        for layer in layers:
+            for r in range(0, h, tl):
+                for c in range(0, w, tw):
+                    block = np.zeros((tl, tw, layer.shape[2]), a.dtype)
+                    part = layer[r:r + tl, c:c + tw]
+                    block[:part.shape[0], :part.shape[1]] = part
+                    chunks.append(encode(block))
         rps = tl
     else:
         rps = h if not rows_per_strip else max(1, min(h, int(rows_per_strip)))
-        chunks = [encode(a3[r:r + rps]) for r in range(0, h, rps)]
+        for layer in layers:
+            chunks += [encode(layer[r:r + rps]) for r in range(0, h, rps)]
     sizes = [len(ch) for ch in chunks]
 
     off_fmt, off_type = ("Q", 16) if bigtiff else ("I", 4)
@@ -433,7 +438,7 @@ def write_tiff(path, array: np.ndarray, big_endian: bool = False, rows_per_strip
         nonlocal entries, extra
         entries, extra = [], b""
         tags = [(256, 4, [w]), (257, 4, [h]), (258, 3, [bits] * spp), (259, 3, [comp]),
-                (262, 3, [2 if spp >= 3 else 1]), (277, 3, [spp]), (284, 3, [1])]
+                (262, 3, [2 if spp >= 3 else 1]), (277, 3, [spp]), (284, 3, [2 if planar else 1])]
         if tile is None:
             tags += [(273, off_type, offsets), (278, 4, [rps]), (279, off_type, sizes)]
         else:
@@ -482,7 +487,7 @@ def device_decodable(source: Source) -> bool:
     of at most 1 MB decoded (what libtiff / Pillow / GDAL write by default for LZW)."""
     def probe(buf):
         info = _tiff_probe(buf)
-        if info is None or info.compression != 5 or info.tile_width > 0:
+        if info is None or info.compression != 5 or info.tile_width > 0 or info.planar_config != 1:
             return False
         rows = min(info.rows_per_strip, info.height)
         return rows * info.width * info.samples_per_pixel * (info.bits_per_sample // 8) <= (1 << 20)

@@ -190,6 +190,40 @@ def test_tiff_layout_sweep_codecs_tiles_bigtiff(tmp_path):
         ingest.write_tiff(p, img, compression="zstd")
 
 
+def test_planar_tiff_layouts(tmp_path):
+    """PlanarConfiguration 2 (band-interleaved files, GDAL's INTERLEAVE=BAND): one run of strips / tiles per sample
+    of the pixel, interleaved on the way out -- every codec / predictor / strips / tiles / BigTIFF / byte order, whole
+    frames and regions, compared with the arrays written and with Pillow's decode where Pillow can open the file."""
+    import itertools
+    from lars_image_processing_b200 import ingest
+    rng = np.random.default_rng(61)
+    p = tmp_path / "pl.tif"
+    n = n_pillow = 0
+    for dtype, shape in itertools.product((np.uint8, np.uint16), ((37, 53, 3), (20, 31, 4))):
+        img = _textured(rng, shape, dtype)
+        for codec, pred, tile, big, be in itertools.product((None, "deflate", "lzw", "packbits"), (False, True), (None, (16, 16)),
+                                                            (False, True), (False, True)):
+            if pred and codec not in ("deflate", "lzw"):
+                continue
+            ingest.write_tiff(p, img, big_endian=be, rows_per_strip=None if tile else 7, compression=codec, predictor=pred,
+                              tile=tile, bigtiff=big, planar=True)
+            info = ingest._tiff_probe(p.read_bytes())
+            assert info is not None and info.planar_config == 2 and not ingest.device_decodable(p)
+            got = ingest.read_frame(p, threads=1 + n % 3)
+            assert got.dtype == dtype and np.array_equal(got, img), (dtype, shape, codec, pred, tile, big, be)
+            assert np.array_equal(ingest.read_region(p, (5, 18), (3, 29)), img[5:18, 3:29])
+            n += 1
+            if dtype == np.uint8 and not (big and be):
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    assert np.array_equal(np.array(Image.open(p)), img), ("pillow", shape, codec, pred, tile, big, be)
+                n_pillow += 1
+    assert n == 192 and n_pillow == 72
+    gray = _textured(rng, (30, 40), np.uint16)
+    ingest.write_tiff(p, gray, planar=True)                        # one sample per pixel: stored chunky
+    assert ingest._tiff_probe(p.read_bytes()).planar_config == 1 and np.array_equal(ingest.read_frame(p), gray)
+
+
 def test_region_reads_touch_only_their_chunks(tmp_path):
     """read_region == a NumPy crop of the whole frame for random rectangles, on strips and tiles, every
     codec, both sample widths -- and on a file whose other chunks are destroyed (only the strips / tiles
@@ -653,7 +687,8 @@ def test_tiff_reader_survives_corrupted_files(tmp_path):
             (False, True), (np.uint8, np.uint16), (None, "lzw", "deflate", "packbits"), (None, (16, 16)), (False, True))):
         img = (rng.integers(0, 256, (19, 23, 3)) * (1 if dtype == np.uint8 else 211)).astype(dtype)
         ingest.write_tiff(p, img, big_endian=big, rows_per_strip=None if tile else 5, compression=codec,
-                          predictor=bool(codec in ("lzw", "deflate") and k % 2), tile=tile, bigtiff=bigtiff)
+                          predictor=bool(codec in ("lzw", "deflate") and k % 2), tile=tile, bigtiff=bigtiff,
+                          planar=k % 3 == 0)
         seeds.append(p.read_bytes())
     ok = rejected = read_rejected = 0
     for it in range(1200):
