@@ -261,7 +261,7 @@ int lars_resize_lanczos_u8(const lars_resize_plan* plan, const void* tables_dev,
                            void* temp, size_t temp_bytes, void* stream);
 
 /* ---- ingest ---------------------------------------------------
- * Host-only TIFF 6.0 / BigTIFF reader: 8- or 16-bit unsigned samples, 1 / 3 / 4 samples per pixel, chunky
+ * Host-only TIFF 6.0 / BigTIFF reader: 8- or 16-bit unsigned (or 32-bit float) samples, 1 / 3 / 4 samples per pixel, chunky
  * or planar (band-interleaved, read back interleaved), either byte order; strips or tiles; uncompressed, LZW (5), Deflate (8 / 32946; needs the
  * system zlib at run time) or PackBits (32773), predictor 1 or 2.  Replaces PIL.Image.open +
  * np.array for such files (process-images.py:183-193; backend-process.py:52; process-ndvi.py:18;
@@ -269,7 +269,7 @@ int lars_resize_lanczos_u8(const lars_resize_plan* plan, const void* tables_dev,
  * 8-bit): the strips / tiles of a (memory-mapped) file go straight into the caller's pinned HWC
  * buffer.  lars_tiff_read_region reads only the chunks that touch a rectangle -- the tiles or row
  * bands one rank owns of an orthomosaic (BASELINE config 4) -- with n_threads host threads decoding
- * independent chunks side by side.  Anything else (JPEG-in-TIFF, float, 1-bit, WhiteIsZero, YCbCr)
+ * independent chunks side by side.  Anything else (JPEG-in-TIFF, 1-bit, WhiteIsZero, YCbCr, float predictor)
  * returns LARS_ERR_UNSUPPORTED and the caller decodes with Pillow. */
 typedef struct lars_tiff_info {
   int32_t width, height, samples_per_pixel, bits_per_sample;

@@ -1047,7 +1047,7 @@ int lars_tiff_lzw_chunks(const void* file, size_t file_bytes, const lars_tiff_in
   const char* why = lars_host::tiff_probe(file, file_bytes, &check, &unsupported);
   if (why) return fail(unsupported ? LARS_ERR_UNSUPPORTED : LARS_ERR_INVALID, "lars_tiff_lzw_chunks: %s", why);
   if (memcmp(&check, info, sizeof(check)) != 0) return fail(LARS_ERR_INVALID, "lars_tiff_lzw_chunks: info does not describe this file");
-  if (check.compression != 5 || check.tile_width > 0 || check.planar_config != 1)
+  if (check.compression != 5 || check.tile_width > 0 || check.planar_config != 1 || check.bits_per_sample > 16)
     return fail(LARS_ERR_UNSUPPORTED, "lars_tiff_lzw_chunks: the device decoder takes LZW-compressed chunky strips");
   if (check.n_strips > max_chunks) return fail(LARS_ERR_INVALID, "lars_tiff_lzw_chunks: %d strips, room for %d", check.n_strips, max_chunks);
   lars_host::TiffCursor c{static_cast<const uint8_t*>(file), file_bytes, check.big_endian != 0};

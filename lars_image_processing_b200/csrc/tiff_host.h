@@ -267,11 +267,15 @@ inline const char* tiff_probe(const void* file, size_t file_bytes, lars_tiff_inf
   // PackBits data are taken as they are
   if (info->compression != 5 && info->compression != 8) info->predictor = 1;
   if (info->predictor != 1 && info->predictor != 2) { *unsupported = true; return "only the horizontal-differencing TIFF predictor is supported"; }
-  if (bits_mixed || (info->bits_per_sample != 8 && info->bits_per_sample != 16)) {
+  // unsigned 8- / 16-bit samples (the frames of the path), or 32-bit IEEE floats (calibrated reflectance stacks
+  // and stored index maps: Pillow opens only single-band float files)
+  const bool is_float = info->sample_format == 3;
+  if (bits_mixed || !((info->sample_format == 1 && (info->bits_per_sample == 8 || info->bits_per_sample == 16)) ||
+                      (is_float && info->bits_per_sample == 32))) {
     *unsupported = true;
-    return "only 8- or 16-bit samples are supported";
+    return "only unsigned 8- / 16-bit or 32-bit float samples are supported";
   }
-  if (info->sample_format != 1) { *unsupported = true; return "only unsigned integer samples are supported"; }
+  if (is_float && info->predictor != 1) { *unsupported = true; return "floating-point predictor: decode it with Pillow"; }
   if (info->samples_per_pixel != 1 && info->samples_per_pixel != 3 && info->samples_per_pixel != 4) {
     *unsupported = true;
     return "only 1, 3 or 4 samples per pixel are supported";
@@ -356,12 +360,27 @@ inline void undo_predictor_row(uint8_t* row, uint64_t width_px, int spp, int sam
   }
 }
 
+inline void swap_inplace(uint8_t* p, uint64_t bytes, int sb) {
+  if (sb == 2) {
+    for (uint64_t i = 0; i + 1 < bytes; i += 2) { const uint8_t t = p[i]; p[i] = p[i + 1]; p[i + 1] = t; }
+  } else {
+    for (uint64_t i = 0; i + 3 < bytes; i += 4) {
+      const uint8_t a = p[i], b = p[i + 1];
+      p[i] = p[i + 3]; p[i + 1] = p[i + 2]; p[i + 2] = b; p[i + 3] = a;
+    }
+  }
+}
+
 inline void swap16_inplace(uint8_t* p, uint64_t bytes) {
   for (uint64_t i = 0; i + 1 < bytes; i += 2) { const uint8_t t = p[i]; p[i] = p[i + 1]; p[i + 1] = t; }
 }
 
-inline void copy_samples(uint8_t* dst, const uint8_t* src, uint64_t bytes, bool swap) {
+inline void copy_samples(uint8_t* dst, const uint8_t* src, uint64_t bytes, bool swap, int sb = 2) {
   if (!swap) { memcpy(dst, src, bytes); return; }
+  if (sb == 4) {
+    for (uint64_t i = 0; i + 3 < bytes; i += 4) { dst[i] = src[i + 3]; dst[i + 1] = src[i + 2]; dst[i + 2] = src[i + 1]; dst[i + 3] = src[i]; }
+    return;
+  }
   for (uint64_t i = 0; i + 1 < bytes; i += 2) { dst[i] = src[i + 1]; dst[i + 1] = src[i]; }
 }
 
@@ -389,7 +408,7 @@ inline const char* tiff_read_region(const void* file, size_t file_bytes, const l
   const int64_t n_cx = cx1 - cx0 + 1, n_grid = (cy1 - cy0 + 1) * n_cx, n_work = n_grid * planes;
   const bool compressed = tiff_compressed(info->compression);
   const bool direct = !compressed && info->predictor == 1;     // no scratch: copy out of the file
-  const bool file_swap = sb == 2 && info->big_endian;
+  const bool file_swap = sb > 1 && info->big_endian;
   TiffCursor c{static_cast<const uint8_t*>(file), file_bytes, info->big_endian != 0};
   uint8_t* out = static_cast<uint8_t*>(dst);
   std::atomic<int64_t> next{0};
@@ -436,7 +455,7 @@ inline const char* tiff_read_region(const void* file, size_t file_bytes, const l
           }
         }
         if (produced < need) { error = "a compressed strip / tile is corrupt or shorter than its rows"; break; }
-        if (swap) { swap16_inplace(scratch, need); swap = false; }
+        if (swap) { swap_inplace(scratch, need, sb); swap = false; }
         if (info->predictor == 2)
           for (int64_t r = 0; r < valid_rows; ++r) undo_predictor_row(scratch + (uint64_t)r * chunk_row_bytes, (uint64_t)chunk_w, file_spp, sb);
         base = scratch;
@@ -456,6 +475,9 @@ inline const char* tiff_read_region(const void* file, size_t file_bytes, const l
           const int64_t n_px = c_hi - c_lo;
           if (sb == 1) {
             for (int64_t x = 0; x < n_px; ++x) o[(uint64_t)x * px_bytes] = src[x];
+          } else if (sb == 4) {
+            for (int64_t x = 0; x < n_px; ++x)
+              for (int b = 0; b < 4; ++b) o[(uint64_t)x * px_bytes + b] = src[4 * x + (swap ? 3 - b : b)];
           } else {
             for (int64_t x = 0; x < n_px; ++x) {
               o[(uint64_t)x * px_bytes] = src[2 * x + (swap ? 1 : 0)];
@@ -464,9 +486,9 @@ inline const char* tiff_read_region(const void* file, size_t file_bytes, const l
           }
         }
       } else if (run == chunk_row_bytes && run == out_row_bytes) {   // full-width rows on both sides: one run
-        copy_samples(o, src, run * (uint64_t)(r_hi - r_lo), swap);
+        copy_samples(o, src, run * (uint64_t)(r_hi - r_lo), swap, sb);
       } else {
-        for (int64_t r = r_lo; r < r_hi; ++r, src += chunk_row_bytes, o += out_row_bytes) copy_samples(o, src, run, swap);
+        for (int64_t r = r_lo; r < r_hi; ++r, src += chunk_row_bytes, o += out_row_bytes) copy_samples(o, src, run, swap, sb);
       }
     }
     free(scratch);

@@ -89,6 +89,10 @@ def _png_shape(info) -> tuple:
     return (info.height, info.width) if info.channels == 1 else (info.height, info.width, info.channels)
 
 
+def _tiff_dtype(info) -> np.dtype:
+    return np.dtype({8: np.uint8, 16: np.uint16, 32: np.float32}[info.bits_per_sample])
+
+
 def _tiff_shape(info) -> tuple:
     spp = info.samples_per_pixel
     return (info.height, info.width) if spp == 1 else (info.height, info.width, spp)
@@ -133,7 +137,7 @@ def _tiff_read_into(buf, info, region, dst: np.ndarray, threads: Optional[int]) 
 def _decode_buffer(buf, out: Optional[np.ndarray], threads: Optional[int] = None) -> np.ndarray:
     info = _tiff_probe(buf)
     if info is not None:
-        dtype = np.uint8 if info.bits_per_sample == 8 else np.uint16
+        dtype = _tiff_dtype(info)
         shape = _tiff_shape(info)
         dst = out if out is not None else np.empty(shape, dtype)
         if dst.dtype != dtype or dst.size != int(np.prod(shape)) or not dst.flags.c_contiguous:
@@ -207,7 +211,7 @@ def _region_of_buffer(buf, rows, cols, out, threads) -> np.ndarray:
     if info is None:
         whole = _decode_buffer(buf, None)
         return _crop_into(whole, _check_region(whole.shape, rows, cols), out)
-    dtype = np.uint8 if info.bits_per_sample == 8 else np.uint16
+    dtype = _tiff_dtype(info)
     full = _tiff_shape(info)
     r0, r1, c0, c1 = _check_region(full, rows, cols)
     shape = (r1 - r0, c1 - c0) + tuple(full[2:])
@@ -291,7 +295,7 @@ def frame_info(source: Source) -> tuple:
             return frame_info(memoryview(mm)) if (_is_tiff(mm) or bytes(mm[:8]) == PNG_SIGNATURE) else _info_via_pillow(bytes(mm))
     info = _tiff_probe(source)
     if info is not None:
-        return _tiff_shape(info), np.dtype(np.uint8 if info.bits_per_sample == 8 else np.uint16)
+        return _tiff_shape(info), _tiff_dtype(info)
     png = _png_probe(source)
     if png is not None:
         return _png_shape(png), np.dtype(np.uint8 if png.bit_depth == 8 else np.uint16)
@@ -371,7 +375,7 @@ def _lzw_encode(data: bytes) -> bytes:
 def write_tiff(path, array: np.ndarray, big_endian: bool = False, rows_per_strip: Optional[int] = None,
                compression: Optional[str] = None, predictor: bool = False, tile: Optional[Sequence[int]] = None,
                bigtiff: bool = False, planar: bool = False) -> None:
-    """TIFF writer for HxW / HxWx3 / HxWx4 uint8 or uint16 frames (chunky).  Pillow cannot write 16-bit
+    """TIFF writer for HxW / HxWx3 / HxWx4 uint8 / uint16 frames and float32 maps or reflectance stacks.  Pillow cannot write 16-bit
     RGB; survey frames of BASELINE config 3 and mosaics of config 4 are stored with this.
     ``compression``: None, "deflate", "lzw" or "packbits"; ``predictor``: horizontal differencing in
     front of the compressor; ``tile``: (tile_length, tile_width) for a tiled layout instead of strips;
@@ -379,8 +383,10 @@ def write_tiff(path, array: np.ndarray, big_endian: bool = False, rows_per_strip
     per sample of the pixel (band-interleaved, as GDAL writes with INTERLEAVE=BAND)."""
     import zlib
     a = np.ascontiguousarray(array)
-    if a.dtype not in (np.uint8, np.uint16) or a.ndim not in (2, 3):
-        raise ValueError("write_tiff needs a uint8 / uint16 HxW or HxWxC array")
+    if a.dtype not in (np.uint8, np.uint16, np.float32) or a.ndim not in (2, 3):
+        raise ValueError("write_tiff needs a uint8 / uint16 / float32 HxW or HxWxC array")
+    if a.dtype == np.float32 and predictor:
+        raise ValueError("the differencing predictor is for integer samples")
     if compression not in TIFF_COMPRESSION:
         raise ValueError(f"compression must be one of {sorted(k for k in TIFF_COMPRESSION if k)} or None")
     comp = TIFF_COMPRESSION[compression]
@@ -445,6 +451,8 @@ def write_tiff(path, array: np.ndarray, big_endian: bool = False, rows_per_strip
             tags += [(322, 4, [tw]), (323, 4, [tl]), (324, off_type, offsets), (325, off_type, sizes)]
         if predictor:
             tags.append((317, 3, [2]))
+        if a.dtype == np.float32:
+            tags.append((339, 3, [3] * spp))                       # SampleFormat: IEEE floating point
         if spp == 4:
             tags.append((338, 3, [2]))
         tags.sort()
@@ -487,7 +495,7 @@ def device_decodable(source: Source) -> bool:
     of at most 1 MB decoded (what libtiff / Pillow / GDAL write by default for LZW)."""
     def probe(buf):
         info = _tiff_probe(buf)
-        if info is None or info.compression != 5 or info.tile_width > 0 or info.planar_config != 1:
+        if info is None or info.compression != 5 or info.tile_width > 0 or info.planar_config != 1 or info.bits_per_sample > 16:
             return False
         rows = min(info.rows_per_strip, info.height)
         return rows * info.width * info.samples_per_pixel * (info.bits_per_sample // 8) <= (1 << 20)
