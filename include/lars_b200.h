@@ -309,6 +309,13 @@ int lars_tiff_lzw_chunks(const void* file, size_t file_bytes, const lars_tiff_in
                          int32_t max_chunks);
 int lars_lzw_decode_device(const uint8_t* src, const lars_lzw_chunk* chunks, int32_t n_chunks, uint8_t* dst,
                            uint32_t* counters, void* stream);
+/* EXPERIMENTAL (pinned against zlib on the CPU, not yet run on hardware): the same for Deflate-compressed strips --
+ * lars_tiff_deflate_chunks fills the table, lars_inflate_decode_device runs one warp per zlib stream.  The Adler-32
+ * trailers are not verified on the device. */
+int lars_tiff_deflate_chunks(const void* file, size_t file_bytes, const lars_tiff_info* info, lars_lzw_chunk* chunks,
+                             int32_t max_chunks);
+int lars_inflate_decode_device(const uint8_t* src, const lars_lzw_chunk* chunks, int32_t n_chunks, uint8_t* dst,
+                               uint32_t* counters, void* stream);
 int lars_tiff_post_device(uint8_t* dst, int32_t n_frames, int64_t frame_stride, int32_t rows, int32_t width,
                           int32_t samples_per_pixel, int32_t sample_bytes, int32_t predictor, int32_t swap16,
                           void* stream);

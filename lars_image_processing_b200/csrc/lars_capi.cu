@@ -47,6 +47,7 @@ constexpr int kMaxDevices = 64;
 struct DeviceState {
   bool ready = false;
   bool lzw_v2 = false;        // the opt-in LZW kernel got its shared memory
+  bool inflate = false;       // the experimental Deflate kernel got its shared memory
   int sm_count = 0;
   uint32_t* cmaps = nullptr;  // [3][256] packed RGB, device
 };
@@ -70,7 +71,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 extern "C" {
 
 const char* lars_last_error(void) { return g_err; }
-int lars_abi_version(void) { return 5; }   // 3: + resize, TIFF ingest; 4: lars_tiff_info grew (tiles, predictor, BigTIFF), lars_tiff_read_region; 5: PNG reader, device-side LZW
+int lars_abi_version(void) { return 6; }   // 3: + resize, TIFF ingest; 4: lars_tiff_info grew (tiles, predictor, BigTIFF), lars_tiff_read_region; 5: PNG reader, device-side LZW; 6: experimental device-side Deflate
 
 int lars_init(int device) {
   std::lock_guard<std::mutex> lock(g_mu);
@@ -116,6 +117,9 @@ int lars_init(int device) {
   st.lzw_v2 = cudaFuncSetAttribute(lars::lzw_decode_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    lars::LZW2_SMEM_BYTES) == cudaSuccess;
   if (!st.lzw_v2) cudaGetLastError();
+  st.inflate = cudaFuncSetAttribute(lars::inflate_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    lars::INF_SMEM_BYTES) == cudaSuccess;
+  if (!st.inflate) cudaGetLastError();
 
   // colormap tables: 3 x 256 packed R | G << 8 | B << 16
   static uint32_t packed[3 * 256];
@@ -1039,16 +1043,17 @@ int lars_png_read(const void* file, size_t file_bytes, const lars_png_info* info
   return LARS_OK;
 }
 
-int lars_tiff_lzw_chunks(const void* file, size_t file_bytes, const lars_tiff_info* info, lars_lzw_chunk* chunks,
-                         int32_t max_chunks) {
+static int tiff_device_chunks(const void* file, size_t file_bytes, const lars_tiff_info* info, lars_lzw_chunk* chunks,
+                              int32_t max_chunks, int compression) {
   if (!file || !info || !chunks) return fail(LARS_ERR_INVALID, "lars_tiff_lzw_chunks: NULL pointer");
   lars_tiff_info check;
   bool unsupported = false;
   const char* why = lars_host::tiff_probe(file, file_bytes, &check, &unsupported);
   if (why) return fail(unsupported ? LARS_ERR_UNSUPPORTED : LARS_ERR_INVALID, "lars_tiff_lzw_chunks: %s", why);
   if (memcmp(&check, info, sizeof(check)) != 0) return fail(LARS_ERR_INVALID, "lars_tiff_lzw_chunks: info does not describe this file");
-  if (check.compression != 5 || check.tile_width > 0 || check.planar_config != 1 || check.bits_per_sample > 16)
-    return fail(LARS_ERR_UNSUPPORTED, "lars_tiff_lzw_chunks: the device decoder takes LZW-compressed chunky strips");
+  if (check.compression != compression || check.tile_width > 0 || check.planar_config != 1 || check.bits_per_sample > 16)
+    return fail(LARS_ERR_UNSUPPORTED, "lars_tiff_lzw_chunks: the device decoder takes %s-compressed chunky strips",
+                compression == 5 ? "LZW" : "Deflate");
   if (check.n_strips > max_chunks) return fail(LARS_ERR_INVALID, "lars_tiff_lzw_chunks: %d strips, room for %d", check.n_strips, max_chunks);
   lars_host::TiffCursor c{static_cast<const uint8_t*>(file), file_bytes, check.big_endian != 0};
   const uint64_t row_bytes = (uint64_t)check.width * check.samples_per_pixel * (check.bits_per_sample / 8);
@@ -1066,6 +1071,34 @@ int lars_tiff_lzw_chunks(const void* file, size_t file_bytes, const lars_tiff_in
     chunks[s].dst_bytes = (uint32_t)need;
   }
   return check.n_strips;
+}
+
+int lars_tiff_lzw_chunks(const void* file, size_t file_bytes, const lars_tiff_info* info, lars_lzw_chunk* chunks,
+                         int32_t max_chunks) {
+  return tiff_device_chunks(file, file_bytes, info, chunks, max_chunks, 5);
+}
+
+int lars_tiff_deflate_chunks(const void* file, size_t file_bytes, const lars_tiff_info* info, lars_lzw_chunk* chunks,
+                             int32_t max_chunks) {
+  return tiff_device_chunks(file, file_bytes, info, chunks, max_chunks, 8);
+}
+
+int lars_inflate_decode_device(const uint8_t* src, const lars_lzw_chunk* chunks, int32_t n_chunks, uint8_t* dst,
+                               uint32_t* counters, void* stream) {
+  DeviceState* st = nullptr;
+  int rc = current_state(&st);
+  if (rc != LARS_OK) return rc;
+  if (!src || !chunks || !dst || !counters) return fail(LARS_ERR_INVALID, "lars_inflate_decode_device: NULL pointer");
+  if (n_chunks < 1) return fail(LARS_ERR_INVALID, "lars_inflate_decode_device: n_chunks=%d", n_chunks);
+  if (reinterpret_cast<uintptr_t>(chunks) & 7u) return fail(LARS_ERR_INVALID, "lars_inflate_decode_device: chunks must be 8-byte aligned");
+  if (!st->inflate) return fail(LARS_ERR_UNSUPPORTED, "lars_inflate_decode_device: the kernel's shared memory was refused on this device");
+  lars::LzwParams p;
+  p.src = src; p.chunks = chunks; p.dst = dst; p.status = counters; p.next = counters + 1; p.n_chunks = n_chunks;
+  const int want = (n_chunks + lars::INF_WARPS - 1) / lars::INF_WARPS;
+  lars::inflate_decode_kernel<<<want < st->sm_count ? want : st->sm_count, lars::INF_WARPS * 32, lars::INF_SMEM_BYTES,
+                                static_cast<cudaStream_t>(stream)>>>(p);
+  LARS_CUDA(cudaGetLastError());
+  return LARS_OK;
 }
 
 int lars_lzw_decode_device(const uint8_t* src, const lars_lzw_chunk* chunks, int32_t n_chunks, uint8_t* dst,

@@ -11,6 +11,7 @@
 
 #include "../../include/lars_b200.h"
 #include "lzw_warp.h"
+#include "inflate_warp.h"
 
 namespace lars {
 
@@ -44,9 +45,9 @@ __global__ void __launch_bounds__(LZW_WARPS * 32) lzw_decode_kernel(const LzwPar
 }
 
 // Variant 2 (opt-in through LARS_LZW_VARIANT=2, see lzw_warp.h): per warp a table, a 16 KB output ring and a
-// 512-byte ring of the compressed stream.
+// 1 KB ring of the compressed stream.
 constexpr int LZW2_WARPS = 6;                                              // per CTA, one CTA per SM
-constexpr int LZW2_WARP_SMEM = 4096 * 4 + (int)LARS_LZW_RING + (int)LARS_LZW_INBUF_WORDS * 4;   // 33,280 B
+constexpr int LZW2_WARP_SMEM = 4096 * 4 + (int)LARS_LZW_RING + (int)LARS_LZW_INBUF_WORDS * 4;   // 33,792 B
 constexpr int LZW2_SMEM_BYTES = LZW2_WARPS * LZW2_WARP_SMEM;               // 195 KB
 
 __global__ void __launch_bounds__(LZW2_WARPS * 32, 1) lzw_decode_v2_kernel(const LzwParams p) {
@@ -63,6 +64,26 @@ __global__ void __launch_bounds__(LZW2_WARPS * 32, 1) lzw_decode_v2_kernel(const
     const lars_lzw_chunk c = p.chunks[k];
     const uint32_t produced = lars_lzw_decode_warp_v2(p.src + c.src_offset, c.src_bytes, p.dst + c.dst_offset,
                                                       c.dst_bytes, table, ring, inbuf);
+    if (lane == 0 && produced < c.dst_bytes) atomicAdd(p.status, 1u);
+    __syncwarp();
+  }
+}
+
+// Experimental (see inflate_warp.h; not yet run on hardware): one warp per zlib stream, 5 warps per CTA, one CTA per SM.
+constexpr int INF_WARPS = 5;
+constexpr int INF_SMEM_BYTES = INF_WARPS * (int)sizeof(LarsInflateSmem);     // 190 KB
+
+__global__ void __launch_bounds__(INF_WARPS * 32, 1) inflate_decode_kernel(const LzwParams p) {
+  extern __shared__ __align__(16) uint32_t lzw_tables[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  LarsInflateSmem* sm = reinterpret_cast<LarsInflateSmem*>(lzw_tables) + warp;
+  for (;;) {
+    unsigned int k = 0;
+    if (lane == 0) k = atomicAdd(p.next, 1u);
+    k = __shfl_sync(0xffffffffu, k, 0);
+    if (k >= (unsigned int)p.n_chunks) break;
+    const lars_lzw_chunk c = p.chunks[k];
+    const uint32_t produced = lars_inflate_warp(p.src + c.src_offset, c.src_bytes, p.dst + c.dst_offset, c.dst_bytes, sm);
     if (lane == 0 && produced < c.dst_bytes) atomicAdd(p.status, 1u);
     __syncwarp();
   }

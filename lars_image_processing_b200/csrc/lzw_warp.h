@@ -93,14 +93,14 @@ LARS_LZW_FN uint32_t lars_lzw_decode_warp(const uint8_t* in, uint32_t n_in, uint
 // of the SM's array): byte loads of the compressed stream and 1-3 byte stores of the output.  This variant
 // (written after that measurement, NOT yet timed on hardware) removes both:
 //   * input: the warp fetches the compressed stream 128 bytes at a time -- every lane one aligned 32-bit word,
-//     the next segment already in flight in a register while the current one is consumed -- into a 512-byte
+//     the next segment already in flight in a register while the current one is consumed -- into a 1 KB
 //     shared ring; the bit buffer refills from there four bytes at a time.  `in - (in & 3)` up to the next
 //     multiple of 4 after the stream must be readable (file starts are 8-byte aligned and padded).
 //   * output: strings are assembled in a 16 KB shared ring that is also the source of every copy no further
 //     back than LARS_LZW_RING - 4096 bytes; completed 128-byte stretches leave for global memory as aligned
 //     32-bit stores, 32 lanes side by side.
 #define LARS_LZW_RING 16384u
-#define LARS_LZW_INBUF_WORDS 128u   /* 512-byte ring of the compressed stream */
+#define LARS_LZW_INBUF_WORDS 256u   /* 1 KB ring of the compressed stream */
 
 LARS_LZW_FN uint32_t lars_lzw_bswap32(uint32_t w) {
   return (w >> 24) | ((w >> 8) & 0xFF00u) | ((w << 8) & 0xFF0000u) | (w << 24);
@@ -206,6 +206,7 @@ LARS_LZW_FN uint32_t lars_lzw_decode_warp_v2(const uint8_t* in, uint32_t n_in, u
           ring[(op + i) & (LARS_LZW_RING - 1u)] = near ? ring[from & (LARS_LZW_RING - 1u)] : out[from];
         }
       }
+      LARS_LZW_SYNC();                                     // nobody still reads the ring when a lane that runs ahead writes on
       op += keep;
     } else {
       return 0;

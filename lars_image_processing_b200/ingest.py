@@ -490,6 +490,11 @@ def write_tiff(path, array: np.ndarray, big_endian: bool = False, rows_per_strip
 # ------------------------------------------------------------------------------------------
 # device-side decode of LZW TIFF frames
 # ------------------------------------------------------------------------------------------
+# Device-side Deflate (inflate_warp.h) is pinned against zlib on the CPU but has not run on hardware yet: it only
+# takes part when this is set, and device_decodable() keeps answering for the LZW path alone.
+EXPERIMENTAL_DEVICE_INFLATE = os.environ.get("LARS_EXPERIMENTAL_DEVICE_INFLATE") == "1"
+
+
 def device_decodable(source: Source) -> bool:
     """True if :func:`decode_tiff_batch_on_device` takes this file: an LZW-compressed TIFF stored in strips
     of at most 1 MB decoded (what libtiff / Pillow / GDAL write by default for LZW)."""
@@ -541,14 +546,18 @@ def decode_tiff_batch_on_device(sources: Sequence[Source], engine: Optional[Engi
             info = _lib.TiffInfo()
             check(lib.lars_tiff_probe(raw.ctypes.data, raw.size, C.byref(info)), "lars_tiff_probe")
             chunks = np.zeros(info.n_strips, _lib.LZW_CHUNK_DTYPE)
-            check(lib.lars_tiff_lzw_chunks(raw.ctypes.data, raw.size, C.byref(info), chunks.ctypes.data, chunks.size),
-                  "lars_tiff_lzw_chunks")
+            if info.compression == 8 and EXPERIMENTAL_DEVICE_INFLATE:
+                check(lib.lars_tiff_deflate_chunks(raw.ctypes.data, raw.size, C.byref(info), chunks.ctypes.data, chunks.size),
+                      "lars_tiff_deflate_chunks")
+            else:
+                check(lib.lars_tiff_lzw_chunks(raw.ctypes.data, raw.size, C.byref(info), chunks.ctypes.data, chunks.size),
+                      "lars_tiff_lzw_chunks")
             infos.append(info)
             tables.append(chunks)
         first = infos[0]
-        key = lambda i: (i.height, i.width, i.samples_per_pixel, i.bits_per_sample, i.predictor, i.big_endian)
+        key = lambda i: (i.height, i.width, i.samples_per_pixel, i.bits_per_sample, i.predictor, i.big_endian, i.compression)
         if any(key(i) != key(first) for i in infos):
-            raise ValueError("all frames of a batch must share shape, sample width, predictor and byte order")
+            raise ValueError("all frames of a batch must share shape, sample width, codec, predictor and byte order")
         sb = first.bits_per_sample // 8
         frames = eng.alloc_frames(len(views), first.height, first.width, first.samples_per_pixel, s, sample_bytes=sb)
         # one staging buffer: the files back to back (8-byte aligned), then the strip table of the whole batch
@@ -590,8 +599,9 @@ def decode_tiff_batch_on_device(sources: Sequence[Source], engine: Optional[Engi
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if timings is not None else None
         if ev:
             ev[0].record(s)
-        check(lib.lars_lzw_decode_device(dev.data_ptr(), dev.data_ptr() + table_at, n_chunks, frames.data.data_ptr(),
-                                         counters.data_ptr(), s.cuda_stream), "lars_lzw_decode_device")
+        decode = lib.lars_inflate_decode_device if first.compression == 8 else lib.lars_lzw_decode_device
+        check(decode(dev.data_ptr(), dev.data_ptr() + table_at, n_chunks, frames.data.data_ptr(),
+                     counters.data_ptr(), s.cuda_stream), "lars_lzw_decode_device")
         check(lib.lars_tiff_post_device(frames.data.data_ptr(), frames.n_frames, frames.stride_bytes, first.height,
                                         first.width, first.samples_per_pixel, sb, first.predictor,
                                         1 if (first.big_endian and sb == 2) else 0, s.cuda_stream),
@@ -604,7 +614,7 @@ def decode_tiff_batch_on_device(sources: Sequence[Source], engine: Optional[Engi
         timings["h2d_bytes"] = total
         timings["strips"] = n_chunks
     if bad:
-        raise LarsError(f"{bad} LZW strip(s) of the batch are corrupt or shorter than their rows")
+        raise LarsError(f"{bad} compressed strip(s) of the batch are corrupt or shorter than their rows")
     return frames
 
 

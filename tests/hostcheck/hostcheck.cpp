@@ -7,6 +7,7 @@
 
 #include "../../lars_image_processing_b200/csrc/pixel_math.h"
 #include "../../lars_image_processing_b200/csrc/lzw_warp.h"
+#include "../../lars_image_processing_b200/csrc/inflate_warp.h"
 #include "../../lars_image_processing_b200/csrc/tiff_host.h"
 
 extern "C" {
@@ -81,6 +82,15 @@ uint32_t hc_lzw_decode_warp_v2(const uint8_t* in, uint32_t n_in, uint8_t* out, u
   uint8_t* base = reinterpret_cast<uint8_t*>(padded.data()) + 4 + (skew & 3u);
   memcpy(base, in, n_in);
   return lars_lzw_decode_warp_v2(base, n_in, out, cap, table, ring, inbuf);
+}
+// The warp inflate of inflate_warp.h, lanes run one after the other; the stream sits at byte offset `skew` of an
+// aligned, padded buffer as on the device.
+uint32_t hc_inflate_warp(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t cap, uint32_t skew) {
+  static thread_local LarsInflateSmem sm;
+  std::vector<uint32_t> padded((n_in + 16) / 4 + 2, 0xA5A5A5A5u);
+  uint8_t* base = reinterpret_cast<uint8_t*>(padded.data()) + 4 + (skew & 3u);
+  memcpy(base, in, n_in);
+  return lars_inflate_warp(base, n_in, out, cap, &sm);
 }
 uint32_t hc_lzw_decode_warp(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t cap) {
   static thread_local uint32_t table[4096];

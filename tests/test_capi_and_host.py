@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in include/lars_b200.h but not exported"
     assert set(_lib.EXPORTED_SYMBOLS) == set(declared)
-    assert lib.lars_abi_version() == 5
+    assert lib.lars_abi_version() == 6
 
 
 def test_struct_layouts_match_header(tmp_path):

@@ -885,3 +885,97 @@ def test_device_decode_plan_on_the_cpu(hostcheck, tmp_path):
     big = np.zeros((600, 700, 3), np.uint8)
     ingest.write_tiff(p, big, compression="lzw")                   # one strip of 1.26 MB
     assert plan(np.fromfile(p, np.uint8))[2] == -3 and not ingest.device_decodable(p)
+
+
+def test_warp_inflate_equals_zlib(hostcheck):
+    """inflate_warp.h (experimental device-side Deflate, one warp per stream) compiled for the host with its 32
+    lanes run in sequence, against zlib: every compression level and strategy (stored, fixed and dynamic blocks,
+    Huffman-only, RLE), textures from noise to constants (matches at every distance up to the 32 KB window, overlapping
+    matches, codes longer than the 10-bit fast tables), every stream / destination alignment, capacities that cut
+    the output; and 3,000 corrupted or truncated streams must be rejected or decode without touching memory past
+    the capacity."""
+    import ctypes as C
+    import zlib
+    hostcheck.hc_inflate_warp.restype = C.c_uint32
+    hostcheck.hc_inflate_warp.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]
+    rng = np.random.default_rng(81)
+
+    def run(blob, cap, skew, dskew):
+        src = np.frombuffer(blob, np.uint8)
+        out = np.full(cap + 72, 0xAA, np.uint8)
+        n = hostcheck.hc_inflate_warp(src.ctypes.data, src.size, out.ctypes.data + dskew, cap, skew)
+        assert (out[:dskew] == 0xAA).all() and (out[dskew + cap:] == 0xAA).all()
+        return n, out[dskew:dskew + cap]
+
+    datas = []
+    for n, kind in ((0, "noise"), (1, "noise"), (300, "noise"), (70000, "noise"), (90000, "ramp"), (40000, "const"),
+                    (150000, "mixed"), (100000, "rows"), (66000, "skewed"), (50000, "text")):
+        if kind == "noise":
+            d = rng.integers(0, 256, n, dtype=np.uint8)
+        elif kind == "ramp":
+            d = (np.arange(n) // 7 % 256).astype(np.uint8)
+        elif kind == "const":
+            d = np.full(n, 77, np.uint8)
+        elif kind == "rows":                         # image-like: every row repeats the one 12,000 bytes above, plus noise
+            row = rng.integers(0, 256, 12000, dtype=np.uint8)
+            d = np.concatenate([np.where(rng.random(12000) < 0.02, rng.integers(0, 256, 12000), row).astype(np.uint8)
+                                for _ in range(n // 12000 + 1)])[:n]
+        elif kind == "skewed":                       # a few very frequent and many rare bytes: long Huffman codes
+            d = rng.choice(256, n, p=np.r_[[0.5, 0.25, 0.125], np.full(253, 0.125 / 253)]).astype(np.uint8)
+        elif kind == "text":
+            d = np.frombuffer((b"white balance NDVI GNDVI NDWI " * (n // 30 + 1))[:n], np.uint8)
+        else:
+            d = np.concatenate([rng.integers(0, 4, n // 2, dtype=np.uint8), (np.arange(n // 2) % 256).astype(np.uint8)])
+        datas.append(d)
+    k = 0
+    streams = []
+    for d in datas:
+        raw = d.tobytes()
+        for level, strategy in ((0, 0), (1, 0), (6, 0), (9, 0), (6, zlib.Z_FIXED), (6, zlib.Z_HUFFMAN_ONLY), (6, zlib.Z_RLE),
+                                (9, zlib.Z_FILTERED)):
+            co = zlib.compressobj(level, zlib.DEFLATED, 15, 9, strategy)
+            blob = co.compress(raw) + co.flush()
+            streams.append(blob)
+            for cap in {len(raw), max(1, len(raw) - 1), max(1, len(raw) // 2), len(raw) + 50}:
+                k += 1
+                n, out = run(blob, cap, k & 3, (k >> 2) & 3)
+                want = min(cap, len(raw))
+                if len(raw) == 0:
+                    assert n == 0
+                    continue
+                assert n == want and np.array_equal(out[:n], d[:n]), (len(raw), level, strategy, cap)
+    # a stream cut into two zlib.compress calls with a full flush in between (several blocks, byte-aligned restarts)
+    co = zlib.compressobj(6)
+    blob = co.compress(datas[6].tobytes()[:70000]) + co.flush(zlib.Z_FULL_FLUSH) + co.compress(datas[6].tobytes()[70000:]) + co.flush()
+    n, out = run(blob, len(datas[6]), 1, 2)
+    assert n == len(datas[6]) and np.array_equal(out, datas[6])
+    # matches further back than the ring is trusted for (distance > 32,256: the bytes are read back from the output)
+    far = np.tile(rng.integers(0, 256, 32400, dtype=np.uint8), 5)
+    blob = zlib.compress(far.tobytes(), 9)
+    assert len(blob) < 40000                                           # zlib did find the matches at distance 32,400
+    n, out = run(blob, len(far), 3, 1)
+    assert n == len(far) and np.array_equal(out, far)
+    # raw garbage, wrong headers
+    for bad in (b"", b"\\x78", b"\\x78\\x9c", b"\\x00\\x00\\x00\\x00", b"\\x78\\x9c\\xff\\xff\\xff\\xff", bytes(rng.integers(0, 256, 500, dtype=np.uint8))):
+        n, _ = run(bad, 1000, 0, 0)
+        assert n == 0 or n <= 1000
+    rejected = agree = 0
+    big = [s for s in streams if len(s) > 2000]
+    for it in range(3000):
+        raw = bytearray(big[it % len(big)])
+        for _ in range(int(rng.integers(1, 4))):
+            raw[int(rng.integers(0, len(raw)))] = int(rng.integers(0, 256))
+        if it % 5 == 4:
+            raw = raw[:int(rng.integers(1, len(raw)))]
+        cap = int(rng.integers(1, 200000))
+        n, out = run(bytes(raw), cap, it & 3, (it >> 2) & 3)
+        rejected += n == 0
+        # whenever zlib accepts the damaged stream as a whole, the warp decoder must give the same bytes
+        try:
+            ref = zlib.decompress(bytes(raw))
+        except zlib.error:
+            continue
+        if n:
+            agree += 1
+            assert n == min(cap, len(ref)) and np.array_equal(out[:n], np.frombuffer(ref, np.uint8)[:n])
+    assert rejected > 300
