@@ -316,6 +316,13 @@ int lars_tiff_deflate_chunks(const void* file, size_t file_bytes, const lars_tif
                              int32_t max_chunks);
 int lars_inflate_decode_device(const uint8_t* src, const lars_lzw_chunk* chunks, int32_t n_chunks, uint8_t* dst,
                                uint32_t* counters, void* stream);
+/* EXPERIMENTAL, with the above: PNG frames on the device.  The caller joins the IDAT payloads of every image into one
+ * zlib stream per image, inflates them with lars_inflate_decode_device into raw = [image][row][1 + row_bytes], and
+ * this call undoes the row filters into the frame slots (16-bit samples leave little-endian).  counters[0] counts
+ * images with an unknown filter type. */
+int lars_png_unfilter_device(const uint8_t* raw, int64_t raw_stride, int32_t n_images, int32_t rows, int32_t width,
+                             int32_t channels, int32_t sample_bytes, uint8_t* dst, int64_t frame_stride,
+                             uint32_t* counters, void* stream);
 int lars_tiff_post_device(uint8_t* dst, int32_t n_frames, int64_t frame_stride, int32_t rows, int32_t width,
                           int32_t samples_per_pixel, int32_t sample_bytes, int32_t predictor, int32_t swap16,
                           void* stream);

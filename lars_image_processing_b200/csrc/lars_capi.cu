@@ -1101,6 +1101,28 @@ int lars_inflate_decode_device(const uint8_t* src, const lars_lzw_chunk* chunks,
   return LARS_OK;
 }
 
+int lars_png_unfilter_device(const uint8_t* raw, int64_t raw_stride, int32_t n_images, int32_t rows, int32_t width,
+                             int32_t channels, int32_t sample_bytes, uint8_t* dst, int64_t frame_stride,
+                             uint32_t* counters, void* stream) {
+  DeviceState* st = nullptr;
+  int rc = current_state(&st);
+  if (rc != LARS_OK) return rc;
+  if (!raw || !dst || !counters) return fail(LARS_ERR_INVALID, "lars_png_unfilter_device: NULL pointer");
+  if (n_images < 1 || rows < 1 || width < 1 || channels < 1 || channels > 4 || (sample_bytes != 1 && sample_bytes != 2))
+    return fail(LARS_ERR_INVALID, "lars_png_unfilter_device: bad geometry");
+  lars::PngUnfilterParams p;
+  p.raw = raw; p.dst = dst; p.status = counters;
+  p.row_bytes = (long long)width * channels * sample_bytes;
+  if (raw_stride < (p.row_bytes + 1) * rows || frame_stride < p.row_bytes * rows)
+    return fail(LARS_ERR_INVALID, "lars_png_unfilter_device: strides smaller than an image");
+  p.raw_stride = raw_stride; p.frame_stride = frame_stride;
+  p.n_images = n_images; p.rows = rows; p.bpp = channels * sample_bytes; p.swap16 = sample_bytes == 2 ? 1 : 0;
+  const long long threads = (long long)n_images * p.bpp;
+  lars::png_unfilter_kernel<<<(unsigned)((threads + 63) / 64), 64, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  LARS_CUDA(cudaGetLastError());
+  return LARS_OK;
+}
+
 int lars_lzw_decode_device(const uint8_t* src, const lars_lzw_chunk* chunks, int32_t n_chunks, uint8_t* dst,
                            uint32_t* counters, void* stream) {
   DeviceState* st = nullptr;

@@ -12,6 +12,7 @@
 #include "../../include/lars_b200.h"
 #include "lzw_warp.h"
 #include "inflate_warp.h"
+#include "png_device.h"
 
 namespace lars {
 
@@ -87,6 +88,23 @@ __global__ void __launch_bounds__(INF_WARPS * 32, 1) inflate_decode_kernel(const
     if (lane == 0 && produced < c.dst_bytes) atomicAdd(p.status, 1u);
     __syncwarp();
   }
+}
+
+// Experimental (png_device.h): the PNG row filters of a batch of inflated images, one thread per byte lane of an image.
+struct PngUnfilterParams {
+  const uint8_t* raw;              // [image][row][1 + row_bytes]
+  uint8_t* dst;                    // frame batch
+  uint32_t* status;                // [1]: images with an unknown row filter
+  long long raw_stride, frame_stride, row_bytes;
+  int n_images, rows, bpp, swap16;
+};
+
+__global__ void __launch_bounds__(64) png_unfilter_kernel(const PngUnfilterParams p) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= p.n_images * p.bpp) return;
+  const int img = t / p.bpp, k = t % p.bpp;
+  if (!lars_png_unfilter_lane(p.raw + img * p.raw_stride, p.dst + img * p.frame_stride, p.rows, p.row_bytes, p.bpp, k, p.swap16))
+    atomicAdd(p.status, 1u);
 }
 
 struct TiffPostParams {

@@ -618,6 +618,86 @@ def decode_tiff_batch_on_device(sources: Sequence[Source], engine: Optional[Engi
     return frames
 
 
+def png_device_plan(blobs: Sequence[np.ndarray]) -> dict:
+    """Host side of the (experimental) device PNG path, no GPU involved: for equally-shaped PNG files given as uint8
+    arrays, the staging buffer -- every image's IDAT payloads joined into one zlib stream, streams 8-byte aligned --
+    the ``lars_lzw_chunk`` table for ``lars_inflate_decode_device`` (one stream per image into raw scratch of
+    ``rows * (1 + row_bytes)`` bytes per image) and the geometry for ``lars_png_unfilter_device``."""
+    lib = _lib.load()
+    infos, spans = [], []
+    for raw in blobs:
+        info = _lib.PngInfo()
+        check(lib.lars_png_probe(raw.ctypes.data, raw.size, C.byref(info)), "lars_png_probe")
+        at, idat = 8, []
+        while at + 12 <= raw.size:                     # the probe has validated the chunk structure
+            n = int.from_bytes(raw[at:at + 4].tobytes(), "big")
+            kind = raw[at + 4:at + 8].tobytes()
+            if kind == b"IDAT":
+                idat.append((at + 8, n))
+            elif kind == b"IEND":
+                break
+            at += 12 + n
+        infos.append(info)
+        spans.append(idat)
+    first = infos[0]
+    key = lambda i: (i.height, i.width, i.channels, i.bit_depth)
+    if any(key(i) != key(first) for i in infos):
+        raise ValueError("all frames of a batch must share shape and sample width")
+    sb = first.bit_depth // 8
+    row_bytes = first.width * first.channels * sb
+    raw_stride = (first.height * (row_bytes + 1) + 15) & ~15
+    starts, pos = [], 0
+    for info in infos:
+        starts.append(pos)
+        pos += (int(info.idat_bytes) + 7) & ~7
+    staging = np.zeros(pos, np.uint8)
+    chunks = np.zeros(len(blobs), _lib.LZW_CHUNK_DTYPE)
+    for i, (raw, idat) in enumerate(zip(blobs, spans)):
+        w = starts[i]
+        for off, n in idat:
+            staging[w:w + n] = raw[off:off + n]
+            w += n
+        chunks[i] = (starts[i], i * raw_stride, w - starts[i], first.height * (row_bytes + 1))
+    return {"staging": staging, "chunks": chunks, "height": first.height, "width": first.width, "channels": first.channels,
+            "sample_bytes": sb, "row_bytes": row_bytes, "raw_stride": raw_stride}
+
+
+def decode_png_batch_on_device(sources: Sequence[Source], engine: Optional[Engine] = None, stream=None) -> DeviceFrames:
+    """EXPERIMENTAL (needs ``LARS_EXPERIMENTAL_DEVICE_INFLATE=1``; pinned on the CPU, not yet run on hardware):
+    equally-shaped PNG frames decoded on the GPU -- one warp inflates each image's zlib stream, one thread per byte lane
+    undoes the row filters -- into a device-resident frame batch."""
+    if not EXPERIMENTAL_DEVICE_INFLATE:
+        raise LarsError("device-side PNG decode is experimental: set LARS_EXPERIMENTAL_DEVICE_INFLATE=1 to try it")
+    eng = engine or get_engine()
+    lib = eng.lib
+    s = stream or eng.stream()
+    blobs = [np.frombuffer(src, dtype=np.uint8) if isinstance(src, (bytes, bytearray, memoryview))
+             else np.fromfile(os.fspath(src), dtype=np.uint8) for src in sources]
+    plan = png_device_plan(blobs)
+    n = len(blobs)
+    frames = eng.alloc_frames(n, plan["height"], plan["width"], plan["channels"], s, sample_bytes=plan["sample_bytes"])
+    table_at = (plan["staging"].size + 7) & ~7
+    total = table_at + plan["chunks"].nbytes
+    host = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+    host_np = host.numpy()
+    host_np[:plan["staging"].size] = plan["staging"]
+    host_np[table_at:] = plan["chunks"].view(np.uint8)
+    with torch.cuda.stream(s), torch.cuda.device(eng.device):
+        dev = torch.empty(total, dtype=torch.uint8, device=eng.device)
+        dev.copy_(host, non_blocking=True)
+        scratch = torch.empty(n * plan["raw_stride"], dtype=torch.uint8, device=eng.device)
+        counters = torch.zeros(4, dtype=torch.int32, device=eng.device)
+        check(lib.lars_inflate_decode_device(dev.data_ptr(), dev.data_ptr() + table_at, n, scratch.data_ptr(),
+                                             counters.data_ptr(), s.cuda_stream), "lars_inflate_decode_device")
+        check(lib.lars_png_unfilter_device(scratch.data_ptr(), plan["raw_stride"], n, plan["height"], plan["width"],
+                                           plan["channels"], plan["sample_bytes"], frames.data.data_ptr(), frames.stride_bytes,
+                                           counters[2:].data_ptr(), s.cuda_stream), "lars_png_unfilter_device")
+        bad = counters.cpu()
+    if int(bad[0]) or int(bad[2]):
+        raise LarsError(f"{int(bad[0])} PNG stream(s) corrupt or short, {int(bad[2])} image(s) with an unknown row filter")
+    return frames
+
+
 # ------------------------------------------------------------------------------------------
 # streaming runner
 # ------------------------------------------------------------------------------------------

@@ -8,6 +8,7 @@
 #include "../../lars_image_processing_b200/csrc/pixel_math.h"
 #include "../../lars_image_processing_b200/csrc/lzw_warp.h"
 #include "../../lars_image_processing_b200/csrc/inflate_warp.h"
+#include "../../lars_image_processing_b200/csrc/png_device.h"
 #include "../../lars_image_processing_b200/csrc/tiff_host.h"
 
 extern "C" {
@@ -91,6 +92,12 @@ uint32_t hc_inflate_warp(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_
   uint8_t* base = reinterpret_cast<uint8_t*>(padded.data()) + 4 + (skew & 3u);
   memcpy(base, in, n_in);
   return lars_inflate_warp(base, n_in, out, cap, &sm);
+}
+// png_device.h: every byte lane of the pixel on its own, as the device threads run them.
+int hc_png_unfilter(const uint8_t* raw, uint8_t* dst, int h, long long row_bytes, int bpp, int swap16) {
+  for (int k = 0; k < bpp; ++k)
+    if (!lars_png_unfilter_lane(raw, dst, h, row_bytes, bpp, k, swap16)) return 0;
+  return 1;
 }
 uint32_t hc_lzw_decode_warp(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t cap) {
   static thread_local uint32_t table[4096];

@@ -979,3 +979,58 @@ def test_warp_inflate_equals_zlib(hostcheck):
             agree += 1
             assert n == min(cap, len(ref)) and np.array_equal(out[:n], np.frombuffer(ref, np.uint8)[:n])
     assert rejected > 300
+
+
+def test_device_png_plan_on_the_cpu(hostcheck, tmp_path):
+    """The (experimental) device PNG path without a GPU: png_device_plan (IDAT payloads joined into one zlib stream per
+    image, the chunk table, the geometry) + the warp inflate + the per-byte-lane row-filter code of png_device.h, both
+    run on the host through hostcheck, reproduce what the host PNG reader decodes -- Pillow-written files at several
+    compression levels, hand-built ones with every filter on every row position, many small IDAT chunks, 8- and
+    16-bit, gray / RGB / RGBA."""
+    import ctypes as C
+    from lars_image_processing_b200 import ingest
+    hostcheck.hc_inflate_warp.restype = C.c_uint32
+    hostcheck.hc_inflate_warp.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]
+    hostcheck.hc_png_unfilter.restype = C.c_int
+    hostcheck.hc_png_unfilter.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int]
+    rng = np.random.default_rng(91)
+    p = tmp_path / "d.png"
+    batches = []
+    for shape, dtype in (((61, 83, 3), np.uint8), ((40, 40), np.uint8), ((25, 31, 4), np.uint8), ((33, 41), np.uint16)):
+        blobs, imgs = [], []
+        for level in (0, 1, 9):
+            img = _textured(rng, shape, dtype)
+            Image.fromarray(img).save(p, compress_level=level)
+            blobs.append(np.fromfile(p, np.uint8))
+            imgs.append(img)
+        batches.append((blobs, imgs))
+    for shape, dtype in (((23, 31, 3), np.uint8), ((21, 17, 3), np.uint16), ((9, 14, 4), np.uint16), ((30, 1, 3), np.uint8)):
+        imgs = [_textured(rng, shape, dtype), rng.integers(0, np.iinfo(dtype).max + 1, shape).astype(dtype)]
+        blobs = [np.frombuffer(_png_bytes(imgs[0], [4, 3, 2, 1, 0], idat=33), np.uint8),
+                 np.frombuffer(_png_bytes(imgs[1], [3, 4, 0, 2, 1, 4], idat=1 << 16), np.uint8)]
+        batches.append((blobs, imgs))
+    for blobs, imgs in batches:
+        plan = ingest.png_device_plan(blobs)
+        h, rb, sb = plan["height"], plan["row_bytes"], plan["sample_bytes"]
+        assert plan["chunks"]["dst_bytes"].tolist() == [h * (rb + 1)] * len(blobs)
+        assert (plan["chunks"]["src_offset"] % 8 == 0).all() and plan["raw_stride"] % 16 == 0
+        scratch = np.zeros(len(blobs) * plan["raw_stride"], np.uint8)
+        for c in plan["chunks"]:
+            src = plan["staging"][int(c["src_offset"]):int(c["src_offset"]) + int(c["src_bytes"])].copy()
+            n = hostcheck.hc_inflate_warp(src.ctypes.data, src.size, scratch.ctypes.data + int(c["dst_offset"]),
+                                          int(c["dst_bytes"]), int(c["src_offset"]) & 3)
+            assert n == c["dst_bytes"]
+        for i, img in enumerate(imgs):
+            out = np.zeros(img.nbytes, np.uint8)
+            assert hostcheck.hc_png_unfilter(scratch.ctypes.data + i * plan["raw_stride"], out.ctypes.data, h, rb,
+                                             plan["channels"] * sb, 1 if sb == 2 else 0) == 1
+            got = out.view(img.dtype).reshape(img.shape)
+            assert np.array_equal(got, img) and np.array_equal(got, ingest.read_frame(blobs[i].tobytes()))
+    # an unknown filter type is reported, not followed
+    raw = np.zeros(2 * (1 + 6), np.uint8)
+    raw[7] = 9
+    assert hostcheck.hc_png_unfilter(raw.ctypes.data, np.zeros(12, np.uint8).ctypes.data, 2, 6, 3, 0) == 0
+    from lars_image_processing_b200._lib import LarsError
+    if not ingest.EXPERIMENTAL_DEVICE_INFLATE:
+        with pytest.raises(LarsError, match="experimental"):
+            ingest.decode_png_batch_on_device([blobs[0].tobytes()])
