@@ -695,6 +695,52 @@ def test_lzw_tiff_frames_decoded_on_the_device(engine, tmp_path):
         ingest.decode_tiff_batch_on_device([bytes(raw)], engine)
 
 
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("LARS_EXPERIMENTAL_DEVICE_INFLATE") != "1",
+                    reason="device-side Deflate / PNG decode is experimental: set LARS_EXPERIMENTAL_DEVICE_INFLATE=1")
+def test_experimental_device_deflate_and_png(engine, tmp_path):
+    """Round-2 entry point for the experimental decoders (pinned on the CPU, first hardware run pending): Deflate TIFF
+    strips and PNG frames decoded on the GPU must equal the host readers' arrays."""
+    import torch
+    from lars_image_processing_b200 import ingest
+    rng = np.random.default_rng(43)
+
+    def to_host(dev, shape, dtype):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        torch.cuda.synchronize()
+        return [dev.data[i, :n].cpu().numpy().view(dtype).reshape(shape) for i in range(dev.n_frames)]
+
+    imgs = [_textured(rng, (211, 333, 3), np.uint8) for _ in range(3)]
+    for kw in ({}, {"tiffinfo": {317: 2}}):
+        paths = []
+        for i, img in enumerate(imgs):
+            p = tmp_path / f"z{i}.tif"
+            Image.fromarray(img).save(p, compression="tiff_adobe_deflate", **kw)
+            paths.append(p)
+        for got, img in zip(to_host(ingest.decode_tiff_batch_on_device(paths, engine), imgs[0].shape, np.uint8), imgs):
+            assert np.array_equal(got, img)
+    img16 = [_textured(rng, (97, 120, 3), np.uint16) for _ in range(2)]
+    paths = []
+    for i, img in enumerate(img16):
+        p = tmp_path / f"z16_{i}.tif"
+        ingest.write_tiff(p, img, compression="deflate", predictor=True, big_endian=bool(i), rows_per_strip=9)
+        paths.append(p)
+    for path, img in zip(paths, img16):                            # byte order differs: one batch each
+        assert np.array_equal(to_host(ingest.decode_tiff_batch_on_device([path], engine), img.shape, np.uint16)[0], img)
+    for shape, dtype in (((240, 320, 3), np.uint8), ((61, 83, 4), np.uint8), ((50, 70, 3), np.uint16)):
+        batch = [_textured(rng, shape, dtype) for _ in range(4)]
+        blobs = []
+        for k, img in enumerate(batch):
+            if dtype == np.uint8:
+                p = tmp_path / f"d{k}.png"
+                Image.fromarray(img).save(p, compress_level=(0, 1, 6, 9)[k])
+                blobs.append(p)
+            else:
+                blobs.append(_png_bytes(img, [4, 3, 2, 1, 0], idat=4096))
+        for got, img in zip(to_host(ingest.decode_png_batch_on_device(blobs, engine), shape, dtype), batch):
+            assert np.array_equal(got, img), (shape, dtype)
+
+
 def test_tiff_round_trip_sweep(tmp_path):
     """Seeded sweep of the writer / native reader pair: shapes, sample widths, channel counts, byte
     orders and strip heights; 8-bit 1/3/4-channel and 16-bit 1-channel files are also handed to Pillow."""
