@@ -26,7 +26,7 @@
 #define LARS_INF_FAST_BITS 10
 #define LARS_INF_FAST_SIZE (1u << LARS_INF_FAST_BITS)
 
-// shared-memory working set of one warp (38,944 bytes)
+// shared-memory working set of one warp (39,520 bytes)
 struct LarsInflateSmem {
   uint8_t ring[LARS_INF_RING];
   uint32_t inbuf[LARS_INF_INBUF_WORDS];
@@ -35,7 +35,8 @@ struct LarsInflateSmem {
   uint16_t sym_ll[288];                   // symbols in canonical order (by length, then value)
   uint16_t sym_d[32];
   uint16_t cnt_ll[16], cnt_d[16];         // codes per length
-  uint16_t work[16];                      // next code / offsets while a table is built
+  uint16_t work[16];                      // next code / offsets while a table is built; [0] = verdict
+  uint16_t codes[288];                    // canonical code of every symbol of the alphabet being built
   uint8_t lens[352];                      // code lengths of the block being set up (32 + 286 + 30, rounded)
 };
 
@@ -53,35 +54,45 @@ LARS_LZW_FN uint32_t lars_inf_bitrev(uint32_t v, int n) {
 }
 
 // Builds the decode tables of one alphabet from lens[0, n): returns false for an over-subscribed set of lengths.
-LARS_LZW_FN bool lars_inf_build(const uint8_t* lens, int n, uint16_t* fast, uint16_t* sym, uint16_t* cnt, uint16_t* work) {
-  for (int l = 0; l < 16; ++l) cnt[l] = 0;
-  for (int s = 0; s < n; ++s) cnt[lens[s]] = (uint16_t)(cnt[lens[s]] + 1);
-  int left = 1;
-  for (int l = 1; l < 16; ++l) {
-    left = (left << 1) - (int)cnt[l];
-    if (left < 0) return false;                   // more codes of this length than the prefix tree has room for
+// The counting and the code assignment are read-modify-write sequences on shared memory, so ONE lane runs them (the
+// lanes of a warp are not guaranteed to move in lockstep); the others wait at the barrier and then share the fill.
+LARS_LZW_FN bool lars_inf_build(const uint8_t* lens, int n, uint16_t* fast, uint16_t* sym, uint16_t* cnt, uint16_t* work,
+                                uint16_t* codes) {
+  LARS_LZW_SYNC();                                  // nobody still decodes with the tables being replaced
+  LARS_LZW_FOR_LANES(lane) {
+    if (lane == 0) {
+      for (int l = 0; l < 16; ++l) cnt[l] = 0;
+      for (int s = 0; s < n; ++s) cnt[lens[s]] = (uint16_t)(cnt[lens[s]] + 1);
+      int left = 1;
+      bool ok = true;
+      for (int l = 1; l < 16; ++l) {
+        left = (left << 1) - (int)cnt[l];
+        if (left < 0) { ok = false; break; }        // more codes of this length than the prefix tree has room for
+      }
+      // canonical order of the symbols (for codes longer than the fast bits)
+      work[1] = 0;
+      for (int l = 1; l < 15; ++l) work[l + 1] = (uint16_t)(work[l] + cnt[l]);
+      for (int s = 0; s < n; ++s)
+        if (lens[s]) { sym[work[lens[s]]] = (uint16_t)s; work[lens[s]] = (uint16_t)(work[lens[s]] + 1); }
+      // first code of every length, then the code of every symbol
+      uint32_t code = 0;
+      for (int l = 1; l < 16; ++l) { code = (code + (l > 1 ? cnt[l - 1] : 0u)) << 1; work[l] = (uint16_t)code; }
+      for (int s = 0; s < n; ++s)
+        if (lens[s]) { codes[s] = work[lens[s]]; work[lens[s]] = (uint16_t)(work[lens[s]] + 1); }
+      work[0] = ok ? 1 : 0;
+    }
   }
-  // canonical order of the symbols (for codes longer than the fast bits)
-  work[1] = 0;
-  for (int l = 1; l < 15; ++l) work[l + 1] = (uint16_t)(work[l] + cnt[l]);
-  for (int s = 0; s < n; ++s)
-    if (lens[s]) { sym[work[lens[s]]] = (uint16_t)s; work[lens[s]] = (uint16_t)(work[lens[s]] + 1); }
-  // first code of every length, then the fast table: every slot whose low `len` bits are the reversed code
   LARS_LZW_SYNC();
+  if (work[0] == 0) return false;
   LARS_LZW_FOR_LANES(lane) { for (uint32_t i = (uint32_t)lane; i < LARS_INF_FAST_SIZE; i += 32u) fast[i] = 0; }
   LARS_LZW_SYNC();
-  uint32_t code = 0;
-  for (int l = 1; l < 16; ++l) { code = (code + (l > 1 ? cnt[l - 1] : 0u)) << 1; work[l] = (uint16_t)code; }
+  // the fast table: every slot whose low `len` bits are the bit-reversed code of a symbol
   for (int s = 0; s < n; ++s) {
     const int l = lens[s];
-    if (l == 0) continue;
-    const uint32_t c = work[l];
-    work[l] = (uint16_t)(c + 1);
-    if (l <= LARS_INF_FAST_BITS) {
-      const uint32_t r = lars_inf_bitrev(c, l), step = 1u << l;
-      const uint16_t e = (uint16_t)((l << 9) | s);
-      LARS_LZW_FOR_LANES(lane) { for (uint32_t i = r + step * (uint32_t)lane; i < LARS_INF_FAST_SIZE; i += step * 32u) fast[i] = e; }
-    }
+    if (l == 0 || l > LARS_INF_FAST_BITS) continue;
+    const uint32_t r = lars_inf_bitrev(codes[s], l), step = 1u << l;
+    const uint16_t e = (uint16_t)((l << 9) | s);
+    LARS_LZW_FOR_LANES(lane) { for (uint32_t i = r + step * (uint32_t)lane; i < LARS_INF_FAST_SIZE; i += step * 32u) fast[i] = e; }
   }
   LARS_LZW_SYNC();
   return true;
@@ -203,9 +214,9 @@ LARS_LZW_FN uint32_t lars_inflate_warp(const uint8_t* in, uint32_t n_in, uint8_t
     if (type == 1u) {                              // fixed codes (RFC 1951 3.2.6)
       if (!fixed_ready) {
         for (int s = 0; s < 288; ++s) sm->lens[s] = (uint8_t)(s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8);
-        if (!lars_inf_build(sm->lens, 288, sm->fast_ll, sm->sym_ll, sm->cnt_ll, sm->work)) return 0;
+        if (!lars_inf_build(sm->lens, 288, sm->fast_ll, sm->sym_ll, sm->cnt_ll, sm->work, sm->codes)) return 0;
         for (int s = 0; s < 30; ++s) sm->lens[s] = 5;
-        if (!lars_inf_build(sm->lens, 30, sm->fast_d, sm->sym_d, sm->cnt_d, sm->work)) return 0;
+        if (!lars_inf_build(sm->lens, 30, sm->fast_d, sm->sym_d, sm->cnt_d, sm->work, sm->codes)) return 0;
         fixed_ready = true;
       }
     } else {                                       // dynamic codes (RFC 1951 3.2.7)
@@ -221,7 +232,7 @@ LARS_LZW_FN uint32_t lars_inflate_warp(const uint8_t* in, uint32_t n_in, uint8_t
         LARS_INF_DROP(3);
       }
       // the code-length alphabet borrows the distance tables
-      if (!lars_inf_build(sm->lens, 19, sm->fast_d, sm->sym_d, sm->cnt_d, sm->work)) return 0;
+      if (!lars_inf_build(sm->lens, 19, sm->fast_d, sm->sym_d, sm->cnt_d, sm->work, sm->codes)) return 0;
       int idx = 0;
       uint8_t prev = 0;
       // lengths are collected behind the 19 code-length lengths and moved down afterwards
@@ -247,11 +258,9 @@ LARS_LZW_FN uint32_t lars_inflate_warp(const uint8_t* in, uint32_t n_in, uint8_t
       }
       if (b.used_bits > total_bits) return 0;
       if (sm->lens[32 + 256] == 0) return 0;       // no end-of-block code
-      // distance lengths first (they sit behind the literal / length ones), then the literal / length table
-      for (int i = 0; i < hdist; ++i) sm->lens[i] = sm->lens[32 + hlit + i];
-      if (!lars_inf_build(sm->lens, hdist, sm->fast_d, sm->sym_d, sm->cnt_d, sm->work)) return 0;
-      for (int i = 0; i < hlit; ++i) sm->lens[i] = sm->lens[32 + i];
-      if (!lars_inf_build(sm->lens, hlit, sm->fast_ll, sm->sym_ll, sm->cnt_ll, sm->work)) return 0;
+      // the collected lengths are used where they are: literal / length ones first, the distance ones behind them
+      if (!lars_inf_build(sm->lens + 32 + hlit, hdist, sm->fast_d, sm->sym_d, sm->cnt_d, sm->work, sm->codes)) return 0;
+      if (!lars_inf_build(sm->lens + 32, hlit, sm->fast_ll, sm->sym_ll, sm->cnt_ll, sm->work, sm->codes)) return 0;
     }
 
     // ---- the symbols of the block
