@@ -9,7 +9,11 @@
 // is a copy from earlier output, never a walk down a prefix chain.  The table lives in shared memory (one
 // 32-bit word per code: position in bits 0..19, length in bits 20..31, hence strips of at most 1 MB); every
 // lane writes every entry itself (same value, same address: one shared-memory transaction), so table reads
-// never depend on another lane and only the output copy needs a warp barrier.
+// never depend on another lane and only the output copy needs a warp barrier.  (Table slots are reused after a Clear
+// code; a lane could only overwrite a slot another lane's pending write still targets if it ran a whole epoch of
+// literal codes ahead between two barriers, which no encoder's stream allows -- a hostile stream could at worst turn its
+// own pixels into different garbage, positions and lengths stay inside the output.  Variant 2 closes even that with a
+// barrier at every Clear.)
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
@@ -175,7 +179,7 @@ LARS_LZW_FN uint32_t lars_lzw_decode_warp_v2(const uint8_t* in, uint32_t n_in, u
     }
     const int code = (int)((acc >> (have - nbits)) & ((1u << nbits) - 1u));
     have -= nbits;
-    if (code == 256) { nbits = 9; next_code = 258; old = -1; continue; }
+    if (code == 256) { LARS_LZW_SYNC(); nbits = 9; next_code = 258; old = -1; continue; }   // no lane drifts across an epoch
     if (code == 257) break;
     const uint32_t at = op;
     uint32_t len;
