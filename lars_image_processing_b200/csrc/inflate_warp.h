@@ -84,7 +84,7 @@ LARS_LZW_FN bool lars_inf_build(const uint8_t* lens, int n, uint16_t* fast, uint
   }
   LARS_LZW_SYNC();
   if (work[0] == 0) return false;
-  LARS_LZW_FOR_LANES(lane) { for (uint32_t i = (uint32_t)lane; i < LARS_INF_FAST_SIZE; i += 32u) fast[i] = 0; }
+  { LARS_LZW_FOR_LANES(lane) { for (uint32_t i = (uint32_t)lane; i < LARS_INF_FAST_SIZE; i += 32u) fast[i] = 0; } }
   LARS_LZW_SYNC();
   // the fast table: every slot whose low `len` bits are the bit-reversed code of a symbol
   for (int s = 0; s < n; ++s) {
