@@ -698,6 +698,39 @@ def decode_png_batch_on_device(sources: Sequence[Source], engine: Optional[Engin
     return frames
 
 
+def survey_with_device_decode(sources: Sequence[Source], chunk: int = 16, engine: Optional[Engine] = None,
+                              threads: Optional[int] = None, white_balance: bool = True, **fused_kw) -> dict:
+    """Statistics of a survey stored as LZW TIFF frames with the decode on the GPU: chunk by chunk the compressed files
+    are staged and uploaded, decoded by :func:`decode_tiff_batch_on_device`, analysed (statistics only) and folded into
+    the dataset record on the device.  Same result dictionary as :meth:`SurveyPipeline.run` (single rank).  A plain
+    loop -- one synchronisation per chunk for the strips' verdict, no overlap of staging and kernels yet."""
+    eng = engine or get_engine()
+    s = eng.stream()
+    per_frame: List[np.ndarray] = []
+    with torch.cuda.stream(s):
+        fold = torch.zeros((2, 3, INDEX_STATS_DTYPE.itemsize), dtype=torch.uint8, device=eng.device)
+    n_frames = 0
+    for a in range(0, len(sources), chunk):
+        part = list(sources[a:a + chunk])
+        frames = decode_tiff_batch_on_device(part, eng, stream=s, threads=threads)
+        res = eng.process_device(frames, outputs=("stats",), white_balance=white_balance, stream=s, **fused_kw)
+        with torch.cuda.stream(s), torch.cuda.device(eng.device):
+            check(eng.lib.lars_stats_merge(res.stats.data_ptr(), len(part), fold[1].data_ptr(), s.cuda_stream), "lars_stats_merge")
+            check(eng.lib.lars_stats_merge(fold.data_ptr(), 2, fold[0].data_ptr(), s.cuda_stream), "lars_stats_merge")
+            host = res.stats.cpu()
+        s.synchronize()
+        per_frame.append(host.numpy().view(INDEX_STATS_DTYPE).reshape(len(part), 3).copy())
+        n_frames += len(part)
+    with torch.cuda.stream(s):
+        whole = fold[0].cpu()
+    s.synchronize()
+    records = np.concatenate(per_frame) if per_frame else np.zeros((0, 3), INDEX_STATS_DTYPE)
+    bins = fused_kw.get("bins", 50)
+    dataset = stats_records_to_dicts(whole.numpy().view(INDEX_STATS_DTYPE).reshape(1, 3), bins)[0]
+    return {"frames": n_frames, "per_frame": records, "dataset": dataset,
+            "per_frame_dicts": lambda: stats_records_to_dicts(records, bins)}
+
+
 # ------------------------------------------------------------------------------------------
 # streaming runner
 # ------------------------------------------------------------------------------------------

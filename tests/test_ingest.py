@@ -741,6 +741,29 @@ def test_experimental_device_deflate_and_png(engine, tmp_path):
             assert np.array_equal(got, img), (shape, dtype)
 
 
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("LARS_RUN_UNVERIFIED") != "1",
+                    reason="composition written after the round's GPU time was spent: set LARS_RUN_UNVERIFIED=1 to run it")
+def test_survey_with_device_decode_matches_the_pipeline(engine, tmp_path):
+    """survey_with_device_decode (LZW files decoded on the GPU, chunk loop) gives the per-frame and dataset records of
+    SurveyPipeline on the same files."""
+    from lars_image_processing_b200 import ingest
+    paths = []
+    for i in range(7):
+        p = tmp_path / f"s{i}.tif"
+        Image.fromarray(synth.vegetation_frame(600 + i, 120, 160)).save(p, compression="tiff_lzw")
+        paths.append(p)
+    got = ingest.survey_with_device_decode(paths, chunk=3, engine=engine)
+    want = ingest.SurveyPipeline(120, 160, chunk=3, engine=engine).run(paths)
+    assert got["frames"] == want["frames"] == 7
+    for name in got["per_frame"].dtype.names:
+        assert np.array_equal(got["per_frame"][name], want["per_frame"][name]), name
+    for t in ("NDVI", "GNDVI", "NDWI"):
+        assert got["dataset"][t]["count"] == want["dataset"][t]["count"]
+        assert np.array_equal(got["dataset"][t]["hist"], want["dataset"][t]["hist"])
+        assert got["dataset"][t]["mean"] == want["dataset"][t]["mean"]
+
+
 def test_tiff_round_trip_sweep(tmp_path):
     """Seeded sweep of the writer / native reader pair: shapes, sample widths, channel counts, byte
     orders and strip heights; 8-bit 1/3/4-channel and 16-bit 1-channel files are also handed to Pillow."""
