@@ -323,6 +323,11 @@ int lars_inflate_decode_device(const uint8_t* src, const lars_lzw_chunk* chunks,
 int lars_png_unfilter_device(const uint8_t* raw, int64_t raw_stride, int32_t n_images, int32_t rows, int32_t width,
                              int32_t channels, int32_t sample_bytes, uint8_t* dst, int64_t frame_stride,
                              uint32_t* counters, void* stream);
+/* Strips / tiles that were decoded into scratch slots of slot_bytes each (rows of slot_row_bytes) are moved to their
+ * place inside one frame, e.g. the row band of a tiled mosaic a rank owns.  table (device, int64 [n_chunks][5]):
+ * first slot row, number of rows, first frame row, byte column in the frame, bytes per row. */
+int lars_untile_device(const uint8_t* scratch, int64_t slot_bytes, int64_t slot_row_bytes, const int64_t* table,
+                       int32_t n_chunks, uint8_t* dst, int64_t dst_row_bytes, void* stream);
 int lars_tiff_post_device(uint8_t* dst, int32_t n_frames, int64_t frame_stride, int32_t rows, int32_t width,
                           int32_t samples_per_pixel, int32_t sample_bytes, int32_t predictor, int32_t swap16,
                           void* stream);

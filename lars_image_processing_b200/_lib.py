@@ -37,7 +37,7 @@ EXPORTED_SYMBOLS = (
     "lars_resize_plan_lanczos", "lars_resize_tables_lanczos", "lars_resize_lanczos_u8",
     "lars_tiff_probe", "lars_tiff_read", "lars_tiff_read_region", "lars_png_probe", "lars_png_read",
     "lars_tiff_lzw_chunks", "lars_lzw_decode_device", "lars_tiff_post_device",
-    "lars_tiff_deflate_chunks", "lars_inflate_decode_device", "lars_png_unfilter_device",
+    "lars_tiff_deflate_chunks", "lars_inflate_decode_device", "lars_png_unfilter_device", "lars_untile_device",
 )
 
 
@@ -186,6 +186,8 @@ def _declare(lib):
     lib.lars_inflate_decode_device.restype = C.c_int
     lib.lars_png_unfilter_device.argtypes = [vp, i64, i32, i32, i32, i32, i32, vp, i64, vp, vp]
     lib.lars_png_unfilter_device.restype = C.c_int
+    lib.lars_untile_device.argtypes = [vp, i64, i64, vp, i32, vp, i64, vp]
+    lib.lars_untile_device.restype = C.c_int
     lib.lars_tiff_post_device.argtypes = [vp, i32, i64, i32, i32, i32, i32, i32, i32, vp]
     lib.lars_tiff_post_device.restype = C.c_int
     lib.lars_resize_plan_lanczos.argtypes = [i32, i32, i32, i32, i32, C.POINTER(ResizePlan)]

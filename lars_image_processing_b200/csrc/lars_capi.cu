@@ -1123,6 +1123,24 @@ int lars_png_unfilter_device(const uint8_t* raw, int64_t raw_stride, int32_t n_i
   return LARS_OK;
 }
 
+int lars_untile_device(const uint8_t* scratch, int64_t slot_bytes, int64_t slot_row_bytes, const int64_t* table,
+                       int32_t n_chunks, uint8_t* dst, int64_t dst_row_bytes, void* stream) {
+  DeviceState* st = nullptr;
+  int rc = current_state(&st);
+  if (rc != LARS_OK) return rc;
+  if (!scratch || !table || !dst) return fail(LARS_ERR_INVALID, "lars_untile_device: NULL pointer");
+  if (n_chunks < 1 || slot_bytes < 1 || slot_row_bytes < 1 || dst_row_bytes < 1)
+    return fail(LARS_ERR_INVALID, "lars_untile_device: bad geometry");
+  if (reinterpret_cast<uintptr_t>(table) & 7u) return fail(LARS_ERR_INVALID, "lars_untile_device: table must be 8-byte aligned");
+  lars::UntileParams p;
+  p.scratch = scratch; p.table = reinterpret_cast<const long long*>(table); p.dst = dst;
+  p.slot_bytes = slot_bytes; p.slot_row_bytes = slot_row_bytes; p.dst_row_bytes = dst_row_bytes; p.n_chunks = n_chunks;
+  const dim3 grid((unsigned)n_chunks, 8);
+  lars::untile_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  LARS_CUDA(cudaGetLastError());
+  return LARS_OK;
+}
+
 int lars_lzw_decode_device(const uint8_t* src, const lars_lzw_chunk* chunks, int32_t n_chunks, uint8_t* dst,
                            uint32_t* counters, void* stream) {
   DeviceState* st = nullptr;

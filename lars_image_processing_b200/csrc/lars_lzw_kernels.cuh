@@ -107,6 +107,28 @@ __global__ void __launch_bounds__(64) png_unfilter_kernel(const PngUnfilterParam
     atomicAdd(p.status, 1u);
 }
 
+// Strips / tiles decoded into scratch slots -> their place inside one frame (a row band of a mosaic): per chunk a
+// row range of the slot goes to a row range of the frame at a byte column.  One CTA per (chunk, row stripe).
+struct UntileParams {
+  const uint8_t* scratch;
+  const long long* table;          // [n_chunks][5]: first slot row, rows, first frame row, byte column in the frame, bytes per row
+  uint8_t* dst;
+  long long slot_bytes, slot_row_bytes, dst_row_bytes;
+  int n_chunks;
+};
+
+__global__ void __launch_bounds__(256) untile_kernel(const UntileParams p) {
+  const long long* t = p.table + 5ll * blockIdx.x;
+  const long long src_row0 = t[0], rows = t[1], dst_row0 = t[2], dst_col = t[3], n = t[4];
+  const uint8_t* src = p.scratch + (long long)blockIdx.x * p.slot_bytes + src_row0 * p.slot_row_bytes;
+  uint8_t* dst = p.dst + dst_row0 * p.dst_row_bytes + dst_col;
+  for (long long r = blockIdx.y; r < rows; r += gridDim.y) {
+    const uint8_t* s = src + r * p.slot_row_bytes;
+    uint8_t* d = dst + r * p.dst_row_bytes;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+  }
+}
+
 struct TiffPostParams {
   uint8_t* dst;
   long long frame_stride;          // bytes between frames

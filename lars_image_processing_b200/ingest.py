@@ -698,6 +698,109 @@ def decode_png_batch_on_device(sources: Sequence[Source], engine: Optional[Engin
     return frames
 
 
+def tiff_region_device_plan(raw: np.ndarray, rows: Optional[Sequence[int]] = None) -> dict:
+    """Host side of decoding a row band of a (possibly tiled) LZW / Deflate TIFF on the device, no GPU involved: which
+    strips / tiles touch rows ``[rows[0], rows[1])``, the ``lars_lzw_chunk`` table that decodes each of them into its
+    own scratch slot, the geometry for ``lars_tiff_post_device`` (the slots are treated as frames of one chunk each) and
+    the move table for ``lars_untile_device`` that places every slot's rows inside the band.  Strips are tiles as wide
+    as the image.  Refuses (``LarsError``) files outside the device decoders: other codecs, planar, float, chunks
+    beyond 1 MB decoded."""
+    lib = _lib.load()
+    info = _lib.TiffInfo()
+    check(lib.lars_tiff_probe(raw.ctypes.data, raw.size, C.byref(info)), "lars_tiff_probe")
+    if info.compression not in (5, 8) or info.planar_config != 1 or info.bits_per_sample > 16:
+        raise LarsError("the device decoders take chunky LZW / Deflate TIFFs with 8- or 16-bit samples")
+    h, w = info.height, info.width
+    r0, r1 = (0, h) if rows is None else (int(rows[0]), int(rows[1]))
+    if not 0 <= r0 < r1 <= h:
+        raise ValueError(f"rows [{r0}, {r1}) are empty or outside the {h}-row image")
+    sb = info.bits_per_sample // 8
+    px = info.samples_per_pixel * sb
+    tiled = info.tile_width > 0
+    cw, chh = (info.tile_width, info.tile_length) if tiled else (w, info.rows_per_strip)
+    across = info.tiles_across if tiled else 1
+    slot_row_bytes = cw * px
+    slot_bytes = chh * slot_row_bytes
+    if slot_bytes > (1 << 20):
+        raise LarsError("a strip / tile decodes to more than 1 MB: outside the device decoders")
+    order = ">" if info.big_endian else "<"
+    kinds = {3: "u2", 4: "u4", 16: "u8"}
+    offs = np.frombuffer(raw, order + kinds[info.strip_offsets_type], info.n_strips, info.strip_offsets_pos).astype(np.int64)
+    cnts = np.frombuffer(raw, order + kinds[info.strip_counts_type], info.n_strips, info.strip_counts_pos).astype(np.int64)
+    cy0, cy1 = r0 // chh, (r1 - 1) // chh
+    n = (cy1 - cy0 + 1) * across
+    chunks = np.zeros(n, _lib.LZW_CHUNK_DTYPE)
+    moves = np.zeros((n, 5), np.int64)
+    k = 0
+    for cy in range(cy0, cy1 + 1):
+        valid = min(chh, h - cy * chh)
+        for cx in range(across):
+            idx = cy * across + cx
+            need = (chh if tiled else valid) * slot_row_bytes             # tiles are stored whole, the last strip is short
+            chunks[k] = (offs[idx], k * slot_bytes, cnts[idx], need)
+            lo, hi = max(r0, cy * chh), min(r1, cy * chh + valid)
+            cols = min(cw, w - cx * cw)
+            moves[k] = (lo - cy * chh, hi - lo, lo - r0, cx * cw * px, cols * px)
+            k += 1
+    return {"info": info, "chunks": chunks, "moves": moves, "slot_bytes": slot_bytes, "slot_row_bytes": slot_row_bytes,
+            "chunk_rows": chh, "chunk_width": cw, "rows": (r0, r1), "band_row_bytes": w * px, "sample_bytes": sb}
+
+
+def decode_tiff_region_on_device(source: Source, rows: Optional[Sequence[int]] = None, engine: Optional[Engine] = None,
+                                 stream=None) -> DeviceFrames:
+    """A row band (default: the whole image) of an LZW / Deflate TIFF -- strips or tiles -- decoded on the GPU into a
+    one-frame device batch, e.g. the band of a tiled mosaic a rank owns (``read_mosaic_band`` without the host decode).
+    Only the chunks under the band are uploaded.  Deflate needs ``LARS_EXPERIMENTAL_DEVICE_INFLATE=1``."""
+    eng = engine or get_engine()
+    lib = eng.lib
+    s = stream or eng.stream()
+    raw = np.frombuffer(source, dtype=np.uint8) if isinstance(source, (bytes, bytearray, memoryview)) \
+        else np.fromfile(os.fspath(source), dtype=np.uint8)
+    plan = tiff_region_device_plan(raw, rows)
+    info = plan["info"]
+    if info.compression == 8 and not EXPERIMENTAL_DEVICE_INFLATE:
+        raise LarsError("device-side Deflate decode is experimental: set LARS_EXPERIMENTAL_DEVICE_INFLATE=1 to try it")
+    chunks, moves = plan["chunks"].copy(), plan["moves"]
+    n = chunks.size
+    # staging: the chunks' compressed bytes back to back (8-byte aligned), then the two tables
+    starts = np.zeros(n, np.int64)
+    pos = 0
+    for k in range(n):
+        starts[k] = pos
+        pos += (int(chunks["src_bytes"][k]) + 7) & ~7
+    table_at = pos
+    moves_at = table_at + chunks.nbytes
+    total = moves_at + moves.nbytes
+    host = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+    host_np = host.numpy()
+    for k in range(n):
+        a, m = int(chunks["src_offset"][k]), int(chunks["src_bytes"][k])
+        host_np[starts[k]:starts[k] + m] = raw[a:a + m]
+    chunks["src_offset"] = starts
+    host_np[table_at:moves_at] = chunks.view(np.uint8)
+    host_np[moves_at:] = moves.reshape(-1).view(np.uint8)
+    r0, r1 = plan["rows"]
+    sb = plan["sample_bytes"]
+    frames = eng.alloc_frames(1, r1 - r0, info.width, info.samples_per_pixel, s, sample_bytes=sb)
+    with torch.cuda.stream(s), torch.cuda.device(eng.device):
+        dev = torch.empty(total, dtype=torch.uint8, device=eng.device)
+        dev.copy_(host, non_blocking=True)
+        scratch = torch.empty(n * plan["slot_bytes"], dtype=torch.uint8, device=eng.device)
+        counters = torch.zeros(2, dtype=torch.int32, device=eng.device)
+        decode = lib.lars_inflate_decode_device if info.compression == 8 else lib.lars_lzw_decode_device
+        check(decode(dev.data_ptr(), dev.data_ptr() + table_at, n, scratch.data_ptr(), counters.data_ptr(), s.cuda_stream),
+              "lars_lzw_decode_device")
+        check(lib.lars_tiff_post_device(scratch.data_ptr(), n, plan["slot_bytes"], plan["chunk_rows"], plan["chunk_width"],
+                                        info.samples_per_pixel, sb, info.predictor, 1 if (info.big_endian and sb == 2) else 0,
+                                        s.cuda_stream), "lars_tiff_post_device")
+        check(lib.lars_untile_device(scratch.data_ptr(), plan["slot_bytes"], plan["slot_row_bytes"], dev.data_ptr() + moves_at,
+                                     n, frames.data.data_ptr(), plan["band_row_bytes"], s.cuda_stream), "lars_untile_device")
+        bad = int(counters[0].item())
+    if bad:
+        raise LarsError(f"{bad} compressed strip(s) / tile(s) of the band are corrupt or shorter than their rows")
+    return frames
+
+
 def survey_with_device_decode(sources: Sequence[Source], chunk: int = 16, engine: Optional[Engine] = None,
                               threads: Optional[int] = None, white_balance: bool = True, **fused_kw) -> dict:
     """Statistics of a survey stored as LZW TIFF frames with the decode on the GPU: chunk by chunk the compressed files

@@ -764,6 +764,30 @@ def test_survey_with_device_decode_matches_the_pipeline(engine, tmp_path):
         assert got["dataset"][t]["mean"] == want["dataset"][t]["mean"]
 
 
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("LARS_RUN_UNVERIFIED") != "1",
+                    reason="written after the round's GPU time was spent: set LARS_RUN_UNVERIFIED=1 to run it")
+def test_mosaic_band_decoded_on_the_device(engine, tmp_path):
+    """decode_tiff_region_on_device: the row band of a tiled / stripped LZW mosaic decoded on the GPU equals the host
+    reader's region (Deflate layouts join when LARS_EXPERIMENTAL_DEVICE_INFLATE=1)."""
+    import torch
+    from lars_image_processing_b200 import ingest
+    rng = np.random.default_rng(47)
+    p = tmp_path / "m.tif"
+    codecs = ["lzw"] + (["deflate"] if ingest.EXPERIMENTAL_DEVICE_INFLATE else [])
+    for codec in codecs:
+        for k, kw in enumerate((dict(tile=(32, 48), predictor=True), dict(rows_per_strip=9), dict(tile=(64, 64), big_endian=True))):
+            dtype = np.uint16 if k % 2 else np.uint8
+            img = _textured(rng, (200, 260, 3), dtype)
+            ingest.write_tiff(p, img, compression=codec, **kw)
+            for r0, r1 in ((0, 200), (37, 150), (190, 200)):
+                dev = ingest.decode_tiff_region_on_device(p, (r0, r1), engine)
+                torch.cuda.synchronize()
+                n = (r1 - r0) * 260 * 3 * np.dtype(dtype).itemsize
+                got = dev.data[0, :n].cpu().numpy().view(dtype).reshape(r1 - r0, 260, 3)
+                assert np.array_equal(got, img[r0:r1]) and np.array_equal(got, ingest.read_region(p, (r0, r1)))
+
+
 def test_tiff_round_trip_sweep(tmp_path):
     """Seeded sweep of the writer / native reader pair: shapes, sample widths, channel counts, byte
     orders and strip heights; 8-bit 1/3/4-channel and 16-bit 1-channel files are also handed to Pillow."""
@@ -1103,3 +1127,54 @@ def test_device_png_plan_on_the_cpu(hostcheck, tmp_path):
     if not ingest.EXPERIMENTAL_DEVICE_INFLATE:
         with pytest.raises(LarsError, match="experimental"):
             ingest.decode_png_batch_on_device([blobs[0].tobytes()])
+
+
+def test_device_region_plan_on_the_cpu(hostcheck, tmp_path):
+    """Row bands of strip and tile files through the device path, emulated on the CPU: tiff_region_device_plan (chunk table
+    into scratch slots, move table) + the warp decoders via hostcheck + predictor / byte order per slot + the moves
+    reproduce img[r0:r1] for LZW and Deflate, strips and tiles (edge tiles narrower and shorter than a tile), 8- and
+    16-bit, both byte orders."""
+    import ctypes as C
+    from lars_image_processing_b200 import ingest
+    from lars_image_processing_b200._lib import LarsError
+    hostcheck.hc_lzw_decode_warp.restype = C.c_uint32
+    hostcheck.hc_lzw_decode_warp.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+    hostcheck.hc_inflate_warp.restype = C.c_uint32
+    hostcheck.hc_inflate_warp.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]
+    rng = np.random.default_rng(101)
+    p = tmp_path / "g.tif"
+    layouts = [dict(compression="lzw", tile=(32, 48), predictor=True), dict(compression="deflate", tile=(16, 16)),
+               dict(compression="lzw", rows_per_strip=9), dict(compression="deflate", rows_per_strip=13, predictor=True, big_endian=True),
+               dict(compression="lzw", tile=(64, 64), big_endian=True, bigtiff=True)]
+    for k, kw in enumerate(layouts):
+        dtype = np.uint16 if k % 2 else np.uint8
+        img = _textured(rng, (100, 130, 3), dtype)
+        ingest.write_tiff(p, img, **kw)
+        raw = np.fromfile(p, np.uint8)
+        for r0, r1 in ((0, 100), (17, 64), (95, 100), (31, 33)):
+            plan = ingest.tiff_region_device_plan(raw, (r0, r1))
+            info, n = plan["info"], plan["chunks"].size
+            scratch = np.zeros(n * plan["slot_bytes"] + 8, np.uint8)
+            for c in plan["chunks"]:
+                args = (raw.ctypes.data + int(c["src_offset"]), int(c["src_bytes"]), scratch.ctypes.data + int(c["dst_offset"]), int(c["dst_bytes"]))
+                got = (hostcheck.hc_inflate_warp(*args, int(c["src_offset"]) & 3) if info.compression == 8
+                       else hostcheck.hc_lzw_decode_warp(*args))
+                assert got == c["dst_bytes"], (kw, r0, r1)
+            sb, spp = plan["sample_bytes"], info.samples_per_pixel
+            slots = scratch[:n * plan["slot_bytes"]].reshape(n, plan["chunk_rows"], plan["chunk_width"] * spp * sb)
+            samples = slots.view(">u2" if (sb == 2 and info.big_endian) else ("<u2" if sb == 2 else np.uint8)).astype(np.uint32)
+            samples = samples.reshape(n, plan["chunk_rows"], plan["chunk_width"], spp)
+            if info.predictor == 2:                                   # what lars_tiff_post_device does to every slot
+                samples = np.cumsum(samples, axis=2) & (0xFFFF if sb == 2 else 0xFF)
+            slots = np.ascontiguousarray(samples.astype(img.dtype)).view(np.uint8).reshape(n, plan["chunk_rows"], -1)
+            band = np.zeros((r1 - r0, plan["band_row_bytes"]), np.uint8)
+            for j, (s_row, rows, d_row, d_col, nbytes) in enumerate(plan["moves"]):   # what lars_untile_device does
+                band[d_row:d_row + rows, d_col:d_col + nbytes] = slots[j, s_row:s_row + rows, :nbytes]
+            assert np.array_equal(band.view(img.dtype).reshape(r1 - r0, 130, 3), img[r0:r1]), (kw, r0, r1)
+    for kw in (dict(), dict(compression="packbits"), dict(compression="lzw", planar=True)):
+        ingest.write_tiff(p, img, **kw)
+        with pytest.raises(LarsError, match="device decoders"):
+            ingest.tiff_region_device_plan(np.fromfile(p, np.uint8))
+    with pytest.raises(ValueError, match="rows"):
+        ingest.write_tiff(p, img, compression="lzw")
+        ingest.tiff_region_device_plan(np.fromfile(p, np.uint8), (5, 5))
