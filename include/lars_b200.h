@@ -311,7 +311,7 @@ int lars_lzw_decode_device(const uint8_t* src, const lars_lzw_chunk* chunks, int
                            uint32_t* counters, void* stream);
 /* EXPERIMENTAL (pinned against zlib on the CPU, not yet run on hardware): the same for Deflate-compressed strips --
  * lars_tiff_deflate_chunks fills the table, lars_inflate_decode_device runs one warp per zlib stream.  The Adler-32
- * trailers are not verified on the device. */
+ * trailers are verified on the device (checksum accumulated as the output leaves shared memory). */
 int lars_tiff_deflate_chunks(const void* file, size_t file_bytes, const lars_tiff_info* info, lars_lzw_chunk* chunks,
                              int32_t max_chunks);
 int lars_inflate_decode_device(const uint8_t* src, const lars_lzw_chunk* chunks, int32_t n_chunks, uint8_t* dst,

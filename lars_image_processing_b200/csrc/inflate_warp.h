@@ -14,7 +14,8 @@
 //   * a 32 KB ring of the most recent output -- the whole Deflate window -- which is the source of every match
 //     (lane l moves bytes l, l + 32, ...; overlapping matches index their period, so no lane waits for another) and
 //     from which completed 128-byte stretches leave for global memory as aligned 32-bit stores.
-// The Adler-32 trailer is not verified (the host readers do verify it).
+// The Adler-32 trailer IS verified: the checksum is accumulated as the output leaves the ring (lane-parallel partial
+// sums per 128-byte stretch), a stream that decodes to the wrong bytes is reported as corrupt like on the host.
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
@@ -26,7 +27,7 @@
 #define LARS_INF_FAST_BITS 10
 #define LARS_INF_FAST_SIZE (1u << LARS_INF_FAST_BITS)
 
-// shared-memory working set of one warp (39,520 bytes)
+// shared-memory working set of one warp (39,776 bytes)
 struct LarsInflateSmem {
   uint8_t ring[LARS_INF_RING];
   uint32_t inbuf[LARS_INF_INBUF_WORDS];
@@ -38,6 +39,7 @@ struct LarsInflateSmem {
   uint16_t work[16];                      // next code / offsets while a table is built; [0] = verdict
   uint16_t codes[288];                    // canonical code of every symbol of the alphabet being built
   uint8_t lens[352];                      // code lengths of the block being set up (32 + 286 + 30, rounded)
+  uint32_t adler_part[64];                // per-lane partial sums of the checksum of one 128-byte stretch
 };
 
 struct LarsInflateBits {
@@ -156,19 +158,34 @@ LARS_LZW_FN uint32_t lars_inflate_warp(const uint8_t* in, uint32_t n_in, uint8_t
   do {                                                                                                \
     LARS_LZW_SYNC();                                                                                  \
     const uint32_t head_ = (4u - ((out_skew + flushed) & 3u)) & 3u;                                   \
+    for (uint32_t i_ = 0; i_ < head_; ++i_) {        /* every lane the same few bytes: checksum */   \
+      ad1 += sm->ring[(flushed + i_) & (LARS_INF_RING - 1u)];                                         \
+      ad2 += ad1;                                                                                     \
+    }                                                                                                 \
     LARS_LZW_FOR_LANES(lane) { if ((uint32_t)lane < head_) out[flushed + lane] = sm->ring[(flushed + lane) & (LARS_INF_RING - 1u)]; } \
     flushed += head_;                                                                                 \
     while (op - flushed >= 128u) {                                                                    \
       LARS_LZW_FOR_LANES(lane) {                                                                      \
         const uint32_t a_ = flushed + 4u * (uint32_t)lane;                                            \
-        const uint32_t w_ = (uint32_t)sm->ring[a_ & (LARS_INF_RING - 1u)] |                           \
-                            ((uint32_t)sm->ring[(a_ + 1u) & (LARS_INF_RING - 1u)] << 8) |             \
-                            ((uint32_t)sm->ring[(a_ + 2u) & (LARS_INF_RING - 1u)] << 16) |            \
-                            ((uint32_t)sm->ring[(a_ + 3u) & (LARS_INF_RING - 1u)] << 24);             \
-        *reinterpret_cast<uint32_t*>(out + a_) = w_;                                                  \
+        const uint32_t b0_ = sm->ring[a_ & (LARS_INF_RING - 1u)], b1_ = sm->ring[(a_ + 1u) & (LARS_INF_RING - 1u)],  \
+                       b2_ = sm->ring[(a_ + 2u) & (LARS_INF_RING - 1u)], b3_ = sm->ring[(a_ + 3u) & (LARS_INF_RING - 1u)]; \
+        *reinterpret_cast<uint32_t*>(out + a_) = b0_ | (b1_ << 8) | (b2_ << 16) | (b3_ << 24);        \
+        /* Adler-32 of the stretch: s1 += sum b, s2 += 128 s1 + sum (128 - offset) b */               \
+        const uint32_t o_ = 4u * (uint32_t)lane;                                                      \
+        sm->adler_part[lane] = b0_ + b1_ + b2_ + b3_;                                                 \
+        sm->adler_part[32 + lane] = (128u - o_) * b0_ + (127u - o_) * b1_ + (126u - o_) * b2_ + (125u - o_) * b3_; \
       }                                                                                               \
+      LARS_LZW_SYNC();                                                                                \
+      {                                                                                               \
+        uint32_t sa_ = 0, sb_ = 0;                                                                    \
+        for (int l_ = 0; l_ < 32; ++l_) { sa_ += sm->adler_part[l_]; sb_ += sm->adler_part[32 + l_]; } \
+        ad2 = (ad2 + 128u * ad1 + sb_) % 65521u;                                                      \
+        ad1 = (ad1 + sa_) % 65521u;                                                                   \
+      }                                                                                               \
+      LARS_LZW_SYNC();                               /* the partial sums are free for the next stretch */ \
       flushed += 128u;                                                                                \
     }                                                                                                 \
+    ad1 %= 65521u; ad2 %= 65521u;                                                                     \
   } while (0)
   const uint64_t total_bits = 8ull * n_in;
   LARS_INF_NEED(32);
@@ -184,9 +201,11 @@ LARS_LZW_FN uint32_t lars_inflate_warp(const uint8_t* in, uint32_t n_in, uint8_t
   }
 
   uint32_t op = 0, flushed = 0;
+  uint32_t ad1 = 1, ad2 = 0;                       // Adler-32 of the bytes that have left the ring
   const uint32_t out_skew = (uint32_t)((uintptr_t)out & 3u);
   bool last = false, fixed_ready = false;
-  while (!last) {
+  bool cut = false;                                // the output filled up before the stream ended
+  while (!last && !cut) {
     LARS_LZW_SYNC();                               // no lane still decodes with the tables the next block replaces
     LARS_INF_NEED(3);
     last = (b.acc & 1u) != 0;
@@ -199,7 +218,8 @@ LARS_LZW_FN uint32_t lars_inflate_warp(const uint8_t* in, uint32_t n_in, uint8_t
       const uint32_t len = (uint32_t)(b.acc & 0xFFFFu), nlen = (uint32_t)((b.acc >> 16) & 0xFFFFu);
       LARS_INF_DROP(32);
       if ((len ^ nlen) != 0xFFFFu) return 0;
-      for (uint32_t i = 0; i < len && op < cap; ++i) {
+      for (uint32_t i = 0; i < len; ++i) {
+        if (op >= cap) { cut = true; break; }
         LARS_INF_NEED(8);
         const uint8_t v = (uint8_t)(b.acc & 0xFFu);
         LARS_INF_DROP(8);
@@ -208,7 +228,6 @@ LARS_LZW_FN uint32_t lars_inflate_warp(const uint8_t* in, uint32_t n_in, uint8_t
         if (op - flushed >= 512u) LARS_INF_FLUSH();
       }
       if (b.used_bits > total_bits) return 0;
-      if (op >= cap) break;
       continue;
     }
     if (type == 1u) {                              // fixed codes (RFC 1951 3.2.6)
@@ -265,7 +284,6 @@ LARS_LZW_FN uint32_t lars_inflate_warp(const uint8_t* in, uint32_t n_in, uint8_t
 
     // ---- the symbols of the block
     for (;;) {
-      if (op >= cap) { last = true; break; }
       LARS_INF_NEED(15 + 5);
       int sym;
       {
@@ -286,11 +304,11 @@ LARS_LZW_FN uint32_t lars_inflate_warp(const uint8_t* in, uint32_t n_in, uint8_t
           LARS_INF_DROP((uint32_t)l);
         }
       }
+      if (sym == 256) break;                       // end of block (also when the output is exactly full)
+      if (op >= cap) { cut = true; break; }        // more data than the caller has room for: stop here
       if (sym < 256) {
         LARS_LZW_FOR_LANES(lane) { if (lane == 0) sm->ring[op & (LARS_INF_RING - 1u)] = (uint8_t)sym; }
         ++op;
-      } else if (sym == 256) {
-        break;
       } else {
         sym -= 257;
         if (sym >= 29) return 0;
@@ -333,6 +351,7 @@ LARS_LZW_FN uint32_t lars_inflate_warp(const uint8_t* in, uint32_t n_in, uint8_t
         }
         LARS_LZW_SYNC();                           // nobody still reads the ring when a lane that runs ahead writes on
         op += keep;
+        if (keep < len) { cut = true; break; }     // the match did not fit: the output is full
       }
       if (b.used_bits > total_bits) return 0;      // the stream ended inside this block
       if (op - flushed >= 512u) LARS_INF_FLUSH();
@@ -342,6 +361,20 @@ LARS_LZW_FN uint32_t lars_inflate_warp(const uint8_t* in, uint32_t n_in, uint8_t
   LARS_LZW_SYNC();
   LARS_LZW_FOR_LANES(lane) {                       // what is left in the ring, byte by byte
     for (uint32_t a = flushed + (uint32_t)lane; a < op; a += 32u) out[a] = sm->ring[a & (LARS_INF_RING - 1u)];
+  }
+  for (uint32_t a = flushed; a < op; ++a) {        // ... and its part of the checksum (fewer than 900 bytes)
+    ad1 += sm->ring[a & (LARS_INF_RING - 1u)];
+    if (ad1 >= 65521u) ad1 -= 65521u;
+    ad2 += ad1;
+    if (ad2 >= 65521u) ad2 -= 65521u;
+  }
+  if (!cut) {                                      // the whole stream was decoded: its Adler-32 trailer must agree
+    LARS_INF_DROP((uint32_t)b.have & 7u);
+    LARS_INF_NEED(32);
+    const uint32_t t = (uint32_t)b.acc;
+    LARS_INF_DROP(32);
+    if (b.used_bits > total_bits) return 0;
+    if (lars_lzw_bswap32(t) != ((ad2 << 16) | ad1)) return 0;
   }
 #undef LARS_INF_FETCH
 #undef LARS_INF_COMMIT

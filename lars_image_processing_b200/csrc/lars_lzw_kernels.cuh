@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(LZW2_WARPS * 32, 1) lzw_decode_v2_kernel(const
 
 // Experimental (see inflate_warp.h; not yet run on hardware): one warp per zlib stream, 5 warps per CTA, one CTA per SM.
 constexpr int INF_WARPS = 5;
-constexpr int INF_SMEM_BYTES = INF_WARPS * (int)sizeof(LarsInflateSmem);     // 190 KB
+constexpr int INF_SMEM_BYTES = INF_WARPS * (int)sizeof(LarsInflateSmem);     // 194 KB
 
 __global__ void __launch_bounds__(INF_WARPS * 32, 1) inflate_decode_kernel(const LzwParams p) {
   extern __shared__ __align__(16) uint32_t lzw_tables[];
