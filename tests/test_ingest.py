@@ -908,6 +908,14 @@ def test_warp_lzw_decoder_equals_the_host_decoder(hostcheck):
         for cap in (len(d), max(1, len(d) - 1), max(1, len(d) // 2), len(d) + 100):
             produced, out = both(blob, cap)
             assert produced == min(cap, len(d)) and np.array_equal(out[:produced], d[:produced]), (kind, n, cap)
+    # strings defined early in an epoch and used again 20 KB later: variant 2 reads them back from global memory
+    # (older than its shared-memory ring is trusted for) -- no Clear in between, the middle part adds few table entries
+    a_part = rng.integers(0, 256, 300, dtype=np.uint8)
+    d = np.concatenate([a_part, ((np.arange(20000) // 50) % 2).astype(np.uint8), a_part, a_part[::-1]])
+    blob = ingest._lzw_encode(d.tobytes())
+    assert len(blob) < 1700                                            # the second A was coded with strings of the first (all literals: ~1,950)
+    produced, out = both(blob, len(d))
+    assert produced == len(d) and np.array_equal(out[:produced], d)
     rejected = 0
     for it in range(3000):
         raw = bytearray(streams[2 + it % 5])
