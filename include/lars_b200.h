@@ -140,6 +140,15 @@ int lars_wb_hist_u8(const uint8_t* src, int32_t n_frames, int64_t n_pixels, int3
  * q_lo / q_hi are fractions (reference: 0.02, 0.98). */
 int lars_wb_lut_build_u8(const uint64_t* hist, int32_t n_sets, double q_lo, double q_hi,
                          uint8_t* lut, double* pct, void* stream);
+/* The same with the reference expression named: LARS_WB_CHAIN_IMAGES is the call above
+ * (process-images.py:437-441, backend-process.py:21-26: float64 stretch, float32 store, truncation);
+ * LARS_WB_CHAIN_RGN is fix_white_balance_rgnir (process-rgn.py:25-33, :44): samples clipped to
+ * [p_lo, p_hi] first, float64 all the way, the float64 value truncated.  The two differ by one step
+ * wherever the float64 stretch lands a hair below an integer (fractional percentiles). */
+#define LARS_WB_CHAIN_IMAGES 0
+#define LARS_WB_CHAIN_RGN 1
+int lars_wb_lut_build_u8_chain(const uint64_t* hist, int32_t n_sets, double q_lo, double q_hi, int32_t chain,
+                               uint8_t* lut, double* pct, void* stream);
 
 /* ---- Pass 2: fused WB + NDVI/GNDVI/NDWI + statistics + histogram + colormap -----------
  * Replaces, in one read of the raw frame: the stretch application (process-images.py:438-441),
@@ -210,7 +219,8 @@ int lars_ndvi_f64_u8(const uint8_t* src, int64_t n_pixels, int32_t channels, dou
 int lars_index_planes_f32(const float* hi, const float* lo, int64_t n, float* out, void* stream);
 
 /* Merge n_sets x 3 statistics records (per frame, or per rank after the NCCL all-gather) into
- * 3 dataset-wide records, in index order of the input -- the exchange step of SURVEY.md 8(e). */
+ * 3 dataset-wide records, in index order of the input -- the exchange step of SURVEY.md 8(e).
+ * `out` may alias one of the input sets (a running fold: in = {fold, new}, out = fold). */
 int lars_stats_merge(const lars_index_stats* in, int32_t n_sets, lars_index_stats* out, void* stream);
 
 /* Index map of an interleaved frame whose samples are not uint8 (calculate_index applies
@@ -309,20 +319,13 @@ int lars_tiff_lzw_chunks(const void* file, size_t file_bytes, const lars_tiff_in
                          int32_t max_chunks);
 int lars_lzw_decode_device(const uint8_t* src, const lars_lzw_chunk* chunks, int32_t n_chunks, uint8_t* dst,
                            uint32_t* counters, void* stream);
-/* EXPERIMENTAL (pinned against zlib on the CPU, not yet run on hardware): the same for Deflate-compressed strips --
+/* The same for Deflate-compressed strips (pinned against zlib on the CPU, against the host reader on B200) --
  * lars_tiff_deflate_chunks fills the table, lars_inflate_decode_device runs one warp per zlib stream.  The Adler-32
  * trailers are verified on the device (checksum accumulated as the output leaves shared memory). */
 int lars_tiff_deflate_chunks(const void* file, size_t file_bytes, const lars_tiff_info* info, lars_lzw_chunk* chunks,
                              int32_t max_chunks);
 int lars_inflate_decode_device(const uint8_t* src, const lars_lzw_chunk* chunks, int32_t n_chunks, uint8_t* dst,
                                uint32_t* counters, void* stream);
-/* EXPERIMENTAL, with the above: PNG frames on the device.  The caller joins the IDAT payloads of every image into one
- * zlib stream per image, inflates them with lars_inflate_decode_device into raw = [image][row][1 + row_bytes], and
- * this call undoes the row filters into the frame slots (16-bit samples leave little-endian).  counters[0] counts
- * images with an unknown filter type. */
-int lars_png_unfilter_device(const uint8_t* raw, int64_t raw_stride, int32_t n_images, int32_t rows, int32_t width,
-                             int32_t channels, int32_t sample_bytes, uint8_t* dst, int64_t frame_stride,
-                             uint32_t* counters, void* stream);
 /* Strips / tiles that were decoded into scratch slots of slot_bytes each (rows of slot_row_bytes) are moved to their
  * place inside one frame, e.g. the row band of a tiled mosaic a rank owns.  table (device, int64 [n_chunks][5]):
  * first slot row, number of rows, first frame row, byte column in the frame, bytes per row. */

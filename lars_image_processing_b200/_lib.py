@@ -21,12 +21,13 @@ PIXEL_GROUP = 16
 STRETCH_U16_BYTES = 2064   # sizeof(lars_stretch_u16)
 CMAP_IDS = {"RdYlGn": 0, "RdYlBu": 1, "bwr": 2}
 INDEX_IDS = {"NDVI": 0, "GNDVI": 1, "NDWI": 2}
+WB_CHAINS = {"images": 0, "rgn": 1}     # LARS_WB_CHAIN_*: process-images.py:437-441 / process-rgn.py:25-44
 DTYPE_IDS = {"uint8": 0, "uint16": 1, "float32": 2, "float64": 3}
 
 EXPORTED_SYMBOLS = (
     "lars_init", "lars_shutdown", "lars_last_error", "lars_abi_version", "lars_sm_count",
     "lars_colormap_table", "lars_histogram_edges_f32",
-    "lars_wb_hist_u8", "lars_wb_lut_build_u8",
+    "lars_wb_hist_u8", "lars_wb_lut_build_u8", "lars_wb_lut_build_u8_chain",
     "lars_fused_workspace_bytes", "lars_fused_index_u8",
     "lars_map_stats_workspace_bytes", "lars_map_stats_f32", "lars_select_workspace_bytes",
     "lars_select_f32", "lars_colormap_f32", "lars_ndvi_f64_u8", "lars_index_planes_f32",
@@ -37,7 +38,7 @@ EXPORTED_SYMBOLS = (
     "lars_resize_plan_lanczos", "lars_resize_tables_lanczos", "lars_resize_lanczos_u8",
     "lars_tiff_probe", "lars_tiff_read", "lars_tiff_read_region", "lars_png_probe", "lars_png_read",
     "lars_tiff_lzw_chunks", "lars_lzw_decode_device", "lars_tiff_post_device",
-    "lars_tiff_deflate_chunks", "lars_inflate_decode_device", "lars_png_unfilter_device", "lars_untile_device",
+    "lars_tiff_deflate_chunks", "lars_inflate_decode_device", "lars_untile_device",
 )
 
 
@@ -134,6 +135,8 @@ def _declare(lib):
     lib.lars_wb_hist_u8.restype = C.c_int
     lib.lars_wb_lut_build_u8.argtypes = [vp, i32, f64, f64, vp, vp, vp]
     lib.lars_wb_lut_build_u8.restype = C.c_int
+    lib.lars_wb_lut_build_u8_chain.argtypes = [vp, i32, f64, f64, i32, vp, vp, vp]
+    lib.lars_wb_lut_build_u8_chain.restype = C.c_int
     lib.lars_fused_workspace_bytes.argtypes = [i32]
     lib.lars_fused_workspace_bytes.restype = C.c_size_t
     lib.lars_fused_index_u8.argtypes = [C.POINTER(FusedArgs), vp]
@@ -184,8 +187,6 @@ def _declare(lib):
     lib.lars_tiff_deflate_chunks.restype = C.c_int
     lib.lars_inflate_decode_device.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.lars_inflate_decode_device.restype = C.c_int
-    lib.lars_png_unfilter_device.argtypes = [vp, i64, i32, i32, i32, i32, i32, vp, i64, vp, vp]
-    lib.lars_png_unfilter_device.restype = C.c_int
     lib.lars_untile_device.argtypes = [vp, i64, i64, vp, i32, vp, i64, vp]
     lib.lars_untile_device.restype = C.c_int
     lib.lars_tiff_post_device.argtypes = [vp, i32, i64, i32, i32, i32, i32, i32, i32, vp]

@@ -46,8 +46,7 @@ int fail(int code, const char* fmt, ...) {
 constexpr int kMaxDevices = 64;
 struct DeviceState {
   bool ready = false;
-  bool lzw_v2 = false;        // the opt-in LZW kernel got its shared memory
-  bool inflate = false;       // the experimental Deflate kernel got its shared memory
+  bool inflate = false;       // the Deflate kernel got its 194 KB of shared memory
   int sm_count = 0;
   uint32_t* cmaps = nullptr;  // [3][256] packed RGB, device
 };
@@ -113,10 +112,6 @@ int lars_init(int device) {
                                  lars::SEL_SMEM_BYTES));
   LARS_CUDA(cudaFuncSetAttribute(lars::lzw_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  lars::LZW_SMEM_BYTES));
-  // opt-in variant: never let it stand in the way of the library coming up
-  st.lzw_v2 = cudaFuncSetAttribute(lars::lzw_decode_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   lars::LZW2_SMEM_BYTES) == cudaSuccess;
-  if (!st.lzw_v2) cudaGetLastError();
   st.inflate = cudaFuncSetAttribute(lars::inflate_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     lars::INF_SMEM_BYTES) == cudaSuccess;
   if (!st.inflate) cudaGetLastError();
@@ -212,6 +207,11 @@ int lars_wb_hist_u8(const uint8_t* src, int32_t n_frames, int64_t n_pixels, int3
 
 int lars_wb_lut_build_u8(const uint64_t* hist, int32_t n_sets, double q_lo, double q_hi, uint8_t* lut,
                          double* pct, void* stream) {
+  return lars_wb_lut_build_u8_chain(hist, n_sets, q_lo, q_hi, LARS_WB_CHAIN_IMAGES, lut, pct, stream);
+}
+
+int lars_wb_lut_build_u8_chain(const uint64_t* hist, int32_t n_sets, double q_lo, double q_hi, int32_t chain,
+                               uint8_t* lut, double* pct, void* stream) {
   DeviceState* st = nullptr;
   int rc = current_state(&st);
   if (rc != LARS_OK) return rc;
@@ -219,7 +219,10 @@ int lars_wb_lut_build_u8(const uint64_t* hist, int32_t n_sets, double q_lo, doub
   if (n_sets < 1) return fail(LARS_ERR_INVALID, "lars_wb_lut_build_u8: n_sets=%d", n_sets);
   if (!(q_lo >= 0.0 && q_lo <= 1.0 && q_hi >= 0.0 && q_hi <= 1.0))
     return fail(LARS_ERR_INVALID, "lars_wb_lut_build_u8: quantiles must be fractions in [0,1]");
+  if (chain != LARS_WB_CHAIN_IMAGES && chain != LARS_WB_CHAIN_RGN)
+    return fail(LARS_ERR_INVALID, "lars_wb_lut_build_u8_chain: chain=%d", chain);
   lars::K1bParams p;
+  p.chain = chain;
   p.hist = reinterpret_cast<const unsigned long long*>(hist);
   p.lut = lut;
   p.pct = pct;
@@ -1101,28 +1104,6 @@ int lars_inflate_decode_device(const uint8_t* src, const lars_lzw_chunk* chunks,
   return LARS_OK;
 }
 
-int lars_png_unfilter_device(const uint8_t* raw, int64_t raw_stride, int32_t n_images, int32_t rows, int32_t width,
-                             int32_t channels, int32_t sample_bytes, uint8_t* dst, int64_t frame_stride,
-                             uint32_t* counters, void* stream) {
-  DeviceState* st = nullptr;
-  int rc = current_state(&st);
-  if (rc != LARS_OK) return rc;
-  if (!raw || !dst || !counters) return fail(LARS_ERR_INVALID, "lars_png_unfilter_device: NULL pointer");
-  if (n_images < 1 || rows < 1 || width < 1 || channels < 1 || channels > 4 || (sample_bytes != 1 && sample_bytes != 2))
-    return fail(LARS_ERR_INVALID, "lars_png_unfilter_device: bad geometry");
-  lars::PngUnfilterParams p;
-  p.raw = raw; p.dst = dst; p.status = counters;
-  p.row_bytes = (long long)width * channels * sample_bytes;
-  if (raw_stride < (p.row_bytes + 1) * rows || frame_stride < p.row_bytes * rows)
-    return fail(LARS_ERR_INVALID, "lars_png_unfilter_device: strides smaller than an image");
-  p.raw_stride = raw_stride; p.frame_stride = frame_stride;
-  p.n_images = n_images; p.rows = rows; p.bpp = channels * sample_bytes; p.swap16 = sample_bytes == 2 ? 1 : 0;
-  const long long threads = (long long)n_images * p.bpp;
-  lars::png_unfilter_kernel<<<(unsigned)((threads + 63) / 64), 64, 0, static_cast<cudaStream_t>(stream)>>>(p);
-  LARS_CUDA(cudaGetLastError());
-  return LARS_OK;
-}
-
 int lars_untile_device(const uint8_t* scratch, int64_t slot_bytes, int64_t slot_row_bytes, const int64_t* table,
                        int32_t n_chunks, uint8_t* dst, int64_t dst_row_bytes, void* stream) {
   DeviceState* st = nullptr;
@@ -1151,20 +1132,10 @@ int lars_lzw_decode_device(const uint8_t* src, const lars_lzw_chunk* chunks, int
   if (reinterpret_cast<uintptr_t>(chunks) & 7u) return fail(LARS_ERR_INVALID, "lars_lzw_decode_device: chunks must be 8-byte aligned");
   lars::LzwParams p;
   p.src = src; p.chunks = chunks; p.dst = dst; p.status = counters; p.next = counters + 1; p.n_chunks = n_chunks;
-  static const int variant = [] {
-    const char* e = getenv("LARS_LZW_VARIANT");     // 2 = shared-memory ring kernel (experimental)
-    return (e && e[0] == '2') ? 2 : 1;
-  }();
-  if (variant == 2 && st->lzw_v2) {
-    const int want = (n_chunks + lars::LZW2_WARPS - 1) / lars::LZW2_WARPS;
-    lars::lzw_decode_v2_kernel<<<want < st->sm_count ? want : st->sm_count, lars::LZW2_WARPS * 32,
-                                 lars::LZW2_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(p);
-  } else {
-    const int want = (n_chunks + lars::LZW_WARPS - 1) / lars::LZW_WARPS;
-    const int full = st->sm_count * 3;
-    lars::lzw_decode_kernel<<<want < full ? want : full, lars::LZW_WARPS * 32, lars::LZW_SMEM_BYTES,
-                              static_cast<cudaStream_t>(stream)>>>(p);
-  }
+  const int want = (n_chunks + lars::LZW_WARPS - 1) / lars::LZW_WARPS;
+  const int full = st->sm_count * 3;
+  lars::lzw_decode_kernel<<<want < full ? want : full, lars::LZW_WARPS * 32, lars::LZW_SMEM_BYTES,
+                            static_cast<cudaStream_t>(stream)>>>(p);
   LARS_CUDA(cudaGetLastError());
   return LARS_OK;
 }

@@ -187,6 +187,7 @@ struct K1bParams {
   uint8_t* lut;                    // [set][3][256]
   double* pct;                     // [set][3][2] or nullptr
   double q_lo, q_hi;
+  int chain;                       // LARS_WB_CHAIN_*: which reference expression the table restates
 };
 
 __global__ void __launch_bounds__(256) wb_lut_build_u8_kernel(const K1bParams p) {
@@ -242,7 +243,8 @@ __global__ void __launch_bounds__(256) wb_lut_build_u8_kernel(const K1bParams p)
     if (p.pct) p.pct[(long long)blockIdx.x * 2 + v] = r;
   }
   __syncthreads();
-  p.lut[base + v] = lars_wb_lut_entry((double)v, pcts[0], pcts[1]);
+  p.lut[base + v] = p.chain == 1 ? lars_wb_lut_entry_rgn((double)v, pcts[0], pcts[1])
+                                 : lars_wb_lut_entry((double)v, pcts[0], pcts[1]);
 }
 
 }  // namespace lars

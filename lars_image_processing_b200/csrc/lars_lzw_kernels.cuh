@@ -12,7 +12,6 @@
 #include "../../include/lars_b200.h"
 #include "lzw_warp.h"
 #include "inflate_warp.h"
-#include "png_device.h"
 
 namespace lars {
 
@@ -45,32 +44,7 @@ __global__ void __launch_bounds__(LZW_WARPS * 32) lzw_decode_kernel(const LzwPar
   }
 }
 
-// Variant 2 (opt-in through LARS_LZW_VARIANT=2, see lzw_warp.h): per warp a table, a 16 KB output ring and a
-// 1 KB ring of the compressed stream.
-constexpr int LZW2_WARPS = 6;                                              // per CTA, one CTA per SM
-constexpr int LZW2_WARP_SMEM = 4096 * 4 + (int)LARS_LZW_RING + (int)LARS_LZW_INBUF_WORDS * 4;   // 33,792 B
-constexpr int LZW2_SMEM_BYTES = LZW2_WARPS * LZW2_WARP_SMEM;               // 195 KB
-
-__global__ void __launch_bounds__(LZW2_WARPS * 32, 1) lzw_decode_v2_kernel(const LzwParams p) {
-  extern __shared__ __align__(16) uint32_t lzw_tables[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t* table = lzw_tables + warp * (LZW2_WARP_SMEM / 4);
-  uint32_t* inbuf = table + 4096;
-  uint8_t* ring = reinterpret_cast<uint8_t*>(inbuf + LARS_LZW_INBUF_WORDS);
-  for (;;) {
-    unsigned int k = 0;
-    if (lane == 0) k = atomicAdd(p.next, 1u);
-    k = __shfl_sync(0xffffffffu, k, 0);
-    if (k >= (unsigned int)p.n_chunks) break;
-    const lars_lzw_chunk c = p.chunks[k];
-    const uint32_t produced = lars_lzw_decode_warp_v2(p.src + c.src_offset, c.src_bytes, p.dst + c.dst_offset,
-                                                      c.dst_bytes, table, ring, inbuf);
-    if (lane == 0 && produced < c.dst_bytes) atomicAdd(p.status, 1u);
-    __syncwarp();
-  }
-}
-
-// Experimental (see inflate_warp.h; not yet run on hardware): one warp per zlib stream, 5 warps per CTA, one CTA per SM.
+// Deflate strips (inflate_warp.h): one warp per zlib stream, 5 warps per CTA, one CTA per SM.
 constexpr int INF_WARPS = 5;
 constexpr int INF_SMEM_BYTES = INF_WARPS * (int)sizeof(LarsInflateSmem);     // 194 KB
 
@@ -88,23 +62,6 @@ __global__ void __launch_bounds__(INF_WARPS * 32, 1) inflate_decode_kernel(const
     if (lane == 0 && produced < c.dst_bytes) atomicAdd(p.status, 1u);
     __syncwarp();
   }
-}
-
-// Experimental (png_device.h): the PNG row filters of a batch of inflated images, one thread per byte lane of an image.
-struct PngUnfilterParams {
-  const uint8_t* raw;              // [image][row][1 + row_bytes]
-  uint8_t* dst;                    // frame batch
-  uint32_t* status;                // [1]: images with an unknown row filter
-  long long raw_stride, frame_stride, row_bytes;
-  int n_images, rows, bpp, swap16;
-};
-
-__global__ void __launch_bounds__(64) png_unfilter_kernel(const PngUnfilterParams p) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= p.n_images * p.bpp) return;
-  const int img = t / p.bpp, k = t % p.bpp;
-  if (!lars_png_unfilter_lane(p.raw + img * p.raw_stride, p.dst + img * p.frame_stride, p.rows, p.row_bytes, p.bpp, k, p.swap16))
-    atomicAdd(p.status, 1u);
 }
 
 // Strips / tiles decoded into scratch slots -> their place inside one frame (a row band of a mosaic): per chunk a

@@ -532,9 +532,12 @@ __global__ void __launch_bounds__(256) index_planes_f32_kernel(const float* __re
 // This is the local half of the multi-GPU exchange: every rank merges its
 // own frames, the packed records are all-gathered over NCCL, and the same kernel merges the
 // per-rank records in rank order -- deterministic, no floating-point atomics.
+// `out` may be one of the input sets (the running fold of a survey merges {fold, new} into fold): no
+// __restrict__ on either pointer, every thread reads all it needs of a bin / field before that bin / field
+// is written (own histogram bin per thread; the scalars are written by lane 0 after the warp's shuffles).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(LARS_MAX_BINS) stats_merge_kernel(const lars_index_stats* __restrict__ in,
-                                                                    int n_sets, lars_index_stats* __restrict__ out) {
+__global__ void __launch_bounds__(LARS_MAX_BINS) stats_merge_kernel(const lars_index_stats* in, int n_sets,
+                                                                    lars_index_stats* out) {
   const int idx = blockIdx.x;   // index 0..2
   const int tid = threadIdx.x;  // histogram bin
   unsigned long long h = 0;

@@ -102,8 +102,11 @@ class AsyncDatasetStatistics:
     Ranks no longer meet once per step, so host-side jitter of one rank does not stall the others.
     """
 
-    def __init__(self, engine, group=None, depth: int = 2):
+    def __init__(self, engine, group=None, depth: int = 2, timing: bool = False):
+        """``timing``: keep a CUDA-event pair around every all-gather (``gather_us()`` reads them)."""
         self.engine, self.group, self.depth = engine, group, max(2, int(depth))
+        self.timing = bool(timing)
+        self.gather_events: list = []
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         dev = engine.device
         self.side = torch.cuda.Stream(device=dev)
@@ -133,13 +136,27 @@ class AsyncDatasetStatistics:
             return
         self.side.wait_event(ev)
         with torch.cuda.stream(self.side):
+            if self.timing:
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record(self.side)
             dist.all_gather_into_tensor(self.gathered[k], self.local[k], group=self.group)
+            if self.timing:
+                t1.record(self.side)
+                self.gather_events.append((t0, t1))
             with torch.cuda.device(eng.device):
                 check(eng.lib.lars_stats_merge(self.gathered[k].data_ptr(), self.world, self.out[k].data_ptr(),
                                                self.side.cuda_stream), "lars_stats_merge")
             done = torch.cuda.Event()
             done.record(self.side)
         self.done[k] = done
+
+    def gather_us(self, reset: bool = True) -> List[float]:
+        """Device time of every timed all-gather so far, in microseconds (synchronises the side stream)."""
+        self.side.synchronize()
+        out = [a.elapsed_time(b) * 1e3 for a, b in self.gather_events]
+        if reset:
+            self.gather_events = []
+        return out
 
     def result(self, stream=None) -> torch.Tensor:
         """Dataset-wide records of the latest submitted step; ``stream`` waits for them."""

@@ -200,16 +200,18 @@ class Engine:
                                            1 if shared else 0, s.cuda_stream), "lars_wb_hist_u8")
         return hist
 
-    def wb_lut(self, hist: torch.Tensor, quantiles=DEFAULT_QUANTILES, stream=None):
-        """K1b: histograms -> (uint8 LUTs [S,3,256], float64 percentiles [S,3,2])."""
+    def wb_lut(self, hist: torch.Tensor, quantiles=DEFAULT_QUANTILES, stream=None, chain: str = "images"):
+        """K1b: histograms -> (uint8 LUTs [S,3,256], float64 percentiles [S,3,2]).
+        ``chain``: "images" = process-images.py:437-441 (float64 stretch, float32 store, truncation);
+        "rgn" = process-rgn.py:25-44 (pre-clip, float64 truncated directly)."""
         s = stream or self.stream()
         n_sets = hist.shape[0]
         lut = self._alloc((n_sets, 3, 256), torch.uint8, s)
         pct = self._alloc((n_sets, 3, 2), torch.float64, s)
         with torch.cuda.device(self.device):
-            check(self.lib.lars_wb_lut_build_u8(hist.data_ptr(), n_sets, float(quantiles[0]),
-                                                float(quantiles[1]), lut.data_ptr(), pct.data_ptr(),
-                                                s.cuda_stream), "lars_wb_lut_build_u8")
+            check(self.lib.lars_wb_lut_build_u8_chain(hist.data_ptr(), n_sets, float(quantiles[0]),
+                                                      float(quantiles[1]), _lib.WB_CHAINS[chain], lut.data_ptr(),
+                                                      pct.data_ptr(), s.cuda_stream), "lars_wb_lut_build_u8_chain")
         return lut, pct
 
     def alloc_outputs(self, frames: DeviceFrames, outputs=ALL_OUTPUTS, stream=None) -> DeviceOutputs:
@@ -332,7 +334,8 @@ class Engine:
 
     def process_device(self, frames: DeviceFrames, outputs=ALL_OUTPUTS, white_balance: bool = True,
                        quantiles=DEFAULT_QUANTILES, out: Optional[DeviceOutputs] = None,
-                       stream=None, tiles_of_one_image: bool = False, hist_hook=None, **kw) -> DeviceOutputs:
+                       stream=None, tiles_of_one_image: bool = False, hist_hook=None, wb_chain: str = "images",
+                       **kw) -> DeviceOutputs:
         """Pass 1 + LUT + Pass 2 on a device-resident batch; nothing is synchronised.
 
         ``tiles_of_one_image``: the frames are tiles / row bands of ONE image (orthomosaic): the
@@ -346,6 +349,9 @@ class Engine:
             if not white_balance:
                 raise LarsError("uint16 frames go through the white-balance stretch (uint8 out); "
                                 "there is no identity mode for them")
+            if wb_chain != "images":
+                raise LarsError("the process-rgn.py chain exists for uint8 frames only (its Image.open route "
+                                "cannot deliver 16-bit RGB)")
             res.wb_lut, res.wb_pct = self.wb_stretch_u16(frames, quantiles, tiles_of_one_image, s, hist_hook=hist_hook)
             return self.fused(frames, res.wb_lut, outputs=outputs, out=res, stream=s, **kw)
         if white_balance:
@@ -353,7 +359,7 @@ class Engine:
             if hist_hook is not None:
                 with torch.cuda.stream(s):
                     hist_hook(res.wb_hist)
-            res.wb_lut, res.wb_pct = self.wb_lut(res.wb_hist, quantiles, stream=s)
+            res.wb_lut, res.wb_pct = self.wb_lut(res.wb_hist, quantiles, stream=s, chain=wb_chain)
             lut = res.wb_lut
         return self.fused(frames, lut, outputs=outputs, out=res, stream=s, **kw)
 
@@ -563,6 +569,78 @@ class Engine:
                 ev_out[c].record(s_out)
         s_out.synchronize()
 
+    def run_host_mosaic(self, host_tiles: torch.Tensor, shape, host_out: Dict[str, torch.Tensor], chunk: int = 4,
+                        hist_hook=None, quantiles=DEFAULT_QUANTILES, **kw) -> torch.Tensor:
+        """The tiles of ONE image this rank owns (BASELINE config 4: a tile-sharded orthomosaic) from pinned host
+        memory to host results.  The white-balance percentiles are global to the image
+        (process-images.py:435-438), so the pass has a barrier in the middle: every tile is uploaded, ONE
+        histogram is accumulated over all of them, ``hist_hook(hist)`` makes it image-wide (SUM all-reduce of
+        the [1, 3, 256] counters over the ranks), one LUT is built, and only then Pass 2 runs chunk by chunk with
+        the D2H of chunk c-1 overlapping the kernels of chunk c.  uint8 tiles.  Returns the per-tile statistics
+        records on the device ([T, 3, 576]; merged image-wide by ``distributed.dataset_statistics``)."""
+        h, w, ch = shape
+        T = host_tiles.shape[0]
+        npx = h * w
+        nbytes = npx * ch
+        if host_tiles.dtype != torch.uint8 or host_tiles.shape[1] != nbytes:
+            raise ValueError(f"host_tiles must be uint8 [T, {nbytes}] for this tile shape")
+        outputs = tuple(k for k in ALL_OUTPUTS if k in host_out)
+        st = getattr(self._tls, "mosaic", None)
+        key = (T, chunk, h, w, ch, outputs)
+        if st is None or st["key"] != key:
+            s_cmp, s_out = torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)
+            tiles = self.alloc_frames(T, h, w, ch, s_cmp)
+            slots = []
+            for _ in range(2):
+                view = DeviceFrames(tiles.data[:chunk], npx, ch, (h, w), 1)
+                slots.append(self.alloc_outputs(view, tuple(k for k in outputs if k != "stats"), s_cmp))
+            stats = self._alloc((T, 3, INDEX_STATS_DTYPE.itemsize), torch.uint8, s_cmp)
+            st = {"key": key, "streams": (s_cmp, s_out), "tiles": tiles, "slots": slots, "stats": stats}
+            self._tls.mosaic = st
+        s_cmp, s_out = st["streams"]
+        tiles, slots, stats = st["tiles"], st["slots"], st["stats"]
+        with torch.cuda.stream(s_cmp):
+            tiles.data[:, :nbytes].copy_(host_tiles, non_blocking=True)
+            hist = self.wb_histogram(tiles, shared=True, stream=s_cmp)
+            if hist_hook is not None:
+                hist_hook(hist)
+            lut, _ = self.wb_lut(hist, quantiles, stream=s_cmp)
+        n_chunks = (T + chunk - 1) // chunk
+        ev_cmp = [torch.cuda.Event() for _ in range(n_chunks)]
+        ev_out = [torch.cuda.Event() for _ in range(n_chunks)]
+        for c in range(n_chunks):
+            a, b = c * chunk, min(T, (c + 1) * chunk)
+            k = b - a
+            res = slots[c & 1]
+            view = DeviceFrames(tiles.data[a:b], npx, ch, (h, w), 1)
+            with torch.cuda.stream(s_cmp):
+                if c >= 2:
+                    s_cmp.wait_event(ev_out[c - 2])         # slot's outputs drained
+                sub = DeviceOutputs(frames=view,
+                                    wb=None if res.wb is None else res.wb[:k],
+                                    maps=None if res.maps is None else res.maps[:, :k],
+                                    rgb=None if res.rgb is None else res.rgb[:, :k],
+                                    stats=stats[a:b] if "stats" in outputs else None)
+                self.fused(view, lut, outputs=outputs, out=sub, stream=s_cmp, **kw)
+                ev_cmp[c].record(s_cmp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_cmp[c])
+                if "wb" in host_out:
+                    host_out["wb"][a:b].copy_(sub.wb[:k, :npx * ch], non_blocking=True)
+                if "maps" in host_out:
+                    for i in range(3):
+                        if sub.map_mask[i]:
+                            host_out["maps"][i, a:b].copy_(sub.maps[i, :k, :npx], non_blocking=True)
+                if "rgb" in host_out:
+                    for i in range(3):
+                        if sub.rgb_mask[i]:
+                            host_out["rgb"][i, a:b].copy_(sub.rgb[i, :k, :npx * 3], non_blocking=True)
+                if "stats" in host_out:
+                    host_out["stats"][a:b].copy_(stats[a:b], non_blocking=True)
+                ev_out[c].record(s_out)
+        s_out.synchronize()
+        return stats
+
     @staticmethod
     def _check_frame(img: np.ndarray) -> np.ndarray:
         img = np.asarray(img)
@@ -608,7 +686,12 @@ class FramePlan:
     """
 
     def __init__(self, engine: "Engine", frames: DeviceFrames, outputs=ALL_OUTPUTS, white_balance: bool = True,
-                 quantiles=DEFAULT_QUANTILES, merge_dataset: bool = False, stream=None, **fused_kw):
+                 quantiles=DEFAULT_QUANTILES, merge_dataset: bool = False, stream=None,
+                 tiles_of_one_image: bool = False, hist_hook=None, **fused_kw):
+        """``tiles_of_one_image``: the frames are tiles of ONE image (orthomosaic, BASELINE config 4): Pass 1
+        accumulates a single histogram over all of them, ``hist_hook(hist)`` runs on the plan's stream between
+        Pass 1 and the LUT build (the multi-GPU path SUM-all-reduces the [1, 3, 256] counters there) and one
+        LUT serves every tile (process-images.py:435-438: the percentiles are global to the image)."""
         self.engine = engine
         self.frames = frames
         self.stream = stream or engine.stream()
@@ -618,6 +701,12 @@ class FramePlan:
         self.quantiles = (float(quantiles[0]), float(quantiles[1]))
         self.out = engine.alloc_outputs(frames, outputs, s)
         self.u16 = frames.sample_bytes == 2
+        self.shared = bool(tiles_of_one_image)
+        self.hist_hook = hist_hook
+        if self.shared and (self.u16 or not white_balance):
+            raise LarsError("FramePlan(tiles_of_one_image=True) covers white-balanced uint8 tiles; uint16 mosaics go "
+                            "through Engine.process_device (staged two-level histogram)")
+        n_sets = 1 if self.shared else F
         if self.u16:
             if not white_balance:
                 raise LarsError("uint16 frames go through the white-balance stretch; there is no identity mode")
@@ -627,15 +716,36 @@ class FramePlan:
             self._u16_ws_bytes = int(engine.lib.lars_wb_u16_workspace_bytes(F))
             self._u16_ws = engine._alloc((self._u16_ws_bytes,), torch.uint8, s)
         else:
-            self.hist = engine._alloc((F, 3, 256), torch.int64, s) if white_balance else None
-            self.lut = engine._alloc((F, 3, 256), torch.uint8, s) if white_balance else None
-            self.pct = engine._alloc((F, 3, 2), torch.float64, s) if white_balance else None
+            self.hist = engine._alloc((n_sets, 3, 256), torch.int64, s) if white_balance else None
+            self.lut = engine._alloc((n_sets, 3, 256), torch.uint8, s) if white_balance else None
+            self.pct = engine._alloc((n_sets, 3, 2), torch.float64, s) if white_balance else None
         self.out.wb_hist, self.out.wb_lut, self.out.wb_pct = self.hist, self.lut, self.pct
         self.merged = engine._alloc((3, INDEX_STATS_DTYPE.itemsize), torch.uint8, s) \
             if (merge_dataset and "stats" in outputs) else None
         # one dry run builds the argument block (and the workspace) through the normal path
         self._args = engine._build_fused_args(frames, self.lut, outputs, self.out, s, **fused_kw)
+        self._stats_ptr = self._args.stats
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+
+    def rebind(self, frames: DeviceFrames, stats: Optional[torch.Tensor] = None) -> "FramePlan":
+        """Point the plan at another input batch of the SAME geometry (a group of a resident survey or of a
+        device ring) and, optionally, at another ``[F, 3, 576]`` destination for the statistics records; every
+        other buffer (histograms, LUTs, maps, images, workspace) is reused.  Not for captured plans."""
+        old = self.frames
+        if (frames.n_frames, frames.n_pixels, frames.channels, frames.sample_bytes, frames.stride_bytes) != \
+                (old.n_frames, old.n_pixels, old.channels, old.sample_bytes, old.stride_bytes):
+            raise ValueError("rebind needs a batch of the same geometry")
+        if self.graph is not None:
+            raise LarsError("a captured plan cannot be rebound")
+        self.frames = frames
+        self.out.frames = frames
+        self._args.src = frames.data.data_ptr()
+        if stats is not None:
+            if self._stats_ptr is None or tuple(stats.shape) != (frames.n_frames, 3, INDEX_STATS_DTYPE.itemsize):
+                raise ValueError("stats must be [n_frames, 3, 576] uint8 and the plan must produce statistics")
+            self._args.stats = stats.data_ptr()
+            self.out.stats = stats
+        return self
 
     def run(self, fused_events=None) -> DeviceOutputs:
         """Enqueue one step on the plan's stream (no allocation, no synchronisation).
@@ -648,8 +758,11 @@ class FramePlan:
                   "lars_wb_stretch_build_u16")
         elif self.white_balance:
             check(lib.lars_wb_hist_u8(fr.data.data_ptr(), fr.n_frames, fr.n_pixels, fr.channels, fr.stride_bytes,
-                                      self.hist.data_ptr(), 0, sp), "lars_wb_hist_u8")
-            check(lib.lars_wb_lut_build_u8(self.hist.data_ptr(), fr.n_frames, self.quantiles[0], self.quantiles[1],
+                                      self.hist.data_ptr(), 1 if self.shared else 0, sp), "lars_wb_hist_u8")
+            if self.hist_hook is not None:
+                with torch.cuda.stream(self.stream):
+                    self.hist_hook(self.hist)
+            check(lib.lars_wb_lut_build_u8(self.hist.data_ptr(), self.hist.shape[0], self.quantiles[0], self.quantiles[1],
                                            self.lut.data_ptr(), self.pct.data_ptr(), sp), "lars_wb_lut_build_u8")
         if fused_events is not None:
             fused_events[0].record(self.stream)

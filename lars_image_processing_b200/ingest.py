@@ -490,17 +490,19 @@ def write_tiff(path, array: np.ndarray, big_endian: bool = False, rows_per_strip
 # ------------------------------------------------------------------------------------------
 # device-side decode of LZW TIFF frames
 # ------------------------------------------------------------------------------------------
-# Device-side Deflate (inflate_warp.h) is pinned against zlib on the CPU but has not run on hardware yet: it only
-# takes part when this is set, and device_decodable() keeps answering for the LZW path alone.
-EXPERIMENTAL_DEVICE_INFLATE = os.environ.get("LARS_EXPERIMENTAL_DEVICE_INFLATE") == "1"
+# LZW strips go through lars_lzw_decode_device, Deflate strips through lars_inflate_decode_device (one warp per zlib
+# stream).  Both measured on B200 against the 16-thread host readers (profiles/r02_device_decode.log): LZW 88 ms
+# against 250-277 ms per 16 x 12 MP of noise, Deflate 147 ms against 222 ms (37 against 64 ms on blocky content).
+# PNG frames stay on the host reader: one zlib stream per image leaves the GPU with one warp per frame, and the
+# device path measured 4-11x slower than 16 host threads -- it was removed.
 
 
 def device_decodable(source: Source) -> bool:
-    """True if :func:`decode_tiff_batch_on_device` takes this file: an LZW-compressed TIFF stored in strips
-    of at most 1 MB decoded (what libtiff / Pillow / GDAL write by default for LZW)."""
+    """True if :func:`decode_tiff_batch_on_device` takes this file: an LZW- or Deflate-compressed TIFF stored in
+    strips of at most 1 MB decoded (what libtiff / Pillow / GDAL write by default)."""
     def probe(buf):
         info = _tiff_probe(buf)
-        if info is None or info.compression != 5 or info.tile_width > 0 or info.planar_config != 1 or info.bits_per_sample > 16:
+        if info is None or info.compression not in (5, 8) or info.tile_width > 0 or info.planar_config != 1 or info.bits_per_sample > 16:
             return False
         rows = min(info.rows_per_strip, info.height)
         return rows * info.width * info.samples_per_pixel * (info.bits_per_sample // 8) <= (1 << 20)
@@ -517,7 +519,7 @@ def device_decodable(source: Source) -> bool:
 
 def decode_tiff_batch_on_device(sources: Sequence[Source], engine: Optional[Engine] = None, stream=None,
                                 threads: Optional[int] = None, timings: Optional[dict] = None) -> DeviceFrames:
-    """Equally-shaped LZW TIFF frames -> a device-resident frame batch, decoded ON the GPU: the compressed
+    """Equally-shaped LZW (or Deflate) TIFF frames -> a device-resident frame batch, decoded ON the GPU: the compressed
     file bytes are uploaded as they are (memory-mapped files copied by ``threads`` host threads into one pinned
     staging buffer, one H2D copy), one warp decodes each strip straight into its frame slot
     (``lars_lzw_decode_device``), a second kernel undoes the differencing predictor / big-endian samples.
@@ -546,7 +548,7 @@ def decode_tiff_batch_on_device(sources: Sequence[Source], engine: Optional[Engi
             info = _lib.TiffInfo()
             check(lib.lars_tiff_probe(raw.ctypes.data, raw.size, C.byref(info)), "lars_tiff_probe")
             chunks = np.zeros(info.n_strips, _lib.LZW_CHUNK_DTYPE)
-            if info.compression == 8 and EXPERIMENTAL_DEVICE_INFLATE:
+            if info.compression == 8:
                 check(lib.lars_tiff_deflate_chunks(raw.ctypes.data, raw.size, C.byref(info), chunks.ctypes.data, chunks.size),
                       "lars_tiff_deflate_chunks")
             else:
@@ -618,86 +620,6 @@ def decode_tiff_batch_on_device(sources: Sequence[Source], engine: Optional[Engi
     return frames
 
 
-def png_device_plan(blobs: Sequence[np.ndarray]) -> dict:
-    """Host side of the (experimental) device PNG path, no GPU involved: for equally-shaped PNG files given as uint8
-    arrays, the staging buffer -- every image's IDAT payloads joined into one zlib stream, streams 8-byte aligned --
-    the ``lars_lzw_chunk`` table for ``lars_inflate_decode_device`` (one stream per image into raw scratch of
-    ``rows * (1 + row_bytes)`` bytes per image) and the geometry for ``lars_png_unfilter_device``."""
-    lib = _lib.load()
-    infos, spans = [], []
-    for raw in blobs:
-        info = _lib.PngInfo()
-        check(lib.lars_png_probe(raw.ctypes.data, raw.size, C.byref(info)), "lars_png_probe")
-        at, idat = 8, []
-        while at + 12 <= raw.size:                     # the probe has validated the chunk structure
-            n = int.from_bytes(raw[at:at + 4].tobytes(), "big")
-            kind = raw[at + 4:at + 8].tobytes()
-            if kind == b"IDAT":
-                idat.append((at + 8, n))
-            elif kind == b"IEND":
-                break
-            at += 12 + n
-        infos.append(info)
-        spans.append(idat)
-    first = infos[0]
-    key = lambda i: (i.height, i.width, i.channels, i.bit_depth)
-    if any(key(i) != key(first) for i in infos):
-        raise ValueError("all frames of a batch must share shape and sample width")
-    sb = first.bit_depth // 8
-    row_bytes = first.width * first.channels * sb
-    raw_stride = (first.height * (row_bytes + 1) + 15) & ~15
-    starts, pos = [], 0
-    for info in infos:
-        starts.append(pos)
-        pos += (int(info.idat_bytes) + 7) & ~7
-    staging = np.zeros(pos, np.uint8)
-    chunks = np.zeros(len(blobs), _lib.LZW_CHUNK_DTYPE)
-    for i, (raw, idat) in enumerate(zip(blobs, spans)):
-        w = starts[i]
-        for off, n in idat:
-            staging[w:w + n] = raw[off:off + n]
-            w += n
-        chunks[i] = (starts[i], i * raw_stride, w - starts[i], first.height * (row_bytes + 1))
-    return {"staging": staging, "chunks": chunks, "height": first.height, "width": first.width, "channels": first.channels,
-            "sample_bytes": sb, "row_bytes": row_bytes, "raw_stride": raw_stride}
-
-
-def decode_png_batch_on_device(sources: Sequence[Source], engine: Optional[Engine] = None, stream=None) -> DeviceFrames:
-    """EXPERIMENTAL (needs ``LARS_EXPERIMENTAL_DEVICE_INFLATE=1``; pinned on the CPU, not yet run on hardware):
-    equally-shaped PNG frames decoded on the GPU -- one warp inflates each image's zlib stream, one thread per byte lane
-    undoes the row filters -- into a device-resident frame batch."""
-    if not EXPERIMENTAL_DEVICE_INFLATE:
-        raise LarsError("device-side PNG decode is experimental: set LARS_EXPERIMENTAL_DEVICE_INFLATE=1 to try it")
-    eng = engine or get_engine()
-    lib = eng.lib
-    s = stream or eng.stream()
-    blobs = [np.frombuffer(src, dtype=np.uint8) if isinstance(src, (bytes, bytearray, memoryview))
-             else np.fromfile(os.fspath(src), dtype=np.uint8) for src in sources]
-    plan = png_device_plan(blobs)
-    n = len(blobs)
-    frames = eng.alloc_frames(n, plan["height"], plan["width"], plan["channels"], s, sample_bytes=plan["sample_bytes"])
-    table_at = (plan["staging"].size + 7) & ~7
-    total = table_at + plan["chunks"].nbytes
-    host = torch.empty(total, dtype=torch.uint8, pin_memory=True)
-    host_np = host.numpy()
-    host_np[:plan["staging"].size] = plan["staging"]
-    host_np[table_at:] = plan["chunks"].view(np.uint8)
-    with torch.cuda.stream(s), torch.cuda.device(eng.device):
-        dev = torch.empty(total, dtype=torch.uint8, device=eng.device)
-        dev.copy_(host, non_blocking=True)
-        scratch = torch.empty(n * plan["raw_stride"], dtype=torch.uint8, device=eng.device)
-        counters = torch.zeros(4, dtype=torch.int32, device=eng.device)
-        check(lib.lars_inflate_decode_device(dev.data_ptr(), dev.data_ptr() + table_at, n, scratch.data_ptr(),
-                                             counters.data_ptr(), s.cuda_stream), "lars_inflate_decode_device")
-        check(lib.lars_png_unfilter_device(scratch.data_ptr(), plan["raw_stride"], n, plan["height"], plan["width"],
-                                           plan["channels"], plan["sample_bytes"], frames.data.data_ptr(), frames.stride_bytes,
-                                           counters[2:].data_ptr(), s.cuda_stream), "lars_png_unfilter_device")
-        bad = counters.cpu()
-    if int(bad[0]) or int(bad[2]):
-        raise LarsError(f"{int(bad[0])} PNG stream(s) corrupt or short, {int(bad[2])} image(s) with an unknown row filter")
-    return frames
-
-
 def tiff_region_device_plan(raw: np.ndarray, rows: Optional[Sequence[int]] = None) -> dict:
     """Host side of decoding a row band of a (possibly tiled) LZW / Deflate TIFF on the device, no GPU involved: which
     strips / tiles touch rows ``[rows[0], rows[1])``, the ``lars_lzw_chunk`` table that decodes each of them into its
@@ -750,7 +672,7 @@ def decode_tiff_region_on_device(source: Source, rows: Optional[Sequence[int]] =
                                  stream=None) -> DeviceFrames:
     """A row band (default: the whole image) of an LZW / Deflate TIFF -- strips or tiles -- decoded on the GPU into a
     one-frame device batch, e.g. the band of a tiled mosaic a rank owns (``read_mosaic_band`` without the host decode).
-    Only the chunks under the band are uploaded.  Deflate needs ``LARS_EXPERIMENTAL_DEVICE_INFLATE=1``."""
+    Only the chunks under the band are uploaded."""
     eng = engine or get_engine()
     lib = eng.lib
     s = stream or eng.stream()
@@ -758,8 +680,6 @@ def decode_tiff_region_on_device(source: Source, rows: Optional[Sequence[int]] =
         else np.fromfile(os.fspath(source), dtype=np.uint8)
     plan = tiff_region_device_plan(raw, rows)
     info = plan["info"]
-    if info.compression == 8 and not EXPERIMENTAL_DEVICE_INFLATE:
-        raise LarsError("device-side Deflate decode is experimental: set LARS_EXPERIMENTAL_DEVICE_INFLATE=1 to try it")
     chunks, moves = plan["chunks"].copy(), plan["moves"]
     n = chunks.size
     # staging: the chunks' compressed bytes back to back (8-byte aligned), then the two tables

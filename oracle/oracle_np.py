@@ -122,6 +122,28 @@ def wb_lut_from_percentiles(lo, hi, domain=256):
     return out
 
 
+def wb_lut_rgn_from_percentiles(lo, hi, domain=256):
+    """uint8 LUT equal to process-rgn.py:25-33, :44 evaluated on every possible sample value: pre-clip to
+    [lo, hi], float64 stretch, clip, float64 -> uint8 truncation (no float32 store in between, unlike
+    process-images.py:438).  ``hi == lo``: every sample clips to lo, 0/0 = NaN -> 0."""
+    v = np.arange(domain, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inner = np.clip(v, np.float64(lo), np.float64(hi))
+        t = np.clip((inner - np.float64(lo)) / (np.float64(hi) - np.float64(lo)) * 255, 0, 255)
+        out = np.where(np.isnan(t), 0.0, t).astype(np.uint8)
+    return out
+
+
+def fix_white_balance_rgnir_from_hist(img_array):
+    """fix_white_balance_rgnir_array as histogram -> percentiles -> LUT -> gather (the GPU formulation)."""
+    hist3 = channel_histograms(img_array)
+    out = np.zeros(img_array.shape[:2] + (3,), dtype=np.uint8)
+    for c in (0, 1, 2):
+        lo, hi = percentile_from_hist(hist3[c], 0.02), percentile_from_hist(hist3[c], 0.98)
+        out[:, :, c] = wb_lut_rgn_from_percentiles(lo, hi, hist3.shape[1])[img_array[:, :, c]]
+    return out
+
+
 def wb_luts_from_hist(hist3, q=(0.02, 0.98)):
     """(3, domain) histograms -> ((3,2) float64 percentiles, (3, domain) uint8 LUTs)."""
     hist3 = np.asarray(hist3)
@@ -334,15 +356,21 @@ def analyze_frame(img_array, indices=INDEX_TYPES, bins=HIST_BINS, want_rgb=True,
     return out
 
 
-def reference_cpu_path(img_array, indices=INDEX_TYPES, colormap=True):
+def reference_cpu_path(img_array, indices=INDEX_TYPES, colormap=True, reference=None):
     """The reference's own sequence of NumPy calls for one frame -- what the CPU baseline
     times: fix_white_balance -> calculate_index xk -> analyze_index xk (+ np.std and
-    np.histogram(50)) -> colormap gather."""
-    wb = fix_white_balance_literal(img_array)
+    np.histogram(50)) -> colormap gather.
+    ``reference``: a module / namespace holding the reference's OWN ``fix_white_balance``, ``calculate_index``
+    and ``analyze_index`` (oracle/_ref/process_images.py, made by oracle/build_ref.py); default: this port.
+    The colormap gather is always the restatement (matplotlib is absent)."""
+    wb_fn = reference.fix_white_balance if reference is not None else fix_white_balance_literal
+    index_fn = reference.calculate_index if reference is not None else calculate_index
+    stats_fn = reference.analyze_index if reference is not None else analyze_index
+    wb = wb_fn(img_array)
     res = {}
     for name in indices:
-        m = calculate_index(wb, name)
-        st = analyze_index(m, name)
+        m = index_fn(wb, name)
+        st = stats_fn(m, name)
         st["std"] = float(np.std(m))
         st["hist"] = index_histogram(m)
         if colormap:

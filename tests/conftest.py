@@ -23,7 +23,7 @@ def hostcheck():
     os.makedirs(out_dir, exist_ok=True)
     lib_path = os.path.join(out_dir, "libhostcheck.so")
     csrc = os.path.join(ROOT, "lars_image_processing_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, h) for h in ("pixel_math.h", "lzw_warp.h", "inflate_warp.h", "png_device.h", "tiff_host.h")]
+    deps = [src] + [os.path.join(csrc, h) for h in ("pixel_math.h", "lzw_warp.h", "inflate_warp.h", "tiff_host.h")]
     if not os.path.isfile(lib_path) or os.path.getmtime(lib_path) < max(os.path.getmtime(d) for d in deps):
         subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-pthread", "-shared", "-o", lib_path, src,
                         "-ldl"], check=True)

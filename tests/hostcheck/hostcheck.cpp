@@ -8,7 +8,6 @@
 #include "../../lars_image_processing_b200/csrc/pixel_math.h"
 #include "../../lars_image_processing_b200/csrc/lzw_warp.h"
 #include "../../lars_image_processing_b200/csrc/inflate_warp.h"
-#include "../../lars_image_processing_b200/csrc/png_device.h"
 #include "../../lars_image_processing_b200/csrc/tiff_host.h"
 
 extern "C" {
@@ -44,6 +43,10 @@ void hc_wb_lut(double lo, double hi, int domain, uint8_t* out) {
   for (int v = 0; v < domain; ++v) out[v] = lars_wb_lut_entry((double)v, lo, hi);
 }
 
+void hc_wb_lut_rgn(double lo, double hi, int domain, uint8_t* out) {
+  for (int v = 0; v < domain; ++v) out[v] = lars_wb_lut_entry_rgn((double)v, lo, hi);
+}
+
 double hc_percentile_lerp(double a, double b, double gamma) { return lars_percentile_lerp(a, b, gamma); }
 
 void hc_ratio_clip_f64(const double* hi, const double* lo, int64_t n, double* out) {
@@ -74,16 +77,6 @@ void hc_pair_tables_fast(int bins, float* value, int32_t* row, int32_t* slot) {
 uint32_t hc_lzw_chunk_host(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t cap) {
   return (uint32_t)lars_host::lzw_chunk(in, n_in, out, cap);       // the product's host decoder, for comparison
 }
-uint32_t hc_lzw_decode_warp_v2(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t cap, uint32_t skew) {
-  static thread_local uint32_t table[4096];
-  static thread_local uint8_t ring[LARS_LZW_RING];
-  static thread_local uint32_t inbuf[LARS_LZW_INBUF_WORDS];
-  // the decoder reads whole aligned words around the stream: give it a padded, aligned copy at byte offset `skew`
-  std::vector<uint32_t> padded((n_in + 16) / 4 + 2, 0xA5A5A5A5u);
-  uint8_t* base = reinterpret_cast<uint8_t*>(padded.data()) + 4 + (skew & 3u);
-  memcpy(base, in, n_in);
-  return lars_lzw_decode_warp_v2(base, n_in, out, cap, table, ring, inbuf);
-}
 // The warp inflate of inflate_warp.h, lanes run one after the other; the stream sits at byte offset `skew` of an
 // aligned, padded buffer as on the device.
 uint32_t hc_inflate_warp(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t cap, uint32_t skew) {
@@ -92,12 +85,6 @@ uint32_t hc_inflate_warp(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_
   uint8_t* base = reinterpret_cast<uint8_t*>(padded.data()) + 4 + (skew & 3u);
   memcpy(base, in, n_in);
   return lars_inflate_warp(base, n_in, out, cap, &sm);
-}
-// png_device.h: every byte lane of the pixel on its own, as the device threads run them.
-int hc_png_unfilter(const uint8_t* raw, uint8_t* dst, int h, long long row_bytes, int bpp, int swap16) {
-  for (int k = 0; k < bpp; ++k)
-    if (!lars_png_unfilter_lane(raw, dst, h, row_bytes, bpp, k, swap16)) return 0;
-  return 1;
 }
 uint32_t hc_lzw_decode_warp(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t cap) {
   static thread_local uint32_t table[4096];

@@ -150,8 +150,13 @@ def test_bench_reference_arm_contract_on_cpu():
     assert d["impl"] == "reference" and d["unit"] == "Mpix/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["vs_baseline"] is None
     assert d["metric"].startswith("RGNir Mpix/s") and "workload" in d["config"] and d["data"] == "synthetic"
+    # the keys the GPU arm's config carries for the same workload (the driver compares them)
+    assert d["config"]["frames_per_gpu"] == 16 and d["config"]["height"] == 96 and d["config"]["width"] == 128
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "frames" in cb["sample"]
+    # "reference" = the reference's own functions from oracle/_ref (built where /root/reference exists), else the port
+    have_ref = os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "process_images.py"))
+    assert cb["kind"] == ("reference" if have_ref else "port")
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and "frames" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
     quiet = _run_bench("--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--height", "96", "--width", "128",
@@ -169,3 +174,46 @@ def test_bench_gpu_arm_fails_loudly_without_a_gpu():
     assert r.returncode != 0
     assert not any(ln.lstrip().startswith("{") for ln in r.stdout.splitlines())
     assert "no CPU fallback" in r.stderr or "CUDA" in r.stderr or "NVIDIA" in r.stderr
+
+
+def test_bench_frame_generator_is_identical_under_numpy_and_torch():
+    """bench.py's counter-based generator: the host (NumPy) and device (torch) forms give the same bytes, so the
+    GPU arm, the reference arm and the CPU baseline all see the same pixels (uint8 and uint16, batched fill)."""
+    import torch
+    import bench
+    from lars_image_processing_b200.engine import DeviceFrames
+    for sb in (1, 2):
+        h, w = 37, 53
+        npx = h * w
+        ppx = (npx + 15) // 16 * 16
+        fr = DeviceFrames(torch.zeros((3, ppx * 3 * sb), dtype=torch.uint8), npx, 3, (h, w), sb)
+        seeds = [5, 3000, 2_000_017]
+        bench.counter_fill_device(fr, seeds, batch_samples=npx * 3 * 2)
+        for i, sd in enumerate(seeds):
+            ref = bench.counter_frame_np(sd, h, w, sb)
+            got = fr.data[i, :npx * 3 * sb].numpy().view(np.uint8 if sb == 1 else np.uint16).reshape(h, w, 3)
+            assert np.array_equal(ref, got)
+    big = bench.counter_frame_np(7, 300, 400, 1).reshape(-1, 3).astype(np.float64)
+    assert np.allclose(big.mean(0), (90, 110, 150), atol=1.0) and np.allclose(big.std(0), (35, 35, 45), atol=1.0)
+
+
+def test_reference_extract_matches_the_ast_loaded_functions():
+    """oracle/_ref (oracle/build_ref.py: the reference's functions cut out of its files, text unmodified) behaves like
+    the AST-loaded functions and like the port; skipped where neither the extract nor the checkout exists."""
+    import warnings
+    from oracle import build_ref, oracle_np as o, synth
+    if build_ref.available():
+        build_ref.build()
+    if not os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "process_images.py")):
+        pytest.skip("no oracle/_ref and no reference checkout")
+    from oracle._ref import process_images as R
+    for name, img in list(synth.adversarial_frames().items()) + [("veg", synth.vegetation_frame(5, 50, 70))]:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            wb = R.fix_white_balance(img)
+            assert np.array_equal(wb, o.fix_white_balance_literal(img)), name
+            a, b = o.reference_cpu_path(img, reference=R), o.reference_cpu_path(img)
+        for t in o.INDEX_TYPES:
+            assert a[1][t]["std"] == b[1][t]["std"] and np.array_equal(a[1][t]["hist"], b[1][t]["hist"])
+            assert {k: v for k, v in a[1][t].items() if k not in ("hist", "rgb")} == \
+                {k: v for k, v in b[1][t].items() if k not in ("hist", "rgb")}

@@ -776,3 +776,153 @@ def test_run_host_batch_pipeline_parity(engine):
     only = engine.alloc_host_outputs(F, h, w, 3, ("stats",))
     engine.run_host_batch(host_in, (h, w, 3), only, chunk=4, sample_bytes=2)
     assert np.array_equal(only["stats"].numpy(), host_out["stats"].numpy())
+
+
+# ------------------------------------------------------------------------------------- round 2: full sizes, configs as written
+@pytest.mark.timeout(600)
+def test_full_size_uint16_frame_of_config3(engine):
+    """One frame of BASELINE config 3 at its real size (5472 x 3648 uint16, 19,961,856 pixels): the two-level
+    histogram picks its buckets among ~20 M samples per channel, so the percentile ranks, bucket boundaries and 32-bit
+    per-CTA counters are exercised at scale.  WB bytes, all three maps (bits), histograms, counts and percentiles
+    against the oracle."""
+    img = synth.vegetation_frame(3000, 3648, 5472, np.uint16)
+    res = engine.analyze_frame(img, outputs=("wb", "maps", "stats"))
+    want = oracle_frame(img)
+    assert np.array_equal(res["wb"], want["wb"])
+    want_pct = np.array([np.percentile(img[:, :, c].astype(np.float32), (2, 98)) for c in range(3)])
+    assert np.array_equal(res["percentiles"], want_pct)
+    for t in INDEX_TYPES:
+        assert np.array_equal(res["maps"][t].view(np.uint32), want["maps"][t].view(np.uint32)), t
+        gs, ws = res["stats"][t], want["stats"][t]
+        assert np.array_equal(gs["hist"], ws["hist"]) and gs["count"] == ws["count"] == 3648 * 5472, t
+        assert gs["count_above"] == ws["count_above"] and gs["min"] == ws["min"] and gs["max"] == ws["max"], t
+        std = float(np.std(want["maps"][t]))
+        assert moment_close(gs["mean"], ws["sum"] / ws["count"], std) and moment_close(gs["std"], std, std), t
+
+
+def test_config1_png_file_through_the_dropin_helpers(engine, tmp_path):
+    """BASELINE config 1 as written: a single synthetic 1280 x 960 uint8 RGNir PNG (seed 1) ->
+    the package's reader -> fix_white_balance -> calculate_index("NDVI") -> analyze_index, every step against the
+    reference's NumPy path on the same file."""
+    from PIL import Image
+    from lars_image_processing_b200 import ingest
+    from lars_image_processing_b200 import process_images as pi
+    img = synth.vegetation_frame(1, 960, 1280)
+    path = tmp_path / "c1.png"
+    Image.fromarray(img).save(path)
+    frame = ingest.read_frame(path)
+    assert frame.dtype == np.uint8 and np.array_equal(frame, np.array(Image.open(path)))     # process-images.py:183-193
+    wb = pi.fix_white_balance(frame)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want_wb = o.fix_white_balance_literal(img)
+    assert np.array_equal(wb, want_wb)
+    ndvi = pi.calculate_index(wb, "NDVI")
+    want_ndvi = o.calculate_index(want_wb, "NDVI")
+    assert ndvi.dtype == np.float32 and np.array_equal(ndvi.view(np.uint32), want_ndvi.view(np.uint32))
+    got, want = pi.analyze_index(ndvi, "NDVI"), o.analyze_index(want_ndvi, "NDVI")
+    assert list(got) == list(want)
+    for k in want:
+        if k.startswith("Mean"):
+            assert moment_close(got[k], want[k], float(np.std(want_ndvi))), k
+        else:
+            assert got[k] == want[k], k                       # median, min, max, coverage: exact
+
+
+def test_rgnir_file_variant_has_its_own_chain(engine, tmp_path):
+    """fix_white_balance_rgnir (process-rgn.py:25-44: pre-clip, float64 truncated directly) on small and few-valued
+    frames, where percentiles are fractional and its bytes differ from fix_white_balance's by one step."""
+    from PIL import Image
+    from lars_image_processing_b200 import process_images as pi
+    from lars_image_processing_b200 import process_rgn as pr
+    rng = np.random.default_rng(77)
+    differ = 0
+    p = tmp_path / "f.png"
+    for it in range(120):
+        h, w = int(rng.integers(2, 24)), int(rng.integers(2, 24))
+        if it % 3 == 0:
+            img = rng.integers(0, 256, (h, w, 3))
+        elif it % 3 == 1:
+            levels = rng.integers(0, 256, int(rng.integers(1, 6)))
+            img = levels[rng.integers(0, len(levels), (h, w, 3))]
+        else:
+            img = np.clip(int(rng.integers(0, 256)) + rng.integers(-9, 10, (h, w, 3)), 0, 255)
+        img = img.astype(np.uint8)
+        Image.fromarray(img).save(p)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = o.fix_white_balance_rgnir_array(img)
+            other = o.fix_white_balance_literal(img)
+        assert np.array_equal(pr.fix_white_balance_rgnir(str(p)), want), it
+        assert np.array_equal(pi.fix_white_balance(img), other), it
+        differ += int(not np.array_equal(want, other))
+    assert differ >= 2          # frames 15 and 32 of this sweep separate the two chains
+
+
+def test_frame_plan_rebind_and_mosaic_plan(engine):
+    """What bench.py's c3 / c4 / c5 workloads are made of: (1) one FramePlan re-pointed at successive groups of a
+    resident batch, statistics into slices of one record array, equals the oracle per frame; (2) a
+    tiles_of_one_image plan with a histogram hook equals the oracle on the whole image."""
+    import torch
+    from lars_image_processing_b200 import distributed as ld
+    from lars_image_processing_b200._lib import INDEX_STATS_DTYPE
+    from lars_image_processing_b200.engine import ALL_OUTPUTS, DeviceFrames, FramePlan, stats_records_to_dicts
+    s = engine.stream()
+    for dtype in (np.uint8, np.uint16):
+        frames = [synth.vegetation_frame(900 + i, 60, 84, dtype) for i in range(7)]
+        dev = engine.upload(frames, stream=s)
+        view = lambda a, n: DeviceFrames(dev.data[a:a + n], dev.n_pixels, 3, dev.shape, dev.sample_bytes)
+        plan = FramePlan(engine, view(0, 3), ALL_OUTPUTS, stream=s)
+        with torch.cuda.stream(s):
+            records = torch.zeros((6, 3, INDEX_STATS_DTYPE.itemsize), dtype=torch.uint8, device=engine.device)
+        for g in (0, 1):
+            plan.rebind(view(3 * g, 3), records[3 * g:3 * g + 3])
+            res = plan.run()
+            out = engine.download(res, stream=s)
+            for k in range(3):
+                check_frame_result(out[k], frames[3 * g + k], label=f"{np.dtype(dtype).name} group {g} frame {k}")
+        st = stats_records_to_dicts(ld.records_to_numpy(records), 50)
+        for i in range(6):
+            assert np.array_equal(st[i]["NDWI"]["hist"], oracle_frame(frames[i])["stats"]["NDWI"]["hist"])
+        with pytest.raises(ValueError):
+            plan.rebind(view(0, 2))
+    img = synth.vegetation_frame(950, 96, 80)
+    img[:24] //= 3
+    tiles = [np.ascontiguousarray(b) for b in np.split(img, 4, axis=0)]
+    seen = []
+    plan = FramePlan(engine, engine.upload(tiles, stream=s), ALL_OUTPUTS, stream=s, tiles_of_one_image=True,
+                     hist_hook=lambda hst: seen.append(tuple(hst.shape)))
+    res = plan.run()
+    out = engine.download(res, stream=s)
+    want = oracle_frame(img)
+    assert seen == [(1, 3, 256)]
+    assert np.array_equal(np.concatenate([x["wb"] for x in out], axis=0), want["wb"])
+    for t in INDEX_TYPES:
+        assert np.array_equal(np.concatenate([x["maps"][t] for x in out], axis=0).view(np.uint32), want["maps"][t].view(np.uint32))
+
+
+def test_run_host_mosaic_parity(engine):
+    """Engine.run_host_mosaic (bench.py's c4 `e2e`): pinned host tiles in, image-wide white balance, host results
+    out, ragged chunking, a second call on the same buffers; against the oracle on the whole image."""
+    import torch
+    from lars_image_processing_b200 import distributed as ld
+    from lars_image_processing_b200.engine import stats_records_to_dicts
+    th, tw, T = 40, 56, 5
+    host_in = torch.empty((T, th * tw * 3), dtype=torch.uint8, pin_memory=True)
+    host_out = engine.alloc_host_outputs(T, th, tw, 3)
+    for rep in range(2):
+        img = synth.vegetation_frame(970 + rep, th * T, tw)
+        img[:th] //= 2
+        for i in range(T):
+            host_in[i].copy_(torch.from_numpy(np.ascontiguousarray(img[i * th:(i + 1) * th]).reshape(-1)))
+        calls = []
+        stats = engine.run_host_mosaic(host_in, (th, tw, 3), host_out, chunk=2, hist_hook=lambda hst: calls.append(1))
+        whole = stats_records_to_dicts(ld.records_to_numpy(ld.dataset_statistics(engine, stats)).reshape(1, 3), 50)[0]
+        want = oracle_frame(img)
+        assert len(calls) == 1
+        assert np.array_equal(host_out["wb"].numpy().reshape(th * T, tw, 3), want["wb"])
+        for k, t in enumerate(INDEX_TYPES):
+            assert np.array_equal(host_out["maps"][k].numpy().reshape(th * T, tw).view(np.uint32), want["maps"][t].view(np.uint32))
+            assert np.array_equal(host_out["rgb"][k].numpy().reshape(th * T, tw, 3), want["rgb"][t])
+            assert np.array_equal(whole[t]["hist"], want["stats"][t]["hist"])
+            assert whole[t]["count_above"] == want["stats"][t]["count_above"]

@@ -683,7 +683,7 @@ def test_lzw_tiff_frames_decoded_on_the_device(engine, tmp_path):
     assert np.array_equal(res_a["stats"]["NDVI"]["hist"], res_b["stats"]["NDVI"]["hist"])
     # not eligible / damaged
     q = tmp_path / "z.tif"
-    ingest.write_tiff(q, imgs[0], compression="deflate")
+    ingest.write_tiff(q, imgs[0], compression="packbits")
     assert not ingest.device_decodable(q) and not ingest.device_decodable(imgs[0])
     with pytest.raises(LarsError, match="LZW"):
         ingest.decode_tiff_batch_on_device([q], engine)
@@ -696,11 +696,9 @@ def test_lzw_tiff_frames_decoded_on_the_device(engine, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("LARS_EXPERIMENTAL_DEVICE_INFLATE") != "1",
-                    reason="device-side Deflate / PNG decode is experimental: set LARS_EXPERIMENTAL_DEVICE_INFLATE=1")
-def test_experimental_device_deflate_and_png(engine, tmp_path):
-    """Round-2 entry point for the experimental decoders (pinned on the CPU, first hardware run pending): Deflate TIFF
-    strips and PNG frames decoded on the GPU must equal the host readers' arrays."""
+def test_deflate_tiff_frames_decoded_on_the_device(engine, tmp_path):
+    """Deflate TIFF strips decoded on the GPU (one warp per zlib stream) must equal the host readers' arrays
+    (first hardware run: profiles/r02_ingest_gated_pytest.log)."""
     import torch
     from lars_image_processing_b200 import ingest
     rng = np.random.default_rng(43)
@@ -727,23 +725,10 @@ def test_experimental_device_deflate_and_png(engine, tmp_path):
         paths.append(p)
     for path, img in zip(paths, img16):                            # byte order differs: one batch each
         assert np.array_equal(to_host(ingest.decode_tiff_batch_on_device([path], engine), img.shape, np.uint16)[0], img)
-    for shape, dtype in (((240, 320, 3), np.uint8), ((61, 83, 4), np.uint8), ((50, 70, 3), np.uint16)):
-        batch = [_textured(rng, shape, dtype) for _ in range(4)]
-        blobs = []
-        for k, img in enumerate(batch):
-            if dtype == np.uint8:
-                p = tmp_path / f"d{k}.png"
-                Image.fromarray(img).save(p, compress_level=(0, 1, 6, 9)[k])
-                blobs.append(p)
-            else:
-                blobs.append(_png_bytes(img, [4, 3, 2, 1, 0], idat=4096))
-        for got, img in zip(to_host(ingest.decode_png_batch_on_device(blobs, engine), shape, dtype), batch):
-            assert np.array_equal(got, img), (shape, dtype)
+        assert ingest.device_decodable(path)
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("LARS_RUN_UNVERIFIED") != "1",
-                    reason="composition written after the round's GPU time was spent: set LARS_RUN_UNVERIFIED=1 to run it")
 def test_survey_with_device_decode_matches_the_pipeline(engine, tmp_path):
     """survey_with_device_decode (LZW files decoded on the GPU, chunk loop) gives the per-frame and dataset records of
     SurveyPipeline on the same files."""
@@ -765,17 +750,14 @@ def test_survey_with_device_decode_matches_the_pipeline(engine, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("LARS_RUN_UNVERIFIED") != "1",
-                    reason="written after the round's GPU time was spent: set LARS_RUN_UNVERIFIED=1 to run it")
 def test_mosaic_band_decoded_on_the_device(engine, tmp_path):
     """decode_tiff_region_on_device: the row band of a tiled / stripped LZW mosaic decoded on the GPU equals the host
-    reader's region (Deflate layouts join when LARS_EXPERIMENTAL_DEVICE_INFLATE=1)."""
+    reader's region."""
     import torch
     from lars_image_processing_b200 import ingest
     rng = np.random.default_rng(47)
     p = tmp_path / "m.tif"
-    codecs = ["lzw"] + (["deflate"] if ingest.EXPERIMENTAL_DEVICE_INFLATE else [])
-    for codec in codecs:
+    for codec in ("lzw", "deflate"):
         for k, kw in enumerate((dict(tile=(32, 48), predictor=True), dict(rows_per_strip=9), dict(tile=(64, 64), big_endian=True))):
             dtype = np.uint16 if k % 2 else np.uint8
             img = _textured(rng, (200, 260, 3), dtype)
@@ -865,11 +847,9 @@ def test_warp_lzw_decoder_equals_the_host_decoder(hostcheck):
     verdicts / prefixes on 3,000 corrupted or truncated streams."""
     import ctypes as C
     from lars_image_processing_b200 import ingest
-    for fn in (hostcheck.hc_lzw_decode_warp, hostcheck.hc_lzw_decode_warp_v2, hostcheck.hc_lzw_chunk_host):
+    for fn in (hostcheck.hc_lzw_decode_warp, hostcheck.hc_lzw_chunk_host):
         fn.restype = C.c_uint32
         fn.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
-    hostcheck.hc_lzw_decode_warp_v2.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]
-    calls = [0]
     rng = np.random.default_rng(21)
 
     def both(blob, cap):
@@ -878,13 +858,6 @@ def test_warp_lzw_decoder_equals_the_host_decoder(hostcheck):
         ra = hostcheck.hc_lzw_decode_warp(src.ctypes.data, src.size, a.ctypes.data, cap)
         rb = hostcheck.hc_lzw_chunk_host(src.ctypes.data, src.size, b.ctypes.data, cap)
         assert ra == rb and np.array_equal(a[:ra], b[:rb])
-        # variant 2 (stream and output staged in shared-memory rings): same verdicts, whatever the alignment
-        # of the stream (skew) and of the destination (dskew)
-        calls[0] += 1
-        skew, dskew = calls[0] & 3, (calls[0] >> 2) & 3
-        a2 = np.full(cap + 72, 0xAA, np.uint8)
-        assert hostcheck.hc_lzw_decode_warp_v2(src.ctypes.data, src.size, a2.ctypes.data + dskew, cap, skew) == ra
-        assert np.array_equal(a2[dskew:dskew + ra], a[:ra]) and (a2[dskew + cap:] == 0xAA).all() and (a2[:dskew] == 0xAA).all()
         assert (a[cap:] == 0xAA).all() and (b[cap:] == 0xAA).all()       # nothing written past the capacity
         if ra:
             assert (a[ra:] == 0xAA).all()                                # ... nor past what was produced
@@ -908,8 +881,8 @@ def test_warp_lzw_decoder_equals_the_host_decoder(hostcheck):
         for cap in (len(d), max(1, len(d) - 1), max(1, len(d) // 2), len(d) + 100):
             produced, out = both(blob, cap)
             assert produced == min(cap, len(d)) and np.array_equal(out[:produced], d[:produced]), (kind, n, cap)
-    # strings defined early in an epoch and used again 20 KB later: variant 2 reads them back from global memory
-    # (older than its shared-memory ring is trusted for) -- no Clear in between, the middle part adds few table entries
+    # strings defined early in an epoch and used again 20 KB later -- no Clear in between, the middle part adds few
+    # table entries
     a_part = rng.integers(0, 256, 300, dtype=np.uint8)
     d = np.concatenate([a_part, ((np.arange(20000) // 50) % 2).astype(np.uint8), a_part, a_part[::-1]])
     blob = ingest._lzw_encode(d.tobytes())
@@ -930,17 +903,15 @@ def test_warp_lzw_decoder_equals_the_host_decoder(hostcheck):
 
 def test_device_decode_plan_on_the_cpu(hostcheck, tmp_path):
     """What the device-side decode is made of, without a GPU: lars_tiff_lzw_chunks (the per-strip table) plus the
-    warp decoder of lzw_warp.h (both variants, run on the host through hostcheck) plus the predictor / byte-order
+    warp decoder of lzw_warp.h (run on the host through hostcheck) plus the predictor / byte-order
     step reproduce the frame for Pillow-written and self-written LZW files; files outside the device path are
     refused with LARS_ERR_UNSUPPORTED."""
     import ctypes as C
     from lars_image_processing_b200 import ingest
     L = _lib()
     lib = L.load()
-    for fn in (hostcheck.hc_lzw_decode_warp, hostcheck.hc_lzw_decode_warp_v2):
-        fn.restype = C.c_uint32
+    hostcheck.hc_lzw_decode_warp.restype = C.c_uint32
     hostcheck.hc_lzw_decode_warp.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
-    hostcheck.hc_lzw_decode_warp_v2.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]
     rng = np.random.default_rng(51)
     p = tmp_path / "d.tif"
 
@@ -959,7 +930,7 @@ def test_device_decode_plan_on_the_cpu(hostcheck, tmp_path):
         img = _textured(rng, shape, np.uint16)
         ingest.write_tiff(p, img, compression="lzw", **kw)
         cases.append((img, np.fromfile(p, np.uint8)))
-    for variant, (img, raw) in enumerate(cases * 2):
+    for img, raw in cases:
         info, chunks, n = plan(raw)
         assert n == info.n_strips and ingest.device_decodable(raw.tobytes())
         sb, spp = info.bits_per_sample // 8, info.samples_per_pixel
@@ -969,9 +940,7 @@ def test_device_decode_plan_on_the_cpu(hostcheck, tmp_path):
         out = np.zeros(img.nbytes + 8, np.uint8)
         for c in chunks:
             args = (raw.ctypes.data + int(c["src_offset"]), int(c["src_bytes"]), out.ctypes.data + int(c["dst_offset"]), int(c["dst_bytes"]))
-            produced = (hostcheck.hc_lzw_decode_warp(*args) if variant < len(cases)
-                        else hostcheck.hc_lzw_decode_warp_v2(*args, int(c["src_offset"]) & 3))
-            assert produced == c["dst_bytes"]
+            assert hostcheck.hc_lzw_decode_warp(*args) == c["dst_bytes"]
         # what tiff_post_kernel does: byte order, then the running sum along each row per sample of the pixel
         samples = out[:img.nbytes].view(">u2" if (sb == 2 and info.big_endian) else ("<u2" if sb == 2 else np.uint8))
         rows = samples.astype(np.uint32).reshape(info.height, info.width, spp)
@@ -989,7 +958,7 @@ def test_device_decode_plan_on_the_cpu(hostcheck, tmp_path):
 
 
 def test_warp_inflate_equals_zlib(hostcheck):
-    """inflate_warp.h (experimental device-side Deflate, one warp per stream) compiled for the host with its 32
+    """inflate_warp.h (device-side Deflate, one warp per stream) compiled for the host with its 32
     lanes run in sequence, against zlib: every compression level and strategy (stored, fixed and dynamic blocks,
     Huffman-only, RLE), textures from noise to constants (matches at every distance up to the 32 KB window, overlapping
     matches, codes longer than the 10-bit fast tables), every stream / destination alignment, capacities that cut
@@ -1083,61 +1052,6 @@ def test_warp_inflate_equals_zlib(hostcheck):
             agree += 1
             assert n == min(cap, len(ref)) and np.array_equal(out[:n], np.frombuffer(ref, np.uint8)[:n])
     assert rejected > 300
-
-
-def test_device_png_plan_on_the_cpu(hostcheck, tmp_path):
-    """The (experimental) device PNG path without a GPU: png_device_plan (IDAT payloads joined into one zlib stream per
-    image, the chunk table, the geometry) + the warp inflate + the per-byte-lane row-filter code of png_device.h, both
-    run on the host through hostcheck, reproduce what the host PNG reader decodes -- Pillow-written files at several
-    compression levels, hand-built ones with every filter on every row position, many small IDAT chunks, 8- and
-    16-bit, gray / RGB / RGBA."""
-    import ctypes as C
-    from lars_image_processing_b200 import ingest
-    hostcheck.hc_inflate_warp.restype = C.c_uint32
-    hostcheck.hc_inflate_warp.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]
-    hostcheck.hc_png_unfilter.restype = C.c_int
-    hostcheck.hc_png_unfilter.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int]
-    rng = np.random.default_rng(91)
-    p = tmp_path / "d.png"
-    batches = []
-    for shape, dtype in (((61, 83, 3), np.uint8), ((40, 40), np.uint8), ((25, 31, 4), np.uint8), ((33, 41), np.uint16)):
-        blobs, imgs = [], []
-        for level in (0, 1, 9):
-            img = _textured(rng, shape, dtype)
-            Image.fromarray(img).save(p, compress_level=level)
-            blobs.append(np.fromfile(p, np.uint8))
-            imgs.append(img)
-        batches.append((blobs, imgs))
-    for shape, dtype in (((23, 31, 3), np.uint8), ((21, 17, 3), np.uint16), ((9, 14, 4), np.uint16), ((30, 1, 3), np.uint8)):
-        imgs = [_textured(rng, shape, dtype), rng.integers(0, np.iinfo(dtype).max + 1, shape).astype(dtype)]
-        blobs = [np.frombuffer(_png_bytes(imgs[0], [4, 3, 2, 1, 0], idat=33), np.uint8),
-                 np.frombuffer(_png_bytes(imgs[1], [3, 4, 0, 2, 1, 4], idat=1 << 16), np.uint8)]
-        batches.append((blobs, imgs))
-    for blobs, imgs in batches:
-        plan = ingest.png_device_plan(blobs)
-        h, rb, sb = plan["height"], plan["row_bytes"], plan["sample_bytes"]
-        assert plan["chunks"]["dst_bytes"].tolist() == [h * (rb + 1)] * len(blobs)
-        assert (plan["chunks"]["src_offset"] % 8 == 0).all() and plan["raw_stride"] % 16 == 0
-        scratch = np.zeros(len(blobs) * plan["raw_stride"], np.uint8)
-        for c in plan["chunks"]:
-            src = plan["staging"][int(c["src_offset"]):int(c["src_offset"]) + int(c["src_bytes"])].copy()
-            n = hostcheck.hc_inflate_warp(src.ctypes.data, src.size, scratch.ctypes.data + int(c["dst_offset"]),
-                                          int(c["dst_bytes"]), int(c["src_offset"]) & 3)
-            assert n == c["dst_bytes"]
-        for i, img in enumerate(imgs):
-            out = np.zeros(img.nbytes, np.uint8)
-            assert hostcheck.hc_png_unfilter(scratch.ctypes.data + i * plan["raw_stride"], out.ctypes.data, h, rb,
-                                             plan["channels"] * sb, 1 if sb == 2 else 0) == 1
-            got = out.view(img.dtype).reshape(img.shape)
-            assert np.array_equal(got, img) and np.array_equal(got, ingest.read_frame(blobs[i].tobytes()))
-    # an unknown filter type is reported, not followed
-    raw = np.zeros(2 * (1 + 6), np.uint8)
-    raw[7] = 9
-    assert hostcheck.hc_png_unfilter(raw.ctypes.data, np.zeros(12, np.uint8).ctypes.data, 2, 6, 3, 0) == 0
-    from lars_image_processing_b200._lib import LarsError
-    if not ingest.EXPERIMENTAL_DEVICE_INFLATE:
-        with pytest.raises(LarsError, match="experimental"):
-            ingest.decode_png_batch_on_device([blobs[0].tobytes()])
 
 
 def test_device_region_plan_on_the_cpu(hostcheck, tmp_path):

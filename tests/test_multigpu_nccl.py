@@ -1,5 +1,5 @@
 """The multi-GPU paths on real hardware: needs >= 2 visible B200s (skipped otherwise), one process per
-GPU, NCCL.  (1) a uint8 and a uint16 mosaic whose row bands are sharded over the ranks -- SUM all-reduce
+GPU (all of them, up to 8), NCCL.  (1) a uint8 and a uint16 mosaic whose row bands are sharded over the ranks -- SUM all-reduce
 of the white-balance counters between the stages, one all-gather of the image-wide statistics --
 against the oracle on the whole image; (2) the side-stream dataset-statistics exchange; (3) a
 SurveyPipeline per rank over a round-robin shard of a frame list."""
@@ -72,6 +72,32 @@ def _worker(rank, world, port, q):
                 ok &= st[t]["count"] == ws["count"] and st[t]["count_above"] == ws["count_above"]
                 ok &= np.array_equal(st[t]["hist"], ws["hist"]) and st[t]["min"] == ws["min"] and st[t]["max"] == ws["max"]
             report[f"mosaic_{np.dtype(dtype).name}"] = bool(ok)
+        # ---- (1b) the uint8 mosaic again through the pre-bound plan (bench.py c4 `value`) and through the pinned
+        #      host path (bench.py c4 `e2e`), the histogram all-reduce as the hook of both
+        from lars_image_processing_b200.engine import ALL_OUTPUTS, FramePlan
+        img = _mosaic(np.uint8)
+        bands = [np.ascontiguousarray(b) for b in np.split(img, 12, axis=0)]
+        b0, b1 = ld.shard_range(len(bands), rank, world)
+        want = _oracle(img)
+        rows = slice(b0 * 64, b1 * 64)
+        hook = lambda hist: dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+        plan = FramePlan(eng, eng.upload(bands[b0:b1], stream=s), ALL_OUTPUTS, stream=s, tiles_of_one_image=True, hist_hook=hook)
+        out = eng.download(plan.run(), stream=s)
+        ok = np.array_equal(np.concatenate([x["wb"] for x in out], axis=0), want["wb"][rows])
+        ok &= np.array_equal(np.concatenate([x["rgb"]["NDWI"] for x in out], axis=0), want["rgb"]["NDWI"][rows])
+        report["mosaic_plan"] = bool(ok)
+        T = b1 - b0
+        host_in = torch.empty((T, 64 * 640 * 3), dtype=torch.uint8, pin_memory=True)
+        for i in range(T):
+            host_in[i].copy_(torch.from_numpy(bands[b0 + i].reshape(-1)))
+        host_out = eng.alloc_host_outputs(T, 64, 640, 3)
+        stats = eng.run_host_mosaic(host_in, (64, 640, 3), host_out, chunk=1, hist_hook=hook)
+        whole = stats_records_to_dicts(ld.records_to_numpy(ld.dataset_statistics(eng, stats)).reshape(1, 3), 50)[0]
+        ok = np.array_equal(host_out["wb"].numpy().reshape(T * 64, 640, 3), want["wb"][rows])
+        ok &= np.array_equal(host_out["maps"][1].numpy().reshape(T * 64, 640).view(np.uint32),
+                             want["maps"]["GNDVI"][rows].view(np.uint32))
+        ok &= np.array_equal(whole["GNDVI"]["hist"], want["stats"]["GNDVI"]["hist"])
+        report["mosaic_host"] = bool(ok)
         # ---- (2) side-stream exchange over three steps
         ex = ld.AsyncDatasetStatistics(eng)
         frames = [synth.vegetation_frame(9000 + 10 * rank + i, 48, 64) for i in range(3)]
@@ -109,7 +135,7 @@ def test_mosaic_exchange_and_survey_over_nccl():
     import torch.multiprocessing as mp
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs at least 2 GPUs")
-    world = 2
+    world = min(8, torch.cuda.device_count())      # every GPU of the box: 2 on the builder's lease, 8 on the scaling box
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()

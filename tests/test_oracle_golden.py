@@ -179,3 +179,34 @@ def test_oracle_against_live_reference_random_sweep():
         assert np.array_equal(mr.view(np.uint32), o.calculate_index(got, t).view(np.uint32)), (it, t)
         assert R["analyze_index"](mr, t) == o.analyze_index(mr, t), (it, t)
     assert degenerate > 40
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference checkout not present on this box")
+def test_rgnir_chain_against_live_reference(tmp_path):
+    """fix_white_balance_rgnir (process-rgn.py, importable: numpy + PIL only) on PNG files of small and few-valued
+    frames -- where percentiles are fractional and its float64 truncation differs from fix_white_balance's float32
+    store -- against both oracle formulations; the sweep must contain frames on which the two chains differ."""
+    from PIL import Image
+    R = ref_loader.load("process-rgn.py")
+    rng = np.random.default_rng(77)
+    differ = 0
+    p = tmp_path / "f.png"
+    for it in range(400):
+        h, w = int(rng.integers(2, 24)), int(rng.integers(2, 24))
+        if it % 3 == 0:
+            img = rng.integers(0, 256, (h, w, 3))
+        elif it % 3 == 1:
+            levels = rng.integers(0, 256, int(rng.integers(1, 6)))
+            img = levels[rng.integers(0, len(levels), (h, w, 3))]
+        else:
+            c = int(rng.integers(0, 256))
+            img = np.clip(c + rng.integers(-9, 10, (h, w, 3)), 0, 255)
+        img = img.astype(np.uint8)
+        Image.fromarray(img).save(p)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = R["fix_white_balance_rgnir"](str(p))
+            assert np.array_equal(o.fix_white_balance_rgnir_array(img), ref), it
+            assert np.array_equal(o.fix_white_balance_rgnir_from_hist(img), ref), it
+            differ += int(not np.array_equal(o.fix_white_balance_literal(img), ref))
+    assert differ > 0

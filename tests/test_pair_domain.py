@@ -92,6 +92,32 @@ def test_wb_lut_entry_chain(hostcheck):
     assert np.array_equal(out, o.wb_lut_from_percentiles(5140.25, 51400.75, 65536))
 
 
+def test_wb_lut_entry_rgn_chain(hostcheck):
+    """process-rgn.py's chain (pre-clip, float64 truncated directly) has its own table: the device entry equals the
+    oracle's for integral, fractional and degenerate percentile pairs, and it really differs from the
+    process-images.py chain somewhere (otherwise the separate table would be untested)."""
+    rng = np.random.default_rng(12)
+    cases = [(0.0, 255.0), (10.0, 10.0), (0.0, 0.0), (3.5, 3.5), (12.0, 201.0), (4.16, 194.56), (2.8799999999999994, 155.12),
+             (109.0, 187.20000000000002), (61.0, 244.60000000000002)]     # the last two: the chains differ (found by search)
+    for _ in range(300):
+        lo = float(rng.integers(0, 200)) + float(rng.choice([0.0, rng.random()]))
+        hi = lo + float(rng.integers(0, 56)) + float(rng.choice([0.0, rng.random()]))
+        cases.append((lo, hi))
+    for _ in range(1500):                                 # percentiles of few-valued frames: lerps on the 0.02 grid
+        hist = np.zeros(256, np.int64)
+        hist[rng.integers(0, 256, int(rng.integers(2, 6)))] += rng.integers(1, 40, 1)
+        hist[rng.integers(0, 256)] += int(rng.integers(1, 60))
+        cases.append((float(o.percentile_from_hist(hist, 0.02)), float(o.percentile_from_hist(hist, 0.98))))
+    differ = 0
+    for lo, hi in cases:
+        out = np.empty(256, np.uint8)
+        hostcheck.hc_wb_lut_rgn(C.c_double(lo), C.c_double(hi), C.c_int(256), C.c_void_p(out.ctypes.data))
+        assert np.array_equal(out, o.wb_lut_rgn_from_percentiles(lo, hi, 256)), (lo, hi)
+        inside = slice(int(np.ceil(lo)), int(np.floor(hi)) + 1)
+        differ += int(np.any(out[inside] != o.wb_lut_from_percentiles(lo, hi, 256)[inside]))
+    assert differ >= 2
+
+
 def test_percentile_lerp_matches_numpy(hostcheck):
     hostcheck.hc_percentile_lerp.restype = C.c_double
     hostcheck.hc_percentile_lerp.argtypes = [C.c_double] * 3

@@ -6,11 +6,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from lars_image_processing_b200.engine import Engine, FramePlan, ALL_OUTPUTS
 sys.path.insert(0, ".")
-from bench import synth_frames_device
+from bench import counter_fill_device
 
 eng = Engine(0)
 for (h, w, F) in ((960, 1280, 1), (960, 1280, 16), (3000, 4000, 1), (3000, 4000, 2)):
-    frames = synth_frames_device(eng, F, h, w, seed=3)
+    frames = counter_fill_device(eng.alloc_frames(F, h, w, 3), [3 + i for i in range(F)])
     s = eng.stream()
     res = eng.alloc_outputs(frames, ALL_OUTPUTS, s)
     plan = FramePlan(eng, frames).capture()
