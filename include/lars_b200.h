@@ -176,11 +176,16 @@ int lars_wb_stretch_build_u16(const uint16_t* src, int32_t n_frames, int64_t n_p
  *   LARS_U16_STAGE_HIST_HI  zero the workspace, level A          -> all-reduce the first block
  *   LARS_U16_STAGE_HIST_LO  bucket selection + level B           -> all-reduce the second block
  *   LARS_U16_STAGE_BUILD    percentiles + thresholds into stretch / pct
- *   LARS_U16_STAGE_ALL      everything (= lars_wb_stretch_build_u16) */
+ *   LARS_U16_STAGE_ALL      everything (= lars_wb_stretch_build_u16).  With one set per frame this is the guided
+ *                           single pass: a 6 % sample of the frame guesses the buckets, ONE full read counts the
+ *                           high bytes and the low bytes of the guessed buckets, and level B only runs for frames
+ *                           whose guess missed (results are exact either way)
+ *   LARS_U16_STAGE_ALL_TWO_LEVEL  everything, always as level A + level B (the round-1 form; tests and A/B timing) */
 #define LARS_U16_STAGE_ALL 0
 #define LARS_U16_STAGE_HIST_HI 1
 #define LARS_U16_STAGE_HIST_LO 2
 #define LARS_U16_STAGE_BUILD 3
+#define LARS_U16_STAGE_ALL_TWO_LEVEL 4
 int lars_wb_stretch_build_u16_staged(const uint16_t* src, int32_t n_frames, int64_t n_pixels, int32_t channels,
                                      int64_t src_frame_stride, double q_lo, double q_hi, lars_stretch_u16* stretch,
                                      double* pct, void* workspace, size_t workspace_bytes, int32_t shared_hist,
@@ -204,6 +209,32 @@ int lars_map_stats_f32(const float* data, int32_t n_maps, int64_t n, int64_t str
  * of the sorted data.  3-pass (11 + 11 + 10 bit) radix select, no sort, no host round trip. */
 size_t lars_select_workspace_bytes(void);
 int lars_select_f32(const float* data, int64_t n, uint64_t rank_lo, uint64_t rank_hi, float* out3,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* The float64 flavour of the two calls above, for the arrays process-ndvi.py works on: calculate_ndvi returns
+ * float64 (process-ndvi.py:18-31) and analyze_ndvi_statistics / generate_ndvi_report reduce it as it is -- min,
+ * max and median are float64 values, `ndvi > 0.2` compares in float64 (:60-71), plt.hist bins against float64
+ * linspace edges (:97).  592 bytes, all fields naturally aligned. */
+typedef struct lars_map_record_f64 {
+  uint64_t count;
+  uint64_t count_above; /* elements with x > threshold, compared in float64 */
+  double sum;
+  double sumsq;
+  double mean;
+  double std;           /* population standard deviation */
+  double min;
+  double max;
+  double threshold;
+  uint32_t bins;
+  uint32_t has_nan;
+  uint64_t hist[LARS_MAX_BINS]; /* np.histogram(x, bins, range=(-1, 1)) with float64 edges */
+} lars_map_record_f64;
+size_t lars_map_stats_f64_workspace_bytes(void);
+int lars_map_stats_f64(const double* data, int64_t n, int32_t bins, double threshold, lars_map_record_f64* stats,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* out3 (device) = { x[rank_lo], x[rank_hi], float64 mean of the two }: 6-pass radix select on 64-bit keys. */
+size_t lars_select_f64_workspace_bytes(void);
+int lars_select_f64(const double* data, int64_t n, uint64_t rank_lo, uint64_t rank_hi, double* out3,
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* Normalize(vmin, vmax) + colormap lookup of a float32 map -> [n][3] uint8 (the per-pixel part of
@@ -269,6 +300,11 @@ int lars_resize_tables_lanczos(const lars_resize_plan* plan, void* tables_host);
 int lars_resize_lanczos_u8(const lars_resize_plan* plan, const void* tables_dev, const uint8_t* src,
                            int64_t src_frame_stride, int32_t n_frames, uint8_t* dst, int64_t dst_frame_stride,
                            void* temp, size_t temp_bytes, void* stream);
+/* RGBA frames are resized with premultiplied alpha, as Pillow does (Image.resize: convert("RGBa"), resize,
+ * convert("RGBA"); libImaging/Convert.c rgbA2rgba / rgba2rgbA): this call converts a batch of RGBA frames in place,
+ * premultiply != 0 before lars_resize_lanczos_u8 and premultiply == 0 on its output. */
+int lars_rgba_alpha_u8(uint8_t* data, int32_t n_frames, int64_t n_pixels, int64_t frame_stride, int32_t premultiply,
+                       void* stream);
 
 /* ---- ingest ---------------------------------------------------
  * Host-only TIFF 6.0 / BigTIFF reader: 8- or 16-bit unsigned (or 32-bit float) samples, 1 / 3 / 4 samples per pixel, chunky

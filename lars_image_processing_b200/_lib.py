@@ -30,12 +30,13 @@ EXPORTED_SYMBOLS = (
     "lars_wb_hist_u8", "lars_wb_lut_build_u8", "lars_wb_lut_build_u8_chain",
     "lars_fused_workspace_bytes", "lars_fused_index_u8",
     "lars_map_stats_workspace_bytes", "lars_map_stats_f32", "lars_select_workspace_bytes",
-    "lars_select_f32", "lars_colormap_f32", "lars_ndvi_f64_u8", "lars_index_planes_f32",
+    "lars_select_f32", "lars_map_stats_f64_workspace_bytes", "lars_map_stats_f64", "lars_select_f64_workspace_bytes",
+    "lars_select_f64", "lars_colormap_f32", "lars_ndvi_f64_u8", "lars_index_planes_f32",
     "lars_stats_merge",
     "lars_wb_u16_workspace_bytes", "lars_wb_stretch_build_u16", "lars_wb_stretch_build_u16_staged",
     "lars_fused_index_u16",
     "lars_index_hwc", "lars_index_change_u8",
-    "lars_resize_plan_lanczos", "lars_resize_tables_lanczos", "lars_resize_lanczos_u8",
+    "lars_resize_plan_lanczos", "lars_resize_tables_lanczos", "lars_resize_lanczos_u8", "lars_rgba_alpha_u8",
     "lars_tiff_probe", "lars_tiff_read", "lars_tiff_read_region", "lars_png_probe", "lars_png_read",
     "lars_tiff_lzw_chunks", "lars_lzw_decode_device", "lars_tiff_post_device",
     "lars_tiff_deflate_chunks", "lars_inflate_decode_device", "lars_untile_device",
@@ -111,6 +112,15 @@ INDEX_STATS_DTYPE = np.dtype([
 ])
 assert INDEX_STATS_DTYPE.itemsize == 576
 
+# numpy view of ``lars_map_record_f64`` (592 bytes)
+MAP_STATS_F64_DTYPE = np.dtype([
+    ("count", "<u8"), ("count_above", "<u8"),
+    ("sum", "<f8"), ("sumsq", "<f8"), ("mean", "<f8"), ("std", "<f8"),
+    ("min", "<f8"), ("max", "<f8"), ("threshold", "<f8"), ("bins", "<u4"), ("has_nan", "<u4"),
+    ("hist", "<u8", (MAX_BINS,)),
+])
+assert MAP_STATS_F64_DTYPE.itemsize == 592
+
 _lock = threading.Lock()
 _lib = None
 
@@ -149,6 +159,16 @@ def _declare(lib):
     lib.lars_select_workspace_bytes.restype = C.c_size_t
     lib.lars_select_f32.argtypes = [vp, i64, C.c_uint64, C.c_uint64, vp, vp, C.c_size_t, vp]
     lib.lars_select_f32.restype = C.c_int
+    lib.lars_map_stats_f64_workspace_bytes.argtypes = []
+    lib.lars_map_stats_f64_workspace_bytes.restype = C.c_size_t
+    lib.lars_map_stats_f64.argtypes = [vp, i64, i32, f64, vp, vp, C.c_size_t, vp]
+    lib.lars_map_stats_f64.restype = C.c_int
+    lib.lars_select_f64_workspace_bytes.argtypes = []
+    lib.lars_select_f64_workspace_bytes.restype = C.c_size_t
+    lib.lars_select_f64.argtypes = [vp, i64, C.c_uint64, C.c_uint64, vp, vp, C.c_size_t, vp]
+    lib.lars_select_f64.restype = C.c_int
+    lib.lars_rgba_alpha_u8.argtypes = [vp, i32, i64, i64, i32, vp]
+    lib.lars_rgba_alpha_u8.restype = C.c_int
     lib.lars_colormap_f32.argtypes = [vp, i64, i32, f32, f32, vp, vp]
     lib.lars_colormap_f32.restype = C.c_int
     lib.lars_ndvi_f64_u8.argtypes = [vp, i64, i32, vp, vp]

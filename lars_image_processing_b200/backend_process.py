@@ -64,15 +64,20 @@ def process_image(image_path, output_dir, process_wb=False, indices=None):
     output_dir = Path(output_dir)
     img_name = Path(image_path).stem
     img = np.array(Image.open(image_path))
-    wanted = tuple(i for i in (indices or ()) if i in INDEX_TYPES)
+    requested = list(indices or ())
+    wanted = tuple(i for i in requested if i in INDEX_TYPES)
     outputs = ("wb", "rgb") if wanted else ("wb",)
     res = get_engine().analyze_frame(img, outputs=outputs, indices=wanted or INDEX_TYPES)
     if process_wb:
         (output_dir / "white_balanced").mkdir(parents=True, exist_ok=True)
-        Image.fromarray(np.ascontiguousarray(res["wb"][:, :, :3])).save(
-            output_dir / "white_balanced" / f"{img_name}_wb.tif")
-    for index_type in wanted:
+        # an RGBA file stays RGBA with alpha 0, as Image.fromarray of the reference's 4-channel result does (:21-26)
+        Image.fromarray(np.ascontiguousarray(res["wb"])).save(output_dir / "white_balanced" / f"{img_name}_wb.tif")
+    for index_type in requested:                      # in the caller's order, like the reference's loop (:67-72)
         (output_dir / index_type).mkdir(parents=True, exist_ok=True)
+        if index_type not in INDEX_TYPES:
+            # the reference's calculate_index falls through to an unbound local (:37) after the directory was made
+            # and the indices before this one were written
+            raise UnboundLocalError("cannot access local variable 'index' where it is not associated with a value")
         Image.fromarray(res["rgb"][index_type]).save(
             output_dir / index_type / f"{img_name}_{index_type.lower()}.png")
 

@@ -16,6 +16,7 @@
 #include "lars_kernels.cuh"
 #include "lars_fused_kernel.cuh"
 #include "lars_map_kernels.cuh"
+#include "lars_map_f64_kernels.cuh"
 #include "lars_u16_kernels.cuh"
 #include "lars_resize_kernels.cuh"
 #include "lars_lzw_kernels.cuh"
@@ -70,7 +71,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 extern "C" {
 
 const char* lars_last_error(void) { return g_err; }
-int lars_abi_version(void) { return 6; }   // 3: + resize, TIFF ingest; 4: lars_tiff_info grew (tiles, predictor, BigTIFF), lars_tiff_read_region; 5: PNG reader, device-side LZW; 6: experimental device-side Deflate
+int lars_abi_version(void) { return 7; }   // 7: float64 map statistics / select, lars_wb_lut_build_u8_chain, device PNG + LZW ring variant removed; 3: + resize, TIFF ingest; 4: lars_tiff_info grew (tiles, predictor, BigTIFF), lars_tiff_read_region; 5: PNG reader, device-side LZW; 6: experimental device-side Deflate
 
 int lars_init(int device) {
   std::lock_guard<std::mutex> lock(g_mu);
@@ -106,9 +107,15 @@ int lars_init(int device) {
                                  lars::K2Smem<4, 2>::TOTAL));
   LARS_CUDA(cudaFuncSetAttribute(lars::wb_hist_u16_hi_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lars::U16_HI_SMEM_BYTES));
   LARS_CUDA(cudaFuncSetAttribute(lars::wb_hist_u16_hi_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lars::U16_HI_SMEM_BYTES));
+  LARS_CUDA(cudaFuncSetAttribute(lars::wb_hist_u16_sample_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lars::U16_HI_SMEM_BYTES));
+  LARS_CUDA(cudaFuncSetAttribute(lars::wb_hist_u16_sample_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lars::U16_HI_SMEM_BYTES));
+  LARS_CUDA(cudaFuncSetAttribute(lars::wb_hist_u16_guided_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lars::U16_GUIDED_SMEM_BYTES));
+  LARS_CUDA(cudaFuncSetAttribute(lars::wb_hist_u16_guided_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lars::U16_GUIDED_SMEM_BYTES));
   LARS_CUDA(cudaFuncSetAttribute(lars::wb_hist_u16_lo_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lars::U16_LO_SMEM_BYTES));
   LARS_CUDA(cudaFuncSetAttribute(lars::wb_hist_u16_lo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lars::U16_LO_SMEM_BYTES));
   LARS_CUDA(cudaFuncSetAttribute(lars::select_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 lars::SEL_SMEM_BYTES));
+  LARS_CUDA(cudaFuncSetAttribute(lars::select64_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  lars::SEL_SMEM_BYTES));
   LARS_CUDA(cudaFuncSetAttribute(lars::lzw_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  lars::LZW_SMEM_BYTES));
@@ -377,7 +384,7 @@ int lars_map_stats_f32(const float* data, int32_t n_maps, int64_t n, int64_t str
   p.data = data; p.n = n; p.stride = stride;
   p.partials = static_cast<lars::MapPartial*>(workspace);
   p.threshold = threshold; p.bins = bins;
-  const size_t smem = (size_t)bins * 128 + (size_t)((bins + 1 + 3) / 4) * 16 + 8 * 8 * 8;
+  const size_t smem = (size_t)bins * 128 + (size_t)((bins + 1 + 3) / 4) * 16 + 8 * 8 * 8 + ((LARS_SUBBIN_COUNT + 15) & ~15);
   lars::map_stats_f32_kernel<<<dim3(parts, n_maps), lars::MAP_THREADS, smem, s>>>(p);
   LARS_CUDA(cudaGetLastError());
   lars::MapFinalizeParams f;
@@ -413,6 +420,62 @@ int lars_select_f32(const float* data, int64_t n, uint64_t rank_lo, uint64_t ran
   LARS_CUDA(cudaGetLastError());
   LARS_CUDA(cudaMemcpyAsync(out3, reinterpret_cast<const char*>(state) + offsetof(lars::SelectState, value),
                             3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return LARS_OK;
+}
+
+size_t lars_map_stats_f64_workspace_bytes(void) { return (size_t)(148 * 4) * sizeof(lars::MapPartialF64); }
+
+int lars_map_stats_f64(const double* data, int64_t n, int32_t bins, double threshold, lars_map_record_f64* stats,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  DeviceState* st = nullptr;
+  int rc = current_state(&st);
+  if (rc != LARS_OK) return rc;
+  if (!data || !stats || !workspace) return fail(LARS_ERR_INVALID, "lars_map_stats_f64: NULL pointer");
+  if (n < 1) return fail(LARS_ERR_INVALID, "lars_map_stats_f64: empty input");
+  if (bins < 1 || bins > LARS_MAX_BINS) return fail(LARS_ERR_INVALID, "lars_map_stats_f64: bins must be in 1..%d", LARS_MAX_BINS);
+  if (!aligned16(data)) return fail(LARS_ERR_INVALID, "lars_map_stats_f64: data must be 16-byte aligned");
+  int parts = map_parts(st->sm_count);
+  if (parts > 148 * 4) parts = 148 * 4;
+  const long long nvec = n / 2;
+  if (parts > nvec) parts = (int)(nvec > 0 ? nvec : 1);
+  if (workspace_bytes < (size_t)parts * sizeof(lars::MapPartialF64) || !aligned16(workspace))
+    return fail(LARS_ERR_INVALID, "lars_map_stats_f64: workspace too small or misaligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  lars::MapStatsF64Params p;
+  p.data = data; p.n = n; p.partials = static_cast<lars::MapPartialF64*>(workspace);
+  p.threshold = threshold; p.bins = bins;
+  const size_t smem = (size_t)bins * 128 + (size_t)((bins + 2) & ~1) * 8 + 8 * 8 * 8;
+  lars::map_stats_f64_kernel<<<parts, lars::MAP_THREADS, smem, s>>>(p);
+  LARS_CUDA(cudaGetLastError());
+  lars::map_stats_f64_finalize_kernel<<<1, lars::MAP_HIST_ROWS, 0, s>>>(p.partials, parts, bins, threshold, stats);
+  LARS_CUDA(cudaGetLastError());
+  return LARS_OK;
+}
+
+size_t lars_select_f64_workspace_bytes(void) { return sizeof(lars::SelectStateF64); }
+
+int lars_select_f64(const double* data, int64_t n, uint64_t rank_lo, uint64_t rank_hi, double* out3,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  DeviceState* st = nullptr;
+  int rc = current_state(&st);
+  if (rc != LARS_OK) return rc;
+  if (!data || !out3 || !workspace) return fail(LARS_ERR_INVALID, "lars_select_f64: NULL pointer");
+  if (n < 1 || rank_lo >= (uint64_t)n || rank_hi >= (uint64_t)n || rank_lo > rank_hi)
+    return fail(LARS_ERR_INVALID, "lars_select_f64: ranks out of range");
+  if (!aligned16(data)) return fail(LARS_ERR_INVALID, "lars_select_f64: data must be 16-byte aligned");
+  if (workspace_bytes < sizeof(lars::SelectStateF64) || !aligned16(workspace))
+    return fail(LARS_ERR_INVALID, "lars_select_f64: workspace too small or misaligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  lars::SelectStateF64* state = static_cast<lars::SelectStateF64*>(workspace);
+  lars::select64_init_kernel<<<1, 256, 0, s>>>(state, rank_lo, rank_hi);
+  long long want = (n / 2 + lars::SEL_THREADS - 1) / lars::SEL_THREADS;
+  int grid = st->sm_count * (lars::SEL_SMEM_BYTES <= 100 * 1024 ? 2 : 1);
+  if (want < grid) grid = (int)(want > 0 ? want : 1);
+  for (int pass = 0; pass < lars::SEL64_PASSES; ++pass)      // 11 + 11 + 11 + 11 + 11 + 9 key bits
+    lars::select64_pass_kernel<<<grid, lars::SEL_THREADS, lars::SEL_SMEM_BYTES, s>>>(data, n, state, pass);
+  LARS_CUDA(cudaGetLastError());
+  LARS_CUDA(cudaMemcpyAsync(out3, reinterpret_cast<const char*>(state) + offsetof(lars::SelectStateF64, value),
+                            3 * sizeof(double), cudaMemcpyDeviceToDevice, s));
   return LARS_OK;
 }
 
@@ -489,7 +552,11 @@ struct U16Workspace {
   unsigned long long* hist_lo;
   lars::U16Select* select;
 };
-constexpr size_t kU16SetBytes = 3 * 256 * 8 + 3 * lars::U16_MAX_BUCKETS * 256 * 8 + 3 * sizeof(lars::U16Select);
+// per set: high-byte histogram, level-B low-byte histograms, selection records (the public layout of the staged call),
+// then the guided pass's private part: sampled high-byte histogram, candidate classes, candidate low-byte histograms
+constexpr size_t kU16PublicBytes = 3 * 256 * 8 + 3 * lars::U16_MAX_BUCKETS * 256 * 8 + 3 * sizeof(lars::U16Select);
+constexpr size_t kU16SetBytes = kU16PublicBytes + 3 * 256 * 8 + 3 * sizeof(lars::U16Candidates) +
+                                3 * lars::U16_CAND_SLOTS * 256 * 8;
 }  // namespace
 
 size_t lars_wb_u16_workspace_bytes(int32_t n_sets) { return n_sets < 1 ? 0 : (size_t)n_sets * kU16SetBytes; }
@@ -524,11 +591,18 @@ int lars_wb_stretch_build_u16_staged(const uint16_t* src, int32_t n_frames, int6
   unsigned long long* hist_hi = reinterpret_cast<unsigned long long*>(ws);
   unsigned long long* hist_lo = reinterpret_cast<unsigned long long*>(ws + (size_t)n_sets * 3 * 256 * 8);
   lars::U16Select* select = reinterpret_cast<lars::U16Select*>(ws + (size_t)n_sets * (3 * 256 * 8 + 3 * lars::U16_MAX_BUCKETS * 256 * 8));
-  if (stage < LARS_U16_STAGE_ALL || stage > LARS_U16_STAGE_BUILD)
+  char* priv = ws + (size_t)n_sets * kU16PublicBytes;
+  unsigned long long* hist_sample = reinterpret_cast<unsigned long long*>(priv);
+  lars::U16Candidates* cand = reinterpret_cast<lars::U16Candidates*>(priv + (size_t)n_sets * 3 * 256 * 8);
+  unsigned long long* cand_lo = reinterpret_cast<unsigned long long*>(priv + (size_t)n_sets * (3 * 256 * 8 + 3 * sizeof(lars::U16Candidates)));
+  if (stage < LARS_U16_STAGE_ALL || stage > LARS_U16_STAGE_ALL_TWO_LEVEL)
     return fail(LARS_ERR_INVALID, "lars_wb_stretch_build_u16: unknown stage %d", stage);
-  const bool do_hi = stage == LARS_U16_STAGE_ALL || stage == LARS_U16_STAGE_HIST_HI;
-  const bool do_lo = stage == LARS_U16_STAGE_ALL || stage == LARS_U16_STAGE_HIST_LO;
-  const bool do_build = stage == LARS_U16_STAGE_ALL || stage == LARS_U16_STAGE_BUILD;
+  const bool all = stage == LARS_U16_STAGE_ALL || stage == LARS_U16_STAGE_ALL_TWO_LEVEL;
+  // per-frame statistics in one call: the guided single pass; tiles of one image and the staged form keep two levels
+  const bool guided = stage == LARS_U16_STAGE_ALL && !shared_hist;
+  const bool do_hi = all || stage == LARS_U16_STAGE_HIST_HI;
+  const bool do_lo = all || stage == LARS_U16_STAGE_HIST_LO;
+  const bool do_build = all || stage == LARS_U16_STAGE_BUILD;
   if (do_hi) LARS_CUDA(cudaMemsetAsync(workspace, 0, (size_t)n_sets * kU16SetBytes, s));
 
   const long long frame_bytes = (long long)n_pixels * channels * 2;
@@ -541,15 +615,30 @@ int lars_wb_stretch_build_u16_staged(const uint16_t* src, int32_t n_frames, int6
   p.total_units = p.units_per_frame * n_frames;
   p.set_stride = shared_hist ? 0 : 1;
   p.n_frames = n_frames; p.lo_pass = 0;
+  p.hist_sample = hist_sample; p.cand = cand; p.cand_lo = cand_lo;
   const long long target = 2ll * st->sm_count;
   const int grid = (int)(p.total_units < target ? p.total_units : target);
-  if (do_hi) {
+  if (guided) {
+    const int sstep = lars::u16_sample_step(p.units_per_frame);
+    const long long sampled = ((p.units_per_frame + sstep - 1) / sstep) * n_frames;
+    const int sgrid = (int)(sampled < target ? sampled : target);
+    if (channels == 3) lars::wb_hist_u16_sample_kernel<3><<<sgrid, lars::K1_THREADS, lars::U16_HI_SMEM_BYTES, s>>>(p);
+    else lars::wb_hist_u16_sample_kernel<4><<<sgrid, lars::K1_THREADS, lars::U16_HI_SMEM_BYTES, s>>>(p);
+    LARS_CUDA(cudaGetLastError());
+    lars::U16CandParams cp; cp.hist_sample = hist_sample; cp.cand = cand; cp.q_lo = q_lo; cp.q_hi = q_hi;
+    lars::wb_u16_candidates_kernel<<<n_sets * 3, 256, 0, s>>>(cp);
+    LARS_CUDA(cudaGetLastError());
+    if (channels == 3) lars::wb_hist_u16_guided_kernel<3><<<grid, lars::K1_THREADS, lars::U16_GUIDED_SMEM_BYTES, s>>>(p);
+    else lars::wb_hist_u16_guided_kernel<4><<<grid, lars::K1_THREADS, lars::U16_GUIDED_SMEM_BYTES, s>>>(p);
+    LARS_CUDA(cudaGetLastError());
+  } else if (do_hi) {
     if (channels == 3) lars::wb_hist_u16_hi_kernel<3><<<grid, lars::K1_THREADS, lars::U16_HI_SMEM_BYTES, s>>>(p);
     else lars::wb_hist_u16_hi_kernel<4><<<grid, lars::K1_THREADS, lars::U16_HI_SMEM_BYTES, s>>>(p);
     LARS_CUDA(cudaGetLastError());
   }
   if (do_lo) {
     lars::U16SelectParams sp; sp.hist_hi = hist_hi; sp.select = select; sp.q_lo = q_lo; sp.q_hi = q_hi;
+    sp.cand = guided ? cand : nullptr; sp.cand_lo = guided ? cand_lo : nullptr; sp.hist_lo = guided ? hist_lo : nullptr;
     lars::wb_u16_select_kernel<<<n_sets * 3, 256, 0, s>>>(sp);
     LARS_CUDA(cudaGetLastError());
     for (int pass = 0; pass < 2; ++pass) {
@@ -889,6 +978,25 @@ int lars_resize_tables_lanczos(const lars_resize_plan* plan, void* tables_host) 
   }
   if (!plan->need_h && !plan->need_v) t[0] = 0;
   free(scratch);
+  return LARS_OK;
+}
+
+int lars_rgba_alpha_u8(uint8_t* data, int32_t n_frames, int64_t n_pixels, int64_t frame_stride, int32_t premultiply,
+                       void* stream) {
+  DeviceState* st = nullptr;
+  int rc = current_state(&st);
+  if (rc != LARS_OK) return rc;
+  if (!data) return fail(LARS_ERR_INVALID, "lars_rgba_alpha_u8: NULL pointer");
+  if (n_frames < 1 || n_frames > 65535 || n_pixels < 1) return fail(LARS_ERR_INVALID, "lars_rgba_alpha_u8: empty input");
+  if ((reinterpret_cast<uintptr_t>(data) & 3u) || (frame_stride & 3) || frame_stride < n_pixels * 4)
+    return fail(LARS_ERR_INVALID, "lars_rgba_alpha_u8: frames must be 4-byte aligned RGBA");
+  long long want = (n_pixels + 255) / 256;
+  const long long cap = (long long)st->sm_count * 8;
+  const dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)n_frames);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (premultiply) lars::rgba_alpha_kernel<true><<<grid, 256, 0, s>>>(data, frame_stride, n_pixels);
+  else lars::rgba_alpha_kernel<false><<<grid, 256, 0, s>>>(data, frame_stride, n_pixels);
+  LARS_CUDA(cudaGetLastError());
   return LARS_OK;
 }
 

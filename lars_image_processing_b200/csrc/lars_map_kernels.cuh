@@ -45,8 +45,8 @@ struct MapStatsParams {
   int bins;
 };
 
-__device__ __forceinline__ void map_stats_accum(float x, float k, float thr, const float* edges_s, int bins,
-                                                uint32_t* hist_lane, float& mn, float& mx, float& gx,
+__device__ __forceinline__ void map_stats_accum(float x, float k, float thr, const float* edges_s, const uint8_t* subbin_s,
+                                                int bins, uint32_t* hist_lane, float& mn, float& mx, float& gx,
                                                 float& gd, float& gdd, uint32_t& above, uint32_t& nan) {
   mn = fminf(mn, x);
   mx = fmaxf(mx, x);
@@ -57,7 +57,10 @@ __device__ __forceinline__ void map_stats_accum(float x, float k, float thr, con
   gd += d;
   gdd = fmaf(d, d, gdd);
   if (x >= -1.0f && x <= 1.0f) {  // np.histogram drops out-of-range values (and NaN)
-    const int b = lars_hist_bin_edges(x, edges_s, bins);
+    // one byte load answers for ~99 % of the elements; the literal edge-corrected chain (two dependent edge loads,
+    // ~14 instructions) only runs for sub-bins that straddle an edge (round 1: K4 was issue- and LDS-bound on it)
+    int b = subbin_s[lars_hist_subbin_index(x)];
+    if (b == LARS_SUBBIN_AMBIGUOUS) b = lars_hist_bin_edges(x, edges_s, bins);
     atomicAdd(hist_lane + b * 32, 1u);
   }
 }
@@ -67,6 +70,7 @@ __global__ void __launch_bounds__(MAP_THREADS) map_stats_f32_kernel(const MapSta
   uint32_t* hist = reinterpret_cast<uint32_t*>(ms_smem);                       // [bins][32]
   float* edges_s = reinterpret_cast<float*>(ms_smem + (size_t)p.bins * 32 * 4);  // [bins + 1]
   double* red = reinterpret_cast<double*>(ms_smem + (size_t)p.bins * 32 * 4 + ((p.bins + 1 + 3) / 4) * 16);
+  uint8_t* subbin_s = reinterpret_cast<uint8_t*>(red + 8 * 8);                    // [LARS_SUBBIN_COUNT]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int map = blockIdx.y;
   const float* x = p.data + (long long)map * p.stride;
@@ -76,6 +80,8 @@ __global__ void __launch_bounds__(MAP_THREADS) map_stats_f32_kernel(const MapSta
     for (int i = tid; i <= p.bins; i += MAP_THREADS)
       edges_s[i] = (i == p.bins) ? 1.0f : (float)LARS_DADD(LARS_DMUL((double)i, step), -1.0);
   }
+  __syncthreads();
+  for (int i = tid; i < LARS_SUBBIN_COUNT; i += MAP_THREADS) subbin_s[i] = lars_hist_subbin_entry(i, edges_s, p.bins);
   __syncthreads();
 
   const float k = x[0];
@@ -101,10 +107,10 @@ __global__ void __launch_bounds__(MAP_THREADS) map_stats_f32_kernel(const MapSta
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       float gx = 0.f, gd = 0.f, gdd = 0.f;
-      map_stats_accum(q[u].x, k, thr, edges_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
-      map_stats_accum(q[u].y, k, thr, edges_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
-      map_stats_accum(q[u].z, k, thr, edges_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
-      map_stats_accum(q[u].w, k, thr, edges_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
+      map_stats_accum(q[u].x, k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
+      map_stats_accum(q[u].y, k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
+      map_stats_accum(q[u].z, k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
+      map_stats_accum(q[u].w, k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
       sx += (double)gx; sd += (double)gd; sdd += (double)gdd;
     }
     count += 16;
@@ -112,17 +118,17 @@ __global__ void __launch_bounds__(MAP_THREADS) map_stats_f32_kernel(const MapSta
   for (; v < v1; v += MAP_THREADS) {
     const float4 q = __ldg(xv + v);
     float gx = 0.f, gd = 0.f, gdd = 0.f;
-    map_stats_accum(q.x, k, thr, edges_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
-    map_stats_accum(q.y, k, thr, edges_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
-    map_stats_accum(q.z, k, thr, edges_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
-    map_stats_accum(q.w, k, thr, edges_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
+    map_stats_accum(q.x, k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
+    map_stats_accum(q.y, k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
+    map_stats_accum(q.z, k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
+    map_stats_accum(q.w, k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
     sx += (double)gx; sd += (double)gd; sdd += (double)gdd;
     count += 4;
   }
   if (blockIdx.x == gridDim.x - 1) {  // scalar tail (n % 4 elements)
     for (long long i = nvec * 4 + tid; i < p.n; i += MAP_THREADS) {
       float gx = 0.f, gd = 0.f, gdd = 0.f;
-      map_stats_accum(x[i], k, thr, edges_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
+      map_stats_accum(x[i], k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
       sx += (double)gx; sd += (double)gd; sdd += (double)gdd;
       count += 1;
     }

@@ -418,4 +418,33 @@ __global__ void __launch_bounds__(RS_THREADS) resize_v_kernel(const ResizeVParam
   else dst[0] = (uint8_t)out[0];
 }
 
+// ------------------------------------------------------------------------------------------
+// RGBA frames: Pillow resizes them with premultiplied alpha (Image.resize: convert("RGBa") -> resize ->
+// convert("RGBA")), so preprocess_large_image (process-images.py:398-422) on np.array(Image.open(upload)) of an RGBA PNG
+// does too.  The two conversions, in place, one thread per pixel (libImaging/Convert.c: rgbA2rgba, rgba2rgbA):
+//   premultiply    c' = MULDIV255(c, a) = ((t = c * a + 128) + (t >> 8)) >> 8
+//   unpremultiply  a in {0, 255}: c unchanged; else c' = min(255, 255 * c / a)   (integer division)
+// ------------------------------------------------------------------------------------------
+template <bool PREMULTIPLY>
+__global__ void __launch_bounds__(256) rgba_alpha_kernel(uint8_t* data, long long frame_stride, long long n_pixels) {
+  uint8_t* frame = data + (long long)blockIdx.y * frame_stride;
+  uint32_t* px = reinterpret_cast<uint32_t*>(frame);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pixels; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t v = px[i];
+    const uint32_t a = v >> 24;
+    uint32_t c[3] = {v & 0xFFu, (v >> 8) & 0xFFu, (v >> 16) & 0xFFu};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (PREMULTIPLY) {
+        const uint32_t t = c[k] * a + 128u;
+        c[k] = ((t >> 8) + t) >> 8;
+      } else if (a != 0u && a != 255u) {
+        const uint32_t q = (255u * c[k]) / a;
+        c[k] = q > 255u ? 255u : q;
+      }
+    }
+    px[i] = c[0] | (c[1] << 8) | (c[2] << 16) | (a << 24);
+  }
+}
+
 }  // namespace lars

@@ -18,6 +18,20 @@
 //                                    reference's fp64 -> fp32 -> uint8 chain on all 65,536 values
 // The stretch is monotone, so Pass 2 maps a sample with a float guess plus a +-1 correction
 // against the thresholds (1 KB per channel in shared memory instead of a 64 KB table).
+//
+// Round 2 -- the guided single pass (per-frame statistics only; tiles of one image keep the two-level form because
+// their counters are all-reduced between the levels).  Level B re-read the whole frame although ~1 % of the samples
+// matter, and it was instruction-bound on its per-sample compare-and-branch (231 us per 8 x 20 MP against 150 us
+// for level A).  Now:
+//   sample   wb_hist_u16_sample_kernel   high-byte histogram of every 16th work unit (6 % of a large frame)
+//   guess    wb_u16_candidates_kernel    per (frame, channel): the bucket the sample puts each percentile in plus
+//                                        the neighbour on the nearer side -> a 256-entry class table (<= 4 slots)
+//   guided   wb_hist_u16_guided_kernel   ONE read of the frame: exact high-byte histogram (as level A) and, for the
+//                                        samples whose high byte has a class (one byte load from shared memory),
+//                                        the low-byte histogram of that slot                      -- reads 6 B/px
+//   select   (as before, on the EXACT high-byte histogram) additionally checks that every bucket it needs was a
+//            candidate; then the slot histograms are the level-B result and level B has nothing to do for that
+//            frame.  A wrong guess costs that frame the old level-B pass -- never exactness.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -37,7 +51,22 @@ struct __align__(16) U16Select {
   int32_t bucket_of_rank[4];        // index into buckets[] for order statistic r
   int32_t buckets[U16_MAX_BUCKETS]; // distinct high bytes, ascending; -1 = unused
   int32_t n_buckets;
-  int32_t pad_[3];
+  int32_t done;                     // 1: the guided pass already counted every bucket of this channel (level B skips it)
+  int32_t pad_[2];
+};
+
+constexpr int U16_CAND_SLOTS = 4;   // candidate high-byte buckets per channel in the guided pass
+constexpr int U16_SAMPLE_STEP = 16; // large frames: the guess is made from every 16th work unit (4,096 pixels each)
+constexpr int U16_SAMPLE_MIN_UNITS = 64;  // ... but from at least 64 units (262,144 pixels per channel): with fewer samples
+                                          // the sampling noise of the 2 % / 98 % positions exceeds half a bucket
+__host__ __device__ inline int u16_sample_step(long long units_per_frame) {
+  const long long s = units_per_frame / U16_SAMPLE_MIN_UNITS;
+  return s < 1 ? 1 : (s > U16_SAMPLE_STEP ? U16_SAMPLE_STEP : (int)s);
+}
+
+// per (frame, channel): which high bytes the guided pass also counts by low byte
+struct __align__(16) U16Candidates {
+  uint8_t cls[256];                 // 0 = not a candidate, k + 1 = slot k
 };
 
 struct U16HistParams {
@@ -51,6 +80,10 @@ struct U16HistParams {
   long long set_stride;             // 1 = one set per frame, 0 = shared set (tiles of one image)
   int n_frames;
   int lo_pass;                      // level B: handles buckets [2 lo_pass, 2 lo_pass + 1]
+  // guided single pass
+  unsigned long long* hist_sample;  // [set][3][256]  high-byte histogram of the sampled units
+  const U16Candidates* cand;        // [set][3]
+  unsigned long long* cand_lo;      // [set][3][U16_CAND_SLOTS][256]
 };
 
 template <int C>
@@ -86,6 +119,37 @@ __device__ __forceinline__ void u16_visit_span(const uint8_t* fsrc, long long b0
     const uint16_t* s16 = reinterpret_cast<const uint16_t*>(fsrc);
     for (long long s = vec_end / 2 + tid; s < b1 / 2; s += K1_THREADS)
       if ((s & 3) < 3) visit((int)(s & 3), (uint32_t)s16[s]);
+  }
+}
+
+// The same walk handing out the 32-bit word and which half holds the sample (a compile-time constant after
+// unrolling), so that a visitor can pick bytes with one PRMT instead of first isolating the 16-bit sample.
+template <int C, class Visit>
+__device__ __forceinline__ void u16_visit_span_words(const uint8_t* fsrc, long long b0, long long b1, int tid, Visit visit) {
+  if (C == 3) {
+    const long long vec_end = b0 + ((b1 - b0) / 48) * 48;
+    for (long long off = b0 + 48ll * tid; off + 48 <= vec_end; off += 48ll * K1_THREADS) {
+      const uint4* q = reinterpret_cast<const uint4*>(fsrc + off);
+      const uint4 v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2);
+      const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        visit((2 * i) % 3, w[i], 0);
+        visit((2 * i + 1) % 3, w[i], 1);
+      }
+    }
+    const uint16_t* s16 = reinterpret_cast<const uint16_t*>(fsrc);
+    for (long long s = vec_end / 2 + tid; s < b1 / 2; s += K1_THREADS) visit((int)(s % 3), (uint32_t)s16[s], 0);
+  } else {
+    const long long vec_end = b0 + ((b1 - b0) / 16) * 16;
+    for (long long off = b0 + 16ll * tid; off + 16 <= vec_end; off += 16ll * K1_THREADS) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(fsrc + off));
+      visit(0, v.x, 0); visit(1, v.x, 1); visit(2, v.y, 0);
+      visit(0, v.z, 0); visit(1, v.z, 1); visit(2, v.w, 0);
+    }
+    const uint16_t* s16 = reinterpret_cast<const uint16_t*>(fsrc);
+    for (long long s = vec_end / 2 + tid; s < b1 / 2; s += K1_THREADS)
+      if ((s & 3) < 3) visit((int)(s & 3), (uint32_t)s16[s], 0);
   }
 }
 
@@ -125,11 +189,201 @@ __global__ void __launch_bounds__(K1_THREADS, 2) wb_hist_u16_hi_kernel(const U16
   }
 }
 
+
+// ---- sample: level A over every U16_SAMPLE_STEP-th work unit ------------------------------------
+template <int C>
+__global__ void __launch_bounds__(K1_THREADS, 2) wb_hist_u16_sample_kernel(const U16HistParams p) {
+  extern __shared__ __align__(16) uint32_t u16_hist[];  // [3][256][32] lane-private
+  const int tid = threadIdx.x, lane = tid & 31;
+  const long long frame_bytes = p.n_pixels * C * 2;
+  const uint32_t base = smem_u32(u16_hist) + 4u * lane;
+  const int step = u16_sample_step(p.units_per_frame);
+  const long long per_frame = (p.units_per_frame + step - 1) / step;
+  const long long total = per_frame * p.n_frames;
+  const long long G = gridDim.x;
+  long long u = ((long long)blockIdx.x * total) / G;
+  const long long u_end = ((long long)(blockIdx.x + 1) * total) / G;
+  while (u < u_end) {
+    const long long frame = u / per_frame;
+    const long long fu0 = frame * per_frame;
+    const long long span_end = (fu0 + per_frame < u_end) ? fu0 + per_frame : u_end;
+    const uint8_t* fsrc = p.src + frame * p.frame_stride;
+    for (int i = tid; i < 3 * 256 * 32; i += K1_THREADS) u16_hist[i] = 0u;
+    __syncthreads();
+    for (; u < span_end; ++u) {
+      const long long b0 = (u - fu0) * step * U16Unit<C>::BYTES;
+      long long b1 = b0 + U16Unit<C>::BYTES;
+      if (b1 > frame_bytes) b1 = frame_bytes;
+      u16_visit_span<C>(fsrc, b0, b1, tid, [&](int ch, uint32_t v) {
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(base + (uint32_t)ch * 32768u + ((v >> 8) << 7)) : "memory");
+      });
+    }
+    __syncthreads();
+    for (int b = tid; b < 3 * 256; b += K1_THREADS) {
+      uint32_t sum = 0;
+#pragma unroll 8
+      for (int l = 0; l < 32; ++l) sum += u16_hist[b * 32 + ((l + tid) & 31)];
+      if (sum) atomicAdd(&p.hist_sample[frame * 768 + b], (unsigned long long)sum);
+    }
+    __syncthreads();
+  }
+}
+
+// ---- guess: candidate buckets from the sampled histogram ----------------------------------------
+struct U16CandParams {
+  const unsigned long long* hist_sample;  // [set][3][256]
+  U16Candidates* cand;                    // [set][3]
+  double q_lo, q_hi;
+};
+
+__global__ void __launch_bounds__(256) wb_u16_candidates_kernel(const U16CandParams p) {
+  __shared__ unsigned long long cum[256];
+  __shared__ unsigned long long warp_tot[8];
+  __shared__ int picked[U16_CAND_SLOTS];
+  const int v = threadIdx.x, lane = v & 31, warp = v >> 5;
+  const long long base = (long long)blockIdx.x * 256;
+  const unsigned long long own = p.hist_sample[base + v];
+  unsigned long long x = own;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d);
+    if (lane >= d) x += y;
+  }
+  if (lane == 31) warp_tot[warp] = x;
+  if (v < U16_CAND_SLOTS) picked[v] = -1;
+  __syncthreads();
+  unsigned long long add = 0;
+  for (int w = 0; w < warp; ++w) add += warp_tot[w];
+  x += add;
+  cum[v] = x;
+  __syncthreads();
+  const unsigned long long m = cum[255];
+  if (v == 0 && m > 0) {
+    // the sample's own percentile positions: bucket of rank floor((m - 1) q), and the non-empty neighbour on the
+    // side the rank sits closer to (below the middle of the bucket's mass -> previous, else next)
+    for (int k = 0; k < 2; ++k) {
+      const unsigned long long r = (unsigned long long)floor((double)(m - 1) * (k == 0 ? p.q_lo : p.q_hi));
+      int b = 0;
+      while (b < 255 && cum[b] <= r) ++b;
+      const unsigned long long below = b ? cum[b - 1] : 0ull;
+      const unsigned long long cnt = cum[b] - below;
+      int nb = -1;
+      if (2 * (r - below) < cnt) { for (int t = b - 1; t >= 0 && nb < 0; --t) if (cum[t] != (t ? cum[t - 1] : 0ull)) nb = t; }
+      else { for (int t = b + 1; t < 256 && nb < 0; ++t) if (cum[t] != cum[t - 1]) nb = t; }
+      picked[2 * k] = b;
+      picked[2 * k + 1] = nb;
+    }
+  }
+  __syncthreads();
+  uint8_t c = 0;
+#pragma unroll
+  for (int k = U16_CAND_SLOTS - 1; k >= 0; --k)     // a bucket picked twice keeps its lowest slot
+    if (picked[k] == v) c = (uint8_t)(k + 1);
+  p.cand[blockIdx.x].cls[v] = c;
+}
+
+// ---- guided: exact high-byte histogram + low-byte histograms of the candidate buckets, one read --
+constexpr int U16_GUIDED_LO_WORDS = 3 * U16_CAND_SLOTS * 256;
+constexpr int U16_GUIDED_SMEM_BYTES = U16_HI_SMEM_BYTES + U16_GUIDED_LO_WORDS * 4 + 3 * 256;   // 96 KB + 12 KB + 768 B
+template <int C>
+__global__ void __launch_bounds__(K1_THREADS, 2) wb_hist_u16_guided_kernel(const U16HistParams p) {
+  extern __shared__ __align__(16) uint32_t u16_hist[];  // [3][256][32] lane-private, then lo[3][slots][256], then cls[3][256]
+  uint32_t* lo_hist = u16_hist + 3 * 256 * 32;
+  uint8_t* cls_s = reinterpret_cast<uint8_t*>(lo_hist + U16_GUIDED_LO_WORDS);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const long long frame_bytes = p.n_pixels * C * 2;
+  const uint32_t base = smem_u32(u16_hist) + 4u * lane;
+  const uint32_t lo_base = smem_u32(lo_hist), cls_base = smem_u32(cls_s);
+  const long long G = gridDim.x;
+  long long u = ((long long)blockIdx.x * p.total_units) / G;
+  const long long u_end = ((long long)(blockIdx.x + 1) * p.total_units) / G;
+  while (u < u_end) {
+    const long long frame = u / p.units_per_frame;
+    const long long fu0 = frame * p.units_per_frame;
+    const long long span_end = (fu0 + p.units_per_frame < u_end) ? fu0 + p.units_per_frame : u_end;
+    const long long b0 = (u - fu0) * U16Unit<C>::BYTES;
+    long long b1 = (span_end - fu0) * U16Unit<C>::BYTES;
+    if (b1 > frame_bytes) b1 = frame_bytes;
+    const uint8_t* fsrc = p.src + frame * p.frame_stride;
+    u = span_end;
+    for (int i = tid; i < 3 * 256 * 32 + U16_GUIDED_LO_WORDS; i += K1_THREADS) u16_hist[i] = 0u;
+    {
+      const uint32_t* src_cls = reinterpret_cast<const uint32_t*>(p.cand + frame * 3);
+      uint32_t* dst_cls = reinterpret_cast<uint32_t*>(cls_s);
+      for (int i = tid; i < 3 * 64; i += K1_THREADS) dst_cls[i] = src_cls[i];
+    }
+    __syncthreads();
+    // rare path (~1 % of the samples): lanes of the warp that hit the same counter send one RED, so a constant
+    // channel or a saturated region -- every sample a hit on one address -- is not serialised 32-fold
+    auto hit = [&](int ch, uint32_t c, uint32_t lob) {
+      const uint32_t addr = lo_base + ((((uint32_t)ch * U16_CAND_SLOTS + (c - 1u)) << 8) + lob) * 4u;
+      const unsigned peers = __match_any_sync(__activemask(), addr);
+      if (lane == __ffs(peers) - 1)
+        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"((uint32_t)__popc(peers)));
+    };
+    auto one = [&](int ch, uint32_t w, int half) {
+      const uint32_t hb = __byte_perm(w, 0u, half ? 0x4443 : 0x4441);   // the sample's high byte, one PRMT
+      asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(base + (uint32_t)ch * 32768u + hb * 128u));
+      const uint32_t c = cls_s[ch * 256 + hb];
+      if (c) hit(ch, c, __byte_perm(w, 0u, half ? 0x4442 : 0x4440));
+    };
+    if (C == 3) {
+      // 48 contiguous bytes per lane = 24 samples, sample s of channel s % 3.  The class bytes of 8 samples are fetched
+      // before the first one is tested: per sample the load -> compare -> branch chain costs a shared-memory
+      // round trip, and issued one after the other those latencies, not bandwidth, set the pace (ncu, first
+      // version: 54 % issue-active, short_scoreboard the top stall next to the global loads).
+      const long long vec_end = b0 + ((b1 - b0) / 48) * 48;
+      for (long long off = b0 + 48ll * tid; off + 48 <= vec_end; off += 48ll * K1_THREADS) {
+        const uint4* q = reinterpret_cast<const uint4*>(fsrc + off);
+        const uint4 v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2);
+        const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {          // one 16-byte vector = 8 samples at a time (24 at once spill)
+          uint32_t hb[8], c[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            hb[2 * i] = __byte_perm(w[4 * g + i], 0u, 0x4441);
+            hb[2 * i + 1] = __byte_perm(w[4 * g + i], 0u, 0x4443);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) c[k] = cls_s[((8 * g + k) % 3) * 256 + hb[k]];
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(base + (uint32_t)((8 * g + k) % 3) * 32768u + hb[k] * 128u));
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (c[k]) hit((8 * g + k) % 3, c[k], __byte_perm(w[4 * g + (k >> 1)], 0u, (k & 1) ? 0x4442 : 0x4440));
+        }
+      }
+      const uint16_t* s16 = reinterpret_cast<const uint16_t*>(fsrc);
+      for (long long sidx = vec_end / 2 + tid; sidx < b1 / 2; sidx += K1_THREADS) one((int)(sidx % 3), (uint32_t)s16[sidx], 0);
+    } else {
+      u16_visit_span_words<C>(fsrc, b0, b1, tid, one);
+    }
+    __syncthreads();
+    for (int b = tid; b < 3 * 256; b += K1_THREADS) {
+      uint32_t sum = 0;
+#pragma unroll 8
+      for (int l = 0; l < 32; ++l) sum += u16_hist[b * 32 + ((l + tid) & 31)];
+      if (sum) atomicAdd(&p.hist_hi[frame * 768 + b], (unsigned long long)sum);
+    }
+    for (int b = tid; b < U16_GUIDED_LO_WORDS; b += K1_THREADS) {
+      const uint32_t sum = lo_hist[b];
+      if (sum) atomicAdd(&p.cand_lo[frame * U16_GUIDED_LO_WORDS + b], (unsigned long long)sum);
+    }
+    __syncthreads();
+  }
+}
+
 // ---- select -------------------------------------------------------------------------------
 struct U16SelectParams {
   const unsigned long long* hist_hi;  // [set][3][256]
   U16Select* select;                  // [set][3]
   double q_lo, q_hi;
+  // guided pass (all three nullptr otherwise): candidate classes, their low-byte histograms, and where level B's go
+  const U16Candidates* cand;          // [set][3]
+  const unsigned long long* cand_lo;  // [set][3][U16_CAND_SLOTS][256]
+  unsigned long long* hist_lo;        // [set][3][U16_MAX_BUCKETS][256]
 };
 
 __device__ __forceinline__ void percentile_ranks(unsigned long long n, double q, unsigned long long& lo,
@@ -148,6 +402,7 @@ __global__ void __launch_bounds__(256) wb_u16_select_kernel(const U16SelectParam
   __shared__ unsigned long long warp_tot[8];
   __shared__ int rank_bucket[4];
   __shared__ unsigned long long rank_resid[4];
+  __shared__ U16Select chosen;
   const int v = threadIdx.x, lane = v & 31, warp = v >> 5;
   const long long base = (long long)blockIdx.x * 256;
   unsigned long long x = p.hist_hi[base + v];
@@ -185,8 +440,24 @@ __global__ void __launch_bounds__(256) wb_u16_select_kernel(const U16SelectParam
       s.bucket_of_rank[k] = slot;
       s.residual[k] = rank_resid[k];
     }
-    s.pad_[0] = s.pad_[1] = s.pad_[2] = 0;
+    s.pad_[0] = s.pad_[1] = 0;
+    // guided pass: usable iff every bucket that holds a rank was one of the candidates
+    s.done = 0;
+    if (p.cand) {
+      s.done = 1;
+      for (int b = 0; b < s.n_buckets; ++b)
+        if (p.cand[blockIdx.x].cls[s.buckets[b]] == 0) s.done = 0;
+    }
+    chosen = s;
     p.select[blockIdx.x] = s;
+  }
+  __syncthreads();
+  if (p.cand && chosen.done) {           // the candidates' low-byte histograms ARE level B's result for this channel
+    for (int b = 0; b < chosen.n_buckets; ++b) {
+      const int slot = (int)p.cand[blockIdx.x].cls[chosen.buckets[b]] - 1;
+      p.hist_lo[((long long)blockIdx.x * U16_MAX_BUCKETS + b) * 256 + v] =
+          p.cand_lo[((long long)blockIdx.x * U16_CAND_SLOTS + slot) * 256 + v];
+    }
   }
 }
 
@@ -216,9 +487,10 @@ __global__ void __launch_bounds__(K1_THREADS, 2) wb_hist_u16_lo_kernel(const U16
     const U16Select* sel = p.select + frame * p.set_stride * 3;
     // six scalars, not an array: the scalar tail indexes by a run-time channel, and a dynamically
     // indexed local array would put the selection in local memory for the hot loop as well
-    const int w00 = sel[0].buckets[2 * p.lo_pass], w01 = sel[0].buckets[2 * p.lo_pass + 1];
-    const int w10 = sel[1].buckets[2 * p.lo_pass], w11 = sel[1].buckets[2 * p.lo_pass + 1];
-    const int w20 = sel[2].buckets[2 * p.lo_pass], w21 = sel[2].buckets[2 * p.lo_pass + 1];
+    // a channel the guided pass has already counted (done) wants nothing from this pass
+    const int w00 = sel[0].done ? -1 : sel[0].buckets[2 * p.lo_pass], w01 = sel[0].done ? -1 : sel[0].buckets[2 * p.lo_pass + 1];
+    const int w10 = sel[1].done ? -1 : sel[1].buckets[2 * p.lo_pass], w11 = sel[1].done ? -1 : sel[1].buckets[2 * p.lo_pass + 1];
+    const int w20 = sel[2].done ? -1 : sel[2].buckets[2 * p.lo_pass], w21 = sel[2].done ? -1 : sel[2].buckets[2 * p.lo_pass + 1];
     const bool any = (w00 >= 0) || (w10 >= 0) || (w20 >= 0);
     if (!any) continue;  // uniform per CTA: this pass has nothing to count for this frame
     for (int i = tid; i < 3 * 2 * 256 * 16; i += K1_THREADS) u16_lo[i] = 0u;

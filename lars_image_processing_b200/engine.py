@@ -386,9 +386,12 @@ class Engine:
                 self._resize_plans[key] = hit
         return hit
 
-    def resize_device(self, frames: DeviceFrames, out_h: int, out_w: int, stream=None) -> DeviceFrames:
+    def resize_device(self, frames: DeviceFrames, out_h: int, out_w: int, stream=None,
+                      premultiplied_alpha: bool = True) -> DeviceFrames:
         """K10: Pillow-exact Lanczos resize of a device-resident uint8 batch (the GPU form of
-        preprocess_large_image, process-images.py:398-422) -> a new padded device batch."""
+        preprocess_large_image, process-images.py:398-422) -> a new padded device batch.
+        4-channel frames are RGBA to Pillow, which resizes them with premultiplied alpha; with
+        ``premultiplied_alpha`` (default) so does this call -- the input batch is premultiplied IN PLACE."""
         if frames.sample_bytes != 1:
             raise LarsError("resize covers uint8 frames (Pillow cannot hold multi-channel 16-bit images)")
         if out_h < 1 or out_w < 1:
@@ -400,11 +403,18 @@ class Engine:
         out = self.alloc_frames(frames.n_frames, out_h, out_w, frames.channels, s)
         temp_bytes = int(plan.temp_frame_bytes) * frames.n_frames
         temp = self._alloc((max(temp_bytes, 16),), torch.uint8, s)
+        rgba = premultiplied_alpha and frames.channels == 4 and (plan.need_h or plan.need_v)
         with torch.cuda.device(self.device):
+            if rgba:
+                check(self.lib.lars_rgba_alpha_u8(frames.data.data_ptr(), frames.n_frames, frames.n_pixels,
+                                                  frames.stride_bytes, 1, s.cuda_stream), "lars_rgba_alpha_u8")
             check(self.lib.lars_resize_lanczos_u8(C.byref(plan), tables.data_ptr(), frames.data.data_ptr(),
                                                   frames.stride_bytes, frames.n_frames, out.data.data_ptr(),
                                                   out.stride_bytes, temp.data_ptr(), temp_bytes, s.cuda_stream),
                   "lars_resize_lanczos_u8")
+            if rgba:
+                check(self.lib.lars_rgba_alpha_u8(out.data.data_ptr(), out.n_frames, out.n_pixels, out.stride_bytes, 0,
+                                                  s.cuda_stream), "lars_rgba_alpha_u8")
         return out
 
     def resize_batch(self, frames: Sequence[np.ndarray], out_h: int, out_w: int) -> List[np.ndarray]:

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import INDEX_STATS_DTYPE, LarsError, check
+from ._lib import INDEX_STATS_DTYPE, MAP_STATS_F64_DTYPE, LarsError, check
 from .engine import DEFAULT_BINS, INDEX_TYPES, Engine, get_engine, stats_records_to_dicts
 
 
@@ -73,11 +73,57 @@ def device_map_median(eng: Engine, dev_map: torch.Tensor, n: int, stream=None) -
     return med
 
 
+def _map_statistics_f64(arr: np.ndarray, threshold: float, bins: int, median: bool) -> dict:
+    """The float64 flavour (process-ndvi.py:60-71, :97): K4d + K3d keep the array's own arithmetic -- float64
+    min / max / median, `x > threshold` in float64, np.histogram with float64 edges."""
+    eng = get_engine()
+    lib = eng.lib
+    s = eng.stream()
+    flat = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)
+    n = flat.size
+    with torch.cuda.stream(s):
+        dev = torch.empty(n, dtype=torch.float64, device=eng.device)
+        eng._staged_h2d(dev.view(torch.uint8), flat.view(np.uint8), s)
+        stats = torch.empty(MAP_STATS_F64_DTYPE.itemsize, dtype=torch.uint8, device=eng.device)
+        ws_bytes = int(lib.lars_map_stats_f64_workspace_bytes())
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=eng.device)
+        med = None
+        with torch.cuda.device(eng.device):
+            check(lib.lars_map_stats_f64(dev.data_ptr(), n, bins, float(threshold), stats.data_ptr(), ws.data_ptr(),
+                                         ws_bytes, s.cuda_stream), "lars_map_stats_f64")
+            if median:
+                med = torch.empty(3, dtype=torch.float64, device=eng.device)
+                sel_bytes = int(lib.lars_select_f64_workspace_bytes())
+                sel_ws = torch.empty(sel_bytes, dtype=torch.uint8, device=eng.device)
+                check(lib.lars_select_f64(dev.data_ptr(), n, (n - 1) // 2, n // 2, med.data_ptr(), sel_ws.data_ptr(),
+                                          sel_bytes, s.cuda_stream), "lars_select_f64")
+        h_stats = stats.cpu()
+        h_med = med.cpu() if med is not None else None
+    s.synchronize()
+    rec = h_stats.numpy().view(MAP_STATS_F64_DTYPE)[0]
+    cnt = int(rec["count"])
+    out = {
+        "count": cnt, "mean": float(rec["mean"]), "std": float(rec["std"]),
+        "min": float(rec["min"]), "max": float(rec["max"]),
+        "count_above": int(rec["count_above"]),
+        "coverage_pct": float(rec["count_above"]) / cnt * 100.0,
+        "sum": float(rec["sum"]), "sumsq": float(rec["sumsq"]),
+        "hist": np.array(rec["hist"][:bins], dtype=np.int64),
+    }
+    if h_med is not None:
+        out["median"] = float(h_med[2])
+        out["middle_values"] = (float(h_med[0]), float(h_med[1]))
+    return out
+
+
 def map_statistics(index_array, threshold: float = 0.2, bins: int = DEFAULT_BINS, median: bool = True) -> dict:
-    """mean / std / min / max / coverage / histogram (/ exact median) of a host float map."""
+    """mean / std / min / max / coverage / histogram (/ exact median) of a host float map.  A float64 array is
+    reduced in float64 (the reference's NumPy calls keep the array's dtype); everything else as float32."""
     arr = np.asarray(index_array)
     if arr.size == 0:
         return {}
+    if arr.dtype == np.float64:
+        return _map_statistics_f64(arr, threshold, bins, median)
     eng = get_engine()
     s = eng.stream()
     dev = _to_device_f32(eng, arr, s)

@@ -42,9 +42,10 @@ def preprocess_large_image(img_array, max_dimension=1024):
     if target is None:
         return img_array
     arr = np.asarray(img_array)
-    if arr.dtype != np.uint8 or arr.ndim not in (2, 3) or (arr.ndim == 3 and arr.shape[2] != 3):
-        # Image.fromarray accepts more layouts (RGBA is resized with premultiplied alpha, float /
-        # int32 single-band images in their own precision); the RGNir path only produces these two
+    if arr.dtype != np.uint8 or arr.ndim not in (2, 3) or (arr.ndim == 3 and arr.shape[2] not in (3, 4)):
+        # Image.fromarray accepts a few more layouts (float / int32 single-band images in their own precision) and
+        # rejects the rest -- uint16 RGB among them -- with this TypeError; gray, RGB and RGBA (np.array(Image.open(png)),
+        # resized with premultiplied alpha like Pillow) are what the app passes
         raise TypeError(f"Cannot handle this data type: {arr.shape[2:] or (1,)}, {arr.dtype.str}")
     return get_engine().resize_batch([arr], target[0], target[1])[0]
 

@@ -30,8 +30,9 @@ def calculate_ndvi(image_path, save_path=None, visualize=True):
 def analyze_ndvi_statistics(ndvi_array):
     """process-ndvi.py:50-73 -- mean / median / min / max / std / vegetation coverage (>0.2).
 
-    The GPU statistics kernels work on float32 maps; a float64 map (``calculate_ndvi``) is
-    rounded to float32 first, which moves every statistic by < 6e-8 relative.
+    The statistics keep the array's dtype as NumPy does: a float64 map (``calculate_ndvi``) goes through the
+    float64 kernels (K4d / K3d) -- median, min, max and the ``> 0.2`` count are exact, mean / std within 1e-12
+    relative (summation order); a float32 map through K4 / K3.
     """
     arr = np.asarray(ndvi_array)
     st = map_statistics(arr, threshold=0.2, median=True)

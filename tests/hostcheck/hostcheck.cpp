@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <vector>
 #include "../../lars_image_processing_b200/csrc/pixel_math.h"
 #include "../../lars_image_processing_b200/csrc/lzw_warp.h"
 #include "../../lars_image_processing_b200/csrc/inflate_warp.h"
@@ -33,6 +34,31 @@ void hc_pair_tables(int bins, const float* edges, float threshold, float* value,
 
 void hc_hist_bin_edges(const float* x, int64_t n, int bins, const float* edges, int32_t* out) {
   for (int64_t i = 0; i < n; ++i) out[i] = lars_hist_bin_edges(x[i], edges, bins);
+}
+
+// K4's fast path: the sub-bin table, with the literal chain behind its ambiguous entries
+void hc_hist_bin_subbin(const float* x, int64_t n, int bins, const float* edges, int32_t* out, int32_t* n_ambiguous) {
+  std::vector<uint8_t> table(LARS_SUBBIN_COUNT);
+  int amb = 0;
+  for (int k = 0; k < LARS_SUBBIN_COUNT; ++k) {
+    table[k] = lars_hist_subbin_entry(k, edges, bins);
+    amb += table[k] == LARS_SUBBIN_AMBIGUOUS;
+  }
+  *n_ambiguous = amb;
+  for (int64_t i = 0; i < n; ++i) {
+    int b = table[lars_hist_subbin_index(x[i])];
+    if (b == LARS_SUBBIN_AMBIGUOUS) b = lars_hist_bin_edges(x[i], edges, bins);
+    out[i] = b;
+  }
+}
+
+// float64 flavour; the edges are built here with the device kernel's own expression (arange * step + start)
+void hc_hist_bin_edges_f64(const double* x, int64_t n, int bins, int32_t* out, double* edges_out) {
+  std::vector<double> edges(bins + 1);
+  const double step = LARS_DDIV(2.0, (double)bins);
+  for (int i = 0; i <= bins; ++i) edges[i] = (i == bins) ? 1.0 : LARS_DADD(LARS_DMUL((double)i, step), -1.0);
+  for (int i = 0; i <= bins; ++i) edges_out[i] = edges[i];
+  for (int64_t i = 0; i < n; ++i) out[i] = lars_hist_bin_edges_f64(x[i], edges.data(), bins);
 }
 
 void hc_cmap_index_range(const float* x, int64_t n, float vmin, float vmax, int32_t* out) {

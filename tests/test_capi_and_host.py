@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in include/lars_b200.h but not exported"
     assert set(_lib.EXPORTED_SYMBOLS) == set(declared)
-    assert lib.lars_abi_version() == 6
+    assert lib.lars_abi_version() == 7
 
 
 def test_struct_layouts_match_header(tmp_path):
@@ -51,9 +51,12 @@ def test_struct_layouts_match_header(tmp_path):
                    'sizeof(lars_stretch_u16));'
                    'printf("%zu %zu %zu %zu\\n", offsetof(lars_tiff_info, tile_width), offsetof(lars_tiff_info, bigtiff),'
                    'sizeof(lars_png_info), offsetof(lars_png_info, frame_bytes));'
-                   'printf("%zu %zu\\n", sizeof(lars_lzw_chunk), offsetof(lars_lzw_chunk, dst_bytes));return 0;}\n')
+                   'printf("%zu %zu\\n", sizeof(lars_lzw_chunk), offsetof(lars_lzw_chunk, dst_bytes));'
+                   'printf("%zu %zu %zu\\n", sizeof(lars_map_record_f64), offsetof(lars_map_record_f64, max), offsetof(lars_map_record_f64, hist));return 0;}\n')
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
-    a, b, c, d, e, f, g, h, i, j, k, l = map(int, subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split())
+    a, b, c, d, e, f, g, h, i, j, k, l, m, n, q = map(int, subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split())
+    assert m == _lib.MAP_STATS_F64_DTYPE.itemsize == 592
+    assert n == _lib.MAP_STATS_F64_DTYPE.fields["max"][1] and q == _lib.MAP_STATS_F64_DTYPE.fields["hist"][1]
     assert a == C.sizeof(_lib.ResizePlan) and b == _lib.ResizePlan.table_bytes.offset
     assert c == _lib.ResizePlan.mma_table_offset.offset
     assert d == C.sizeof(_lib.TiffInfo) and e == _lib.TiffInfo.frame_bytes.offset

@@ -75,6 +75,48 @@ def test_generic_edge_bins_on_random_floats(hostcheck):
                               np.histogram(xc, bins=bins, range=(-1, 1))[0])
 
 
+def test_subbin_table_path_matches_numpy(hostcheck):
+    """K4's fast path (4097-entry sub-bin table, literal chain behind the ambiguous entries) gives np.histogram's bin
+    for every float32 tried: random values, every edge and its neighbours, every sub-bin boundary and its neighbours,
+    for every bin count 1..64; and the table stays nearly unambiguous (<= 2 (bins + 1) of 4097 entries)."""
+    rng = np.random.default_rng(5)
+    grid = (np.arange(4097, dtype=np.float64) / 2048 - 1).astype(np.float32)
+    around = np.concatenate([grid, np.nextafter(grid, np.float32(-2)), np.nextafter(grid, np.float32(2)),
+                             np.nextafter(np.nextafter(grid, np.float32(-2)), np.float32(-2))])
+    for bins in list(range(1, 65)):
+        edges = o.histogram_edges(bins)
+        x = np.concatenate([rng.uniform(-1, 1, 20000).astype(np.float32), around, edges,
+                            np.nextafter(edges, np.float32(-2)), np.nextafter(edges, np.float32(2))])
+        xc = np.ascontiguousarray(np.clip(x, -1, 1))
+        out = np.empty(xc.size, np.int32)
+        amb = C.c_int32(0)
+        hostcheck.hc_hist_bin_subbin(C.c_void_p(xc.ctypes.data), C.c_int64(xc.size), C.c_int(bins), C.c_void_p(edges.ctypes.data),
+                                     C.c_void_p(out.ctypes.data), C.byref(amb))
+        assert np.array_equal(out, o.histogram_bin_by_edges(xc, bins)), bins
+        assert np.array_equal(np.bincount(out, minlength=bins), np.histogram(xc, bins=bins, range=(-1, 1))[0]), bins
+        assert amb.value <= 2 * (bins + 1), (bins, amb.value)     # an edge on a sub-bin boundary marks both neighbours
+
+
+def test_float64_edge_bins_match_numpy(hostcheck):
+    """K4d's bin chain: float64 linspace edges as the kernel builds them == np.linspace, and the corrected bin ==
+    np.histogram on a float64 array for on-edge / next-to-edge / random values, bins 1..64."""
+    rng = np.random.default_rng(4)
+    for bins in (1, 2, 7, 49, 50, 51, 63, 64):
+        ref_edges = np.linspace(-1, 1, bins + 1)
+        x = rng.uniform(-1, 1, 100000)
+        x[:bins + 1] = ref_edges
+        x[bins + 1:2 * bins + 2] = np.nextafter(ref_edges, -2.0)
+        x[2 * bins + 2:3 * bins + 3] = np.nextafter(ref_edges, 2.0)
+        x[3 * bins + 3:3 * bins + 3 + 5000] = np.float64(rng.uniform(-1, 1, 5000).astype(np.float32))
+        xc = np.ascontiguousarray(np.clip(x, -1, 1))
+        out = np.empty(xc.size, np.int32)
+        edges = np.empty(bins + 1, np.float64)
+        hostcheck.hc_hist_bin_edges_f64(C.c_void_p(xc.ctypes.data), C.c_int64(xc.size), C.c_int(bins),
+                                        C.c_void_p(out.ctypes.data), C.c_void_p(edges.ctypes.data))
+        assert np.array_equal(edges, ref_edges), bins
+        assert np.array_equal(np.bincount(out, minlength=bins), np.histogram(xc, bins=bins, range=(-1, 1))[0]), bins
+
+
 def test_wb_lut_entry_chain(hostcheck):
     rng = np.random.default_rng(11)
     cases = [(0.0, 255.0), (10.0, 10.0), (0.0, 0.0), (255.0, 255.0), (3.5, 3.5), (12.0, 201.0),

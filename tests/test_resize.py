@@ -229,3 +229,31 @@ def test_gpu_resize_against_committed_pillow_vectors(engine, golden):
         assert np.array_equal(engine.resize_batch([img], want.shape[0], want.shape[1])[0], want)
     g = golden["resize"]
     assert np.array_equal(pi.preprocess_large_image(g["pre_in"], 1024), g["pre_out"])
+
+
+@pytest.mark.gpu
+def test_gpu_rgba_frames_are_resized_with_premultiplied_alpha(engine):
+    """np.array(Image.open(upload)) of an RGBA PNG reaches preprocess_large_image as HxWx4; Pillow resizes RGBA with
+    premultiplied alpha (convert("RGBa") -> resize -> convert("RGBA")), and so must the drop-in -- bit for bit, for
+    opaque, transparent, partly transparent and random alpha."""
+    from lars_image_processing_b200 import process_images as pi
+    rng = np.random.default_rng(61)
+    for h, w in ((1500, 2100), (1200, 1030)):
+        rgb = synth.vegetation_frame(h, h, w)
+        alphas = [np.full((h, w), 255, np.uint8), np.zeros((h, w), np.uint8), rng.integers(0, 256, (h, w), dtype=np.uint8),
+                  np.where(rng.random((h, w)) < 0.5, 255, rng.integers(0, 256, (h, w))).astype(np.uint8),
+                  np.tile(np.arange(w, dtype=np.int64) * 255 // (w - 1), (h, 1)).astype(np.uint8)]
+        for a in alphas:
+            img = np.dstack([rgb, a])
+            got = pi.preprocess_large_image(img, 1024)
+            t = resize_np.target_size(h, w, 1024)
+            want = pil_resize(img, t[0], t[1])
+            assert got.shape == want.shape == (t[0], t[1], 4) and np.array_equal(got, want)
+    # the device-side form used by analyze_batch(max_dimension=...) follows the same policy
+    img = np.dstack([synth.vegetation_frame(7, 1300, 1100), rng.integers(0, 256, (1300, 1100), dtype=np.uint8)])
+    dev = engine.upload([img])
+    out = engine.resize_device(dev, 1024, 866)
+    import torch
+    torch.cuda.synchronize()
+    got = out.data[0, :1024 * 866 * 4].cpu().numpy().reshape(1024, 866, 4)
+    assert np.array_equal(got, pil_resize(img, 1024, 866))

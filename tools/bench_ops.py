@@ -59,3 +59,27 @@ timed("K8 index_hwc uint16 frame -> index", 10,
 timed("K9 index_change_u8 (2 frames -> 2 maps + diff + bwr RGB)", 21,
       lambda: [check(lib.lars_index_change_u8(frames[i].data_ptr(), frames[(i + 1) % M].data_ptr(), n, 3, 0, -0.5, 0.5,
                                               out32[0, i].data_ptr(), out32[1, i].data_ptr(), out32[2, i].data_ptr(), rgb[i].data_ptr(), sp)) for i in range(M)])
+
+# ---- round 2: the float64 flavour of K4 / K3 and uint16 Pass 1 (guided single pass against the two-level form)
+from lars_image_processing_b200._lib import MAP_STATS_F64_DTYPE, STRETCH_U16_BYTES
+with torch.cuda.stream(s):
+    f64.copy_(maps.double())
+    stats64 = torch.empty((M, MAP_STATS_F64_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    ws64 = torch.empty(int(lib.lars_map_stats_f64_workspace_bytes()), dtype=torch.uint8, device=dev)
+    sel64 = torch.empty(int(lib.lars_select_f64_workspace_bytes()), dtype=torch.uint8, device=dev)
+    med64 = torch.empty((M, 3), dtype=torch.float64, device=dev)
+    stretch = torch.empty((M, 3, STRETCH_U16_BYTES), dtype=torch.uint8, device=dev)
+    pct = torch.empty((M, 3, 2), dtype=torch.float64, device=dev)
+    ws16 = torch.empty(int(lib.lars_wb_u16_workspace_bytes(M)), dtype=torch.uint8, device=dev)
+    # vegetation-like uint16 frames (the uniform frames16 above put ~0.4 % of the samples in every bucket)
+    veg = (torch.randn((M, n, 3), generator=g, device=dev) * torch.tensor([8995., 8995., 11565.], device=dev)
+           + torch.tensor([23130., 28270., 38550.], device=dev)).round_().clamp_(0, 65535).to(torch.int32).to(torch.int16).reshape(M, n * 3)
+timed("K4d map_stats_f64 (stats + hist(50), float64 map)", 8,
+      lambda: [check(lib.lars_map_stats_f64(f64[i].data_ptr(), n, 50, 0.2, stats64[i].data_ptr(), ws64.data_ptr(), ws64.numel(), sp)) for i in range(M)])
+timed("K3d select_f64 (exact median, 6 radix passes)", 48,
+      lambda: [check(lib.lars_select_f64(f64[i].data_ptr(), n, (n - 1) // 2, n // 2, med64[i].data_ptr(), sel64.data_ptr(), sel64.numel(), sp)) for i in range(M)])
+for label, stage, b in (("K1u uint16 Pass 1, guided single pass (8 frames per launch)", 0, 6),
+                        ("K1u uint16 Pass 1, two-level form (8 frames per launch)", 4, 12)):
+    timed(label, b * 3 // 3,
+          lambda: check(lib.lars_wb_stretch_build_u16_staged(veg.data_ptr(), M, n, 3, n * 6, 0.02, 0.98, stretch.data_ptr(), pct.data_ptr(),
+                                                             ws16.data_ptr(), ws16.numel(), 0, stage, sp)))
