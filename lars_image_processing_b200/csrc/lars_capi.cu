@@ -360,7 +360,7 @@ static int map_parts(int sm_count) { return sm_count * 4; }
 
 size_t lars_map_stats_workspace_bytes(int32_t n_maps) {
   if (n_maps < 1) return 0;
-  return (size_t)n_maps * (size_t)(148 * 4) * sizeof(lars::MapPartial);
+  return (size_t)n_maps * (size_t)(148 * 4) * sizeof(lars::MapPartial) + lars::MAP_SUBBIN_BYTES;
 }
 
 int lars_map_stats_f32(const float* data, int32_t n_maps, int64_t n, int64_t stride, int32_t bins,
@@ -373,18 +373,26 @@ int lars_map_stats_f32(const float* data, int32_t n_maps, int64_t n, int64_t str
   if (n_maps < 1 || n < 1) return fail(LARS_ERR_INVALID, "lars_map_stats_f32: empty input");
   if (bins < 1 || bins > LARS_MAX_BINS) return fail(LARS_ERR_INVALID, "lars_map_stats_f32: bins must be in 1..%d", LARS_MAX_BINS);
   if (!aligned16(data) || (n_maps > 1 && (stride & 3))) return fail(LARS_ERR_INVALID, "lars_map_stats_f32: rows must be 16-byte aligned");
-  int parts = map_parts(st->sm_count);
+  // about 4 CTAs per SM over the whole batch: a CTA's prologue (counters, table copy) and epilogue (32-copy
+  // histogram fold) cost as much as ~20,000 elements, and round 1 launched 592 CTAs per map
+  int parts = map_parts(st->sm_count) / n_maps;
+  if (parts < 8) parts = 8;
   if (parts > 148 * 4) parts = 148 * 4;
   const long long nvec = n / 4;
   if (parts > nvec) parts = (int)(nvec > 0 ? nvec : 1);
-  if (workspace_bytes < (size_t)n_maps * parts * sizeof(lars::MapPartial) || !aligned16(workspace))
+  const size_t partial_bytes = (size_t)n_maps * (size_t)(148 * 4) * sizeof(lars::MapPartial);
+  if (workspace_bytes < partial_bytes + lars::MAP_SUBBIN_BYTES || !aligned16(workspace))
     return fail(LARS_ERR_INVALID, "lars_map_stats_f32: workspace too small or misaligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint8_t* subbin = static_cast<uint8_t*>(workspace) + partial_bytes;
+  lars::map_subbin_table_kernel<<<lars::MAP_SUBBIN_BYTES / 256, 256, 0, s>>>(subbin, bins);
+  LARS_CUDA(cudaGetLastError());
   lars::MapStatsParams p;
   p.data = data; p.n = n; p.stride = stride;
   p.partials = static_cast<lars::MapPartial*>(workspace);
+  p.subbin = subbin;
   p.threshold = threshold; p.bins = bins;
-  const size_t smem = (size_t)bins * 128 + (size_t)((bins + 1 + 3) / 4) * 16 + 8 * 8 * 8 + ((LARS_SUBBIN_COUNT + 15) & ~15);
+  const size_t smem = lars::MAP_SUBBIN_BYTES + (size_t)(bins + 1) * 128 + (size_t)((bins + 1 + 3) / 4) * 16 + 8 * 8 * 8;
   lars::map_stats_f32_kernel<<<dim3(parts, n_maps), lars::MAP_THREADS, smem, s>>>(p);
   LARS_CUDA(cudaGetLastError());
   lars::MapFinalizeParams f;
@@ -628,8 +636,9 @@ int lars_wb_stretch_build_u16_staged(const uint16_t* src, int32_t n_frames, int6
     lars::U16CandParams cp; cp.hist_sample = hist_sample; cp.cand = cand; cp.q_lo = q_lo; cp.q_hi = q_hi;
     lars::wb_u16_candidates_kernel<<<n_sets * 3, 256, 0, s>>>(cp);
     LARS_CUDA(cudaGetLastError());
-    if (channels == 3) lars::wb_hist_u16_guided_kernel<3><<<grid, lars::K1_THREADS, lars::U16_GUIDED_SMEM_BYTES, s>>>(p);
-    else lars::wb_hist_u16_guided_kernel<4><<<grid, lars::K1_THREADS, lars::U16_GUIDED_SMEM_BYTES, s>>>(p);
+    const int ggrid = (int)(p.total_units < st->sm_count ? p.total_units : st->sm_count);   // one 1,024-thread CTA per SM
+    if (channels == 3) lars::wb_hist_u16_guided_kernel<3><<<ggrid, lars::U16_GUIDED_THREADS, lars::U16_GUIDED_SMEM_BYTES, s>>>(p);
+    else lars::wb_hist_u16_guided_kernel<4><<<ggrid, lars::U16_GUIDED_THREADS, lars::U16_GUIDED_SMEM_BYTES, s>>>(p);
     LARS_CUDA(cudaGetLastError());
   } else if (do_hi) {
     if (channels == 3) lars::wb_hist_u16_hi_kernel<3><<<grid, lars::K1_THREADS, lars::U16_HI_SMEM_BYTES, s>>>(p);

@@ -41,54 +41,73 @@ struct MapStatsParams {
   long long n;             // elements per map
   long long stride;        // elements
   MapPartial* partials;    // [n_maps][gridDim.x]
+  const uint8_t* subbin;   // [MAP_SUBBIN_BYTES] built by map_subbin_table_kernel for this bin count
   float threshold;
   int bins;
 };
 
+constexpr int MAP_SUBBIN_BYTES = 8192;   // 4097 entries; the rest is padding so that ANY 13-bit index is a valid load
+
+// The sub-bin table of one bin count, built once per call (every CTA of the statistics kernel copies it).
+__global__ void __launch_bounds__(256) map_subbin_table_kernel(uint8_t* table, int bins) {
+  __shared__ float edges_s[LARS_MAX_BINS + 1];
+  const double step = LARS_DDIV(2.0, (double)bins);
+  for (int i = threadIdx.x; i <= bins; i += blockDim.x)
+    edges_s[i] = (i == bins) ? 1.0f : (float)LARS_DADD(LARS_DMUL((double)i, step), -1.0);
+  __syncthreads();
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < MAP_SUBBIN_BYTES; k += gridDim.x * blockDim.x)
+    table[k] = k < LARS_SUBBIN_COUNT ? lars_hist_subbin_entry(k, edges_s, bins) : (uint8_t)LARS_SUBBIN_AMBIGUOUS;
+}
+
+// One element.  Branch-free except for the ~1 % of elements in a sub-bin that straddles an edge:
+//   * sub-bin index without a float->int conversion (the XU pipe was 30 % busy with them): y = fma(x, 2048, 2047.5),
+//     then adding 1.5 * 2^23 rounds y to an integer that sits in the low mantissa bits.  Round-to-nearest instead of
+//     truncation moves the index by at most one sub-bin at a boundary, which the table's 2^-20 margin covers
+//     (pixel_math.h);
+//   * out-of-range values and NaN (np.histogram drops them) go to a trash row instead of around a branch;
+//   * NaN is detected from the sum afterwards, not per element.
 __device__ __forceinline__ void map_stats_accum(float x, float k, float thr, const float* edges_s, const uint8_t* subbin_s,
                                                 int bins, uint32_t* hist_lane, float& mn, float& mx, float& gx,
-                                                float& gd, float& gdd, uint32_t& above, uint32_t& nan) {
+                                                float& gd, float& gdd, uint32_t& above) {
   mn = fminf(mn, x);
   mx = fmaxf(mx, x);
   above += (x > thr) ? 1u : 0u;
-  nan |= (x != x) ? 1u : 0u;
   const float d = LARS_FSUB(x, k);
   gx += x;
   gd += d;
   gdd = fmaf(d, d, gdd);
-  if (x >= -1.0f && x <= 1.0f) {  // np.histogram drops out-of-range values (and NaN)
-    // one byte load answers for ~99 % of the elements; the literal edge-corrected chain (two dependent edge loads,
-    // ~14 instructions) only runs for sub-bins that straddle an edge (round 1: K4 was issue- and LDS-bound on it)
-    int b = subbin_s[lars_hist_subbin_index(x)];
-    if (b == LARS_SUBBIN_AMBIGUOUS) b = lars_hist_bin_edges(x, edges_s, bins);
-    atomicAdd(hist_lane + b * 32, 1u);
-  }
+  const bool in_range = fabsf(x) <= 1.0f;
+  const uint32_t idx = lars_hist_subbin_index_rn(x);
+  int b = subbin_s[idx];
+  if (b == LARS_SUBBIN_AMBIGUOUS && in_range) b = lars_hist_bin_edges(x, edges_s, bins);
+  b = in_range ? b : bins;                                   // row `bins` is the trash row
+  atomicAdd(hist_lane + b * 32, 1u);
 }
 
 __global__ void __launch_bounds__(MAP_THREADS) map_stats_f32_kernel(const MapStatsParams p) {
   extern __shared__ __align__(16) uint8_t ms_smem[];
-  uint32_t* hist = reinterpret_cast<uint32_t*>(ms_smem);                       // [bins][32]
-  float* edges_s = reinterpret_cast<float*>(ms_smem + (size_t)p.bins * 32 * 4);  // [bins + 1]
-  double* red = reinterpret_cast<double*>(ms_smem + (size_t)p.bins * 32 * 4 + ((p.bins + 1 + 3) / 4) * 16);
-  uint8_t* subbin_s = reinterpret_cast<uint8_t*>(red + 8 * 8);                    // [LARS_SUBBIN_COUNT]
+  uint8_t* subbin_s = ms_smem;                                                                  // [MAP_SUBBIN_BYTES]
+  uint32_t* hist = reinterpret_cast<uint32_t*>(ms_smem + MAP_SUBBIN_BYTES);                     // [bins + 1][32]
+  float* edges_s = reinterpret_cast<float*>(ms_smem + MAP_SUBBIN_BYTES + (size_t)(p.bins + 1) * 32 * 4);  // [bins + 1]
+  double* red = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(edges_s) + ((p.bins + 1 + 3) / 4) * 16);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int map = blockIdx.y;
   const float* x = p.data + (long long)map * p.stride;
-  for (int i = tid; i < p.bins * 32; i += MAP_THREADS) hist[i] = 0u;
+  for (int i = tid; i < (p.bins + 1) * 32; i += MAP_THREADS) hist[i] = 0u;
   {  // np.linspace(-1, 1, bins + 1) in float64, rounded to float32, last edge exact
     const double step = LARS_DDIV(2.0, (double)p.bins);
     for (int i = tid; i <= p.bins; i += MAP_THREADS)
       edges_s[i] = (i == p.bins) ? 1.0f : (float)LARS_DADD(LARS_DMUL((double)i, step), -1.0);
   }
-  __syncthreads();
-  for (int i = tid; i < LARS_SUBBIN_COUNT; i += MAP_THREADS) subbin_s[i] = lars_hist_subbin_entry(i, edges_s, p.bins);
+  for (int i = tid; i < MAP_SUBBIN_BYTES / 16; i += MAP_THREADS)
+    reinterpret_cast<uint4*>(subbin_s)[i] = __ldg(reinterpret_cast<const uint4*>(p.subbin) + i);
   __syncthreads();
 
   const float k = x[0];
   const float thr = p.threshold;
   float mn = INFINITY, mx = -INFINITY;
   double sx = 0.0, sd = 0.0, sdd = 0.0;
-  uint32_t above = 0, nan = 0;
+  uint32_t above = 0;
   unsigned long long count = 0;
   uint32_t* hist_lane = hist + lane;
 
@@ -98,37 +117,38 @@ __global__ void __launch_bounds__(MAP_THREADS) map_stats_f32_kernel(const MapSta
   const long long v0 = (long long)blockIdx.x * per;
   const long long v1 = (v0 + per < nvec) ? v0 + per : nvec;
   const float4* xv = reinterpret_cast<const float4*>(x);
-  // four independent 128-bit loads in flight per thread (one per trip is latency-bound: measured 2.0 TB/s)
+  // four independent 128-bit loads in flight per thread (one per trip is latency-bound: measured 2.0 TB/s);
+  // the moments of the 16 elements are summed in float32 and promoted to float64 once
   long long v = v0 + tid;
   for (; v + 3ll * MAP_THREADS < v1; v += 4ll * MAP_THREADS) {
     float4 q[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) q[u] = __ldg(xv + v + (long long)u * MAP_THREADS);
+    float gx = 0.f, gd = 0.f, gdd = 0.f;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      float gx = 0.f, gd = 0.f, gdd = 0.f;
-      map_stats_accum(q[u].x, k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
-      map_stats_accum(q[u].y, k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
-      map_stats_accum(q[u].z, k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
-      map_stats_accum(q[u].w, k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
-      sx += (double)gx; sd += (double)gd; sdd += (double)gdd;
+      map_stats_accum(q[u].x, k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above);
+      map_stats_accum(q[u].y, k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above);
+      map_stats_accum(q[u].z, k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above);
+      map_stats_accum(q[u].w, k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above);
     }
+    sx += (double)gx; sd += (double)gd; sdd += (double)gdd;
     count += 16;
   }
   for (; v < v1; v += MAP_THREADS) {
     const float4 q = __ldg(xv + v);
     float gx = 0.f, gd = 0.f, gdd = 0.f;
-    map_stats_accum(q.x, k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
-    map_stats_accum(q.y, k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
-    map_stats_accum(q.z, k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
-    map_stats_accum(q.w, k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
+    map_stats_accum(q.x, k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above);
+    map_stats_accum(q.y, k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above);
+    map_stats_accum(q.z, k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above);
+    map_stats_accum(q.w, k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above);
     sx += (double)gx; sd += (double)gd; sdd += (double)gdd;
     count += 4;
   }
   if (blockIdx.x == gridDim.x - 1) {  // scalar tail (n % 4 elements)
     for (long long i = nvec * 4 + tid; i < p.n; i += MAP_THREADS) {
       float gx = 0.f, gd = 0.f, gdd = 0.f;
-      map_stats_accum(x[i], k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above, nan);
+      map_stats_accum(x[i], k, thr, edges_s, subbin_s, p.bins, hist_lane, mn, mx, gx, gd, gdd, above);
       sx += (double)gx; sd += (double)gd; sdd += (double)gdd;
       count += 1;
     }
@@ -142,13 +162,12 @@ __global__ void __launch_bounds__(MAP_THREADS) map_stats_f32_kernel(const MapSta
     mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d));
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
     above += __shfl_xor_sync(0xffffffffu, above, d);
-    nan |= __shfl_xor_sync(0xffffffffu, nan, d);
     count += __shfl_xor_sync(0xffffffffu, count, d);
   }
   if (lane == 0) {
     double* r = red + warp * 8;
     r[0] = sx; r[1] = sd; r[2] = sdd; r[3] = (double)mn; r[4] = (double)mx;
-    r[5] = (double)above; r[6] = (double)nan; r[7] = (double)count;
+    r[5] = (double)above; r[6] = 0.0; r[7] = (double)count;
   }
   __syncthreads();
   MapPartial* rec = p.partials + (long long)map * gridDim.x + blockIdx.x;
@@ -164,11 +183,12 @@ __global__ void __launch_bounds__(MAP_THREADS) map_stats_f32_kernel(const MapSta
       const double* r = red + w * 8;
       a[0] += r[0]; a[1] += r[1]; a[2] += r[2];
       a[3] = fmin(a[3], r[3]); a[4] = fmax(a[4], r[4]);
-      a[5] += r[5]; a[6] += r[6]; a[7] += r[7];
+      a[5] += r[5]; a[7] += r[7];
     }
     rec->sx = a[0]; rec->sd = a[1]; rec->sdd = a[2];
     rec->mn = (float)a[3]; rec->mx = (float)a[4];
-    rec->above = (uint32_t)a[5]; rec->has_nan = a[6] != 0.0 ? 1u : 0u;
+    rec->above = (uint32_t)a[5];
+    rec->has_nan = (a[0] != a[0]) ? 1u : 0u;     // a NaN anywhere poisons the sum (fminf / fmaxf skip NaN)
     rec->count = (unsigned long long)a[7];
   }
 }
@@ -248,6 +268,13 @@ __global__ void __launch_bounds__(MAP_HIST_ROWS * MAP_FIN_SPLIT) map_stats_final
 // K3: exact order statistics by radix select
 // ------------------------------------------------------------------------------------------
 // Three passes over 11 + 11 + 10 key bits (a fourth 8-bit pass costs another full read of the map).
+// Round 2, measured and NOT kept: after the first pass the prefix bucket holds a few per cent of the map, so passes
+// 2 and 3 were given a mode without the shared histogram (matching elements straight to the global counters, one
+// atomic per warp and digit; nothing to clear or fold).  59.4 us per 12 MP map against 59.8 us: the shared histogram
+// is not what a pass costs.  ncu (profiles/r02_k3_select_ncu_summary.txt): 8 M warp instructions and 48 MB per pass
+// in ~21 us, long_scoreboard on top -- a pass is ~80 elements per thread, i.e. launch, ramp-up and the last CTA's
+// digit scan around ~7 us of streaming.  What would help is one pass less (the first digit counted inside K4's read
+// of the same map), not a cheaper pass.
 constexpr int SEL_BINS = 2048;                 // bins of the widest digit
 #ifndef LARS_SEL_LANES
 #define LARS_SEL_LANES 4

@@ -258,21 +258,31 @@ __global__ void __launch_bounds__(256) wb_u16_candidates_kernel(const U16CandPar
   cum[v] = x;
   __syncthreads();
   const unsigned long long m = cum[255];
-  if (v == 0 && m > 0) {
-    // the sample's own percentile positions: bucket of rank floor((m - 1) q), and the non-empty neighbour on the
-    // side the rank sits closer to (below the middle of the bucket's mass -> previous, else next)
+  __shared__ uint8_t nonempty[256];
+  __shared__ int bucket_of[2];
+  nonempty[v] = own ? 1 : 0;
+  // the sample's own percentile positions: every thread tests its bucket for rank floor((m - 1) q)
+  const unsigned long long below_v = v ? cum[v - 1] : 0ull;
+  if (m > 0) {
+#pragma unroll
     for (int k = 0; k < 2; ++k) {
       const unsigned long long r = (unsigned long long)floor((double)(m - 1) * (k == 0 ? p.q_lo : p.q_hi));
-      int b = 0;
-      while (b < 255 && cum[b] <= r) ++b;
-      const unsigned long long below = b ? cum[b - 1] : 0ull;
-      const unsigned long long cnt = cum[b] - below;
-      int nb = -1;
-      if (2 * (r - below) < cnt) { for (int t = b - 1; t >= 0 && nb < 0; --t) if (cum[t] != (t ? cum[t - 1] : 0ull)) nb = t; }
-      else { for (int t = b + 1; t < 256 && nb < 0; ++t) if (cum[t] != cum[t - 1]) nb = t; }
-      picked[2 * k] = b;
-      picked[2 * k + 1] = nb;
+      if (below_v <= r && r < x) bucket_of[k] = v;
     }
+  }
+  __syncthreads();
+  if (v < 2 && m > 0) {
+    // ... and the non-empty neighbour on the side the rank sits closer to (below the middle of the bucket's mass ->
+    // previous, else next)
+    const int k = v, b = bucket_of[k];
+    const unsigned long long r = (unsigned long long)floor((double)(m - 1) * (k == 0 ? p.q_lo : p.q_hi));
+    const unsigned long long below = b ? cum[b - 1] : 0ull;
+    const unsigned long long cnt = cum[b] - below;
+    int nb = -1;
+    if (2 * (r - below) < cnt) { for (int t = b - 1; t >= 0 && nb < 0; --t) if (nonempty[t]) nb = t; }
+    else { for (int t = b + 1; t < 256 && nb < 0; ++t) if (nonempty[t]) nb = t; }
+    picked[2 * k] = b;
+    picked[2 * k + 1] = nb;
   }
   __syncthreads();
   uint8_t c = 0;
@@ -283,20 +293,57 @@ __global__ void __launch_bounds__(256) wb_u16_candidates_kernel(const U16CandPar
 }
 
 // ---- guided: exact high-byte histogram + low-byte histograms of the candidate buckets, one read --
-constexpr int U16_GUIDED_LO_WORDS = 3 * U16_CAND_SLOTS * 256;
-constexpr int U16_GUIDED_SMEM_BYTES = U16_HI_SMEM_BYTES + U16_GUIDED_LO_WORDS * 4 + 3 * 256;   // 96 KB + 12 KB + 768 B
+// One CTA of 1,024 threads per SM.  Shared memory: hi[3][256][32] lane-private as in level A (96 KB),
+// lo[3][slots][256][8] (96 KB: lanes congruent modulo 8 share a counter, so a constant channel or a saturated
+// region -- every sample a hit on one address -- is serialised 4-fold at most) and the class bytes (768 B).
+// Per sample: PRMT (address of the class byte), LDS.U8, IMAD + RED (high-byte counter), ISETP and a branch around
+// the low-byte counter's three instructions.  History (ncu, 8 x 20 MP): a branch per sample with the
+// class load in front of it 287 us (54 % issue-active, short_scoreboard); class loads hoisted eight at a time
+// 271 us (190 M warp instructions: the ~1 % hits made 27 % of the warp-level sample slots take a 17-instruction
+// divergent path with a warp match; the assembler turns a predicated shared atomic back into a branch, so the
+// branch stays and what it guards shrank to PRMT + IMAD + RED); this form: see profiles/.
+constexpr int U16_GUIDED_THREADS = 1024;
+constexpr int U16_GUIDED_LO_COPIES = 8;
+constexpr int U16_GUIDED_LO_BINS = 3 * U16_CAND_SLOTS * 256;
+constexpr int U16_GUIDED_LO_WORDS = U16_GUIDED_LO_BINS * U16_GUIDED_LO_COPIES;
+constexpr int U16_GUIDED_SMEM_BYTES = U16_HI_SMEM_BYTES + U16_GUIDED_LO_WORDS * 4 + 3 * 256;   // 96 KB + 96 KB + 768 B
 template <int C>
-__global__ void __launch_bounds__(K1_THREADS, 2) wb_hist_u16_guided_kernel(const U16HistParams p) {
-  extern __shared__ __align__(16) uint32_t u16_hist[];  // [3][256][32] lane-private, then lo[3][slots][256], then cls[3][256]
+__global__ void __launch_bounds__(U16_GUIDED_THREADS, 1) wb_hist_u16_guided_kernel(const U16HistParams p) {
+  extern __shared__ __align__(16) uint32_t u16_hist[];  // hi[3][256][32], then lo[3][slots][256][8], then cls[3][256]
   uint32_t* lo_hist = u16_hist + 3 * 256 * 32;
   uint8_t* cls_s = reinterpret_cast<uint8_t*>(lo_hist + U16_GUIDED_LO_WORDS);
   const int tid = threadIdx.x, lane = tid & 31;
   const long long frame_bytes = p.n_pixels * C * 2;
   const uint32_t base = smem_u32(u16_hist) + 4u * lane;
-  const uint32_t lo_base = smem_u32(lo_hist), cls_base = smem_u32(cls_s);
+  // low-byte counter of (channel ch, class c, low byte lo): lo_lane + ((ch * slots + c - 1) * 256 + lo) * 32
+  const uint32_t lo_lane = smem_u32(lo_hist) + 4u * (lane & (U16_GUIDED_LO_COPIES - 1)) - 256u * U16_GUIDED_LO_COPIES * 4u;
+  const uint32_t cls_base = smem_u32(cls_s);
   const long long G = gridDim.x;
   long long u = ((long long)blockIdx.x * p.total_units) / G;
   const long long u_end = ((long long)(blockIdx.x + 1) * p.total_units) / G;
+  // Per-channel constants so that a sample costs PRMT, LDS.U8, IMAD, RED, ISETP and a branch:
+  //   the class tables are 256-byte aligned in the shared window, so ONE byte permute forms the class byte's address
+  //   (the table's address with the sample's high byte as its low byte), and the high-byte counter's address is that
+  //   address times 128 plus a constant (counters are 128 bytes apart: hi[ch][byte][32 lanes]).
+  // (scalars selected by ternaries, not arrays: the scalar tails index by a run-time channel, which would put arrays
+  // in local memory for the hot loop as well)
+  const uint32_t lo_ch = U16_CAND_SLOTS * 256u * U16_GUIDED_LO_COPIES * 4u;
+  uint32_t cls0 = cls_base, cls1 = cls_base + 256u, cls2 = cls_base + 512u;
+  asm("" : "+r"(cls0), "+r"(cls1), "+r"(cls2));     // opaque: keep them in registers instead of re-adding per sample
+  const uint32_t red0 = base - cls0 * 128u, red1 = base + 32768u - cls1 * 128u, red2 = base + 65536u - cls2 * 128u;
+  const uint32_t lo0 = lo_lane, lo1 = lo_lane + lo_ch, lo2 = lo_lane + 2u * lo_ch;
+  auto one = [&](int ch, uint32_t w, int half) {
+    const uint32_t cls_at = ch == 0 ? cls0 : (ch == 1 ? cls1 : cls2);
+    const uint32_t red_k = ch == 0 ? red0 : (ch == 1 ? red1 : red2);
+    const uint32_t la = __byte_perm(w, cls_at, half ? 0x7653 : 0x7651);
+    uint32_t c;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(c) : "r"(la));
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(la * 128u + red_k));
+    if (c) {       // ~1 % of the samples
+      const uint32_t lob = __byte_perm(w, 0u, half ? 0x4442 : 0x4440);
+      asm volatile("red.shared.add.u32 [%0], 1;" ::"r"((ch == 0 ? lo0 : (ch == 1 ? lo1 : lo2)) + c * (256u * U16_GUIDED_LO_COPIES * 4u) + lob * (U16_GUIDED_LO_COPIES * 4u)));
+    }
+  };
   while (u < u_end) {
     const long long frame = u / p.units_per_frame;
     const long long fu0 = frame * p.units_per_frame;
@@ -306,70 +353,64 @@ __global__ void __launch_bounds__(K1_THREADS, 2) wb_hist_u16_guided_kernel(const
     if (b1 > frame_bytes) b1 = frame_bytes;
     const uint8_t* fsrc = p.src + frame * p.frame_stride;
     u = span_end;
-    for (int i = tid; i < 3 * 256 * 32 + U16_GUIDED_LO_WORDS; i += K1_THREADS) u16_hist[i] = 0u;
+    for (int i = tid; i < 3 * 256 * 32 + U16_GUIDED_LO_WORDS; i += U16_GUIDED_THREADS) u16_hist[i] = 0u;
     {
       const uint32_t* src_cls = reinterpret_cast<const uint32_t*>(p.cand + frame * 3);
       uint32_t* dst_cls = reinterpret_cast<uint32_t*>(cls_s);
-      for (int i = tid; i < 3 * 64; i += K1_THREADS) dst_cls[i] = src_cls[i];
+      for (int i = tid; i < 3 * 64; i += U16_GUIDED_THREADS) dst_cls[i] = src_cls[i];
     }
     __syncthreads();
-    // rare path (~1 % of the samples): lanes of the warp that hit the same counter send one RED, so a constant
-    // channel or a saturated region -- every sample a hit on one address -- is not serialised 32-fold
-    auto hit = [&](int ch, uint32_t c, uint32_t lob) {
-      const uint32_t addr = lo_base + ((((uint32_t)ch * U16_CAND_SLOTS + (c - 1u)) << 8) + lob) * 4u;
-      const unsigned peers = __match_any_sync(__activemask(), addr);
-      if (lane == __ffs(peers) - 1)
-        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"((uint32_t)__popc(peers)));
-    };
-    auto one = [&](int ch, uint32_t w, int half) {
-      const uint32_t hb = __byte_perm(w, 0u, half ? 0x4443 : 0x4441);   // the sample's high byte, one PRMT
-      asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(base + (uint32_t)ch * 32768u + hb * 128u));
-      const uint32_t c = cls_s[ch * 256 + hb];
-      if (c) hit(ch, c, __byte_perm(w, 0u, half ? 0x4442 : 0x4440));
-    };
+    const uint16_t* s16 = reinterpret_cast<const uint16_t*>(fsrc);
     if (C == 3) {
-      // 48 contiguous bytes per lane = 24 samples, sample s of channel s % 3.  The class bytes of 8 samples are fetched
-      // before the first one is tested: per sample the load -> compare -> branch chain costs a shared-memory
-      // round trip, and issued one after the other those latencies, not bandwidth, set the pace (ncu, first
-      // version: 54 % issue-active, short_scoreboard the top stall next to the global loads).
+      // 48 contiguous bytes per lane = 24 samples, sample s of channel s % 3
       const long long vec_end = b0 + ((b1 - b0) / 48) * 48;
-      for (long long off = b0 + 48ll * tid; off + 48 <= vec_end; off += 48ll * K1_THREADS) {
-        const uint4* q = reinterpret_cast<const uint4*>(fsrc + off);
-        const uint4 v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2);
+      auto chunk = [&](const uint4& v0, const uint4& v1, const uint4& v2) {
         const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
 #pragma unroll
-        for (int g = 0; g < 3; ++g) {          // one 16-byte vector = 8 samples at a time (24 at once spill)
-          uint32_t hb[8], c[8];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            hb[2 * i] = __byte_perm(w[4 * g + i], 0u, 0x4441);
-            hb[2 * i + 1] = __byte_perm(w[4 * g + i], 0u, 0x4443);
-          }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) c[k] = cls_s[((8 * g + k) % 3) * 256 + hb[k]];
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(base + (uint32_t)((8 * g + k) % 3) * 32768u + hb[k] * 128u));
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            if (c[k]) hit((8 * g + k) % 3, c[k], __byte_perm(w[4 * g + (k >> 1)], 0u, (k & 1) ? 0x4442 : 0x4440));
+        for (int i = 0; i < 12; ++i) {
+          one((2 * i) % 3, w[i], 0);
+          one((2 * i + 1) % 3, w[i], 1);
         }
+      };
+      // two 48-byte chunks per trip, all six 128-bit loads issued before the first sample is counted: with one chunk
+      // per trip the kernel waited on global loads (ncu: long_scoreboard the top stall, 48 % of the DRAM peak)
+      long long off = b0 + 48ll * tid;
+      for (; off + 48ll * U16_GUIDED_THREADS + 48 <= vec_end; off += 96ll * U16_GUIDED_THREADS) {
+        const uint4* q = reinterpret_cast<const uint4*>(fsrc + off);
+        const uint4* r = reinterpret_cast<const uint4*>(fsrc + off + 48ll * U16_GUIDED_THREADS);
+        const uint4 a0 = __ldg(q), a1 = __ldg(q + 1), a2 = __ldg(q + 2);
+        const uint4 c0 = __ldg(r), c1 = __ldg(r + 1), c2 = __ldg(r + 2);
+        chunk(a0, a1, a2);
+        chunk(c0, c1, c2);
       }
-      const uint16_t* s16 = reinterpret_cast<const uint16_t*>(fsrc);
-      for (long long sidx = vec_end / 2 + tid; sidx < b1 / 2; sidx += K1_THREADS) one((int)(sidx % 3), (uint32_t)s16[sidx], 0);
+      for (; off + 48 <= vec_end; off += 48ll * U16_GUIDED_THREADS) {
+        const uint4* q = reinterpret_cast<const uint4*>(fsrc + off);
+        const uint4 a0 = __ldg(q), a1 = __ldg(q + 1), a2 = __ldg(q + 2);
+        chunk(a0, a1, a2);
+      }
+      for (long long sidx = vec_end / 2 + tid; sidx < b1 / 2; sidx += U16_GUIDED_THREADS) one((int)(sidx % 3), (uint32_t)s16[sidx], 0);
     } else {
-      u16_visit_span_words<C>(fsrc, b0, b1, tid, one);
+      const long long vec_end = b0 + ((b1 - b0) / 16) * 16;
+      for (long long off = b0 + 16ll * tid; off + 16 <= vec_end; off += 16ll * U16_GUIDED_THREADS) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(fsrc + off));
+        one(0, v.x, 0); one(1, v.x, 1); one(2, v.y, 0);
+        one(0, v.z, 0); one(1, v.z, 1); one(2, v.w, 0);
+      }
+      for (long long sidx = vec_end / 2 + tid; sidx < b1 / 2; sidx += U16_GUIDED_THREADS)
+        if ((sidx & 3) < 3) one((int)(sidx & 3), (uint32_t)s16[sidx], 0);
     }
     __syncthreads();
-    for (int b = tid; b < 3 * 256; b += K1_THREADS) {
+    for (int b = tid; b < 3 * 256; b += U16_GUIDED_THREADS) {
       uint32_t sum = 0;
 #pragma unroll 8
       for (int l = 0; l < 32; ++l) sum += u16_hist[b * 32 + ((l + tid) & 31)];
       if (sum) atomicAdd(&p.hist_hi[frame * 768 + b], (unsigned long long)sum);
     }
-    for (int b = tid; b < U16_GUIDED_LO_WORDS; b += K1_THREADS) {
-      const uint32_t sum = lo_hist[b];
-      if (sum) atomicAdd(&p.cand_lo[frame * U16_GUIDED_LO_WORDS + b], (unsigned long long)sum);
+    for (int b = tid; b < U16_GUIDED_LO_BINS; b += U16_GUIDED_THREADS) {
+      uint32_t sum = 0;
+#pragma unroll
+      for (int l = 0; l < U16_GUIDED_LO_COPIES; ++l) sum += lo_hist[b * U16_GUIDED_LO_COPIES + ((l + tid) & (U16_GUIDED_LO_COPIES - 1))];
+      if (sum) atomicAdd(&p.cand_lo[frame * U16_GUIDED_LO_BINS + b], (unsigned long long)sum);
     }
     __syncthreads();
   }

@@ -37,7 +37,7 @@ void hc_hist_bin_edges(const float* x, int64_t n, int bins, const float* edges, 
 }
 
 // K4's fast path: the sub-bin table, with the literal chain behind its ambiguous entries
-void hc_hist_bin_subbin(const float* x, int64_t n, int bins, const float* edges, int32_t* out, int32_t* n_ambiguous) {
+void hc_hist_bin_subbin(const float* x, int64_t n, int bins, const float* edges, int32_t* out, int32_t* n_ambiguous, int rn) {
   std::vector<uint8_t> table(LARS_SUBBIN_COUNT);
   int amb = 0;
   for (int k = 0; k < LARS_SUBBIN_COUNT; ++k) {
@@ -46,7 +46,7 @@ void hc_hist_bin_subbin(const float* x, int64_t n, int bins, const float* edges,
   }
   *n_ambiguous = amb;
   for (int64_t i = 0; i < n; ++i) {
-    int b = table[lars_hist_subbin_index(x[i])];
+    int b = table[rn ? (int)lars_hist_subbin_index_rn(x[i]) : lars_hist_subbin_index(x[i])];
     if (b == LARS_SUBBIN_AMBIGUOUS) b = lars_hist_bin_edges(x[i], edges, bins);
     out[i] = b;
   }

@@ -81,8 +81,10 @@ def test_subbin_table_path_matches_numpy(hostcheck):
     for every bin count 1..64; and the table stays nearly unambiguous (<= 2 (bins + 1) of 4097 entries)."""
     rng = np.random.default_rng(5)
     grid = (np.arange(4097, dtype=np.float64) / 2048 - 1).astype(np.float32)
+    half = (np.arange(4096, dtype=np.float64) / 2048 - 1 + 1 / 4096).astype(np.float32)      # where the rounding index ties
     around = np.concatenate([grid, np.nextafter(grid, np.float32(-2)), np.nextafter(grid, np.float32(2)),
-                             np.nextafter(np.nextafter(grid, np.float32(-2)), np.float32(-2))])
+                             np.nextafter(np.nextafter(grid, np.float32(-2)), np.float32(-2)),
+                             half, np.nextafter(half, np.float32(-2)), np.nextafter(half, np.float32(2))])
     for bins in list(range(1, 65)):
         edges = o.histogram_edges(bins)
         x = np.concatenate([rng.uniform(-1, 1, 20000).astype(np.float32), around, edges,
@@ -90,10 +92,11 @@ def test_subbin_table_path_matches_numpy(hostcheck):
         xc = np.ascontiguousarray(np.clip(x, -1, 1))
         out = np.empty(xc.size, np.int32)
         amb = C.c_int32(0)
-        hostcheck.hc_hist_bin_subbin(C.c_void_p(xc.ctypes.data), C.c_int64(xc.size), C.c_int(bins), C.c_void_p(edges.ctypes.data),
-                                     C.c_void_p(out.ctypes.data), C.byref(amb))
-        assert np.array_equal(out, o.histogram_bin_by_edges(xc, bins)), bins
-        assert np.array_equal(np.bincount(out, minlength=bins), np.histogram(xc, bins=bins, range=(-1, 1))[0]), bins
+        for rn in (0, 1):          # truncating index, and the conversion-free round-to-nearest index the kernel uses
+            hostcheck.hc_hist_bin_subbin(C.c_void_p(xc.ctypes.data), C.c_int64(xc.size), C.c_int(bins), C.c_void_p(edges.ctypes.data),
+                                         C.c_void_p(out.ctypes.data), C.byref(amb), C.c_int(rn))
+            assert np.array_equal(out, o.histogram_bin_by_edges(xc, bins)), (bins, rn)
+            assert np.array_equal(np.bincount(out, minlength=bins), np.histogram(xc, bins=bins, range=(-1, 1))[0]), (bins, rn)
         assert amb.value <= 2 * (bins + 1), (bins, amb.value)     # an edge on a sub-bin boundary marks both neighbours
 
 
