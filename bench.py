@@ -880,6 +880,28 @@ def run_e2e(a, eng, ld, wl, rank, world, barrier, reduce_max):
                                                             f" (bounded sample of the rank's {wl.local_frames})")}
     rec_h = host_out["stats"].numpy().view(rec_dtype).reshape(F, 3)
     assert int(rec_h["count"][0, 0]) == npx and int(rec_h["hist"][-1, 2].sum()) == npx    # the host results are the real thing
+    # what the box allows: every rank copies device -> pinned host at the same time (the e2e path returns 24 B/px and
+    # takes 3 B/px in, so D2H is its wire); the aggregate saturates on the host side of multi-GPU boxes
+    # (profiles/r02_pcie_probe_n*.log), and `e2e` is to be read against this ceiling, not against N x one GPU's link
+    if d2h > (64 << 20):
+        nbytes = 256 << 20
+        dsrc = torch.empty(nbytes, dtype=torch.uint8, device=eng.device)
+        hdst = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        hdst.copy_(dsrc, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(4):
+            hdst.copy_(dsrc, non_blocking=True)
+        torch.cuda.synchronize()
+        dt_c = reduce_max([time.perf_counter() - t0])[0]
+        ceiling = world * 4 * nbytes / dt_c / 1e9
+        used = world * d2h * k_e2e / dt / 1e9
+        e2e["host_ceiling_GBps"] = ceiling
+        e2e["d2h_GBps"] = used
+        e2e["d2h_frac_of_ceiling"] = used / ceiling
+        e2e["ceiling_note"] = (f"aggregate pinned D2H of {world} rank(s) copying at once, 4 x 256 MiB each, measured right after the "
+                               "e2e leg; the e2e path moves 8x more bytes back than in")
+        del dsrc, hdst
     if a.workload == "c2":
         # survey mode (BASELINE config 5's result: statistics only): same call, only the records come back
         host_stats = eng.alloc_host_outputs(F, h, wd, 3, ("stats",))
