@@ -49,6 +49,7 @@ struct DeviceState {
   bool ready = false;
   bool inflate = false;       // the Deflate kernel got its 194 KB of shared memory
   int sm_count = 0;
+  int select_ctas_per_sm = 1; // co-resident CTAs of the persistent select kernels (grid barrier)
   uint32_t* cmaps = nullptr;  // [3][256] packed RGB, device
 };
 DeviceState g_dev[kMaxDevices];
@@ -66,6 +67,34 @@ int current_state(DeviceState** out) {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+}  // namespace
+
+namespace {
+// One launch for all passes (cooperative: the CTAs meet at a grid barrier after every pass).
+template <typename T>
+int run_select(const char* who, DeviceState* st, const T* data, int64_t n, uint64_t rank_lo, uint64_t rank_hi, T* out3,
+               void* workspace, size_t workspace_bytes, void* stream) {
+  if (!data || !out3 || !workspace) return fail(LARS_ERR_INVALID, "%s: NULL pointer", who);
+  if (n < 1 || rank_lo >= (uint64_t)n || rank_hi >= (uint64_t)n || rank_lo > rank_hi)
+    return fail(LARS_ERR_INVALID, "%s: ranks out of range", who);
+  if (!aligned16(data)) return fail(LARS_ERR_INVALID, "%s: data must be 16-byte aligned", who);
+  if (workspace_bytes < sizeof(lars::SelectState<T>) || !aligned16(workspace))
+    return fail(LARS_ERR_INVALID, "%s: workspace too small or misaligned", who);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  lars::SelectState<T>* state = static_cast<lars::SelectState<T>*>(workspace);
+  LARS_CUDA(cudaMemsetAsync(state, 0, sizeof(lars::SelectState<T>), s));      // barrier counter + every pass's histogram
+  long long want = (n / lars::SelectTraits<T>::PER_VEC + lars::SEL_THREADS - 1) / lars::SEL_THREADS;
+  int grid = st->sm_count * st->select_ctas_per_sm;
+  if (want < grid) grid = (int)(want > 0 ? want : 1);
+  long long n_ll = n;
+  unsigned long long r0 = rank_lo, r1 = rank_hi;
+  void* args[] = {(void*)&data, (void*)&n_ll, (void*)&state, (void*)&r0, (void*)&r1};
+  LARS_CUDA(cudaLaunchCooperativeKernel((const void*)lars::select_kernel<T>, dim3(grid), dim3(lars::SEL_THREADS), args,
+                                        (size_t)lars::SEL_SMEM_BYTES, s));
+  LARS_CUDA(cudaMemcpyAsync(out3, reinterpret_cast<const char*>(state) + offsetof(lars::SelectState<T>, value),
+                            3 * sizeof(T), cudaMemcpyDeviceToDevice, s));
+  return LARS_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -113,10 +142,18 @@ int lars_init(int device) {
   LARS_CUDA(cudaFuncSetAttribute(lars::wb_hist_u16_guided_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lars::U16_GUIDED_SMEM_BYTES));
   LARS_CUDA(cudaFuncSetAttribute(lars::wb_hist_u16_lo_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lars::U16_LO_SMEM_BYTES));
   LARS_CUDA(cudaFuncSetAttribute(lars::wb_hist_u16_lo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lars::U16_LO_SMEM_BYTES));
-  LARS_CUDA(cudaFuncSetAttribute(lars::select_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  LARS_CUDA(cudaFuncSetAttribute(lars::select_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  lars::SEL_SMEM_BYTES));
-  LARS_CUDA(cudaFuncSetAttribute(lars::select64_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  LARS_CUDA(cudaFuncSetAttribute(lars::select_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  lars::SEL_SMEM_BYTES));
+  {  // the select kernels meet at a grid barrier: how many of their CTAs are resident per SM
+    int a = 0, b = 0;
+    LARS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, lars::select_kernel<float>, lars::SEL_THREADS, lars::SEL_SMEM_BYTES));
+    LARS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, lars::select_kernel<double>, lars::SEL_THREADS, lars::SEL_SMEM_BYTES));
+    st.select_ctas_per_sm = a < b ? a : b;
+    if (st.select_ctas_per_sm < 1) return fail(LARS_ERR_CUDA, "select kernels do not fit on an SM");
+    if (st.select_ctas_per_sm > 2) st.select_ctas_per_sm = 2;
+  }
   LARS_CUDA(cudaFuncSetAttribute(lars::lzw_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  lars::LZW_SMEM_BYTES));
   st.inflate = cudaFuncSetAttribute(lars::inflate_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -403,32 +440,15 @@ int lars_map_stats_f32(const float* data, int32_t n_maps, int64_t n, int64_t str
   return LARS_OK;
 }
 
-size_t lars_select_workspace_bytes(void) { return sizeof(lars::SelectState); }
+
+size_t lars_select_workspace_bytes(void) { return sizeof(lars::SelectState<float>); }
 
 int lars_select_f32(const float* data, int64_t n, uint64_t rank_lo, uint64_t rank_hi, float* out3,
                     void* workspace, size_t workspace_bytes, void* stream) {
   DeviceState* st = nullptr;
   int rc = current_state(&st);
   if (rc != LARS_OK) return rc;
-  if (!data || !out3 || !workspace) return fail(LARS_ERR_INVALID, "lars_select_f32: NULL pointer");
-  if (n < 1 || rank_lo >= (uint64_t)n || rank_hi >= (uint64_t)n || rank_lo > rank_hi)
-    return fail(LARS_ERR_INVALID, "lars_select_f32: ranks out of range");
-  if (!aligned16(data)) return fail(LARS_ERR_INVALID, "lars_select_f32: data must be 16-byte aligned");
-  if (workspace_bytes < sizeof(lars::SelectState) || !aligned16(workspace))
-    return fail(LARS_ERR_INVALID, "lars_select_f32: workspace too small or misaligned");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  lars::SelectState* state = static_cast<lars::SelectState*>(workspace);
-  lars::select_init_kernel<<<1, 256, 0, s>>>(state, rank_lo, rank_hi);
-  long long want = (n / 4 + lars::SEL_THREADS - 1) / lars::SEL_THREADS;
-  int grid = st->sm_count * (lars::SEL_SMEM_BYTES <= 100 * 1024 ? 2 : 1);   // co-resident CTAs by shared counters
-  if (want < grid) grid = (int)(want > 0 ? want : 1);
-  for (int pass = 0; pass < 3; ++pass) {      // 11 + 11 + 10 key bits
-    lars::select_pass_kernel<<<grid, lars::SEL_THREADS, lars::SEL_SMEM_BYTES, s>>>(data, n, state, pass);
-  }
-  LARS_CUDA(cudaGetLastError());
-  LARS_CUDA(cudaMemcpyAsync(out3, reinterpret_cast<const char*>(state) + offsetof(lars::SelectState, value),
-                            3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  return LARS_OK;
+  return run_select<float>("lars_select_f32", st, data, n, rank_lo, rank_hi, out3, workspace, workspace_bytes, stream);
 }
 
 size_t lars_map_stats_f64_workspace_bytes(void) { return (size_t)(148 * 4) * sizeof(lars::MapPartialF64); }
@@ -460,31 +480,14 @@ int lars_map_stats_f64(const double* data, int64_t n, int32_t bins, double thres
   return LARS_OK;
 }
 
-size_t lars_select_f64_workspace_bytes(void) { return sizeof(lars::SelectStateF64); }
+size_t lars_select_f64_workspace_bytes(void) { return sizeof(lars::SelectState<double>); }
 
 int lars_select_f64(const double* data, int64_t n, uint64_t rank_lo, uint64_t rank_hi, double* out3,
                     void* workspace, size_t workspace_bytes, void* stream) {
   DeviceState* st = nullptr;
   int rc = current_state(&st);
   if (rc != LARS_OK) return rc;
-  if (!data || !out3 || !workspace) return fail(LARS_ERR_INVALID, "lars_select_f64: NULL pointer");
-  if (n < 1 || rank_lo >= (uint64_t)n || rank_hi >= (uint64_t)n || rank_lo > rank_hi)
-    return fail(LARS_ERR_INVALID, "lars_select_f64: ranks out of range");
-  if (!aligned16(data)) return fail(LARS_ERR_INVALID, "lars_select_f64: data must be 16-byte aligned");
-  if (workspace_bytes < sizeof(lars::SelectStateF64) || !aligned16(workspace))
-    return fail(LARS_ERR_INVALID, "lars_select_f64: workspace too small or misaligned");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  lars::SelectStateF64* state = static_cast<lars::SelectStateF64*>(workspace);
-  lars::select64_init_kernel<<<1, 256, 0, s>>>(state, rank_lo, rank_hi);
-  long long want = (n / 2 + lars::SEL_THREADS - 1) / lars::SEL_THREADS;
-  int grid = st->sm_count * (lars::SEL_SMEM_BYTES <= 100 * 1024 ? 2 : 1);
-  if (want < grid) grid = (int)(want > 0 ? want : 1);
-  for (int pass = 0; pass < lars::SEL64_PASSES; ++pass)      // 11 + 11 + 11 + 11 + 11 + 9 key bits
-    lars::select64_pass_kernel<<<grid, lars::SEL_THREADS, lars::SEL_SMEM_BYTES, s>>>(data, n, state, pass);
-  LARS_CUDA(cudaGetLastError());
-  LARS_CUDA(cudaMemcpyAsync(out3, reinterpret_cast<const char*>(state) + offsetof(lars::SelectStateF64, value),
-                            3 * sizeof(double), cudaMemcpyDeviceToDevice, s));
-  return LARS_OK;
+  return run_select<double>("lars_select_f64", st, data, n, rank_lo, rank_hi, out3, workspace, workspace_bytes, stream);
 }
 
 int lars_colormap_f32(const float* data, int64_t n, int32_t cmap_id, float vmin, float vmax, uint8_t* rgb,

@@ -7,7 +7,7 @@
 //   K4d  map_stats_f64     min / max / count / count > thr / sum / sum of squares (about the first element) /
 //                          np.histogram with float64 linspace edges and the +-1 edge correction
 //   K3d  select_f64        exact x[rank] by radix select on order-preserving 64-bit keys: 6 passes over
-//                          11 + 11 + 11 + 11 + 11 + 9 bits, last CTA of a pass picks the digit
+//                          11 + 11 + 11 + 11 + 11 + 9 bits (select_kernel<double>, lars_map_kernels.cuh)
 //
 // Both are HBM-bound streaming reads of 8 B per element; the float64 path is the report path of one script, so
 // they follow the float32 kernels' structure without their tuning.
@@ -169,142 +169,6 @@ __global__ void __launch_bounds__(MAP_HIST_ROWS) map_stats_f64_finalize_kernel(c
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// K3d: radix select on 64-bit keys
-// ------------------------------------------------------------------------------------------
-constexpr int SEL64_PASSES = 6;
-__host__ __device__ constexpr int sel64_bits(int pass) { return pass == 5 ? 9 : 11; }
-__host__ __device__ constexpr int sel64_shift(int pass) { return pass == 5 ? 0 : 53 - 11 * pass; }
-
-struct SelectStateF64 {
-  unsigned long long rank[2];
-  unsigned long long prefix[2];
-  double value[2];
-  double median;
-  uint32_t arrivals, pad_;
-  unsigned long long hist[2][SEL_BINS];
-};
-
-__global__ void select64_init_kernel(SelectStateF64* st, unsigned long long r0, unsigned long long r1) {
-  const int t = threadIdx.x;
-  if (t == 0) {
-    st->rank[0] = r0; st->rank[1] = r1;
-    st->prefix[0] = st->prefix[1] = 0ull;
-    st->value[0] = st->value[1] = st->median = 0.0;
-    st->arrivals = 0u; st->pad_ = 0u;
-  }
-  for (int b = t; b < SEL_BINS; b += blockDim.x) { st->hist[0][b] = 0ull; st->hist[1][b] = 0ull; }
-}
-
-__device__ __forceinline__ double double_from_order_key(unsigned long long k) {
-  return __longlong_as_double((long long)((k & 0x8000000000000000ull) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k));
-}
-
-// Digit selection by all SEL_THREADS threads of the last CTA; thread t owns bins 4 t .. 4 t + 3.
-__device__ __forceinline__ void select64_scan(SelectStateF64* st, int pass, unsigned long long* wtot) {
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int bits = sel64_bits(pass);
-  const int nb = 1 << bits;
-  const bool same = (pass == 0) || (st->prefix[0] == st->prefix[1]);
-  __syncthreads();
-  for (int r = 0; r < 2; ++r) {
-    const int src = same ? 0 : r;
-    unsigned long long c[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) c[j] = (4 * t + j < nb) ? __ldcg(&st->hist[src][4 * t + j]) : 0ull;
-    unsigned long long x = c[0] + c[1] + c[2] + c[3];
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d);
-      if (lane >= d) x += y;
-    }
-    if (lane == 31) wtot[warp] = x;
-    __syncthreads();
-    unsigned long long add = 0;
-    for (int w = 0; w < warp; ++w) add += wtot[w];
-    x += add;
-    const unsigned long long rk = st->rank[r];
-    __syncthreads();
-    unsigned long long below = x - (c[0] + c[1] + c[2] + c[3]);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (below <= rk && rk < below + c[j]) {
-        st->prefix[r] = (st->prefix[r] << bits) | (unsigned long long)(4 * t + j);
-        st->rank[r] = rk - below;
-      }
-      below += c[j];
-    }
-    __syncthreads();
-  }
-  for (int b = t; b < SEL_BINS; b += SEL_THREADS) { st->hist[0][b] = 0ull; st->hist[1][b] = 0ull; }
-  if (pass == SEL64_PASSES - 1 && t == 0) {
-    const double a = double_from_order_key(st->prefix[0]);
-    const double b = double_from_order_key(st->prefix[1]);
-    st->value[0] = a;
-    st->value[1] = b;
-    st->median = LARS_DMUL(LARS_DADD(a, b), 0.5);        // np.mean of the two middle float64 values
-  }
-}
-
-__global__ void __launch_bounds__(SEL_THREADS) select64_pass_kernel(const double* __restrict__ data, long long n,
-                                                                     SelectStateF64* st, int pass) {
-  extern __shared__ __align__(16) uint32_t sel_hist[];  // [2][SEL_BINS][SEL_LANES]
-  __shared__ unsigned long long wtot[SEL_THREADS / 32];
-  __shared__ unsigned int is_last;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int bits = sel64_bits(pass), dg_shift = sel64_shift(pass);
-  const int nb = 1 << bits;
-  for (int i = tid; i < 2 * SEL_BINS * SEL_LANES; i += SEL_THREADS) sel_hist[i] = 0u;
-  __syncthreads();
-  const unsigned long long p0 = st->prefix[0], p1 = st->prefix[1];
-  const bool same = (pass == 0) || (p0 == p1);
-  const int hi_shift = dg_shift + bits;                  // 64 in pass 0
-  const unsigned long long hi_mask = pass == 0 ? 0ull : (~0ull << hi_shift);
-  const unsigned long long want0 = pass == 0 ? 0ull : (p0 << hi_shift);
-  const unsigned long long want1 = pass == 0 ? 0ull : (p1 << hi_shift);
-  const uint32_t dg_mask = (uint32_t)nb - 1u;
-  const uint32_t a0 = smem_u32(sel_hist) + 4u * (lane & (SEL_LANES - 1)), a1 = a0 + (uint32_t)SEL_BINS * SEL_LANES * 4u;
-  auto visit = [&](double x) {
-    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
-    const unsigned long long key = b ^ ((unsigned long long)((long long)b >> 63) | 0x8000000000000000ull);
-    const uint32_t off = ((uint32_t)(key >> dg_shift) & dg_mask) * (SEL_LANES * 4u);
-    if (((key ^ want0) & hi_mask) == 0ull) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a0 + off) : "memory");
-    if (!same && ((key ^ want1) & hi_mask) == 0ull) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a1 + off) : "memory");
-  };
-  const long long nvec = n / 2;
-  const double2* xv = reinterpret_cast<const double2*>(data);
-  const long long stride = (long long)gridDim.x * SEL_THREADS;
-  long long v = (long long)blockIdx.x * SEL_THREADS + tid;
-  for (; v + 3 * stride < nvec; v += 4 * stride) {
-    const double2 q0 = __ldg(xv + v), q1 = __ldg(xv + v + stride), q2 = __ldg(xv + v + 2 * stride), q3 = __ldg(xv + v + 3 * stride);
-    visit(q0.x); visit(q0.y); visit(q1.x); visit(q1.y); visit(q2.x); visit(q2.y); visit(q3.x); visit(q3.y);
-  }
-  for (; v < nvec; v += stride) {
-    const double2 q = __ldg(xv + v);
-    visit(q.x); visit(q.y);
-  }
-  if (blockIdx.x == 0 && tid == 0 && (n & 1)) visit(data[n - 1]);
-  __syncthreads();
-  for (int b = tid; b < 2 * nb; b += SEL_THREADS) {
-    const int set = b >= nb ? 1 : 0, bin = b - set * nb;
-    if (same && set) break;
-    uint32_t s = 0;
-#pragma unroll
-    for (int l = 0; l < SEL_LANES; ++l) s += sel_hist[(set * SEL_BINS + bin) * SEL_LANES + ((l + tid) & (SEL_LANES - 1))];
-    if (s) atomicAdd(&st->hist[set][bin], (unsigned long long)s);
-  }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned int ticket = atomicAdd(&st->arrivals, 1u);
-    is_last = (ticket == gridDim.x - 1) ? 1u : 0u;
-  }
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    select64_scan(st, pass, wtot);
-    if (tid == 0) st->arrivals = 0u;
-  }
-}
+// K3d (exact order statistics of a float64 map) is select_kernel<double> in lars_map_kernels.cuh.
 
 }  // namespace lars

@@ -265,176 +265,179 @@ __global__ void __launch_bounds__(MAP_HIST_ROWS * MAP_FIN_SPLIT) map_stats_final
 }
 
 // ------------------------------------------------------------------------------------------
-// K3: exact order statistics by radix select
+// K3 / K3d: exact order statistics by radix select, ONE persistent kernel for all passes
 // ------------------------------------------------------------------------------------------
-// Three passes over 11 + 11 + 10 key bits (a fourth 8-bit pass costs another full read of the map).
-// Round 2, measured and NOT kept: after the first pass the prefix bucket holds a few per cent of the map, so passes
-// 2 and 3 were given a mode without the shared histogram (matching elements straight to the global counters, one
-// atomic per warp and digit; nothing to clear or fold).  59.4 us per 12 MP map against 59.8 us: the shared histogram
-// is not what a pass costs.  ncu (profiles/r02_k3_select_ncu_summary.txt): 8 M warp instructions and 48 MB per pass
-// in ~21 us, long_scoreboard on top -- a pass is ~80 elements per thread, i.e. launch, ramp-up and the last CTA's
-// digit scan around ~7 us of streaming.  What would help is one pass less (the first digit counted inside K4's read
-// of the same map), not a cheaper pass.
+// float32: 11 + 11 + 10 key bits (3 passes); float64: 11 + 11 + 11 + 11 + 11 + 9 (6 passes).  A pass streams the map,
+// counts the current digit of the elements that match the prefix chosen so far in a shared histogram (2,048 bins, 4
+// lane copies, one set per rank while the two ranks still share a prefix), folds it into the global histogram of that
+// pass, meets the other CTAs at a grid barrier, and then EVERY CTA scans the global histogram for itself and extends
+// the prefix -- no separate scan launch, no second barrier, nothing to clear between passes (each pass has its own
+// global histogram, zeroed by one memset in front of the launch).
+// Round 1 / early round 2 launched one kernel per pass: 59 us per 12 MP float32 map = 3 x ~20 us, of which ~7 us is
+// streaming (ncu: 8 M warp instructions and 48 MB per pass, long_scoreboard on top) and the rest launch, ramp-up of
+// 296 CTAs x 512 threads for ~80 elements per thread, and the last CTA's scan.  A cheaper pass (no shared histogram
+// for the sparse passes) measured no gain; removing the launches and ramps is what this form does.  The launch is
+// cooperative (all CTAs must be co-resident for the barrier).
 constexpr int SEL_BINS = 2048;                 // bins of the widest digit
 #ifndef LARS_SEL_LANES
 #define LARS_SEL_LANES 4
 #endif
 constexpr int SEL_LANES = LARS_SEL_LANES;      // lane copies of each counter (lanes congruent modulo this share one)
-__host__ __device__ constexpr int sel_digit_bits(int pass) { return pass == 2 ? 10 : 11; }
-__host__ __device__ constexpr int sel_digit_shift(int pass) { return pass == 0 ? 21 : (pass == 1 ? 10 : 0); }
+constexpr int SEL_THREADS = 512;
+constexpr int SEL_SMEM_BYTES = 2 * SEL_BINS * SEL_LANES * 4;   // 64 KB: [2][2048][4]
 
-struct SelectState {
-  unsigned long long rank[2];   // remaining rank inside the current prefix bucket
-  uint32_t prefix[2];           // selected high digits so far
-  float value[2];               // the two order statistics (written after the last pass)
-  float median;                 // float32 mean of the two (np.median for even n)
-  uint32_t pad_;                // arrival counter of the pass kernel
-  unsigned long long hist[2][SEL_BINS];
+template <typename T> struct SelectTraits;
+template <> struct SelectTraits<float> {
+  typedef uint32_t Key;
+  typedef float4 Vec;
+  static constexpr int PASSES = 3, PER_VEC = 4;
+  __host__ __device__ static constexpr int bits(int pass) { return pass == 2 ? 10 : 11; }
+  __host__ __device__ static constexpr int shift(int pass) { return pass == 0 ? 21 : (pass == 1 ? 10 : 0); }
+  __device__ static __forceinline__ Key key(float x) {
+    const uint32_t b = __float_as_uint(x);
+    return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);          // order-preserving
+  }
+  __device__ static __forceinline__ float value(Key k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k); }
+  __device__ static __forceinline__ float mean2(float a, float b) { return LARS_FMUL(LARS_FADD(a, b), 0.5f); }   // np.mean of the two middle values
+};
+template <> struct SelectTraits<double> {
+  typedef unsigned long long Key;
+  typedef double2 Vec;
+  static constexpr int PASSES = 6, PER_VEC = 2;
+  __host__ __device__ static constexpr int bits(int pass) { return pass == 5 ? 9 : 11; }
+  __host__ __device__ static constexpr int shift(int pass) { return pass == 5 ? 0 : 53 - 11 * pass; }
+  __device__ static __forceinline__ Key key(double x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return b ^ ((unsigned long long)((long long)b >> 63) | 0x8000000000000000ull);
+  }
+  __device__ static __forceinline__ double value(Key k) {
+    return __longlong_as_double((long long)((k & 0x8000000000000000ull) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k));
+  }
+  __device__ static __forceinline__ double mean2(double a, double b) { return LARS_DMUL(LARS_DADD(a, b), 0.5); }
 };
 
-__device__ __forceinline__ uint32_t float_order_key(float x) {
-  const uint32_t b = __float_as_uint(x);
-  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float float_from_order_key(uint32_t k) {
-  return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
-}
+template <typename T>
+struct SelectState {
+  unsigned int barrier;         // arrivals at the grid barrier (zeroed with the histograms)
+  unsigned int pad_[3];
+  T value[2];                   // the two order statistics
+  T median;                     // their mean in T (np.median for even n)
+  T pad2_;
+  unsigned long long hist[SelectTraits<T>::PASSES][2][SEL_BINS];
+};
 
-__global__ void select_init_kernel(SelectState* st, unsigned long long r0, unsigned long long r1) {
-  const int t = threadIdx.x;
-  if (t == 0) {
-    st->rank[0] = r0; st->rank[1] = r1;
-    st->prefix[0] = st->prefix[1] = 0u;
-    st->value[0] = st->value[1] = st->median = 0.f;
-    st->pad_ = 0u;
-  }
-  for (int b = t; b < SEL_BINS; b += blockDim.x) {
-    st->hist[0][b] = 0ull;
-    st->hist[1][b] = 0ull;
-  }
-}
-
-constexpr int SEL_THREADS = 512;
-constexpr int SEL_SMEM_BYTES = 2 * SEL_BINS * SEL_LANES * 4;   // 128 KB: [2][2048][8]
-
-// Digit selection after a pass: scan the digit histogram(s), pick the bin that holds each rank, extend
-// the prefixes, clear the histograms.  Called by ALL 512 threads of one CTA; thread t owns bins 4 t .. 4 t + 3.
-__device__ __forceinline__ void select_scan(SelectState* st, int pass, unsigned long long* wtot) {
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int bits = sel_digit_bits(pass);
-  const int nb = 1 << bits;
-  const bool same = (pass == 0) || (st->prefix[0] == st->prefix[1]);
-  __syncthreads();
-  for (int r = 0; r < 2; ++r) {
-    const int src = same ? 0 : r;
-    unsigned long long c[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) c[j] = (4 * t + j < nb) ? __ldcg(&st->hist[src][4 * t + j]) : 0ull;
-    unsigned long long x = c[0] + c[1] + c[2] + c[3];       // inclusive scan over threads of the 4-bin sums
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d);
-      if (lane >= d) x += y;
-    }
-    if (lane == 31) wtot[warp] = x;
-    __syncthreads();
-    unsigned long long add = 0;
-    for (int w = 0; w < warp; ++w) add += wtot[w];
-    x += add;
-    const unsigned long long rk = st->rank[r];
-    __syncthreads();
-    unsigned long long below = x - (c[0] + c[1] + c[2] + c[3]);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (below <= rk && rk < below + c[j]) {
-        st->prefix[r] = (st->prefix[r] << bits) | (uint32_t)(4 * t + j);
-        st->rank[r] = rk - below;
-      }
-      below += c[j];
-    }
-    __syncthreads();
-  }
-  for (int b = t; b < SEL_BINS; b += SEL_THREADS) {
-    st->hist[0][b] = 0ull;
-    st->hist[1][b] = 0ull;
-  }
-  if (pass == 2 && t == 0) {
-    const float a = float_from_order_key(st->prefix[0]);
-    const float b = float_from_order_key(st->prefix[1]);
-    st->value[0] = a;
-    st->value[1] = b;
-    st->median = LARS_FMUL(LARS_FADD(a, b), 0.5f);  // np.mean of the two middle float32 values
-  }
-}
-
-// One radix pass.  The last CTA to finish (arrival counter) also performs the digit selection, so a
-// select is three launches with nothing in between.
-__global__ void __launch_bounds__(SEL_THREADS) select_pass_kernel(const float* __restrict__ data, long long n,
-                                                                   SelectState* st, int pass) {
+template <typename T>
+__global__ void __launch_bounds__(SEL_THREADS) select_kernel(const T* __restrict__ data, long long n, SelectState<T>* st,
+                                                             unsigned long long rank_lo, unsigned long long rank_hi) {
+  typedef SelectTraits<T> Tr;
+  typedef typename Tr::Key Key;
   extern __shared__ __align__(16) uint32_t sel_hist[];  // [2][SEL_BINS][SEL_LANES]
   __shared__ unsigned long long wtot[SEL_THREADS / 32];
-  __shared__ unsigned int is_last;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int bits = sel_digit_bits(pass), dg_shift = sel_digit_shift(pass);
-  const int nb = 1 << bits;
-  for (int i = tid; i < 2 * SEL_BINS * SEL_LANES; i += SEL_THREADS) sel_hist[i] = 0u;
+  __shared__ unsigned long long sh_rank[2];
+  __shared__ Key sh_prefix[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { sh_rank[0] = rank_lo; sh_rank[1] = rank_hi; sh_prefix[0] = 0; sh_prefix[1] = 0; }
   __syncthreads();
-  const uint32_t p0 = st->prefix[0], p1 = st->prefix[1];
-  const bool same = (pass == 0) || (p0 == p1);
-  // 32-bit shared addresses and RED (no return value); the prefix test is one masked compare:
-  // (key ^ prefix_bits) & hi_mask == 0, with hi_mask = 0 in pass 0
-  const int hi_shift = dg_shift + bits;                   // 32 in pass 0
-  const uint32_t hi_mask = pass == 0 ? 0u : (0xFFFFFFFFu << hi_shift);
-  const uint32_t want0 = pass == 0 ? 0u : (p0 << hi_shift);
-  const uint32_t want1 = pass == 0 ? 0u : (p1 << hi_shift);
-  const uint32_t dg_mask = (uint32_t)nb - 1u;
   const uint32_t a0 = smem_u32(sel_hist) + 4u * (lane & (SEL_LANES - 1)), a1 = a0 + (uint32_t)SEL_BINS * SEL_LANES * 4u;
-
-  auto visit = [&](float x) {
-    const uint32_t b = __float_as_uint(x);
-    const uint32_t key = b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);   // order-preserving key
-    const uint32_t off = ((key >> dg_shift) & dg_mask) * (SEL_LANES * 4u);
-    if (((key ^ want0) & hi_mask) == 0u) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a0 + off) : "memory");
-    if (!same && ((key ^ want1) & hi_mask) == 0u) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a1 + off) : "memory");
-  };
-  const long long nvec = n / 4;
-  const float4* xv = reinterpret_cast<const float4*>(data);
+  const long long nvec = n / Tr::PER_VEC;
+  const typename Tr::Vec* xv = reinterpret_cast<const typename Tr::Vec*>(data);
   const long long stride = (long long)gridDim.x * SEL_THREADS;
-  long long v = (long long)blockIdx.x * SEL_THREADS + tid;
-  for (; v + 3 * stride < nvec; v += 4 * stride) {     // four independent 128-bit loads in flight
-    const float4 q0 = __ldg(xv + v), q1 = __ldg(xv + v + stride), q2 = __ldg(xv + v + 2 * stride), q3 = __ldg(xv + v + 3 * stride);
-    visit(q0.x); visit(q0.y); visit(q0.z); visit(q0.w);
-    visit(q1.x); visit(q1.y); visit(q1.z); visit(q1.w);
-    visit(q2.x); visit(q2.y); visit(q2.z); visit(q2.w);
-    visit(q3.x); visit(q3.y); visit(q3.z); visit(q3.w);
-  }
-  for (; v < nvec; v += stride) {
-    const float4 q = __ldg(xv + v);
-    visit(q.x); visit(q.y); visit(q.z); visit(q.w);
-  }
-  if (blockIdx.x == 0)
-    for (long long i = nvec * 4 + tid; i < n; i += SEL_THREADS) visit(data[i]);
-  __syncthreads();
-  for (int b = tid; b < 2 * nb; b += SEL_THREADS) {
-    const int set = b >= nb ? 1 : 0, bin = b - set * nb;
-    if (same && set) break;
-    uint32_t s = 0;
+
+#pragma unroll 1
+  for (int pass = 0; pass < Tr::PASSES; ++pass) {
+    const int bits = Tr::bits(pass), dg_shift = Tr::shift(pass);
+    const int nb = 1 << bits;
+    const Key p0 = sh_prefix[0], p1 = sh_prefix[1];
+    const bool same = (pass == 0) || (p0 == p1);
+    for (int i = tid; i < (same ? 1 : 2) * SEL_BINS * SEL_LANES; i += SEL_THREADS) sel_hist[i] = 0u;
+    __syncthreads();
+    // the prefix test is one masked compare: (key ^ prefix_bits) & hi_mask == 0, with hi_mask = 0 in pass 0
+    const int hi_shift = dg_shift + bits;                  // the key's width in pass 0
+    const Key hi_mask = pass == 0 ? (Key)0 : (Key)(~(Key)0 << hi_shift);
+    const Key want0 = pass == 0 ? (Key)0 : (Key)(p0 << hi_shift);
+    const Key want1 = pass == 0 ? (Key)0 : (Key)(p1 << hi_shift);
+    const uint32_t dg_mask = (uint32_t)nb - 1u;
+    auto visit = [&](T x) {
+      const Key key = Tr::key(x);
+      const uint32_t off = ((uint32_t)(key >> dg_shift) & dg_mask) * (SEL_LANES * 4u);
+      if (((key ^ want0) & hi_mask) == (Key)0) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a0 + off) : "memory");
+      if (!same && ((key ^ want1) & hi_mask) == (Key)0) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a1 + off) : "memory");
+    };
+    auto visit_vec = [&](const typename Tr::Vec& q) {
+      if constexpr (Tr::PER_VEC == 4) { visit(q.x); visit(q.y); visit(q.z); visit(q.w); }
+      else { visit(q.x); visit(q.y); }
+    };
+    long long v = (long long)blockIdx.x * SEL_THREADS + tid;
+    for (; v + 3 * stride < nvec; v += 4 * stride) {     // four independent 128-bit loads in flight
+      const typename Tr::Vec q0 = __ldg(xv + v), q1 = __ldg(xv + v + stride), q2 = __ldg(xv + v + 2 * stride), q3 = __ldg(xv + v + 3 * stride);
+      visit_vec(q0); visit_vec(q1); visit_vec(q2); visit_vec(q3);
+    }
+    for (; v < nvec; v += stride) visit_vec(__ldg(xv + v));
+    if (blockIdx.x == 0)
+      for (long long i = nvec * Tr::PER_VEC + tid; i < n; i += SEL_THREADS) visit(data[i]);
+    __syncthreads();
+    for (int b = tid; b < (same ? 1 : 2) * nb; b += SEL_THREADS) {
+      const int set = b >= nb ? 1 : 0, bin = b - set * nb;
+      uint32_t s = 0;
 #pragma unroll
-    for (int l = 0; l < SEL_LANES; ++l) s += sel_hist[(set * SEL_BINS + bin) * SEL_LANES + ((l + tid) & (SEL_LANES - 1))];
-    if (s) atomicAdd(&st->hist[set][bin], (unsigned long long)s);
-  }
-  // last CTA standing does the selection
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned int ticket = atomicAdd(&st->pad_, 1u);
-    is_last = (ticket == gridDim.x - 1) ? 1u : 0u;
-  }
-  __syncthreads();
-  if (is_last) {
+      for (int l = 0; l < SEL_LANES; ++l) s += sel_hist[(set * SEL_BINS + bin) * SEL_LANES + ((l + tid) & (SEL_LANES - 1))];
+      if (s) atomicAdd(&st->hist[pass][set][bin], (unsigned long long)s);
+    }
+    // ---- grid barrier: every CTA's counts of this pass are in the global histogram
     __threadfence();
-    select_scan(st, pass, wtot);
-    if (tid == 0) st->pad_ = 0u;
+    __syncthreads();
+    if (tid == 0) {
+      atomicAdd(&st->barrier, 1u);
+      const unsigned int target = gridDim.x * (unsigned int)(pass + 1);
+      unsigned int seen;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(&st->barrier) : "memory");
+        if (seen < target) __nanosleep(40);
+      } while (seen < target);
+    }
+    __syncthreads();
+    // ---- digit selection, by every CTA for itself; thread t owns bins 4 t .. 4 t + 3.  While both ranks share a
+    // prefix they read the same histogram: one load + scan serves both
+#pragma unroll 1
+    for (int r = 0; r < (same ? 1 : 2); ++r) {
+      unsigned long long c[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) c[j] = (4 * tid + j < nb) ? __ldcg(&st->hist[pass][r][4 * tid + j]) : 0ull;
+      unsigned long long x = c[0] + c[1] + c[2] + c[3];       // inclusive scan over threads of the 4-bin sums
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
+      }
+      if (lane == 31) wtot[warp] = x;
+      __syncthreads();
+      unsigned long long add = 0;
+      for (int w = 0; w < warp; ++w) add += wtot[w];
+      x += add;
+      const unsigned long long rk0 = sh_rank[same ? 0 : r], rk1 = sh_rank[1];
+      const Key pref0 = sh_prefix[same ? 0 : r], pref1 = sh_prefix[1];
+      __syncthreads();
+      unsigned long long below = x - (c[0] + c[1] + c[2] + c[3]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (below <= rk0 && rk0 < below + c[j]) {
+          sh_prefix[same ? 0 : r] = (Key)(pref0 << bits) | (Key)(4 * tid + j);
+          sh_rank[same ? 0 : r] = rk0 - below;
+        }
+        if (same && below <= rk1 && rk1 < below + c[j]) {
+          sh_prefix[1] = (Key)(pref1 << bits) | (Key)(4 * tid + j);
+          sh_rank[1] = rk1 - below;
+        }
+        below += c[j];
+      }
+      __syncthreads();
+    }
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    const T a = Tr::value(sh_prefix[0]), b = Tr::value(sh_prefix[1]);
+    st->value[0] = a;
+    st->value[1] = b;
+    st->median = Tr::mean2(a, b);
   }
 }
 
