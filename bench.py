@@ -75,6 +75,10 @@ def parse_args():
                     help="seconds of the sustained leg (default: 2 s for c2, off for the other workloads)")
     ap.add_argument("--chunk", type=int, default=0, help="frames per pipeline chunk in the e2e path")
     ap.add_argument("--no-parity", action="store_true", help="c4: skip the reduced-mosaic check against the oracle")
+    ap.add_argument("--exchange", default="peer", choices=["nccl", "peer"],
+                    help="c4: white-balance histogram exchange -- NCCL all-reduce between Pass 1 and the LUT build, or the "
+                         "LUT kernel exchanging the counters itself over NVLink peer memory (falls back to nccl if "
+                         "symmetric memory cannot be set up)")
     a = ap.parse_args()
     w = dict(WORKLOADS[a.workload])
     for k in ("height", "width", "dtype", "group"):
@@ -408,7 +412,7 @@ def run_reference(a):
 # ------------------------------------------------------------------------------------------
 # GPU side
 # ------------------------------------------------------------------------------------------
-def reduced_mosaic_parity(eng, ld, rank, world, s):
+def reduced_mosaic_parity(a, eng, ld, rank, world, s):
     """"C4 on a reduced mosaic with the same tiling logic" -- a 1,024^2 mosaic as 64 tiles of
     128^2, row band per rank, through the same plan / hook / exchange code as the timed run, against the oracle on
     the WHOLE image (checker only: nothing here is timed)."""
@@ -429,7 +433,8 @@ def reduced_mosaic_parity(eng, ld, rank, world, s):
     def hook(hist):
         if world > 1:
             dist.all_reduce(hist, op=dist.ReduceOp.SUM)
-    plan = FramePlan(eng, dev, ALL_OUTPUTS, stream=s, tiles_of_one_image=True, hist_hook=hook)
+    peer, _ = make_peer_exchange(a, eng, ld, world)
+    plan = FramePlan(eng, dev, ALL_OUTPUTS, stream=s, tiles_of_one_image=True, hist_hook=None if peer else hook, peer_exchange=peer)
     res = plan.run()
     whole = ld.dataset_statistics(eng, res.stats, None, s)
     out = eng.download(res, stream=s)
@@ -456,9 +461,38 @@ def reduced_mosaic_parity(eng, ld, rank, world, s):
     if world > 1:
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     assert int(flag[0]) == 1, "reduced C4 mosaic differs from the oracle"
+    assert peer is None or not peer.timed_out(), "peer exchange timed out"
     return {"checked": f"{side}x{side} mosaic, {grid * grid} tiles of {tile}x{tile}, row band per rank, against the NumPy "
                        "oracle on the whole image: WB bytes, fp32 maps (bits), RGB, histograms, counts, min / max exact; "
                        "mean within 1e-6", "ok": True}
+
+
+class TimedPeerExchange:
+    """A PeerHistogramExchange whose fused exchange + LUT launches are bracketed by CUDA events (bench evidence)."""
+
+    def __init__(self, inner, events):
+        self.inner, self.events = inner, events
+
+    def lut_build(self, hist, lut, pct, quantiles=(0.02, 0.98), stream=None, chain=0):
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        self.inner.lut_build(hist, lut, pct, quantiles, stream=stream, chain=chain)
+        e1.record(stream)
+        self.events.append((e0, e1))
+
+    def timed_out(self):
+        return self.inner.timed_out()
+
+
+def make_peer_exchange(a, eng, ld, world):
+    """--exchange peer on more than one rank -> a PeerHistogramExchange, or None (with the reason) -> NCCL hook."""
+    if a.exchange != "peer" or world == 1:
+        return None, None
+    try:
+        return ld.PeerHistogramExchange(eng), None
+    except Exception as exc:
+        return None, str(exc)[:200]
 
 
 class Workload:
@@ -497,7 +531,12 @@ class Workload:
                     dist.all_reduce(hist, op=dist.ReduceOp.SUM)
                 e1.record(s)
                 self.allreduce_events.append((e0, e1))
-            self.plan = FramePlan(eng, self.frames, ALL_OUTPUTS, stream=s, tiles_of_one_image=True, hist_hook=hook)
+            self.peer, self.peer_note = make_peer_exchange(a, eng, ld, world)
+            if self.peer is not None:
+                self.plan = FramePlan(eng, self.frames, ALL_OUTPUTS, stream=s, tiles_of_one_image=True,
+                                      peer_exchange=TimedPeerExchange(self.peer, self.allreduce_events))
+            else:
+                self.plan = FramePlan(eng, self.frames, ALL_OUTPUTS, stream=s, tiles_of_one_image=True, hist_hook=hook)
             self.groups = None
             self.launches_per_step = 5
         else:
@@ -580,7 +619,7 @@ def run_ours(a):
 
     parity = None
     if a.workload == "c4" and not a.no_parity:
-        parity = reduced_mosaic_parity(eng, ld, rank, world, s)
+        parity = reduced_mosaic_parity(a, eng, ld, rank, world, s)
 
     wl = Workload(a, eng, ld, rank, world, s)
     exchange = wl.exchange
@@ -639,7 +678,7 @@ def run_ours(a):
     host_s[0] = 0.0
     barrier()
     exchange.gather_us()                                    # drop the warm-up's timings
-    wl.allreduce_events = []
+    wl.allreduce_events.clear()
     sampler.recording = True
     aligned_start(t_start)
     for _ in range(a.steps):
@@ -687,7 +726,7 @@ def run_ours(a):
         sus_k2_ms, sus_k2_frames, _ = k2_stats()
         sus_ms, sus_k2_ms = reduce_max([t0e.elapsed_time(t1e), sus_k2_ms])
         exchange.gather_us()
-        wl.allreduce_events = []
+        wl.allreduce_events.clear()
         sustained = {"seconds": sus_ms * 1e-3, "steps": n_sus, "value": total_px * n_sus / (sus_ms * 1e-3) / 1e6,
                      "unit": UNIT, "k2_ms_per_launch": sus_k2_ms, "clocks": sus_clocks}
     sampler.stop()
@@ -739,8 +778,11 @@ def run_ours(a):
         "parallelism": ("single GPU" if world == 1 else {
             "c2": f"frames sharded over {world} GPUs, one dataset-statistics all-gather per step on a side stream (overlaps the next step)",
             "c3": f"frames round-robin over {world} GPUs, no data-path collective, one dataset-statistics all-gather per step",
-            "c4": f"row bands of tiles over {world} GPUs, SUM all-reduce of the white-balance histogram between Pass 1 and the LUT "
-                  "build inside every step, one image-statistics all-gather per step",
+            "c4": (f"row bands of tiles over {world} GPUs, white-balance histogram exchanged inside every step by the LUT kernel "
+                   "itself over NVLink peer memory (symmetric buffers, per-rank flags), one image-statistics all-gather per step"
+                   if getattr(wl, "peer", None) is not None else
+                   f"row bands of tiles over {world} GPUs, SUM all-reduce of the white-balance histogram between Pass 1 and the LUT "
+                   "build inside every step, one image-statistics all-gather per step"),
             "c5": f"contiguous shards over {world} GPUs, no data-path collective, one dataset-statistics all-gather per step"}[a.workload]),
     })
     if a.workload in ("c3", "c5"):
@@ -775,6 +817,14 @@ def run_ours(a):
     }
     if parity is not None:
         line["parity_check"] = parity
+    if a.workload == "c4":
+        line["collectives"]["wb_hist_exchange"] = "peer" if getattr(wl, "peer", None) is not None else "nccl"
+        if getattr(wl, "peer", None) is not None:
+            line["collectives"]["note"] += ("; with the peer exchange wb_hist_all_reduce_us is the fused exchange + LUT kernel "
+                                            "(3.9 us of it is the LUT build)")
+            assert not wl.peer.timed_out(), "peer exchange timed out"
+        elif getattr(wl, "peer_note", None):
+            line["collectives"]["wb_hist_exchange_note"] = "peer exchange unavailable, NCCL used: " + wl.peer_note
     if sustained is not None:
         sustained["roofline_frac"] = pass2_b * sus_k2_frames * npx / (sustained["k2_ms_per_launch"] * 1e-3) / 1e9 / peak
         line["sustained"] = sustained

@@ -150,6 +150,20 @@ int lars_wb_lut_build_u8(const uint64_t* hist, int32_t n_sets, double q_lo, doub
 int lars_wb_lut_build_u8_chain(const uint64_t* hist, int32_t n_sets, double q_lo, double q_hi, int32_t chain,
                                uint8_t* lut, double* pct, void* stream);
 
+/* K1b fused with the exchange of a tile-sharded image (BASELINE config 4; the percentiles of
+ * process-images.py:435-438 are global to the image, so the ranks' local histograms must be summed between Pass 1 and
+ * the LUT build).  Instead of an NCCL all-reduce of 3 x 256 counters, ONE kernel pushes this rank's counts into every
+ * peer's symmetric buffer over NVLink, raises / awaits per-rank flags there, sums the world contributions in rank
+ * order and builds the table: `hist` ([1][3][256], device) holds the local counts on entry and the image-wide counts
+ * on return.  peer_bufs is a DEVICE array of `world` pointers: every rank's buffer of lars_wb_peer_buffer_bytes(world)
+ * bytes (zero-initialised once) as mapped into this process (torch.distributed._symmetric_memory: `buffer_ptrs_dev`;
+ * any CUDA IPC / VMM mapping works).  epoch = 1, 2, 3, ... must advance by one per call on every rank.  *status
+ * (device) is set to 1 if a peer did not arrive within ~10 s (the call never hangs). */
+size_t lars_wb_peer_buffer_bytes(int32_t world);
+int lars_wb_lut_build_u8_peers(uint64_t* hist, uint64_t* const* peer_bufs, int32_t rank, int32_t world,
+                               uint32_t epoch, double q_lo, double q_hi, int32_t chain, uint8_t* lut, double* pct,
+                               uint32_t* status, void* stream);
+
 /* ---- Pass 2: fused WB + NDVI/GNDVI/NDWI + statistics + histogram + colormap -----------
  * Replaces, in one read of the raw frame: the stretch application (process-images.py:438-441),
  * calculate_index x3 (:449-490), analyze_index x3 (:492-513) minus the median, np.std

@@ -28,6 +28,7 @@ EXPORTED_SYMBOLS = (
     "lars_init", "lars_shutdown", "lars_last_error", "lars_abi_version", "lars_sm_count",
     "lars_colormap_table", "lars_histogram_edges_f32",
     "lars_wb_hist_u8", "lars_wb_lut_build_u8", "lars_wb_lut_build_u8_chain",
+    "lars_wb_peer_buffer_bytes", "lars_wb_lut_build_u8_peers",
     "lars_fused_workspace_bytes", "lars_fused_index_u8",
     "lars_map_stats_workspace_bytes", "lars_map_stats_f32", "lars_select_workspace_bytes",
     "lars_select_f32", "lars_map_stats_f64_workspace_bytes", "lars_map_stats_f64", "lars_select_f64_workspace_bytes",
@@ -147,6 +148,10 @@ def _declare(lib):
     lib.lars_wb_lut_build_u8.restype = C.c_int
     lib.lars_wb_lut_build_u8_chain.argtypes = [vp, i32, f64, f64, i32, vp, vp, vp]
     lib.lars_wb_lut_build_u8_chain.restype = C.c_int
+    lib.lars_wb_peer_buffer_bytes.argtypes = [i32]
+    lib.lars_wb_peer_buffer_bytes.restype = C.c_size_t
+    lib.lars_wb_lut_build_u8_peers.argtypes = [vp, vp, i32, i32, C.c_uint32, f64, f64, i32, vp, vp, vp, vp]
+    lib.lars_wb_lut_build_u8_peers.restype = C.c_int
     lib.lars_fused_workspace_bytes.argtypes = [i32]
     lib.lars_fused_workspace_bytes.restype = C.c_size_t
     lib.lars_fused_index_u8.argtypes = [C.POINTER(FusedArgs), vp]

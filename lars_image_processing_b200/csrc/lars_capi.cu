@@ -277,6 +277,35 @@ int lars_wb_lut_build_u8_chain(const uint64_t* hist, int32_t n_sets, double q_lo
   return LARS_OK;
 }
 
+size_t lars_wb_peer_buffer_bytes(int32_t world) {
+  if (world < 1) return 0;
+  return ((size_t)2 * world * 768 * 8 + (size_t)world * 3 * 4 + 255) & ~(size_t)255;
+}
+
+int lars_wb_lut_build_u8_peers(uint64_t* hist, uint64_t* const* peer_bufs, int32_t rank, int32_t world,
+                               uint32_t epoch, double q_lo, double q_hi, int32_t chain, uint8_t* lut, double* pct,
+                               uint32_t* status, void* stream) {
+  DeviceState* st = nullptr;
+  int rc = current_state(&st);
+  if (rc != LARS_OK) return rc;
+  if (!hist || !peer_bufs || !lut || !status) return fail(LARS_ERR_INVALID, "lars_wb_lut_build_u8_peers: NULL pointer");
+  if (world < 1 || world > 256 || rank < 0 || rank >= world)
+    return fail(LARS_ERR_INVALID, "lars_wb_lut_build_u8_peers: rank %d of %d", rank, world);
+  if (epoch == 0) return fail(LARS_ERR_INVALID, "lars_wb_lut_build_u8_peers: epochs start at 1 (flags start at 0)");
+  if (!(q_lo >= 0.0 && q_lo <= 1.0 && q_hi >= 0.0 && q_hi <= 1.0))
+    return fail(LARS_ERR_INVALID, "lars_wb_lut_build_u8_peers: quantiles must be fractions in [0,1]");
+  if (chain != LARS_WB_CHAIN_IMAGES && chain != LARS_WB_CHAIN_RGN)
+    return fail(LARS_ERR_INVALID, "lars_wb_lut_build_u8_peers: chain=%d", chain);
+  lars::K1bPeerParams p;
+  p.k1b.hist = reinterpret_cast<const unsigned long long*>(hist);
+  p.k1b.lut = lut; p.k1b.pct = pct; p.k1b.q_lo = q_lo; p.k1b.q_hi = q_hi; p.k1b.chain = chain;
+  p.peer_bufs = reinterpret_cast<unsigned long long* const*>(peer_bufs);
+  p.status = status; p.rank = rank; p.world = world; p.epoch = epoch;
+  lars::wb_lut_build_u8_peers_kernel<<<3, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  LARS_CUDA(cudaGetLastError());
+  return LARS_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // Pass 2
 // ------------------------------------------------------------------------------------------

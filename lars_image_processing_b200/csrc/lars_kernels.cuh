@@ -190,17 +190,17 @@ struct K1bParams {
   int chain;                       // LARS_WB_CHAIN_*: which reference expression the table restates
 };
 
-__global__ void __launch_bounds__(256) wb_lut_build_u8_kernel(const K1bParams p) {
+// Body of K1b for one (set, channel): `x` is this thread's count of value v = threadIdx.x; sc = set * 3 + channel.
+__device__ __forceinline__ void wb_lut_build_body(unsigned long long x, const K1bParams& p, long long sc) {
   __shared__ unsigned long long cum[256];
   __shared__ unsigned long long warp_tot[8];
   __shared__ int order_stat[4];
   __shared__ double pcts[2];
   const int v = threadIdx.x;
   const int lane = v & 31, warp = v >> 5;
-  const long long base = (long long)blockIdx.x * 256;  // blockIdx.x = set * 3 + channel
+  const long long base = sc * 256;
 
   // inclusive scan of the 256 bins
-  unsigned long long x = p.hist[base + v];
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d);
@@ -240,11 +240,71 @@ __global__ void __launch_bounds__(256) wb_lut_build_u8_kernel(const K1bParams p)
     const double a = (double)order_stat[2 * v], b = (double)order_stat[2 * v + 1];
     const double r = (vi >= nm1) ? a : lars_percentile_lerp(a, b, gamma);
     pcts[v] = r;
-    if (p.pct) p.pct[(long long)blockIdx.x * 2 + v] = r;
+    if (p.pct) p.pct[sc * 2 + v] = r;
   }
   __syncthreads();
   p.lut[base + v] = p.chain == 1 ? lars_wb_lut_entry_rgn((double)v, pcts[0], pcts[1])
                                  : lars_wb_lut_entry((double)v, pcts[0], pcts[1]);
+}
+
+__global__ void __launch_bounds__(256) wb_lut_build_u8_kernel(const K1bParams p) {
+  wb_lut_build_body(p.hist[(long long)blockIdx.x * 256 + threadIdx.x], p, blockIdx.x);   // blockIdx.x = set * 3 + channel
+}
+
+// ------------------------------------------------------------------------------------------
+// K1b fused with the exchange of a tile-sharded image (BASELINE config 4): the image-wide white-balance histogram is
+// the SUM of the ranks' local histograms (process-images.py:435-438: the percentiles are global to the image).  The
+// payload is 3 x 256 counters, so the exchange is pure latency; instead of an NCCL all-reduce between K1 and K1b
+// (launch + ring / tree protocol, ~20-65 us observed) this kernel does it itself over NVLink peer memory:
+//   every rank owns a symmetric buffer  slots[2][world][3][256] u64 + flags[world][3] u32  that all peers have mapped;
+//   CTA ch (one per channel): thread v STOREs its local count into slots[epoch & 1][rank][ch][v] of EVERY peer,
+//   fences at system scope, then threads 0..world-1 raise flags[rank][ch] = epoch on every peer (release) and wait for
+//   flags[w][ch] >= epoch in their own buffer (acquire); then every rank sums the world slots in rank order
+//   (deterministic, identical on all ranks) and goes on to the percentiles and the table.
+// Two slot sets alternate by epoch parity: a rank can be at most one exchange ahead of a peer (its next exchange needs
+// that peer's next flag), so it never overwrites counters a peer still reads.  The wait is bounded (~10 s): on timeout
+// the kernel sets *status and uses what it has instead of hanging the GPU.
+// ------------------------------------------------------------------------------------------
+struct K1bPeerParams {
+  K1bParams k1b;                         // hist: [1][3][256] local counts in, image-wide counts out; lut / pct: one set
+  unsigned long long* const* peer_bufs;  // device array [world]: every rank's symmetric buffer as mapped here
+  uint32_t* status;                      // [1] set to 1 on a timed-out wait
+  int rank, world;
+  uint32_t epoch;                        // 1, 2, 3, ... (flags start at 0)
+};
+
+__device__ __forceinline__ size_t peer_slot_index(int parity, int world, int src_rank, int ch, int v) {
+  return (((size_t)parity * world + src_rank) * 3 + ch) * 256 + v;
+}
+
+__global__ void __launch_bounds__(256) wb_lut_build_u8_peers_kernel(const K1bPeerParams p) {
+  const int ch = blockIdx.x, v = threadIdx.x;
+  const int parity = (int)(p.epoch & 1u);
+  const size_t flags_at = (size_t)2 * p.world * 768;                 // in u64 units: flags follow the slots
+  unsigned long long* hist = const_cast<unsigned long long*>(p.k1b.hist);
+  const unsigned long long mine = hist[ch * 256 + v];
+  for (int w = 0; w < p.world; ++w) p.peer_bufs[w][peer_slot_index(parity, p.world, p.rank, ch, v)] = mine;
+  __threadfence_system();
+  __syncthreads();
+  if (v < p.world) {
+    uint32_t* remote = reinterpret_cast<uint32_t*>(p.peer_bufs[v] + flags_at) + p.rank * 3 + ch;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(p.epoch) : "memory");
+    const uint32_t* local = reinterpret_cast<const uint32_t*>(p.peer_bufs[p.rank] + flags_at) + v * 3 + ch;
+    const long long t0 = clock64();
+    uint32_t seen;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(local) : "memory");
+      if ((int32_t)(seen - p.epoch) >= 0) break;
+      if (clock64() - t0 > 20000000000ll) { *p.status = 1u; break; }  // ~10 s at 2 GHz: report, do not hang
+      __nanosleep(100);
+    }
+  }
+  __syncthreads();
+  unsigned long long total = 0;
+  const unsigned long long* own = p.peer_bufs[p.rank];
+  for (int w = 0; w < p.world; ++w) total += __ldcg(own + peer_slot_index(parity, p.world, w, ch, v));
+  hist[ch * 256 + v] = total;                                         // the caller sees the image-wide histogram
+  wb_lut_build_body(total, p.k1b, ch);
 }
 
 }  // namespace lars

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from ._lib import INDEX_STATS_DTYPE, check
+from ._lib import INDEX_STATS_DTYPE, LarsError, check
 
 RECORD_BYTES = INDEX_STATS_DTYPE.itemsize
 
@@ -186,6 +186,58 @@ def process_mosaic_tiles(engine, tiles, outputs=("wb", "maps", "rgb", "stats"), 
                                 hist_hook=lambda h: allreduce_wb_histogram(h, group), stream=s, **kw)
     whole = dataset_statistics(engine, res.stats, group, s) if res.stats is not None else None
     return res, whole
+
+
+class PeerHistogramExchange:
+    """The white-balance exchange of a tile-sharded image done by the LUT kernel itself over NVLink peer memory
+    (``lars_wb_lut_build_u8_peers``) instead of an NCCL all-reduce between Pass 1 and the LUT build: 3 x 256 counters are
+    pure latency, and one kernel that pushes them into every peer's buffer, waits for the peers' flags and sums in
+    rank order replaces two launches and the collective's protocol.
+
+    Every rank allocates one symmetric buffer (``torch.distributed._symmetric_memory``: CUDA VMM allocations that all
+    ranks of the node map into their address space), so the kernel gets a device array of ``world`` pointers.
+    Collective: construct it on every rank of the group.  Raises ``LarsError`` when symmetric memory cannot be set up
+    on this box -- callers then keep the NCCL hook (``allreduce_wb_histogram``)."""
+
+    def __init__(self, engine, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+            raise LarsError("PeerHistogramExchange needs an initialised process group with more than one rank")
+        self.engine = engine
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        nbytes = int(engine.lib.lars_wb_peer_buffer_bytes(self.world))
+        try:
+            with torch.cuda.device(engine.device):
+                try:
+                    symm_mem.set_backend("CUDA")                  # plain CUDA VMM / IPC mappings (NVSHMEM is not in this image)
+                except Exception:
+                    pass
+                self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=engine.device)
+                self.buf.zero_()
+                torch.cuda.synchronize(engine.device)
+                self.handle = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+            self.peer_ptrs_dev = int(self.handle.buffer_ptrs_dev)
+        except Exception as exc:                                   # no VMM / fabric support, old driver, ...
+            raise LarsError(f"symmetric memory is not available here: {exc}") from exc
+        self.status = torch.zeros(1, dtype=torch.int32, device=engine.device)
+        self.epoch = 0
+        dist.barrier(group)                                        # every rank's buffer is zeroed and mapped
+
+    def lut_build(self, hist: torch.Tensor, lut: torch.Tensor, pct: Optional[torch.Tensor], quantiles=(0.02, 0.98),
+                  stream=None, chain: int = 0) -> None:
+        """hist [1, 3, 256] int64: local counts in, image-wide counts out; lut [1, 3, 256] uint8, pct [1, 3, 2] float64."""
+        s = stream or self.engine.stream()
+        self.epoch += 1
+        with torch.cuda.device(self.engine.device):
+            check(self.engine.lib.lars_wb_lut_build_u8_peers(
+                hist.data_ptr(), self.peer_ptrs_dev, self.rank, self.world, self.epoch & 0xFFFFFFFF or 1,
+                float(quantiles[0]), float(quantiles[1]), int(chain), lut.data_ptr(),
+                pct.data_ptr() if pct is not None else None, self.status.data_ptr(), s.cuda_stream),
+                "lars_wb_lut_build_u8_peers")
+
+    def timed_out(self) -> bool:
+        """True if any exchange so far gave up waiting for a peer (synchronises)."""
+        return bool(int(self.status.item()))
 
 
 def records_to_numpy(records: torch.Tensor) -> np.ndarray:

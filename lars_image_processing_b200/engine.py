@@ -697,11 +697,13 @@ class FramePlan:
 
     def __init__(self, engine: "Engine", frames: DeviceFrames, outputs=ALL_OUTPUTS, white_balance: bool = True,
                  quantiles=DEFAULT_QUANTILES, merge_dataset: bool = False, stream=None,
-                 tiles_of_one_image: bool = False, hist_hook=None, **fused_kw):
+                 tiles_of_one_image: bool = False, hist_hook=None, peer_exchange=None, **fused_kw):
         """``tiles_of_one_image``: the frames are tiles of ONE image (orthomosaic, BASELINE config 4): Pass 1
         accumulates a single histogram over all of them, ``hist_hook(hist)`` runs on the plan's stream between
         Pass 1 and the LUT build (the multi-GPU path SUM-all-reduces the [1, 3, 256] counters there) and one
-        LUT serves every tile (process-images.py:435-438: the percentiles are global to the image)."""
+        LUT serves every tile (process-images.py:435-438: the percentiles are global to the image).
+        ``peer_exchange`` (a ``distributed.PeerHistogramExchange``) replaces hook + LUT build by the one kernel that
+        exchanges the counters over NVLink peer memory itself."""
         self.engine = engine
         self.frames = frames
         self.stream = stream or engine.stream()
@@ -713,6 +715,9 @@ class FramePlan:
         self.u16 = frames.sample_bytes == 2
         self.shared = bool(tiles_of_one_image)
         self.hist_hook = hist_hook
+        self.peer_exchange = peer_exchange
+        if peer_exchange is not None and not self.shared:
+            raise LarsError("peer_exchange belongs to a tiles_of_one_image plan")
         if self.shared and (self.u16 or not white_balance):
             raise LarsError("FramePlan(tiles_of_one_image=True) covers white-balanced uint8 tiles; uint16 mosaics go "
                             "through Engine.process_device (staged two-level histogram)")
@@ -769,11 +774,14 @@ class FramePlan:
         elif self.white_balance:
             check(lib.lars_wb_hist_u8(fr.data.data_ptr(), fr.n_frames, fr.n_pixels, fr.channels, fr.stride_bytes,
                                       self.hist.data_ptr(), 1 if self.shared else 0, sp), "lars_wb_hist_u8")
-            if self.hist_hook is not None:
-                with torch.cuda.stream(self.stream):
-                    self.hist_hook(self.hist)
-            check(lib.lars_wb_lut_build_u8(self.hist.data_ptr(), self.hist.shape[0], self.quantiles[0], self.quantiles[1],
-                                           self.lut.data_ptr(), self.pct.data_ptr(), sp), "lars_wb_lut_build_u8")
+            if self.peer_exchange is not None:
+                self.peer_exchange.lut_build(self.hist, self.lut, self.pct, self.quantiles, stream=self.stream)
+            else:
+                if self.hist_hook is not None:
+                    with torch.cuda.stream(self.stream):
+                        self.hist_hook(self.hist)
+                check(lib.lars_wb_lut_build_u8(self.hist.data_ptr(), self.hist.shape[0], self.quantiles[0], self.quantiles[1],
+                                               self.lut.data_ptr(), self.pct.data_ptr(), sp), "lars_wb_lut_build_u8")
         if fused_events is not None:
             fused_events[0].record(self.stream)
         if self.u16:
