@@ -276,14 +276,16 @@ __global__ void __launch_bounds__(MAP_HIST_ROWS * MAP_FIN_SPLIT) map_stats_final
 // Round 1 / early round 2 launched one kernel per pass: 59 us per 12 MP float32 map = 3 x ~20 us, of which ~7 us is
 // streaming (ncu: 8 M warp instructions and 48 MB per pass, long_scoreboard on top) and the rest launch, ramp-up of
 // 296 CTAs x 512 threads for ~80 elements per thread, and the last CTA's scan.  A cheaper pass (no shared histogram
-// for the sparse passes) measured no gain; removing the launches and ramps is what this form does.  The launch is
-// cooperative (all CTAs must be co-resident for the barrier).
+// for the sparse passes) measured no gain; removing the launches and ramps is what this form does: 59.4 -> 53.6 us,
+// 50.1 with one scan for both ranks while they share a prefix, 47.4 with one 1,024-thread CTA per SM instead of two
+// of 512 (half the barrier arrivals and fold atomics); float64 155 -> 122 us.  The launch is cooperative (all CTAs
+// must be co-resident for the barrier).
 constexpr int SEL_BINS = 2048;                 // bins of the widest digit
 #ifndef LARS_SEL_LANES
 #define LARS_SEL_LANES 4
 #endif
 constexpr int SEL_LANES = LARS_SEL_LANES;      // lane copies of each counter (lanes congruent modulo this share one)
-constexpr int SEL_THREADS = 512;
+constexpr int SEL_THREADS = 1024;
 constexpr int SEL_SMEM_BYTES = 2 * SEL_BINS * SEL_LANES * 4;   // 64 KB: [2][2048][4]
 
 template <typename T> struct SelectTraits;
