@@ -12,8 +12,9 @@ A "step" is one pass of the hot path over the workload's batch of synthetic fram
   c3            1,024 frames 5472x3648 uint16, round-robin over the GPUs (strong scaling), all resident in HBM,
                 processed in launch groups of 8 (two-level histogram, stretch build, fused pass per group).
   c4            one 32,768^2 uint8 mosaic as 64 tiles of 4,096^2, a row band of tiles per GPU (strong scaling):
-                ONE white-balance histogram over the local tiles, SUM all-reduce (NCCL) of the 3 x 256 counters
-                INSIDE the step, one LUT, fused pass over the tiles, image-wide statistics by one all-gather.
+                ONE white-balance histogram over the local tiles, the 3 x 256 counters summed over the GPUs INSIDE
+                the step (--exchange peer: by the LUT kernel itself over NVLink peer memory; nccl: all-reduce),
+                one LUT, fused pass over the tiles, image-wide statistics by one all-gather.
   c5            100,000 frames 1280x960 uint8 over the GPUs (strong scaling) in launch groups of 256 cycling through
                 a device ring of 2,048 distinct resident frames (368.6 GB do not fit in HBM; refilling the ring is
                 the ingest side and outside `value`), one dataset merge at the end.

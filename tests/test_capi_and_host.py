@@ -220,3 +220,47 @@ def test_reference_extract_matches_the_ast_loaded_functions():
             assert a[1][t]["std"] == b[1][t]["std"] and np.array_equal(a[1][t]["hist"], b[1][t]["hist"])
             assert {k: v for k, v in a[1][t].items() if k not in ("hist", "rgb")} == \
                 {k: v for k, v in b[1][t].items() if k not in ("hist", "rgb")}
+
+
+def test_bench_workload_sharding_covers_every_frame_once():
+    """bench.py's layout of the four workloads over 1 / 2 / 4 / 8 ranks (host logic, no GPU): c3 round-robin and c4 row
+    bands partition the job's frames exactly, c2 and c5's device rings get disjoint seeds per rank, and the reference
+    arm's config carries the same keys as the GPU arm's."""
+    import types
+    import bench
+    for world in (1, 2, 3, 4, 8):
+        for wl in ("c2", "c3", "c4", "c5"):
+            a = types.SimpleNamespace(workload=wl, w=dict(bench.WORKLOADS[wl]))
+            per_rank = [bench.frame_seeds(a, r, world) for r in range(world)]
+            flat = [s for seeds in per_rank for s in seeds]
+            assert len(set(flat)) == len(flat), (wl, world)                       # no frame on two ranks
+            w = a.w
+            if wl in ("c3", "c4"):
+                assert sorted(flat) == [w["seed0"] + i for i in range(w["total_frames"])], (wl, world)
+                assert max(map(len, per_rank)) - min(map(len, per_rank)) <= 1
+            if wl == "c3":
+                assert per_rank[0][:2] == [w["seed0"], w["seed0"] + world][:len(per_rank[0][:2])]   # frame i -> rank i % world
+            if wl == "c4" and world > 1:
+                assert per_rank[0] == list(range(w["seed0"], w["seed0"] + len(per_rank[0])))        # contiguous band
+            if wl == "c2":
+                assert all(len(p) == w["frames_per_gpu"] for p in per_rank)
+            if wl == "c5":
+                assert all(len(p) == w["ring_groups"] * w["group"] for p in per_rank)
+            cfg = bench.common_config(a, world)
+            assert {"workload", "height", "width", "frames_per_gpu"} <= set(cfg)
+    from lars_image_processing_b200 import distributed as ld
+    for n, world in ((100000, 8), (64, 8), (7, 3), (2, 4)):
+        ranges = [ld.shard_range(n, r, world) for r in range(world)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == n and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+
+
+def test_peer_exchange_refuses_a_single_process():
+    """PeerHistogramExchange is a collective over more than one rank; without a process group it raises LarsError
+    (callers then keep the NCCL hook) instead of failing inside the kernel."""
+    from lars_image_processing_b200 import distributed as ld
+    from lars_image_processing_b200._lib import LarsError, load
+    with pytest.raises(LarsError):
+        ld.PeerHistogramExchange(engine=None)
+    lib = load()
+    assert lib.lars_wb_peer_buffer_bytes(8) >= 2 * 8 * 768 * 8 + 8 * 3 * 4 and lib.lars_wb_peer_buffer_bytes(8) % 256 == 0
+    assert lib.lars_wb_peer_buffer_bytes(0) == 0
