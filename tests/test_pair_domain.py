@@ -277,3 +277,66 @@ def test_uint16_stretch_guess_is_within_one_step_for_every_sample_value(hostchec
         got = g + (v >= thr[g + 1]) - (v < thr[g])
         assert np.array_equal(got, lut), (it, lo, hi)
     assert worst == 1                                                     # the correction is needed, and one step suffices
+
+
+def _guided_candidates(sample_hist, q=(0.02, 0.98)):
+    """NumPy restatement of wb_u16_candidates_kernel (lars_u16_kernels.cuh): per percentile the bucket of rank
+    floor((m - 1) q) in the SAMPLED high-byte histogram and its non-empty neighbour on the nearer side."""
+    cum = np.cumsum(sample_hist)
+    m = int(cum[-1])
+    picked = set()
+    if m == 0:
+        return picked
+    for qq in q:
+        r = int(np.floor((m - 1) * qq))
+        b = int(np.searchsorted(cum, r, side="right"))
+        below = int(cum[b - 1]) if b else 0
+        cnt = int(cum[b]) - below
+        nz = np.nonzero(sample_hist)[0]
+        if 2 * (r - below) < cnt:
+            nb = nz[nz < b]
+            nb = int(nb[-1]) if nb.size else -1
+        else:
+            nb = nz[nz > b]
+            nb = int(nb[0]) if nb.size else -1
+        picked.update(x for x in (b, nb) if x >= 0)
+    return picked
+
+
+def test_guided_uint16_guess_covers_the_true_buckets_on_ordinary_frames():
+    """Design check of the uint16 guided pass without a GPU: the high-byte histogram of every k-th 4,096-pixel work unit
+    (k as u16_sample_step picks it) must put the 2 % / 98 % ranks of the FULL frame inside the <= 4 candidate buckets,
+    otherwise the frame pays the level-B fallback.  Vegetation-like noise and a smooth (spatially correlated) frame,
+    sizes from 0.3 to 20 MP.  (Exactness never depends on this -- test_uint16_guided_single_pass_equals_two_level
+    covers frames built to defeat the guess -- only the speed does.)"""
+    def step_for(units):
+        s = units // 64
+        return 1 if s < 1 else min(16, s)
+    rng = np.random.default_rng(9)
+    misses = total = 0
+    for h, w in ((480, 640), (960, 1280), (3000, 4000), (3648, 5472)):
+        n = h * w
+        units = (n * 6 + 24575) // 24576
+        step = step_for(units)
+        for kind in ("noise", "smooth"):
+            for c, (mu, sd) in enumerate(((23130, 8995), (28270, 8995), (38550, 11565))):
+                if kind == "noise":
+                    plane = np.clip(rng.normal(mu, sd, n), 0, 65535).astype(np.uint16)
+                else:
+                    yy = np.arange(n, dtype=np.float64) / w
+                    plane = np.clip(mu + sd * np.sin(yy / (37.0 + 11 * c)) + rng.normal(0, 300, n), 0, 65535).astype(np.uint16)
+                hb = plane >> 8
+                # sample: pixels of every step-th unit (a unit is 4,096 consecutive pixels of the interleaved frame)
+                unit_of_px = np.arange(n) // 4096
+                sample_hist = np.bincount(hb[unit_of_px % step == 0], minlength=256)
+                cand = _guided_candidates(sample_hist)
+                full = np.cumsum(np.bincount(hb, minlength=256))
+                need = set()
+                for qq in (0.02, 0.98):
+                    vi = (n - 1) * qq
+                    for r in (int(np.floor(vi)), min(int(np.floor(vi)) + 1, n - 1)):
+                        need.add(int(np.searchsorted(full, r, side="right")))
+                total += 1
+                misses += not need <= cand
+                assert len(cand) <= 4
+    assert misses == 0, (misses, total)
